@@ -1,0 +1,225 @@
+// extern "C" net-level entry points of include/fn2.h over caffe::Net<float>.
+#include <cstring>
+
+#include "net.hpp"
+
+namespace fn2 { void set_error(const char* fmt, ...); }
+
+struct fn2_net {
+    std::unique_ptr<caffe::Net<float> > net;
+    std::vector<std::string> input_names, output_names;
+    std::string caffemodel_cache;
+};
+
+#define FN2_TRY try {
+#define FN2_CATCH                                                        \
+    } catch (const caffe::ParseError& e) {                               \
+        fn2::set_error("%s", e.what());                                  \
+        return FN2_ERR_PARSE;                                            \
+    } catch (const std::exception& e) {                                  \
+        fn2::set_error("%s", e.what());                                  \
+        return strstr(e.what(), "Unknown") ? FN2_ERR_NOTFOUND : FN2_ERR_INVALID; \
+    }
+
+extern "C" {
+
+int fn2_net_create(const char* prototxt_text, int phase, fn2_net** out) {
+    return fn2_net_create_batch(prototxt_text, phase, 0, out);
+}
+
+int fn2_net_create_batch(const char* prototxt_text, int phase, int batch, fn2_net** out) {
+    if (!prototxt_text || !out) { fn2::set_error("net_create: null argument"); return FN2_ERR_INVALID; }
+    *out = nullptr;
+    FN2_TRY
+        caffe::NetParameter np = caffe::NetParameter::FromText(prototxt_text);
+        if (batch > 0) {
+            for (auto& lp : np.layers) {
+                if (lp.type() != "Input") continue;
+                caffe::Message* ip = lp.m->mutable_msg("input_param");
+                for (auto& f : ip->fields)
+                    if (f.name == "shape" && f.is_msg)
+                        for (auto& d : f.msg->fields)
+                            if (d.name == "dim") { d.scalar = std::to_string(batch); break; }
+            }
+        }
+        std::unique_ptr<fn2_net> h(new fn2_net());
+        h->net.reset(new caffe::Net<float>(np, phase == 0 ? caffe::TRAIN : caffe::TEST));
+        for (int i : h->net->input_blob_indices()) h->input_names.push_back(h->net->blob_names()[i]);
+        for (int i : h->net->output_blob_indices()) h->output_names.push_back(h->net->blob_names()[i]);
+        *out = h.release();
+        return FN2_OK;
+    FN2_CATCH
+}
+
+void fn2_net_destroy(fn2_net* net) { delete net; }
+
+int fn2_net_copy_trained_layers(fn2_net* net, const void* caffemodel, size_t bytes) {
+    if (!net || !caffemodel) { fn2::set_error("copy_trained_layers: null argument"); return FN2_ERR_INVALID; }
+    FN2_TRY
+        net->net->CopyTrainedLayersFrom(caffemodel, bytes);
+        return FN2_OK;
+    FN2_CATCH
+}
+
+int fn2_net_to_caffemodel(fn2_net* net, void* buf, size_t* bytes) {
+    if (!net || !bytes) { fn2::set_error("to_caffemodel: null argument"); return FN2_ERR_INVALID; }
+    FN2_TRY
+        if (!buf || net->caffemodel_cache.empty()) net->caffemodel_cache = net->net->ToCaffemodel();
+        if (!buf) { *bytes = net->caffemodel_cache.size(); return FN2_OK; }
+        if (*bytes < net->caffemodel_cache.size()) { fn2::set_error("to_caffemodel: buffer too small"); return FN2_ERR_INVALID; }
+        memcpy(buf, net->caffemodel_cache.data(), net->caffemodel_cache.size());
+        *bytes = net->caffemodel_cache.size();
+        net->caffemodel_cache.clear();
+        net->caffemodel_cache.shrink_to_fit();
+        return FN2_OK;
+    FN2_CATCH
+}
+
+int fn2_net_fill_params(fn2_net* net, uint64_t seed) {
+    if (!net) { fn2::set_error("fill_params: null net"); return FN2_ERR_INVALID; }
+    FN2_TRY
+        net->net->FillParams(seed);
+        return FN2_OK;
+    FN2_CATCH
+}
+
+int fn2_net_param_arena(fn2_net* net, void** dev_ptr, size_t* bytes) {
+    if (!net || !dev_ptr || !bytes) { fn2::set_error("param_arena: null argument"); return FN2_ERR_INVALID; }
+    net->net->ParamArena(dev_ptr, bytes);
+    return FN2_OK;
+}
+
+int fn2_net_params_changed(fn2_net* net) {
+    if (!net) { fn2::set_error("params_changed: null net"); return FN2_ERR_INVALID; }
+    FN2_TRY
+        net->net->ParamsChanged();
+        return FN2_OK;
+    FN2_CATCH
+}
+
+int fn2_net_num_inputs(fn2_net* net) { return net ? (int)net->input_names.size() : 0; }
+const char* fn2_net_input_name(fn2_net* net, int i) {
+    return (net && i >= 0 && i < (int)net->input_names.size()) ? net->input_names[i].c_str() : nullptr;
+}
+int fn2_net_num_outputs(fn2_net* net) { return net ? (int)net->output_names.size() : 0; }
+const char* fn2_net_output_name(fn2_net* net, int i) {
+    return (net && i >= 0 && i < (int)net->output_names.size()) ? net->output_names[i].c_str() : nullptr;
+}
+int fn2_net_num_blobs(fn2_net* net) { return net ? (int)net->net->blob_names().size() : 0; }
+const char* fn2_net_blob_name(fn2_net* net, int i) {
+    return (net && i >= 0 && i < (int)net->net->blob_names().size()) ? net->net->blob_names()[i].c_str() : nullptr;
+}
+int fn2_net_num_layers(fn2_net* net) { return net ? (int)net->net->layer_names().size() : 0; }
+const char* fn2_net_layer_name(fn2_net* net, int i) {
+    return (net && i >= 0 && i < (int)net->net->layer_names().size()) ? net->net->layer_names()[i].c_str() : nullptr;
+}
+const char* fn2_net_layer_type(fn2_net* net, int i) {
+    return (net && i >= 0 && i < (int)net->net->layers().size()) ? net->net->layers()[i]->type() : nullptr;
+}
+
+int fn2_net_blob_shape(fn2_net* net, const char* blob, int shape[4]) {
+    if (!net || !blob || !shape) { fn2::set_error("blob_shape: null argument"); return FN2_ERR_INVALID; }
+    FN2_TRY
+        auto b = net->net->blob_by_name(blob);
+        for (int i = 0; i < 4; i++) shape[i] = b->shape(i);
+        return FN2_OK;
+    FN2_CATCH
+}
+
+int fn2_net_set_input(fn2_net* net, const char* blob, const float* host_nchw) {
+    if (!net || !blob || !host_nchw) { fn2::set_error("set_input: null argument"); return FN2_ERR_INVALID; }
+    FN2_TRY
+        net->net->SetInput(blob, host_nchw);
+        return FN2_OK;
+    FN2_CATCH
+}
+int fn2_net_set_input_device(fn2_net* net, const char* blob, const float* dev_nchw) {
+    if (!net || !blob || !dev_nchw) { fn2::set_error("set_input_device: null argument"); return FN2_ERR_INVALID; }
+    FN2_TRY
+        net->net->SetInputDevice(blob, dev_nchw);
+        return FN2_OK;
+    FN2_CATCH
+}
+int fn2_net_get_blob(fn2_net* net, const char* blob, float* host_nchw) {
+    if (!net || !blob || !host_nchw) { fn2::set_error("get_blob: null argument"); return FN2_ERR_INVALID; }
+    FN2_TRY
+        net->net->GetBlob(blob, host_nchw);
+        return FN2_OK;
+    FN2_CATCH
+}
+int fn2_net_get_blob_device(fn2_net* net, const char* blob, float* dev_nchw) {
+    if (!net || !blob || !dev_nchw) { fn2::set_error("get_blob_device: null argument"); return FN2_ERR_INVALID; }
+    FN2_TRY
+        net->net->GetBlobDevice(blob, dev_nchw);
+        return FN2_OK;
+    FN2_CATCH
+}
+
+int fn2_net_forward(fn2_net* net) {
+    if (!net) { fn2::set_error("forward: null net"); return FN2_ERR_INVALID; }
+    FN2_TRY
+        net->net->Forward();
+        return FN2_OK;
+    FN2_CATCH
+}
+int fn2_net_sync(fn2_net* net) {
+    if (!net) { fn2::set_error("sync: null net"); return FN2_ERR_INVALID; }
+    FN2_TRY
+        net->net->Sync();
+        return FN2_OK;
+    FN2_CATCH
+}
+void* fn2_net_stream(fn2_net* net) { return net ? (void*)net->net->stream() : nullptr; }
+
+int fn2_net_time_layers(fn2_net* net, float* ms) {
+    if (!net || !ms) { fn2::set_error("time_layers: null argument"); return FN2_ERR_INVALID; }
+    FN2_TRY
+        net->net->TimeLayers(ms);
+        return FN2_OK;
+    FN2_CATCH
+}
+int fn2_net_launches_per_forward(fn2_net* net) { return net ? net->net->launches_per_forward() : 0; }
+
+static int emit_string(const std::string& s, char* out, size_t* bytes) {
+    if (!bytes) { fn2::set_error("null size pointer"); return FN2_ERR_INVALID; }
+    if (!out) { *bytes = s.size() + 1; return FN2_OK; }
+    if (*bytes < s.size() + 1) { fn2::set_error("buffer too small"); return FN2_ERR_INVALID; }
+    memcpy(out, s.c_str(), s.size() + 1);
+    *bytes = s.size() + 1;
+    return FN2_OK;
+}
+
+int fn2_proto_canonical(const char* prototxt_text, char* out, size_t* bytes) {
+    if (!prototxt_text) { fn2::set_error("proto_canonical: null text"); return FN2_ERR_INVALID; }
+    FN2_TRY
+        caffe::NetParameter np = caffe::NetParameter::FromText(prototxt_text);
+        std::string s;
+        if (!np.name.empty()) s += "name: \"" + np.name + "\"\n";
+        for (const auto& l : np.layers) s += "layer {\n" + caffe::PrintTextFormat(*l.m, 1) + "}\n";
+        return emit_string(s, out, bytes);
+    FN2_CATCH
+}
+
+int fn2_caffemodel_summary(const void* caffemodel, size_t n, char* out, size_t* bytes) {
+    if (!caffemodel) { fn2::set_error("caffemodel_summary: null data"); return FN2_ERR_INVALID; }
+    FN2_TRY
+        std::vector<caffe::LayerBlobs> ls = caffe::ParseCaffemodel(caffemodel, n);
+        std::string s;
+        char buf[128];
+        for (const auto& l : ls) {
+            s += l.name + " " + l.type;
+            for (const auto& b : l.blobs) {
+                s += " [";
+                for (size_t i = 0; i < b.shape.size(); i++) { snprintf(buf, sizeof(buf), i ? ",%d" : "%d", b.shape[i]); s += buf; }
+                double sum = 0;
+                for (float v : b.data) sum += (double)v;
+                snprintf(buf, sizeof(buf), "] n=%zu sum=%.9g", b.data.size(), sum);
+                s += buf;
+            }
+            s += "\n";
+        }
+        return emit_string(s, out, bytes);
+    FN2_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,689 @@
+// Layer classes on the FlowNet2 deploy graph.  Each mirrors the reference class of the same
+// name (type string, parameter handling, shape rules, error messages) and forwards the device
+// work to the fn2_* C-ABI.  Reference files are cited per class.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+
+#include "layer.hpp"
+
+namespace caffe {
+
+typedef Blob<float> BlobF;
+
+static cudaStream_t S() { return Caffe::stream(); }
+
+// ---------------------------------------------------------------------------------------------
+// Fillers (include/caffe/filler.hpp).  Deterministic host RNG (the reference draws from boost
+// mt19937, util/rng.hpp:16-20; bit-matching boost is out of scope -- weights come from a
+// .caffemodel in real use and from this generator for synthetic benchmarks).
+// ---------------------------------------------------------------------------------------------
+struct HostRng {
+    std::mt19937_64 gen;
+    explicit HostRng(uint64_t seed) : gen(seed) {}
+    double uniform() { return (double)(gen() >> 11) * (1.0 / 9007199254740992.0); }
+    bool has_spare = false;
+    double spare = 0;
+    double gaussian() {
+        if (has_spare) { has_spare = false; return spare; }
+        double u, v, s;
+        do {
+            u = uniform() * 2 - 1; v = uniform() * 2 - 1; s = u * u + v * v;
+        } while (s >= 1 || s == 0);
+        double m = std::sqrt(-2.0 * std::log(s) / s);
+        spare = v * m; has_spare = true;
+        return u * m;
+    }
+};
+
+static void FillBlob(const FillerParameter& fp, BlobF* blob, uint64_t seed) {
+    CHECK(blob->count()) << "filler: empty blob";
+    float* d = blob->mutable_cpu_data();
+    const int count = blob->count();
+    const string type = fp.type();
+    HostRng rng(seed);
+    if (type == "constant") {                                     // filler.hpp:45-60
+        for (int i = 0; i < count; i++) d[i] = fp.value();
+    } else if (type == "uniform") {                               // :63-76
+        for (int i = 0; i < count; i++) d[i] = (float)(fp.min() + (fp.max() - fp.min()) * rng.uniform());
+    } else if (type == "gaussian") {                              // :79-113 (no sparsity)
+        for (int i = 0; i < count; i++) d[i] = (float)(fp.mean() + fp.std() * rng.gaussian());
+    } else if (type == "xavier" || type == "msra") {              // :145-208
+        const int fan_in = count / blob->num();
+        const int fan_out = count / blob->channels();
+        double n = fan_in;
+        const string vn = fp.variance_norm();
+        if (vn == "AVERAGE" || vn == "2") n = (fan_in + fan_out) / 2.0;
+        else if (vn == "FAN_OUT" || vn == "1") n = fan_out;
+        if (type == "xavier") {
+            const double scale = std::sqrt(3.0 / n);
+            for (int i = 0; i < count; i++) d[i] = (float)(-scale + 2 * scale * rng.uniform());
+        } else {
+            const double sd = std::sqrt(2.0 / n);
+            for (int i = 0; i < count; i++) d[i] = (float)(sd * rng.gaussian());
+        }
+    } else if (type == "diagonal") {                              // filler.hpp:265-290 (fork)
+        for (int i = 0; i < count; i++) d[i] = 0.f;
+        const int kernel_area = blob->height() * blob->width();
+        const int channels = blob->channels(), num = blob->num();
+        for (int n = 0; n < num && n < channels; ++n) {
+            float v = fp.diag_val_size() > n ? fp.diag_val(n) : 1.f;
+            v /= (float)kernel_area;
+            for (int k = 0; k < kernel_area; k++) d[kernel_area * (channels * n + n) + k] = v;
+        }
+    } else {
+        CHECK(false) << "Unknown filler name: " << type;          // filler.hpp:318
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Input (input_layer.cpp:8-22), Split / Silence pass-throughs.
+// ---------------------------------------------------------------------------------------------
+template <typename Dtype>
+class InputLayer : public Layer<Dtype> {
+ public:
+    explicit InputLayer(const LayerParameter& p) : Layer<Dtype>(p) {}
+    const char* type() const override { return "Input"; }
+    int ExactNumBottomBlobs() const override { return 0; }
+    int MinTopBlobs() const override { return 1; }
+    void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        const Message& ip = this->layer_param_.m->msg("input_param");
+        const int num_top = (int)top.size(), num_shape = ip.count("shape");
+        CHECK(num_shape == 0 || num_shape == 1 || num_shape == num_top)
+            << "Must specify 'shape' once, once per top blob, or not at all: " << num_top << " tops vs. "
+            << num_shape << " shapes.";
+        for (int i = 0; i < num_top && num_shape > 0; ++i) {
+            const Message& sh = ip.msg("shape", num_shape == 1 ? 0 : i);
+            vector<int> dims;
+            for (int j = 0; j < sh.count("dim"); j++) dims.push_back(sh.i("dim", 1, j));
+            CHECK_EQ(dims.size(), 4u) << "Input blobs on the FlowNet2 path are 4-D (N,C,H,W)";
+            top[i]->Reshape(dims);
+        }
+    }
+    void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {}
+ protected:
+    void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {}
+};
+REGISTER_LAYER_CLASS(Input);
+
+template <typename Dtype>
+class SilenceLayer : public Layer<Dtype> {                         // silence_layer.cpp
+ public:
+    explicit SilenceLayer(const LayerParameter& p) : Layer<Dtype>(p) {}
+    const char* type() const override { return "Silence"; }
+    int MinBottomBlobs() const override { return 1; }
+    int ExactNumTopBlobs() const override { return 0; }
+    void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {}
+ protected:
+    void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {}
+};
+REGISTER_LAYER_CLASS(Silence);
+
+// ---------------------------------------------------------------------------------------------
+// ReLU (relu_layer.cpp / relu_layer.cu:9-14).  Usually fused into the producing conv by
+// Net::Init; this standalone kernel remains for non-fusable placements.
+// ---------------------------------------------------------------------------------------------
+template <typename Dtype>
+class ReLULayer : public Layer<Dtype> {
+ public:
+    explicit ReLULayer(const LayerParameter& p) : Layer<Dtype>(p) {}
+    const char* type() const override { return "ReLU"; }
+    int ExactNumBottomBlobs() const override { return 1; }
+    int ExactNumTopBlobs() const override { return 1; }
+    void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        top[0]->ReshapeLike(*bottom[0]);
+    }
+    float negative_slope() const { return this->layer_param_.relu_negative_slope(); }
+    void set_fused(bool f) { fused_ = f; }
+ protected:
+    void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        if (fused_) return;     // applied in the producer's epilogue
+        fn2_tensor b = bottom[0]->tensor(), t = top[0]->mutable_tensor();
+        FN2_CALL(fn2_relu_forward(&b, &t, negative_slope(), S()));
+    }
+    bool fused_ = false;
+};
+REGISTER_LAYER_CLASS(ReLU);
+
+// ---------------------------------------------------------------------------------------------
+// Eltwise (eltwise_layer.cpp:10-65): SUM with coefficients is what the deploy nets use
+// (input scaling by 1/255, flow * 20, img0 - warped).
+// ---------------------------------------------------------------------------------------------
+template <typename Dtype>
+class EltwiseLayer : public Layer<Dtype> {
+ public:
+    explicit EltwiseLayer(const LayerParameter& p) : Layer<Dtype>(p) {}
+    const char* type() const override { return "Eltwise"; }
+    int MinBottomBlobs() const override { return 1; }
+    int ExactNumTopBlobs() const override { return 1; }
+    void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        EltwiseParameter ep = this->layer_param_.eltwise_param();
+        CHECK(ep.coeff_size() == 0 || ep.coeff_size() == (int)bottom.size())
+            << "Eltwise Layer takes one coefficient per bottom blob.";
+        const string op = ep.operation();
+        CHECK(op == "SUM" || op == "1") << "Eltwise: only operation SUM is implemented on this path (got " << op << ")";
+        CHECK_LE(bottom.size(), 4u) << "Eltwise: at most 4 bottoms";
+        coeffs_.assign(bottom.size(), 1.f);
+        for (int i = 0; i < ep.coeff_size(); i++) coeffs_[i] = ep.coeff(i);
+    }
+    void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        for (size_t i = 1; i < bottom.size(); ++i) CHECK(bottom[i]->shape() == bottom[0]->shape());
+        top[0]->ReshapeLike(*bottom[0]);
+    }
+ protected:
+    void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        fn2_tensor bs[4];
+        const fn2_tensor* bp[4];
+        for (size_t i = 0; i < bottom.size(); i++) { bs[i] = bottom[i]->tensor(); bp[i] = &bs[i]; }
+        fn2_tensor t = top[0]->mutable_tensor();
+        FN2_CALL(fn2_eltwise_sum(bp, coeffs_.data(), (int)bottom.size(), &t, S()));
+    }
+    vector<float> coeffs_;
+};
+REGISTER_LAYER_CLASS(Eltwise);
+
+// ---------------------------------------------------------------------------------------------
+// Concat along channels (concat_layer.cpp:14-75).  When Net::Init could alias the bottoms into
+// the top's storage (zero-copy), Forward is a no-op for those bottoms.
+// ---------------------------------------------------------------------------------------------
+template <typename Dtype>
+class ConcatLayer : public Layer<Dtype> {
+ public:
+    explicit ConcatLayer(const LayerParameter& p) : Layer<Dtype>(p) {}
+    const char* type() const override { return "Concat"; }
+    int MinBottomBlobs() const override { return 1; }
+    int ExactNumTopBlobs() const override { return 1; }
+    void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        const int axis = this->layer_param_.concat_axis();
+        CHECK_EQ(axis, 1) << "Concat: only the channel axis is used on the FlowNet2 path";
+        vector<int> ts = bottom[0]->shape();
+        for (size_t i = 1; i < bottom.size(); ++i) {
+            CHECK_EQ(bottom[0]->num_axes(), bottom[i]->num_axes()) << "All inputs must have the same #axes.";
+            for (int j = 0; j < 4; j++)
+                if (j != 1) CHECK_EQ(ts[j], bottom[i]->shape(j)) << "All inputs must have the same shape, except at concat_axis.";
+            ts[1] += bottom[i]->shape(1);
+        }
+        top[0]->Reshape(ts);
+    }
+ protected:
+    void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        int c0 = 0;
+        for (size_t i = 0; i < bottom.size(); i++) {
+            const int c = bottom[i]->channels();
+            if (!(bottom[i]->alias_parent() == top[0] && bottom[i]->alias_offset() == c0)) {
+                fn2_tensor s = bottom[i]->tensor(), d = top[0]->mutable_tensor(c0, c);
+                FN2_CALL(fn2_copy(&s, &d, S()));
+            }
+            c0 += c;
+        }
+    }
+};
+REGISTER_LAYER_CLASS(Concat);
+
+// Slice along channels (slice_layer.cpp), used by some FlowNet variants to split stacked inputs.
+template <typename Dtype>
+class SliceLayer : public Layer<Dtype> {
+ public:
+    explicit SliceLayer(const LayerParameter& p) : Layer<Dtype>(p) {}
+    const char* type() const override { return "Slice"; }
+    int ExactNumBottomBlobs() const override { return 1; }
+    int MinTopBlobs() const override { return 1; }
+    void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        const Message& sp = this->layer_param_.m->msg("slice_param");
+        const int axis = sp.has("slice_dim") ? sp.i("slice_dim", 1) : sp.i("axis", 1);
+        CHECK_EQ(axis, 1) << "Slice: only the channel axis is supported";
+        const int C = bottom[0]->channels(), nt = (int)top.size();
+        points_.clear();
+        if (sp.count("slice_point")) {
+            CHECK_EQ(sp.count("slice_point"), nt - 1);
+            int prev = 0;
+            for (int i = 0; i < nt - 1; i++) { int pt = sp.i("slice_point", 0, i); CHECK_GT(pt, prev); points_.push_back(pt); prev = pt; }
+        } else {
+            CHECK_EQ(C % nt, 0) << "Number of top blobs (" << nt << ") should evenly divide input slice axis (" << C << ")";
+            for (int i = 1; i < nt; i++) points_.push_back(i * (C / nt));
+        }
+        int prev = 0;
+        for (int i = 0; i < nt; i++) {
+            int end = i < nt - 1 ? points_[i] : C;
+            top[i]->Reshape(bottom[0]->num(), end - prev, bottom[0]->height(), bottom[0]->width());
+            prev = end;
+        }
+    }
+ protected:
+    void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        int prev = 0;
+        for (size_t i = 0; i < top.size(); i++) {
+            const int c = top[i]->channels();
+            fn2_tensor s = bottom[0]->tensor(prev, c), d = top[i]->mutable_tensor();
+            FN2_CALL(fn2_copy(&s, &d, S()));
+            prev += c;
+        }
+    }
+    vector<int> points_;
+};
+REGISTER_LAYER_CLASS(Slice);
+
+// ---------------------------------------------------------------------------------------------
+// ChannelNorm (channel_norm_layer.cpp:21-36, .cu:17-30)
+// ---------------------------------------------------------------------------------------------
+template <typename Dtype>
+class ChannelNormLayer : public Layer<Dtype> {
+ public:
+    explicit ChannelNormLayer(const LayerParameter& p) : Layer<Dtype>(p) {}
+    const char* type() const override { return "ChannelNorm"; }
+    void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        CHECK_EQ(bottom.size(), 1u) << "ChannelNormLayer takes one input blob.";
+        CHECK_EQ(top.size(), 1u) << "ChannelNormLayer outputs one blob.";
+        top[0]->Reshape(bottom[0]->num(), 1, bottom[0]->height(), bottom[0]->width());
+    }
+ protected:
+    void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        fn2_tensor b = bottom[0]->tensor(), t = top[0]->mutable_tensor();
+        FN2_CALL(fn2_channel_norm_forward(&b, &t, S()));
+    }
+};
+REGISTER_LAYER_CLASS(ChannelNorm);
+
+// ---------------------------------------------------------------------------------------------
+// FlowWarp (flow_warp_layer.cpp:29-52 shapes; forward .cpp:57-117 / .cu:357-458)
+// ---------------------------------------------------------------------------------------------
+template <typename Dtype>
+class FlowWarpLayer : public Layer<Dtype> {
+ public:
+    explicit FlowWarpLayer(const LayerParameter& p) : Layer<Dtype>(p) {}
+    const char* type() const override { return "FlowWarp"; }
+    void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        CHECK_EQ(bottom.size(), 2u) << "FlowWarpLayer takes two input blobs: image and flow.";
+        CHECK_EQ(top.size(), 1u) << "FlowWarpLayer outputs one blob.";
+        CHECK_EQ(bottom[0]->num(), bottom[1]->num()) << "Num of the inputs should be the same";
+        CHECK_EQ(2, bottom[1]->channels()) << "Flow should have 2 channels: x-flow and y-flow";
+        CHECK_EQ(bottom[0]->width(), bottom[1]->width()) << "Width of the inputs should be the same";
+        CHECK_EQ(bottom[0]->height(), bottom[1]->height()) << "Height of the inputs should be the same";
+        top[0]->ReshapeLike(*bottom[0]);
+    }
+ protected:
+    void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        fn2_tensor img = bottom[0]->tensor(), fl = bottom[1]->tensor(), t = top[0]->mutable_tensor();
+        FN2_CALL(fn2_flow_warp_forward(&img, &fl, &t, this->layer_param_.flow_warp_param().fill_nan() ? 1 : 0, S()));
+    }
+};
+REGISTER_LAYER_CLASS(FlowWarp);
+
+// ---------------------------------------------------------------------------------------------
+// Resample (resample_layer.cpp:11-55, .cu:128-206)
+// ---------------------------------------------------------------------------------------------
+template <typename Dtype>
+class ResampleLayer : public Layer<Dtype> {
+ public:
+    explicit ResampleLayer(const LayerParameter& p) : Layer<Dtype>(p) {}
+    const char* type() const override { return "Resample"; }
+    bool AllowBackward() const override { return false; }           // resample_layer.hpp:25
+    void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        const int t = this->layer_param_.resample_param().type();
+        CHECK(t == 1 || t == 2 || t == 3) << "ResampleLayer: only CUBIC, LINEAR and NEAREST interpolation is supported for now";
+    }
+    void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        this->layer_param_.m->set("reshape_every_iter", "false");   // resample_layer.cpp:27
+        CHECK_GE(bottom.size(), 1u);
+        CHECK_LE(bottom.size(), 2u);
+        CHECK_EQ(top.size(), 1u);
+        int top_h, top_w;
+        if (bottom.size() == 1) {
+            top_h = this->layer_param_.resample_param().height();
+            top_w = this->layer_param_.resample_param().width();
+        } else {
+            top_h = bottom[1]->height();
+            top_w = bottom[1]->width();
+        }
+        CHECK_GE(top_h, 1) << "ResampleLayer must have top_height > 0";
+        CHECK_GE(top_w, 1) << "ResampleLayer must have top_width > 0";
+        top[0]->Reshape(bottom[0]->num(), bottom[0]->channels(), top_h, top_w);
+    }
+ protected:
+    void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        ResampleParameter rp = this->layer_param_.resample_param();
+        fn2_tensor b = bottom[0]->tensor(), t = top[0]->mutable_tensor();
+        FN2_CALL(fn2_resample_forward(&b, &t, rp.type(), rp.antialias() ? 1 : 0, S()));
+    }
+};
+REGISTER_LAYER_CLASS(Resample);
+
+// ---------------------------------------------------------------------------------------------
+// Correlation (correlation_layer.cpp:13-84, .cu:431-504)
+// ---------------------------------------------------------------------------------------------
+template <typename Dtype>
+class CorrelationLayer : public Layer<Dtype> {
+ public:
+    explicit CorrelationLayer(const LayerParameter& p) : Layer<Dtype>(p) {}
+    ~CorrelationLayer() override { if (ws_) cudaFree(ws_); }
+    const char* type() const override { return "Correlation"; }
+    int ExactNumBottomBlobs() const override { return 2; }
+    int ExactNumTopBlobs() const override { return 1; }
+    void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        CorrelationParameter cp = this->layer_param_.correlation_param();
+        CHECK(cp.has_kernel_size()) << "Filter kernel_size is not set";
+        CHECK(cp.has_max_displacement()) << "Max displacement is required.";
+        kernel_size_ = cp.kernel_size();
+        CHECK(kernel_size_ % 2 == 1) << "Odd kernel size required";
+        max_displacement_ = cp.max_displacement();
+        pad_size_ = cp.pad();
+        stride1_ = cp.stride_1();
+        stride2_ = cp.stride_2();
+        corr_type_ = cp.correlation_type();      // do_abs is parsed and unused in the reference too
+    }
+    void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        CHECK_EQ(bottom[0]->width(), bottom[1]->width()) << "Both bottom blobs must have same width";
+        CHECK_EQ(bottom[0]->height(), bottom[1]->height()) << "Both bottom blobs must have same height";
+        CHECK_EQ(bottom[0]->channels(), bottom[1]->channels()) << "Both bottom blobs must have same height";
+        int tc, th, tw;
+        FN2_CALL(fn2_correlation_shape(bottom[0]->height(), bottom[0]->width(), pad_size_, kernel_size_,
+                                       max_displacement_, stride1_, stride2_, &tc, &th, &tw));
+        top[0]->Reshape(bottom[0]->num(), tc, th, tw);
+        size_t need = 0;
+        FN2_CALL(fn2_correlation_workspace_bytes(bottom[0]->num(), bottom[0]->channels(), bottom[0]->height(),
+                                                 bottom[0]->width(), pad_size_, kernel_size_, max_displacement_,
+                                                 stride1_, stride2_, corr_type_, &need));
+        if (need > ws_bytes_) {
+            if (ws_) cudaFree(ws_);
+            CUDA_CHECK(cudaMalloc(&ws_, need));
+            CUDA_CHECK(cudaMemset(ws_, 0, need));
+            ws_bytes_ = need;
+        }
+    }
+ protected:
+    void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        fn2_tensor b0 = bottom[0]->tensor(), b1 = bottom[1]->tensor(), t = top[0]->mutable_tensor();
+        FN2_CALL(fn2_correlation_forward(&b0, &b1, &t, pad_size_, kernel_size_, max_displacement_, stride1_,
+                                         stride2_, corr_type_, ws_, ws_bytes_, S()));
+    }
+    int kernel_size_ = 0, max_displacement_ = 0, pad_size_ = 0, stride1_ = 1, stride2_ = 1, corr_type_ = 0;
+    void* ws_ = nullptr;
+    size_t ws_bytes_ = 0;
+};
+REGISTER_LAYER_CLASS(Correlation);
+
+// ---------------------------------------------------------------------------------------------
+// Convolution / Deconvolution (base_conv_layer.cpp:12-254, conv_layer.cpp, deconv_layer.cpp).
+// group == 1 and dilation == 1 (all FlowNet2 layers); several bottom/top pairs share the weights
+// (conv_layer.cpp:28).  Engine selection follows GetConvolutionLayer (layer_factory.cpp:37-71):
+// engine CAFFE -> exact FP32 SIMT kernel, DEFAULT/CUDNN -> tcgen05 tensor-core kernel when the
+// shape is eligible.
+// ---------------------------------------------------------------------------------------------
+template <typename Dtype>
+class BaseConvolutionLayer : public Layer<Dtype> {
+ public:
+    explicit BaseConvolutionLayer(const LayerParameter& p, bool deconv) : Layer<Dtype>(p), deconv_(deconv) {}
+    ~BaseConvolutionLayer() override { if (packed_) cudaFree(packed_); }
+    int MinBottomBlobs() const override { return 1; }
+    int MinTopBlobs() const override { return 1; }
+    bool EqualNumBottomTopBlobs() const override { return true; }
+
+    void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        ConvolutionParameter cp = this->layer_param_.convolution_param();
+        memset(&d_, 0, sizeof(d_));
+        int kh, kw, sh, sw, ph, pw, dh, dw;
+        cp.kernel(&kh, &kw); cp.stride(&sh, &sw); cp.pad(&ph, &pw); cp.dilation(&dh, &dw);
+        CHECK(dh == 1 && dw == 1) << "dilated convolution is not used on the FlowNet2 path";
+        CHECK_EQ(cp.group(), 1) << "grouped convolution is not used on the FlowNet2 path";
+        CHECK_GT(cp.num_output(), 0);
+        d_.ci = bottom[0]->channels(); d_.co = cp.num_output();
+        d_.kh = kh; d_.kw = kw; d_.stride_h = sh; d_.stride_w = sw; d_.pad_h = ph; d_.pad_w = pw;
+        d_.deconv = deconv_ ? 1 : 0;
+        d_.has_bias = cp.bias_term() ? 1 : 0;
+        const string eng = cp.engine();
+        d_.engine = (eng == "CAFFE" || eng == "1") ? 1 : 0;
+        if (const char* e = getenv("FN2_CONV_ENGINE")) {
+            if (!strcmp(e, "simt")) d_.engine = 1;
+            else if (!strcmp(e, "tc")) d_.engine = 0;
+        }
+        relu_.assign(top.size(), 0);
+        slope_.assign(top.size(), 0.f);
+        if (this->blobs_.size() > 0) {
+            CHECK_EQ(1 + d_.has_bias, (int)this->blobs_.size()) << "Incorrect number of weight blobs.";
+        } else {
+            this->blobs_.resize(1 + d_.has_bias);
+            // conv [co][ci][kh][kw]; deconv [ci][co][kh][kw] (base_conv_layer.cpp:125-140)
+            if (!deconv_) this->blobs_[0].reset(new Blob<Dtype>(d_.co, d_.ci, kh, kw));
+            else          this->blobs_[0].reset(new Blob<Dtype>(d_.ci, d_.co, kh, kw));
+            if (d_.has_bias) { this->blobs_[1].reset(new Blob<Dtype>()); this->blobs_[1]->Reshape(vector<int>{d_.co}); }
+        }
+    }
+    void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        CHECK_EQ(bottom[0]->channels(), d_.ci) << "Input size incompatible with convolution kernel.";
+        for (size_t i = 1; i < bottom.size(); ++i)
+            CHECK(bottom[0]->shape() == bottom[i]->shape()) << "All inputs must have the same shape.";
+        int Ho, Wo;
+        FN2_CALL(fn2_conv_out_shape(&d_, bottom[0]->height(), bottom[0]->width(), &Ho, &Wo));
+        for (size_t i = 0; i < top.size(); ++i) top[i]->Reshape(bottom[0]->num(), d_.co, Ho, Wo);
+        bottom_cstride_ = bottom[0]->channel_stride();
+    }
+    void FillParams(uint64_t seed) override {
+        ConvolutionParameter cp = this->layer_param_.convolution_param();
+        FillBlob(cp.weight_filler(), this->blobs_[0].get(), seed * 2 + 1);
+        if (d_.has_bias) FillBlob(cp.bias_filler(), this->blobs_[1].get(), seed * 2 + 2);
+    }
+    void ParamsChanged() override {
+        size_t floats = 0;
+        const int cis = bottom_cstride_ > 0 ? bottom_cstride_ : d_.ci;
+        FN2_CALL(fn2_conv_packed_floats(&d_, cis, &floats));
+        if (floats > packed_floats_) {
+            if (packed_) cudaFree(packed_);
+            CUDA_CHECK(cudaMalloc(&packed_, floats * sizeof(float)));
+            packed_floats_ = floats;
+        }
+        FN2_CALL(fn2_conv_pack_weights(&d_, cis, this->blobs_[0]->gpu_data(), packed_, S()));
+    }
+    bool FuseReLU(int top_index, float negative_slope) override {
+        if (top_index < 0 || top_index >= (int)relu_.size() || relu_[top_index]) return false;
+        relu_[top_index] = 1; slope_[top_index] = negative_slope;
+        return true;
+    }
+ protected:
+    void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        CHECK(packed_) << "convolution weights were never loaded/packed";
+        for (size_t i = 0; i < bottom.size(); ++i) {
+            fn2_conv_desc d = d_;
+            d.relu = relu_[i]; d.negative_slope = slope_[i];
+            fn2_tensor b = bottom[i]->tensor(), t = top[i]->mutable_tensor();
+            FN2_CALL(fn2_conv_forward(&d, &b, packed_, d_.has_bias ? this->blobs_[1]->gpu_data() : nullptr, &t, S()));
+        }
+    }
+    bool deconv_;
+    fn2_conv_desc d_;
+    vector<int> relu_;
+    vector<float> slope_;
+    float* packed_ = nullptr;
+    size_t packed_floats_ = 0;
+    int bottom_cstride_ = 0;
+};
+
+template <typename Dtype>
+class ConvolutionLayer : public BaseConvolutionLayer<Dtype> {
+ public:
+    explicit ConvolutionLayer(const LayerParameter& p) : BaseConvolutionLayer<Dtype>(p, false) {}
+    const char* type() const override { return "Convolution"; }
+};
+REGISTER_LAYER_CLASS(Convolution);
+
+template <typename Dtype>
+class DeconvolutionLayer : public BaseConvolutionLayer<Dtype> {
+ public:
+    explicit DeconvolutionLayer(const LayerParameter& p) : BaseConvolutionLayer<Dtype>(p, true) {}
+    const char* type() const override { return "Deconvolution"; }
+};
+REGISTER_LAYER_CLASS(Deconvolution);
+
+// ---------------------------------------------------------------------------------------------
+// DataAugmentation (data_augmentation_layer.cpp:34-205, .cu:321-637,
+// augmentation_layer_base.cpp:15-48).  Deploy use: crop == bottom size, no random generators ->
+// default coefficients -> "identity" affine through SpatialAugmentation (with its dim-1.05 clamp)
+// followed by mean subtraction.  Random coefficient sampling (training) is not built yet and is
+// rejected loudly.
+// ---------------------------------------------------------------------------------------------
+struct TransMat {   // augmentation_layer_base.cpp:15-48, float arithmetic in the same order
+    float t0, t1, t2, t3, t4, t5;
+    void toIdentity() { t0 = 1; t2 = 0; t4 = 0; t1 = 0; t3 = 1; t5 = 0; }
+    void leftMultiply(float u0, float u1, float u2, float u3, float u4, float u5) {
+        float a0 = t0, a2 = t2, a4 = t4, a1 = t1, a3 = t3, a5 = t5;
+        t0 = a0 * u0 + a1 * u2; t1 = a0 * u1 + a1 * u3;
+        t2 = a2 * u0 + a3 * u2; t3 = a2 * u1 + a3 * u3;
+        t4 = a4 * u0 + a5 * u2 + u4; t5 = a4 * u1 + a5 * u3 + u5;
+    }
+};
+
+template <typename Dtype>
+class DataAugmentationLayer : public Layer<Dtype> {
+ public:
+    explicit DataAugmentationLayer(const LayerParameter& p) : Layer<Dtype>(p) {}
+    ~DataAugmentationLayer() override { if (mats_dev_) cudaFree(mats_dev_); if (fixed_mean_dev_) cudaFree(fixed_mean_dev_); }
+    const char* type() const override { return "DataAugmentation"; }
+    bool AllowBackward() const override { return false; }              // data_augmentation_layer.hpp:29
+    bool DoesUseCustomCopyBlobs() const override { return true; }      // data_augmentation_layer.hpp:43-46
+    void CustomCopyBlobs(const vector<Blob<Dtype>*>& blobs) override { adjust_blobs(blobs); }
+
+    void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        AugmentationParameter aug = this->layer_param_.augmentation_param();
+        this->layer_param_.m->set("reshape_every_iter", "false");      // data_augmentation_layer.cpp:39
+        if (this->blobs_.size() == 0) {
+            this->blobs_.resize(aug.recompute_mean() ? 3 : 1);
+            for (auto& b : this->blobs_) b.reset(new Blob<Dtype>());
+            this->blobs_[0]->Reshape(1, 1, 1, 1);
+        }
+    }
+    void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        CHECK_GE(bottom.size(), 1u) << "Data augmentation layer takes one or two input blobs.";
+        CHECK_LE(bottom.size(), 2u) << "Data augmentation layer takes one or two input blobs.";
+        CHECK_GE(top.size(), 1u) << "Data augmentation layer outputs one or two output blobs.";
+        CHECK_LE(top.size(), 2u) << "Data augmentation layer outputs one or two output blobs.";
+        CHECK(bottom.size() == 1 && top.size() == 1)
+            << "DataAugmentation: coefficient input/output blobs (training graphs) are not built yet";
+        AugmentationParameter aug = this->layer_param_.augmentation_param();
+        CHECK(!(aug.has_any_generator() && (this->phase_ == TRAIN || aug.augment_during_test())))
+            << "DataAugmentation: random coefficient generators (training augmentation) are not built yet";
+        const int num = bottom[0]->num(), channels = bottom[0]->channels();
+        const int height = bottom[0]->height(), width = bottom[0]->width();
+        do_cropping_ = aug.has_crop_width() && aug.has_crop_height();
+        if (!do_cropping_) { cropped_width_ = width; cropped_height_ = height; }
+        else {
+            cropped_width_ = aug.crop_width();   CHECK_GE(width, cropped_width_) << "crop width greater than original";
+            cropped_height_ = aug.crop_height(); CHECK_GE(height, cropped_height_) << "crop height greater than original";
+        }
+        top[0]->Reshape(num, channels, cropped_height_, cropped_width_);
+        // default coefficients -> one matrix per sample (data_augmentation_layer.cu:462-468)
+        vector<float> mats((size_t)num * 6);
+        for (int n = 0; n < num; n++) {
+            TransMat t; t.toIdentity();
+            t.leftMultiply(1, 0, 0, 1, -.5f * (float)cropped_width_, -.5f * (float)cropped_height_);
+            t.leftMultiply(1, 0, 0, 1, .5f * (float)width, .5f * (float)height);
+            float* m = &mats[(size_t)n * 6];
+            m[0] = t.t0; m[1] = t.t1; m[2] = t.t2; m[3] = t.t3; m[4] = t.t4; m[5] = t.t5;
+        }
+        if (mats_dev_) cudaFree(mats_dev_);
+        CUDA_CHECK(cudaMalloc(&mats_dev_, mats.size() * sizeof(float)));
+        CUDA_CHECK(cudaMemcpy(mats_dev_, mats.data(), mats.size() * sizeof(float), cudaMemcpyHostToDevice));
+        if (aug.recompute_mean()) {
+            this->blobs_[1]->Reshape(1, channels, cropped_height_, cropped_width_);
+            this->blobs_[2]->Reshape(1, channels, 1, 1);
+        } else if (aug.mean_size() == 3 && !aug.mean_per_pixel()) {
+            float mv[3] = {aug.mean(0), aug.mean(1), aug.mean(2)};
+            if (!fixed_mean_dev_) CUDA_CHECK(cudaMalloc(&fixed_mean_dev_, 3 * sizeof(float)));
+            CUDA_CHECK(cudaMemcpy(fixed_mean_dev_, mv, sizeof(mv), cudaMemcpyHostToDevice));
+        }
+        *(this->blobs_[0]->mutable_cpu_data()) = 0;                    // data_augmentation_layer.cpp:155
+    }
+    void FillParams(uint64_t seed) override {
+        // synthetic "trained" state: iteration counter past recompute_mean, plausible RGB means
+        AugmentationParameter aug = this->layer_param_.augmentation_param();
+        *(this->blobs_[0]->mutable_cpu_data()) = (float)(aug.recompute_mean() + 1);
+        if (aug.recompute_mean()) {
+            float* pc = this->blobs_[2]->mutable_cpu_data();
+            float* pp = this->blobs_[1]->mutable_cpu_data();
+            const int C = this->blobs_[2]->count(), area = this->blobs_[1]->count() / C;
+            for (int c = 0; c < C; c++) {
+                pc[c] = 0.40f + 0.02f * (float)c;
+                for (int i = 0; i < area; i++) pp[(size_t)c * area + i] = pc[c];
+            }
+        }
+    }
+    void HostTick() override {
+        float& num_iter = *(this->blobs_[0]->mutable_cpu_data());
+        num_iter = (float)((int)num_iter + 1);                         // data_augmentation_layer.cu:353-354
+        num_iter_ = num_iter;
+    }
+    bool GraphSafe() const override {
+        AugmentationParameter aug = this->layer_param_.augmentation_param();
+        // while the running mean is still being updated the launch sequence changes per call
+        return !(aug.recompute_mean() > 0 && num_iter_ <= (float)aug.recompute_mean());
+    }
+
+ protected:
+    void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        AugmentationParameter aug = this->layer_param_.augmentation_param();
+        fn2_tensor b = bottom[0]->tensor(), t = top[0]->mutable_tensor();
+        if (do_cropping_) FN2_CALL(fn2_spatial_augmentation(&b, &t, mats_dev_, S()));
+        else              FN2_CALL(fn2_copy(&b, &t, S()));            // data_augmentation_layer.cu:589
+        if (aug.recompute_mean() > 0) {
+            fn2_tensor mpp = this->blobs_[1]->mutable_tensor();
+            float* mpc = this->blobs_[2]->mutable_gpu_data();
+            if (num_iter_ <= (float)aug.recompute_mean()) FN2_CALL(fn2_mean_update(&t, &mpp, mpc, num_iter_, S()));
+            FN2_CALL(fn2_mean_subtract(&t, &mpp, mpc, aug.mean_per_pixel() ? 1 : 0, S()));
+        } else if (aug.mean_size() == 3 && !aug.mean_per_pixel()) {
+            FN2_CALL(fn2_mean_subtract(&t, nullptr, fixed_mean_dev_, 0, S()));
+        }
+    }
+
+    // data_augmentation_layer.cpp:162-205
+    void adjust_blobs(const vector<Blob<Dtype>*>& blobs) {
+        AugmentationParameter aug = this->layer_param_.augmentation_param();
+        if (aug.recompute_mean() > 0 && blobs.size() >= 2) {
+            CHECK_GE(blobs.size(), 3u) << "DataAugmentation: source layer must carry 3 blobs";
+            CHECK_EQ(this->blobs_[1]->channels(), blobs[1]->shape(1));
+            const bool same_size = this->blobs_[1]->width() == blobs[1]->shape(3) && this->blobs_[1]->height() == blobs[1]->shape(2);
+            const int channels = this->blobs_[1]->channels();
+            const int area = this->blobs_[1]->height() * this->blobs_[1]->width();
+            const int source_area = blobs[1]->shape(2) * blobs[1]->shape(3);
+            *(this->blobs_[0]->mutable_cpu_data()) = blobs[0]->cpu_data()[0];
+            if (!aug.mean_per_pixel()) {
+                CHECK_EQ(this->blobs_[2]->count(), blobs[2]->count());
+                memcpy(this->blobs_[2]->mutable_cpu_data(), blobs[2]->cpu_data(), sizeof(float) * this->blobs_[2]->count());
+            } else {
+                const float* src = blobs[1]->cpu_data();
+                float* pc = this->blobs_[2]->mutable_cpu_data();
+                // per-channel average (caffe_cpu_gemv with ones; CBLAS order unpinned -> double)
+                for (int c = 0; c < channels; c++) {
+                    double acc = 0;
+                    for (int i = 0; i < source_area; i++) acc += src[(size_t)c * source_area + i];
+                    pc[c] = (float)((1.0 / source_area) * acc);
+                }
+                float* pp = this->blobs_[1]->mutable_cpu_data();
+                if (same_size) memcpy(pp, src, sizeof(float) * (size_t)channels * area);
+                else for (int c = 0; c < channels; c++) for (int i = 0; i < area; i++) pp[(size_t)c * area + i] = pc[c];
+            }
+        }
+    }
+
+    bool do_cropping_ = false;
+    int cropped_width_ = 0, cropped_height_ = 0;
+    float num_iter_ = 0;
+    float* mats_dev_ = nullptr;
+    float* fixed_mean_dev_ = nullptr;
+};
+REGISTER_LAYER_CLASS(DataAugmentation);
+
+// referenced by net.cpp to force this translation unit (and its static registrars) to link
+void RegisterFlowNetLayers() {}
+
+// helpers for net.cpp's ReLU fusion
+bool IsReLULayer(Layer<float>* l, float* slope) {
+    auto* r = dynamic_cast<ReLULayer<float>*>(l);
+    if (!r) return false;
+    *slope = r->negative_slope();
+    return true;
+}
+void MarkReLUFused(Layer<float>* l) {
+    if (auto* r = dynamic_cast<ReLULayer<float>*>(l)) r->set_fused(true);
+}
+
+}  // namespace caffe

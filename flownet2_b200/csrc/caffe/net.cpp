@@ -1,0 +1,384 @@
+#include "net.hpp"
+
+#include <cstdlib>
+#include <cstring>
+#include <set>
+
+namespace caffe {
+
+void RegisterFlowNetLayers();
+bool IsReLULayer(Layer<float>* l, float* slope);
+void MarkReLUFused(Layer<float>* l);
+
+template <typename Dtype>
+Net<Dtype>::Net(const NetParameter& param, Phase phase) : phase_(phase) {
+    RegisterFlowNetLayers();
+    CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    if (getenv("FN2_NO_GRAPH")) graph_disabled_ = true;
+    Init(param);
+}
+
+template <typename Dtype>
+Net<Dtype>::~Net() {
+    if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+    if (graph_) cudaGraphDestroy(graph_);
+    layers_.clear();
+    blobs_.clear();
+    for (auto& kv : staging_) if (kv.second.first) cudaFree(kv.second.first);
+    if (arena_) cudaFree(arena_);
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+// Net::Init, net.cpp:40-286 (FilterNet by phase; no Split insertion: fan-out needs no copies
+// in a forward-only executor, so the reference's "<blob>_<layer>_<idx>_split" blobs do not
+// exist here -- results are unaffected).
+template <typename Dtype>
+void Net<Dtype>::Init(const NetParameter& param) {
+    Caffe::stream() = stream_;
+    name_ = param.name;
+    std::set<string> available;
+    for (const LayerParameter& lp : param.layers) {
+        if (!lp.included_in_phase((int)phase_)) continue;
+        // deep-copy the message so layers may edit their own parameters (reshape_every_iter)
+        LayerParameter own(std::make_shared<Message>(*lp.m));
+        shared_ptr<Layer<Dtype> > layer = LayerRegistry<Dtype>::CreateLayer(own);
+        layer->set_phase(phase_);
+        const int li = (int)layers_.size();
+        layers_.push_back(layer);
+        layer_names_.push_back(own.name());
+        bottom_vecs_.emplace_back(); top_vecs_.emplace_back();
+        bottom_id_vecs_.emplace_back(); top_id_vecs_.emplace_back();
+        // AppendBottom, net.cpp:423-448
+        for (int b = 0; b < own.bottom_size(); b++) {
+            const string& bn = own.bottom(b);
+            auto it = blob_names_index_.find(bn);
+            CHECK(it != blob_names_index_.end())
+                << "Unknown bottom blob '" << bn << "' (layer '" << own.name() << "', bottom index " << b << ")";
+            bottom_vecs_[li].push_back(blobs_[it->second].get());
+            bottom_id_vecs_[li].push_back(it->second);
+        }
+        // AppendTop, net.cpp:386-420
+        for (int t = 0; t < own.top_size(); t++) {
+            const string& tn = own.top(t);
+            if (t < own.bottom_size() && own.bottom(t) == tn) {               // in-place
+                top_vecs_[li].push_back(blobs_[bottom_id_vecs_[li][t]].get());
+                top_id_vecs_[li].push_back(bottom_id_vecs_[li][t]);
+            } else {
+                CHECK(blob_names_index_.find(tn) == blob_names_index_.end())
+                    << "Top blob '" << tn << "' produced by multiple sources.";
+                shared_ptr<Blob<Dtype> > nb(new Blob<Dtype>());
+                nb->set_layout(layer->TopLayout(), -1);
+                const int id = (int)blobs_.size();
+                blobs_.push_back(nb);
+                blob_names_.push_back(tn);
+                blob_names_index_[tn] = id;
+                top_vecs_[li].push_back(nb.get());
+                top_id_vecs_[li].push_back(id);
+                if (string(layer->type()) == "Input") net_input_blob_indices_.push_back(id);   // net.cpp:110-114
+            }
+            available.insert(tn);
+        }
+        layer->SetUp(bottom_vecs_[li], top_vecs_[li]);
+        for (int b = 0; b < own.bottom_size(); b++) {
+            // a blob stays a candidate net output until some layer consumes it (net.cpp:270-276);
+            // in-place tops re-insert themselves above
+            bool is_top_too = false;
+            for (int t = 0; t < own.top_size(); t++) if (own.top(t) == own.bottom(b)) is_top_too = true;
+            if (!is_top_too) available.erase(own.bottom(b));
+        }
+        // re-mark bottoms as usable by later layers (fan-out): availability for *consumption* is
+        // tracked by name existence, `available` only decides net outputs
+    }
+    for (size_t i = 0; i < blob_names_.size(); i++)
+        if (available.count(blob_names_[i])) net_output_blob_indices_.push_back((int)i);
+    FuseReLUs();
+    AliasConcats();
+    BuildArena();
+}
+
+template <typename Dtype>
+shared_ptr<Blob<Dtype> > Net<Dtype>::blob_by_name(const string& name) const {
+    auto it = blob_names_index_.find(name);
+    CHECK(it != blob_names_index_.end()) << "Unknown blob name " << name;
+    return blobs_[it->second];
+}
+
+// Conv/Deconv top followed directly (first consumer, in place) by ReLU -> epilogue fusion.
+template <typename Dtype>
+void Net<Dtype>::FuseReLUs() {
+    if (getenv("FN2_NO_FUSE")) return;
+    for (size_t li = 0; li < layers_.size(); li++) {
+        const string type = layers_[li]->type();
+        if (type != "Convolution" && type != "Deconvolution") continue;
+        for (size_t t = 0; t < top_id_vecs_[li].size(); t++) {
+            const int bid = top_id_vecs_[li][t];
+            // first later layer that touches this blob
+            for (size_t lj = li + 1; lj < layers_.size(); lj++) {
+                bool touches = false;
+                for (int b : bottom_id_vecs_[lj]) if (b == bid) touches = true;
+                if (!touches) continue;
+                float slope = 0;
+                if (IsReLULayer(layers_[lj].get(), &slope) && top_id_vecs_[lj].size() == 1 && top_id_vecs_[lj][0] == bid) {
+                    if (layers_[li]->FuseReLU((int)t, slope)) MarkReLUFused(layers_[lj].get());
+                }
+                break;
+            }
+        }
+    }
+}
+
+// Zero-copy channel Concat: bottoms become channel-range views of the top's NHWC storage.
+template <typename Dtype>
+void Net<Dtype>::AliasConcats() {
+    if (getenv("FN2_NO_ALIAS")) return;
+    std::set<int> inputs(net_input_blob_indices_.begin(), net_input_blob_indices_.end());
+    for (size_t li = 0; li < layers_.size(); li++) {
+        if (string(layers_[li]->type()) != "Concat" || bottom_id_vecs_[li].size() < 2) continue;
+        Blob<Dtype>* top = top_vecs_[li][0];
+        if (top->layout() != Blob<Dtype>::NHWC) continue;
+        int c0 = 0;
+        std::set<int> seen;
+        for (size_t b = 0; b < bottom_id_vecs_[li].size(); b++) {
+            const int bid = bottom_id_vecs_[li][b];
+            Blob<Dtype>* bl = bottom_vecs_[li][b];
+            bool ok = !inputs.count(bid) && !bl->is_alias() && bl->layout() == Blob<Dtype>::NHWC && !seen.count(bid) && bl != top;
+            // nobody may write the bottom after the concat ran (it would also change the top)
+            for (size_t lj = li + 1; lj < layers_.size() && ok; lj++)
+                for (int t : top_id_vecs_[lj]) if (t == bid) ok = false;
+            // the top must not be an in-place target of a later layer that some other reader of
+            // the bottom must not observe
+            for (size_t lj = li + 1; lj < layers_.size() && ok; lj++) {
+                bool writes_top = false;
+                for (int t : top_id_vecs_[lj]) if (t == top_id_vecs_[li][0]) writes_top = true;
+                if (writes_top) ok = false;
+            }
+            seen.insert(bid);
+            if (ok) bl->AliasInto(top, c0);
+            c0 += bl->channels();
+        }
+    }
+}
+
+template <typename Dtype>
+void Net<Dtype>::BuildArena() {
+    size_t total = 0;
+    for (auto& l : layers_)
+        for (auto& b : l->blobs()) total += ((size_t)b->count() + 63) / 64 * 64;
+    arena_floats_ = total;
+    if (!total) return;
+    CUDA_CHECK(cudaMalloc(&arena_, total * sizeof(Dtype)));
+    CUDA_CHECK(cudaMemset(arena_, 0, total * sizeof(Dtype)));
+    size_t off = 0;
+    for (auto& l : layers_)
+        for (auto& b : l->blobs()) {
+            b->BindExternal(arena_ + off);
+            off += ((size_t)b->count() + 63) / 64 * 64;
+        }
+}
+
+template <typename Dtype>
+void Net<Dtype>::ParamsChanged() {
+    Caffe::stream() = stream_;
+    // host-side edits (FromProto / fillers) -> arena
+    for (auto& l : layers_) for (auto& b : l->blobs()) b->gpu_data();
+    for (auto& l : layers_) l->ParamsChanged();
+    params_ready_ = true;
+    if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+    if (graph_) { cudaGraphDestroy(graph_); graph_ = nullptr; }
+}
+
+template <typename Dtype>
+void Net<Dtype>::FillParams(uint64_t seed) {
+    for (size_t i = 0; i < layers_.size(); i++) layers_[i]->FillParams(seed * 1000003ULL + i);
+    ParamsChanged();
+}
+
+static vector<int> strip_leading_ones(const vector<int>& s) {
+    size_t i = 0;
+    while (i + 1 < s.size() && s[i] == 1) i++;
+    return vector<int>(s.begin() + i, s.end());
+}
+
+// Net::CopyTrainedLayersFrom(const NetParameter&), net.cpp:752-802
+template <typename Dtype>
+void Net<Dtype>::CopyTrainedLayersFrom(const void* caffemodel, size_t bytes) {
+    Caffe::stream() = stream_;
+    vector<LayerBlobs> src = ParseCaffemodel(caffemodel, bytes);
+    for (const LayerBlobs& sl : src) {
+        size_t ti = 0;
+        while (ti != layer_names_.size() && layer_names_[ti] != sl.name) ++ti;
+        if (ti == layer_names_.size()) continue;                               // "Ignoring source layer"
+        auto& target = layers_[ti]->blobs();
+        if (layers_[ti]->DoesUseCustomCopyBlobs()) {                            // net.cpp:769-780 (fork)
+            vector<shared_ptr<Blob<Dtype> > > tmp;
+            vector<Blob<Dtype>*> ptrs;
+            for (const auto& bp : sl.blobs) {
+                tmp.emplace_back(new Blob<Dtype>());
+                vector<int> s = bp.shape;
+                while (s.size() < 4) s.insert(s.begin(), 1);
+                BlobProtoData p4 = bp; p4.shape = s;
+                tmp.back()->FromProto(p4, true);
+                ptrs.push_back(tmp.back().get());
+            }
+            layers_[ti]->CustomCopyBlobs(ptrs);
+            continue;
+        }
+        CHECK_EQ(target.size(), sl.blobs.size()) << "Incompatible number of blobs for layer " << sl.name;
+        for (size_t j = 0; j < target.size(); ++j) {
+            const bool same = strip_leading_ones(target[j]->shape()) == strip_leading_ones(sl.blobs[j].shape);
+            CHECK(same) << "Cannot copy param " << j << " weights from layer '" << sl.name
+                        << "'; shape mismatch (net.cpp:782-795)";
+            target[j]->FromProto(sl.blobs[j], false);
+        }
+    }
+    ParamsChanged();
+}
+
+template <typename Dtype>
+std::string Net<Dtype>::ToCaffemodel() {
+    Caffe::stream() = stream_;
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    vector<LayerBlobs> out;
+    for (size_t i = 0; i < layers_.size(); i++) {
+        if (layers_[i]->blobs().empty()) continue;
+        LayerBlobs lb;
+        lb.name = layer_names_[i];
+        lb.type = layers_[i]->type();
+        for (auto& b : layers_[i]->blobs()) {
+            lb.blobs.emplace_back();
+            b->ToProto(&lb.blobs.back());
+        }
+        out.push_back(std::move(lb));
+    }
+    return SerializeCaffemodel(name_, out);
+}
+
+template <typename Dtype>
+void Net<Dtype>::ForwardEager() {
+    for (size_t i = 0; i < layers_.size(); ++i) layers_[i]->Forward(bottom_vecs_[i], top_vecs_[i]);
+}
+
+// Net::ForwardFromTo(0, L-1), net.cpp:546-557 -- replayed from a CUDA graph once warm.
+template <typename Dtype>
+void Net<Dtype>::Forward() {
+    Caffe::stream() = stream_;
+    if (!params_ready_) ParamsChanged();
+    bool safe = !graph_disabled_;
+    for (auto& l : layers_) l->HostTick();
+    for (auto& l : layers_) if (!l->GraphSafe()) safe = false;
+    if (safe && graph_exec_) {
+        CUDA_CHECK(cudaGraphLaunch(graph_exec_, stream_));
+        return;
+    }
+    if (safe && launches_per_forward_ > 0) {
+        // second safe call: every lazy allocation happened during the first eager pass
+        cudaError_t e = cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            bool ok = true;
+            std::string why;
+            try { ForwardEager(); } catch (const std::exception& ex) { ok = false; why = ex.what(); }
+            cudaGraph_t g = nullptr;
+            e = cudaStreamEndCapture(stream_, &g);
+            if (ok && e == cudaSuccess && g) {
+                cudaGraphExec_t ge = nullptr;
+                if (cudaGraphInstantiate(&ge, g, 0) == cudaSuccess) {
+                    graph_ = g; graph_exec_ = ge;
+                    CUDA_CHECK(cudaGraphLaunch(graph_exec_, stream_));
+                    return;
+                }
+            }
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            graph_disabled_ = true;
+            CHECK(ok) << "forward failed during graph capture: " << why;
+        } else {
+            cudaGetLastError();
+            graph_disabled_ = true;
+        }
+    }
+    const uint64_t before = fn2_launch_count();
+    ForwardEager();
+    launches_per_forward_ = (int)(fn2_launch_count() - before);
+}
+
+template <typename Dtype>
+void Net<Dtype>::Sync() {
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+template <typename Dtype>
+Dtype* Net<Dtype>::staging(const string& blob, size_t floats) {
+    auto& s = staging_[blob];
+    if (s.second < floats) {
+        if (s.first) cudaFree(s.first);
+        CUDA_CHECK(cudaMalloc(&s.first, floats * sizeof(Dtype)));
+        s.second = floats;
+    }
+    return s.first;
+}
+
+static fn2_tensor nchw_view(float* p, int n, int c, int h, int w) {
+    fn2_tensor t;
+    t.data = p; t.n = n; t.c = c; t.h = h; t.w = w;
+    t.sw = 1; t.sh = w; t.sc = (int64_t)h * w; t.sn = (int64_t)c * h * w;
+    return t;
+}
+
+template <typename Dtype>
+void Net<Dtype>::SetInputDevice(const string& blob, const Dtype* dev_nchw) {
+    Caffe::stream() = stream_;
+    shared_ptr<Blob<Dtype> > b = blob_by_name(blob);
+    fn2_tensor src = nchw_view(const_cast<Dtype*>(dev_nchw), b->num(), b->channels(), b->height(), b->width());
+    fn2_tensor dst = b->mutable_tensor();
+    FN2_CALL(fn2_copy(&src, &dst, stream_));
+}
+
+template <typename Dtype>
+void Net<Dtype>::SetInput(const string& blob, const Dtype* host_nchw) {
+    Caffe::stream() = stream_;
+    shared_ptr<Blob<Dtype> > b = blob_by_name(blob);
+    Dtype* st = staging(blob, (size_t)b->count());
+    CUDA_CHECK(cudaMemcpyAsync(st, host_nchw, (size_t)b->count() * sizeof(Dtype), cudaMemcpyHostToDevice, stream_));
+    SetInputDevice(blob, st);
+}
+
+template <typename Dtype>
+void Net<Dtype>::GetBlobDevice(const string& blob, Dtype* dev_nchw) {
+    Caffe::stream() = stream_;
+    shared_ptr<Blob<Dtype> > b = blob_by_name(blob);
+    fn2_tensor src = b->tensor();
+    fn2_tensor dst = nchw_view(dev_nchw, b->num(), b->channels(), b->height(), b->width());
+    FN2_CALL(fn2_copy(&src, &dst, stream_));
+}
+
+template <typename Dtype>
+void Net<Dtype>::GetBlob(const string& blob, Dtype* host_nchw) {
+    shared_ptr<Blob<Dtype> > b = blob_by_name(blob);
+    Dtype* st = staging(blob + "#out", (size_t)b->count());
+    GetBlobDevice(blob, st);
+    CUDA_CHECK(cudaMemcpyAsync(host_nchw, st, (size_t)b->count() * sizeof(Dtype), cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+// Per-layer timing in the style of `caffe time` (tools/caffe.cpp:346-385): CUDA events around
+// each layer's Forward on the net's stream.
+template <typename Dtype>
+void Net<Dtype>::TimeLayers(float* ms) {
+    Caffe::stream() = stream_;
+    if (!params_ready_) ParamsChanged();
+    for (auto& l : layers_) l->HostTick();
+    vector<cudaEvent_t> ev(layers_.size() + 1);
+    for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
+    CUDA_CHECK(cudaEventRecord(ev[0], stream_));
+    for (size_t i = 0; i < layers_.size(); ++i) {
+        layers_[i]->Forward(bottom_vecs_[i], top_vecs_[i]);
+        CUDA_CHECK(cudaEventRecord(ev[i + 1], stream_));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    for (size_t i = 0; i < layers_.size(); ++i) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+    for (auto& e : ev) cudaEventDestroy(e);
+}
+
+template class Net<float>;
+
+}  // namespace caffe

@@ -1,0 +1,75 @@
+// Net: in-order graph executor over the Layer surface (reference: include/caffe/net.hpp,
+// src/caffe/net.cpp Init :40-286, AppendTop/AppendBottom :386-448, ForwardFromTo :546-557,
+// CopyTrainedLayersFrom :752-802).  New underneath: one stream, fused conv+ReLU, zero-copy
+// channel Concat, one contiguous parameter arena, CUDA-graph replay of the whole forward pass.
+#pragma once
+#include <map>
+
+#include "layer.hpp"
+
+namespace caffe {
+
+template <typename Dtype>
+class Net {
+ public:
+    Net(const NetParameter& param, Phase phase);
+    ~Net();
+
+    void Forward();                                    // async on stream()
+    void Sync();
+    cudaStream_t stream() const { return stream_; }
+
+    void CopyTrainedLayersFrom(const void* caffemodel, size_t bytes);     // net.cpp:752-802
+    std::string ToCaffemodel();
+    void FillParams(uint64_t seed);
+    void ParamsChanged();
+    void ParamArena(void** dev, size_t* bytes) { *dev = arena_; *bytes = arena_floats_ * sizeof(Dtype); }
+
+    const vector<string>& layer_names() const { return layer_names_; }
+    const vector<shared_ptr<Layer<Dtype> > >& layers() const { return layers_; }
+    const vector<string>& blob_names() const { return blob_names_; }
+    const vector<shared_ptr<Blob<Dtype> > >& blobs() const { return blobs_; }
+    const vector<int>& input_blob_indices() const { return net_input_blob_indices_; }
+    const vector<int>& output_blob_indices() const { return net_output_blob_indices_; }
+    bool has_blob(const string& name) const { return blob_names_index_.count(name) > 0; }
+    shared_ptr<Blob<Dtype> > blob_by_name(const string& name) const;
+
+    // NCHW host/device buffers <-> blob (layout conversion on the net's stream)
+    void SetInput(const string& blob, const Dtype* host_nchw);
+    void SetInputDevice(const string& blob, const Dtype* dev_nchw);
+    void GetBlob(const string& blob, Dtype* host_nchw);
+    void GetBlobDevice(const string& blob, Dtype* dev_nchw);
+
+    void TimeLayers(float* ms);
+    int launches_per_forward() const { return launches_per_forward_; }
+
+ private:
+    void Init(const NetParameter& param);
+    void FuseReLUs();
+    void AliasConcats();
+    void BuildArena();
+    void ForwardEager();
+    Dtype* staging(const string& blob, size_t floats);
+
+    Phase phase_;
+    string name_;
+    vector<shared_ptr<Layer<Dtype> > > layers_;
+    vector<string> layer_names_;
+    vector<vector<Blob<Dtype>*> > bottom_vecs_, top_vecs_;
+    vector<vector<int> > bottom_id_vecs_, top_id_vecs_;
+    vector<shared_ptr<Blob<Dtype> > > blobs_;
+    vector<string> blob_names_;
+    std::map<string, int> blob_names_index_;
+    vector<int> net_input_blob_indices_, net_output_blob_indices_;
+    Dtype* arena_ = nullptr;
+    size_t arena_floats_ = 0;
+    cudaStream_t stream_ = nullptr;
+    cudaGraph_t graph_ = nullptr;
+    cudaGraphExec_t graph_exec_ = nullptr;
+    bool graph_disabled_ = false;
+    bool params_ready_ = false;
+    int launches_per_forward_ = 0;
+    std::map<string, std::pair<Dtype*, size_t> > staging_;
+};
+
+}  // namespace caffe

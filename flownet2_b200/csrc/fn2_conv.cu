@@ -1,0 +1,335 @@
+// Convolution / Deconvolution forward with fused bias + leaky ReLU -- FP32 SIMT engine.
+//
+// Reference: ConvolutionLayer::Forward_gpu conv_layer.cu:8-23 (per-sample im2col + cublasSgemm,
+// base_conv_layer.cpp:326-349, separate bias GEMM :351-356), DeconvolutionLayer::Forward_gpu
+// deconv_layer.cu:8-23 (GEMM + col2im), ReLUForward relu_layer.cu:9-14.
+//
+// Here: one implicit-GEMM kernel over the whole batch (M = N*Ho*Wo output pixels, N = Co,
+// K = kh*kw*Ci), no materialised col buffer, bias and ReLU applied in the epilogue.  This is the
+// exact-FP32 engine (`engine: CAFFE` in the prototxt, fn2_conv_desc.engine == 1) and the fallback
+// for shapes the tcgen05 engine (fn2_conv_tc.cu) does not take (tiny Ci / Co).
+//
+// Packed weight layout (built once at load time by fn2_conv_pack_weights):
+//   Wp[k][co], k = (r*kw + s)*ci_stride + ci, rows for padded channels ci >= Ci are zero.
+#include "fn2_common.cuh"
+
+namespace fn2 {
+
+int conv_tc_eligible(const fn2_conv_desc* d, const T4& in, const T4& out);
+int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const float* bias,
+                    const T4& out, cudaStream_t st);
+int conv_tc_packed_floats(const fn2_conv_desc* d, int ci_stride, size_t* floats);
+int conv_tc_pack(const fn2_conv_desc* d, int ci_stride, const float* w, float* wp, cudaStream_t st);
+
+struct ConvP {
+    int Ci, Co, kh, kw, sh, sw, ph, pw;
+    int H, W, Ho, Wo, N;
+    int cis;          // ci_stride used in the packed-weight k index
+    int K;            // kh*kw*cis
+    int relu, has_bias;
+    float slope;
+};
+
+// k -> (r, s, ci); returns false when the k row is a padded channel or beyond K
+__device__ __forceinline__ bool decode_k(const ConvP& p, int k, int& r, int& s, int& ci) {
+    if (k >= p.K) return false;
+    ci = k % p.cis;
+    const int rs = k / p.cis;
+    s = rs % p.kw;
+    r = rs / p.kw;
+    return ci < p.Ci;
+}
+
+// Input coordinate for output (oy, ox) and tap (r, s).  Convolution: iy = oy*sh - ph + r.
+// Deconvolution (gather form of col2im, util/im2col.cpp:158-190): oy = iy*sh - ph + r, so
+// iy = (oy + ph - r)/sh when divisible.
+template <bool DECONV>
+__device__ __forceinline__ bool in_coord(const ConvP& p, int oy, int ox, int r, int s, int& iy, int& ix) {
+    if (!DECONV) {
+        iy = oy * p.sh - p.ph + r;
+        ix = ox * p.sw - p.pw + s;
+    } else {
+        const int ty = oy + p.ph - r, tx = ox + p.pw - s;
+        if (ty < 0 || tx < 0 || (ty % p.sh) || (tx % p.sw)) return false;
+        iy = ty / p.sh;
+        ix = tx / p.sw;
+    }
+    return iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+}
+
+constexpr int BM = 128, BN = 128, BK = 16;
+
+// 256 threads, 8x8 outputs per thread arranged as 2x2 blocks of 4x4 (rows ty*4 + {0,64},
+// cols tx*4 + {0,64}) so that shared-memory float4 reads are conflict free.
+template <bool DECONV>
+__global__ void __launch_bounds__(256) conv_igemm_kernel(T4 in, const float* __restrict__ wp,
+                                                         const float* __restrict__ bias, T4 out, ConvP p) {
+    __shared__ __align__(16) float As[2][BK][BM + 4];
+    __shared__ __align__(16) float Bs[2][BK][BN];
+    const int tid = threadIdx.x;
+    const long long M = (long long)p.N * p.Ho * p.Wo;
+    const long long m0 = (long long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+
+    // A loader: thread owns k_local = tid % 16 and rows m_local = tid/16 + 16*i
+    const int a_k = tid & 15;
+    const int a_m = tid >> 4;
+    int a_n[8], a_oy[8], a_ox[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const long long m = m0 + a_m + 16 * i;
+        if (m < M) {
+            a_ox[i] = (int)(m % p.Wo);
+            a_oy[i] = (int)((m / p.Wo) % p.Ho);
+            a_n[i] = (int)(m / ((long long)p.Wo * p.Ho));
+        } else {
+            a_n[i] = -1; a_oy[i] = 0; a_ox[i] = 0;
+        }
+    }
+    // B loader: rows k = tid/32 + 8*i (i=0,1), cols (tid%32)*4 .. +3
+    const int b_k = tid >> 5;
+    const int b_n = (tid & 31) * 4;
+
+    float a_reg[8];
+    float4 b_reg[2];
+    auto load_tiles = [&](int k0) {
+        int r, s, ci;
+        const bool kv = decode_k(p, k0 + a_k, r, s, ci);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            float v = 0.f;
+            int iy, ix;
+            if (kv && a_n[i] >= 0 && in_coord<DECONV>(p, a_oy[i], a_ox[i], r, s, iy, ix))
+                v = __ldg(in.p + in.off(a_n[i], ci, iy, ix));
+            a_reg[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int k = k0 + b_k + 8 * i;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < p.K) {
+                const float* src = wp + (long long)k * p.Co + n0 + b_n;
+                if (n0 + b_n + 3 < p.Co && ((p.Co & 3) == 0)) {
+                    v = __ldg(reinterpret_cast<const float4*>(src));
+                } else {
+                    if (n0 + b_n + 0 < p.Co) v.x = __ldg(src + 0);
+                    if (n0 + b_n + 1 < p.Co) v.y = __ldg(src + 1);
+                    if (n0 + b_n + 2 < p.Co) v.z = __ldg(src + 2);
+                    if (n0 + b_n + 3 < p.Co) v.w = __ldg(src + 3);
+                }
+            }
+            b_reg[i] = v;
+        }
+    };
+    auto store_tiles = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) As[buf][a_k][a_m + 16 * i] = a_reg[i];
+#pragma unroll
+        for (int i = 0; i < 2; i++) *reinterpret_cast<float4*>(&Bs[buf][b_k + 8 * i][b_n]) = b_reg[i];
+    };
+
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+
+    const int ktiles = (p.K + BK - 1) / BK;
+    load_tiles(0);
+    store_tiles(0);
+    __syncthreads();
+    for (int kt = 0; kt < ktiles; kt++) {
+        const int buf = kt & 1;
+        if (kt + 1 < ktiles) load_tiles((kt + 1) * BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; kk++) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4 + 64]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4 + 64]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (kt + 1 < ktiles) {
+            store_tiles(buf ^ 1);
+            __syncthreads();
+        }
+    }
+
+    // epilogue: bias (base_conv_layer.cpp:351-356) + ReLU (relu_layer.cu:9-14)
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const long long m = m0 + ty * 4 + (i & 3) + (i >> 2) * 64;
+        if (m >= M) continue;
+        const int ox = (int)(m % p.Wo);
+        const int oy = (int)((m / p.Wo) % p.Ho);
+        const int n = (int)(m / ((long long)p.Wo * p.Ho));
+        float* orow = out.p + out.off(n, 0, oy, ox);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int co = n0 + tx * 4 + (j & 3) + (j >> 2) * 64;
+            if (co >= p.Co) continue;
+            float v = acc[i][j];
+            if (p.has_bias) v += __ldg(bias + co);
+            if (p.relu) v = v > 0 ? v : v * p.slope;
+            orow[co * out.sc] = v;
+        }
+    }
+}
+
+// Small-Co path (flow predictors: Co = 2): one warp per output pixel, lanes stride K, shuffle
+// reduce.  Avoids padding Co to a 128-wide tile.
+template <bool DECONV, int CO>
+__global__ void __launch_bounds__(256) conv_smallco_kernel(T4 in, const float* __restrict__ wp,
+                                                           const float* __restrict__ bias, T4 out, ConvP p) {
+    const long long M = (long long)p.N * p.Ho * p.Wo;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long m = warp0; m < M; m += nwarps) {
+        const int ox = (int)(m % p.Wo);
+        const int oy = (int)((m / p.Wo) % p.Ho);
+        const int n = (int)(m / ((long long)p.Wo * p.Ho));
+        float acc[CO];
+#pragma unroll
+        for (int j = 0; j < CO; j++) acc[j] = 0.f;
+        for (int rs = 0; rs < p.kh * p.kw; rs++) {
+            const int r = rs / p.kw, s = rs % p.kw;
+            int iy, ix;
+            if (!in_coord<DECONV>(p, oy, ox, r, s, iy, ix)) continue;
+            const float* ip = in.p + in.off(n, 0, iy, ix);
+            const float* wr = wp + (long long)rs * p.cis * p.Co;
+            for (int ci = lane; ci < p.Ci; ci += 32) {
+                const float a = __ldg(ip + ci * in.sc);
+#pragma unroll
+                for (int j = 0; j < CO; j++)
+                    if (j < p.Co) acc[j] = fmaf(a, __ldg(wr + (long long)ci * p.Co + j), acc[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < CO; j++)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < CO; j++) {
+                if (j >= p.Co) break;
+                float v = acc[j];
+                if (p.has_bias) v += __ldg(bias + j);
+                if (p.relu) v = v > 0 ? v : v * p.slope;
+                out.p[out.off(n, j, oy, ox)] = v;
+            }
+        }
+    }
+}
+
+// Caffe weights -> packed [k][co].  conv: w[co][ci][r][s]; deconv: w[ci][co][r][s].
+__global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ wp, int Ci, int Co,
+                                    int kh, int kw, int cis, int deconv) {
+    const long long total = (long long)kh * kw * cis * Co;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(idx % Co);
+        const long long k = idx / Co;
+        const int ci = (int)(k % cis);
+        const int rs = (int)(k / cis);
+        const int s = rs % kw, r = rs / kw;
+        float v = 0.f;
+        if (ci < Ci)
+            v = deconv ? w[(((long long)ci * Co + co) * kh + r) * kw + s]
+                       : w[(((long long)co * Ci + ci) * kh + r) * kw + s];
+        wp[idx] = v;
+    }
+}
+
+static int make_params(const fn2_conv_desc* d, const T4& in, const T4& out, ConvP* p) {
+    FN2_CHECK_ARG(d->ci > 0 && d->co > 0 && d->kh > 0 && d->kw > 0 && d->stride_h > 0 && d->stride_w > 0 &&
+                  d->pad_h >= 0 && d->pad_w >= 0, "conv: bad descriptor");
+    FN2_CHECK_ARG(in.c == d->ci, "conv: bottom has %d channels, descriptor says %d", in.c, d->ci);
+    int Ho, Wo;
+    int rc = fn2_conv_out_shape(d, in.h, in.w, &Ho, &Wo);
+    if (rc) return rc;
+    FN2_CHECK_ARG(out.n == in.n && out.c == d->co && out.h == Ho && out.w == Wo,
+                  "conv: top must be (%d,%d,%d,%d), got (%d,%d,%d,%d)", in.n, d->co, Ho, Wo, out.n, out.c, out.h, out.w);
+    p->Ci = d->ci; p->Co = d->co; p->kh = d->kh; p->kw = d->kw; p->sh = d->stride_h; p->sw = d->stride_w;
+    p->ph = d->pad_h; p->pw = d->pad_w; p->H = in.h; p->W = in.w; p->Ho = Ho; p->Wo = Wo; p->N = in.n;
+    p->relu = d->relu; p->has_bias = d->has_bias; p->slope = d->negative_slope;
+    return FN2_OK;
+}
+
+}  // namespace fn2
+
+using namespace fn2;
+
+extern "C" {
+
+int fn2_conv_out_shape(const fn2_conv_desc* d, int H, int W, int* Ho, int* Wo) {
+    FN2_CHECK_ARG(d && Ho && Wo, "conv_out_shape: null argument");
+    if (!d->deconv) {
+        *Ho = (H + 2 * d->pad_h - d->kh) / d->stride_h + 1;      // conv_layer.cpp:8-22 (dilation 1)
+        *Wo = (W + 2 * d->pad_w - d->kw) / d->stride_w + 1;
+    } else {
+        *Ho = d->stride_h * (H - 1) + d->kh - 2 * d->pad_h;      // deconv_layer.cpp:18-19
+        *Wo = d->stride_w * (W - 1) + d->kw - 2 * d->pad_w;
+    }
+    FN2_CHECK_ARG(*Ho >= 1 && *Wo >= 1, "conv: empty output (%d x %d)", *Ho, *Wo);
+    return FN2_OK;
+}
+
+// ci_stride: for the SIMT engine the k index uses the real Ci (no padded rows); the argument is
+// what the tcgen05 engine needs (padded channel count of the bottom tensor).
+int fn2_conv_packed_floats(const fn2_conv_desc* d, int ci_stride, size_t* floats) {
+    FN2_CHECK_ARG(d && floats, "conv_packed_floats: null argument");
+    size_t simt = (size_t)d->kh * d->kw * d->ci * d->co;
+    size_t tc = 0;
+    int rc = conv_tc_packed_floats(d, ci_stride, &tc);
+    if (rc) return rc;
+    *floats = simt + tc;
+    return FN2_OK;
+}
+
+int fn2_conv_pack_weights(const fn2_conv_desc* d, int ci_stride, const float* caffe_weights_dev,
+                          float* packed_dev, void* stream) {
+    FN2_CHECK_ARG(d && caffe_weights_dev && packed_dev, "conv_pack_weights: null argument");
+    const long long total = (long long)d->kh * d->kw * d->ci * d->co;
+    pack_weights_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        caffe_weights_dev, packed_dev, d->ci, d->co, d->kh, d->kw, d->ci, d->deconv);
+    FN2_LAUNCH_CHECK();
+    return conv_tc_pack(d, ci_stride, caffe_weights_dev, packed_dev + total, (cudaStream_t)stream);
+}
+
+int fn2_conv_forward(const fn2_conv_desc* d, const fn2_tensor* bottom, const float* packed_weights_dev,
+                     const float* bias_dev, const fn2_tensor* top, void* stream) {
+    FN2_CHECK_ARG(d && valid(bottom) && valid(top) && packed_weights_dev, "conv: null argument");
+    FN2_CHECK_ARG(!d->has_bias || bias_dev, "conv: bias_term set but no bias given");
+    T4 in = view(bottom), out = view(top);
+    ConvP p;
+    int rc = make_params(d, in, out, &p);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long simt_floats = (long long)d->kh * d->kw * d->ci * d->co;
+    if (d->engine != 1 && conv_tc_eligible(d, in, out))
+        return conv_tc_forward(d, in, packed_weights_dev + simt_floats, bias_dev, out, st);
+    FN2_CHECK_ARG(d->engine != 2, "conv: tcgen05 engine requested but the shape/layout is not eligible");
+    p.cis = d->ci;
+    p.K = d->kh * d->kw * p.cis;
+    const long long M = (long long)p.N * p.Ho * p.Wo;
+    if (d->co <= 4) {
+        const int grid = ew_grid(M * 32, 256);
+        if (d->deconv) conv_smallco_kernel<true, 4><<<grid, 256, 0, st>>>(in, packed_weights_dev, bias_dev, out, p);
+        else           conv_smallco_kernel<false, 4><<<grid, 256, 0, st>>>(in, packed_weights_dev, bias_dev, out, p);
+    } else {
+        dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((d->co + BN - 1) / BN));
+        if (d->deconv) conv_igemm_kernel<true><<<grid, 256, 0, st>>>(in, packed_weights_dev, bias_dev, out, p);
+        else           conv_igemm_kernel<false><<<grid, 256, 0, st>>>(in, packed_weights_dev, bias_dev, out, p);
+    }
+    FN2_LAUNCH_CHECK();
+    return FN2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,571 @@
+// Streaming (HBM-bound) layers of the FlowNet2 forward path: FlowWarp, Resample,
+// DataAugmentation kernels, ReLU, Eltwise, ChannelNorm, strided copy/fill.
+//
+// This translation unit is compiled with -fmad=false: every expression below is evaluated
+// with separately rounded multiplies and adds in the order written, which is also how the CPU
+// oracle (oracle/oracle.c, -ffp-contract=off) evaluates the reference arithmetic, so these
+// layers are compared bit-for-bit.  They are bandwidth-bound; FMA contraction buys nothing.
+//
+// All kernels take strided tensor views (fn2::T4) so the same code serves the reference's NCHW
+// blobs (drop-in use) and the engine's NHWC activations / concat views.
+#include <math.h>
+#include "fn2_common.cuh"
+
+namespace fn2 {
+
+// ---------------------------------------------------------------------------------------------
+// FlowWarp forward.  Reference: flow_warp_layer.cpp:57-117 (CPU), flow_warp_layer.cu:59-122.
+// One thread per output pixel; the reference's NCHW->NHWC transpose pass (.cu:24-52) is not
+// needed: taps are read straight from the strided view.
+// ---------------------------------------------------------------------------------------------
+__global__ void flow_warp_fwd_kernel(T4 img, T4 flow, T4 out, float fill) {
+    const long long total = (long long)out.n * out.h * out.w;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % out.w);
+        const int y = (int)((idx / out.w) % out.h);
+        const int n = (int)(idx / ((long long)out.w * out.h));
+        const float fx = flow.p[flow.off(n, 0, y, x)];
+        const float fy = flow.p[flow.off(n, 1, y, x)];
+        const float x2 = (float)x + fx;
+        const float y2 = (float)y + fy;
+        const int width = img.w, height = img.h;
+        if (x2 >= 0 && y2 >= 0 && x2 < width && y2 < height) {      // flow_warp_layer.cpp:86
+            const int ix2_L = (int)x2;
+            const int iy2_T = (int)y2;
+            const int ix2_R = min(ix2_L + 1, width - 1);
+            const int iy2_B = min(iy2_T + 1, height - 1);
+            const float alpha = x2 - ix2_L;
+            const float beta = y2 - iy2_T;
+            const float cTL = (1 - alpha) * (1 - beta);
+            const float cTR = alpha * (1 - beta);
+            const float cBL = (1 - alpha) * beta;
+            const float cBR = alpha * beta;
+            const long long oTL = img.off(n, 0, iy2_T, ix2_L), oTR = img.off(n, 0, iy2_T, ix2_R);
+            const long long oBL = img.off(n, 0, iy2_B, ix2_L), oBR = img.off(n, 0, iy2_B, ix2_R);
+            for (int c = 0; c < img.c; c++) {
+                const float TL = __ldg(img.p + oTL + c * img.sc);
+                const float TR = __ldg(img.p + oTR + c * img.sc);
+                const float BL = __ldg(img.p + oBL + c * img.sc);
+                const float BR = __ldg(img.p + oBR + c * img.sc);
+                out.p[out.off(n, c, y, x)] = ((cTL * TL + cTR * TR) + cBL * BL) + cBR * BR;
+            }
+        } else {
+            for (int c = 0; c < img.c; c++) out.p[out.off(n, c, y, x)] = fill;
+        }
+    }
+}
+
+// FlowWarp backward.  Reference: flow_warp_layer.cu:170-229 / flow_warp_layer.cpp:120-198.
+// image_diff must be zero-filled by the caller side (done in the entry point).  Scatter via
+// atomicAdd exactly like the reference (order-nondeterministic in the last ulp).
+__global__ void flow_warp_bwd_kernel(T4 img, T4 flow, T4 wdiff, T4 idiff, T4 fdiff) {
+    const long long total = (long long)img.n * img.h * img.w;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % img.w);
+        const int y = (int)((idx / img.w) % img.h);
+        const int n = (int)(idx / ((long long)img.w * img.h));
+        const float x2 = (float)x + flow.p[flow.off(n, 0, y, x)];
+        const float y2 = (float)y + flow.p[flow.off(n, 1, y, x)];
+        const int width = img.w, height = img.h;
+        float du = 0.f, dv = 0.f;
+        if (x2 >= 0 && y2 >= 0 && x2 < width && y2 < height) {
+            const int L = (int)x2, T = (int)y2;
+            const int R = min(L + 1, width - 1), B = min(T + 1, height - 1);
+            const float alpha = x2 - L, beta = y2 - T;
+            const float gy = B - y2, gx = R - x2;
+            for (int c = 0; c < img.c; c++) {
+                const float wd = wdiff.p[wdiff.off(n, c, y, x)];
+                atomicAdd(idiff.p + idiff.off(n, c, T, L), wd * (1 - alpha) * (1 - beta));
+                atomicAdd(idiff.p + idiff.off(n, c, T, R), wd * alpha * (1 - beta));
+                atomicAdd(idiff.p + idiff.off(n, c, B, L), wd * (1 - alpha) * beta);
+                atomicAdd(idiff.p + idiff.off(n, c, B, R), wd * alpha * beta);
+                const float TL = img.p[img.off(n, c, T, L)], TR = img.p[img.off(n, c, T, R)];
+                const float BL = img.p[img.off(n, c, B, L)], BR = img.p[img.off(n, c, B, R)];
+                float tu = 0; tu += gy * (TR - TL); tu += (1 - gy) * (BR - BL);
+                float tv = 0; tv += gx * (BL - TL); tv += (1 - gx) * (BR - TR);
+                du += wd * tu;
+                dv += wd * tv;
+            }
+        }
+        fdiff.p[fdiff.off(n, 0, y, x)] = du;
+        fdiff.p[fdiff.off(n, 1, y, x)] = dv;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Resample.  Reference: resample_layer.cu:14-33 (filters), :40-95 InterpolationKernel,
+// :98-125 NearestNeighborKernel.  Including the swapped half-pixel offsets (:62-63).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bicubicCoeff(float x_) {
+    float x = fabsf(x_);
+    if (x <= 1.0f) return x * x * (1.5f * x - 2.5f) + 1.0f;
+    else if (x < 2.0f) return x * (x * (-0.5f * x + 2.5f) - 4.0f) + 2.0f;
+    else return 0.0f;
+}
+__device__ __forceinline__ float triangleCoeff(float x) {
+    if (-1 <= x && x < 0) return x + 1;
+    if (0 <= x && x <= 1) return 1 - x;
+    return 0;
+}
+
+template <int TYPE>   // 1 nearest, 2 linear(triangle), 3 cubic
+__global__ void resample_kernel(T4 in, T4 out, float fx, float fy, int antialias) {
+    const long long total = out.count();
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        // decode with x fastest, then channel (so NHWC views stay roughly coalesced), then y, n
+        const int x_out = (int)(idx % out.w);
+        long long r = idx / out.w;
+        const int c = (int)(r % out.c); r /= out.c;
+        const int y_out = (int)(r % out.h);
+        const int n = (int)(r / out.h);
+        const float x_in = (x_out * fx + fy / 2.0f) - 0.5f;
+        const float y_in = (y_out * fy + fx / 2.0f) - 0.5f;
+        const int x_in_round = (int)roundf(x_in);
+        const int y_in_round = (int)roundf(y_in);
+        float result;
+        if (TYPE == 1) {
+            // the reference does not clamp (resample_layer.cu:120-123) and can read out of
+            // bounds; clamp instead (documented deviation)
+            const int xr = min(max(x_in_round, 0), in.w - 1);
+            const int yr = min(max(y_in_round, 0), in.h - 1);
+            result = in.p[in.off(n, c, yr, xr)];
+        } else {
+            const int kernel_width = (TYPE == 3) ? 4 : 2;
+            float sum = 0, wsum = 0;
+            const float ax = 1.0f / (antialias ? fx : 1.0f);
+            const float ay = 1.0f / (antialias ? fy : 1.0f);
+            const int rx = (fx < 1.0f) ? 2 : (int)ceilf((float)kernel_width / ax);
+            const int ry = (fy < 1.0f) ? 2 : (int)ceilf((float)kernel_width / ay);
+            for (int y = y_in_round - ry; y <= y_in_round + ry; y++)
+                for (int x = x_in_round - rx; x <= x_in_round + rx; x++) {
+                    if (y < 0 || x < 0) continue;
+                    if (y >= in.h || x >= in.w) continue;
+                    const float dx = x_in - x;
+                    const float dy = y_in - y;
+                    float w;
+                    if (TYPE == 3) w = (ax * bicubicCoeff(ax * dx)) * ay * bicubicCoeff(ay * dy);
+                    else           w = (ax * triangleCoeff(ax * dx)) * ay * triangleCoeff(ay * dy);
+                    sum = sum + w * __ldg(in.p + in.off(n, c, y, x));
+                    wsum += w;
+                }
+            result = (!wsum) ? 0 : (sum / wsum);
+        }
+        out.p[out.off(n, c, y_out, x_out)] = result;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// DataAugmentation device kernels.
+// SpatialAugmentation: data_augmentation_layer.cu:25-70.  The reference forms the flat source
+// index in float arithmetic (:52), exact while the blob has < 2^24 elements; integer arithmetic
+// here (identical in that range).  The min(idx, src_count) clamps of :53-55 can never trigger
+// for width,height >= 2 because of the dim-1.05 clamp.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float clampf(float f, float a, float b) { return fmaxf(a, fminf(f, b)); }
+
+__global__ void spatial_aug_kernel(T4 src, T4 dst, const float* __restrict__ mats) {
+    const long long total = (long long)dst.n * dst.h * dst.w;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % dst.w);
+        const int y = (int)((idx / dst.w) % dst.h);
+        const int n = (int)(idx / ((long long)dst.w * dst.h));
+        const float* m = mats + 6 * n;
+        float xpos = (x * m[0] + y * m[2]) + m[4];
+        float ypos = (x * m[1] + y * m[3]) + m[5];
+        xpos = clampf(xpos, 0.0f, (float)(src.w) - 1.05f);
+        ypos = clampf(ypos, 0.0f, (float)(src.h) - 1.05f);
+        const float tlx = floorf(xpos);
+        const float tly = floorf(ypos);
+        const int ix = (int)tlx, iy = (int)tly;
+        const float xdist = xpos - tlx;
+        const float ydist = ypos - tly;
+        const float cTL = (1 - xdist) * (1 - ydist), cBR = xdist * ydist;
+        const float cBL = (1 - xdist) * ydist, cTR = xdist * (1 - ydist);
+        const long long oTL = src.off(n, 0, iy, ix);
+        for (int c = 0; c < src.c; c++) {
+            const float* s = src.p + oTL + c * src.sc;
+            const float TL = __ldg(s), TR = __ldg(s + src.sw);
+            const float BL = __ldg(s + src.sh), BR = __ldg(s + src.sh + src.sw);
+            // term order TL, BR, BL, TR (data_augmentation_layer.cu:62-65)
+            dst.p[dst.off(n, c, y, x)] = ((cTL * TL + cBR * BR) + cBL * BL) + cTR * TR;
+        }
+    }
+}
+
+// ColorContrastAugmentation: data_augmentation_layer.cu:73-117 (in place, 3 channels).
+__global__ void color_contrast_kernel(T4 d, const float* __restrict__ chroma, float max_multiplier) {
+    const long long total = (long long)d.n * d.h * d.w;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % d.w);
+        const int y = (int)((idx / d.w) % d.h);
+        const int n = (int)(idx / ((long long)d.w * d.h));
+        const float* ch = chroma + 6 * n;
+        float rgb[3];
+        float mean_in = 0, mean_out = 0;
+        for (int c = 0; c < 3; c++) {
+            rgb[c] = d.p[d.off(n, c, y, x)];
+            mean_in += rgb[c];
+            rgb[c] *= ch[3 + c];
+            mean_out += rgb[c];
+        }
+        const float brightness_coeff = mean_in / (mean_out + 0.01f);
+        for (int c = 0; c < 3; c++) {
+            float v = clampf(rgb[c] * brightness_coeff, 0.f, 1.f);
+            v = powf(v, ch[0]);
+            v = v + ch[1];
+            v = 0.5f + (v - 0.5f) * ch[2];
+            d.p[d.off(n, c, y, x)] = clampf(v, 0.f, max_multiplier);
+        }
+    }
+}
+
+// Running mean update: data_augmentation_layer.cu:600-607 (scal, axpy per sample, scal).
+__global__ void mean_update_kernel(T4 top, T4 mean, float num_iter) {
+    const long long total = (long long)top.c * top.h * top.w;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % top.w);
+        const int y = (int)((idx / top.w) % top.h);
+        const int c = (int)(idx / ((long long)top.w * top.h));
+        float* mp = mean.p + mean.off(0, c, y, x);
+        float m = *mp * (num_iter - 1.0f);
+        const float inv = 1.0f / (float)top.n;
+        for (int n = 0; n < top.n; n++) m = m + inv * top.p[top.off(n, c, y, x)];
+        *mp = m * (1.0f / num_iter);
+    }
+}
+// Per-channel average of the mean image (caffe_gpu_gemv with ones, :608); one CTA per channel,
+// double accumulation (the cuBLAS order is unpinned).
+__global__ void mean_per_channel_kernel(T4 mean, float* __restrict__ mean_pc) {
+    const int c = blockIdx.x;
+    const int area = mean.h * mean.w;
+    double acc = 0;
+    for (int i = threadIdx.x; i < area; i += blockDim.x)
+        acc += (double)mean.p[mean.off(0, c, i / mean.w, i % mean.w)];
+    __shared__ double sh[256];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) mean_pc[c] = (float)((1.0 / (double)area) * sh[0]);
+}
+// Mean subtraction :610-634.
+__global__ void mean_subtract_kernel(T4 top, T4 mean, const float* __restrict__ mean_pc, int per_pixel) {
+    const long long total = top.count();
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % top.w);
+        long long r = idx / top.w;
+        const int c = (int)(r % top.c); r /= top.c;
+        const int y = (int)(r % top.h);
+        const int n = (int)(r / top.h);
+        const float m = per_pixel ? mean.p[mean.off(0, c, y, x)] : mean_pc[c];
+        float* t = top.p + top.off(n, c, y, x);
+        *t = *t - m;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Glue.
+// ---------------------------------------------------------------------------------------------
+// ReLU: relu_layer.cu:9-14  x > 0 ? x : x*slope
+__global__ void relu_kernel(T4 in, T4 out, float slope) {
+    const long long total = out.count();
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % out.c);
+        long long r = idx / out.c;
+        const int x = (int)(r % out.w); r /= out.w;
+        const int y = (int)(r % out.h);
+        const int n = (int)(r / out.h);
+        const float v = in.p[in.off(n, c, y, x)];
+        out.p[out.off(n, c, y, x)] = v > 0 ? v : v * slope;
+    }
+}
+
+struct EltArgs { T4 b[4]; float coeff[4]; int nb; };
+// Eltwise SUM: eltwise_layer.cpp:59-65 (zero, then axpy in bottom order).
+__global__ void eltwise_sum_kernel(EltArgs a, T4 out) {
+    const long long total = out.count();
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % out.w);
+        long long r = idx / out.w;
+        const int c = (int)(r % out.c); r /= out.c;
+        const int y = (int)(r % out.h);
+        const int n = (int)(r / out.h);
+        float acc = 0.f;
+        for (int b = 0; b < a.nb; b++) acc = acc + a.coeff[b] * a.b[b].p[a.b[b].off(n, c, y, x)];
+        out.p[out.off(n, c, y, x)] = acc;
+    }
+}
+
+// ChannelNorm: channel_norm_layer.cu:17-30.
+__global__ void channel_norm_kernel(T4 in, T4 out) {
+    const long long total = (long long)in.n * in.h * in.w;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % in.w);
+        const int y = (int)((idx / in.w) % in.h);
+        const int n = (int)(idx / ((long long)in.w * in.h));
+        float norm = 0;
+        for (int c = 0; c < in.c; c++) {
+            const float v = in.p[in.off(n, c, y, x)];
+            norm = norm + v * v;
+        }
+        out.p[out.off(n, 0, y, x)] = sqrtf(norm);
+    }
+}
+
+// Strided copy (Concat, layout conversion).  Two index decodings so that either side can be
+// the coalesced one: SRC_CFAST decodes channel-fastest (good when src or dst is NHWC).
+template <bool CFAST>
+__global__ void copy_kernel(T4 src, T4 dst) {
+    const long long total = dst.count();
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int n, c, y, x;
+        if (CFAST) {
+            c = (int)(idx % dst.c);
+            long long r = idx / dst.c;
+            x = (int)(r % dst.w); r /= dst.w;
+            y = (int)(r % dst.h);
+            n = (int)(r / dst.h);
+        } else {
+            x = (int)(idx % dst.w);
+            long long r = idx / dst.w;
+            y = (int)(r % dst.h); r /= dst.h;
+            c = (int)(r % dst.c);
+            n = (int)(r / dst.c);
+        }
+        dst.p[dst.off(n, c, y, x)] = src.p[src.off(n, c, y, x)];
+    }
+}
+// Tiled transpose copy between a channel-planar side and a channel-fast side: 32 pixels x 32
+// channels per tile through shared memory so that both global sides are coalesced.
+__global__ void copy_transpose_kernel(T4 src, T4 dst, int src_cfast) {
+    __shared__ float tile[32][33];          // [channel][pixel]
+    const long long hw = (long long)dst.h * dst.w;
+    const int n = blockIdx.z;
+    const long long p0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        // the fast thread index follows the source's contiguous dimension
+        const int ci = src_cfast ? tx : j;
+        const int pi = src_cfast ? j : tx;
+        const long long p = p0 + pi;
+        if (c0 + ci < dst.c && p < hw)
+            tile[ci][pi] = src.p[src.off(n, c0 + ci, (int)(p / dst.w), (int)(p % dst.w))];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        // ... and the destination's contiguous dimension on the way out
+        const int ci = src_cfast ? j : tx;
+        const int pi = src_cfast ? tx : j;
+        const long long p = p0 + pi;
+        if (c0 + ci < dst.c && p < hw)
+            dst.p[dst.off(n, c0 + ci, (int)(p / dst.w), (int)(p % dst.w))] = tile[ci][pi];
+    }
+}
+
+__global__ void fill_kernel(T4 dst, float v) {
+    const long long total = dst.count();
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % dst.c);
+        long long r = idx / dst.c;
+        const int x = (int)(r % dst.w); r /= dst.w;
+        const int y = (int)(r % dst.h);
+        const int n = (int)(r / dst.h);
+        dst.p[dst.off(n, c, y, x)] = v;
+    }
+}
+
+}  // namespace fn2
+
+using namespace fn2;
+
+extern "C" {
+
+int fn2_flow_warp_forward(const fn2_tensor* image, const fn2_tensor* flow, const fn2_tensor* warped,
+                          int fill_nan, void* stream) {
+    FN2_CHECK_ARG(valid(image) && valid(flow) && valid(warped), "flow_warp: null/empty tensor");
+    T4 img = view(image), fl = view(flow), out = view(warped);
+    FN2_CHECK_ARG(fl.c == 2, "flow_warp: flow must have 2 channels (flow_warp_layer.cpp:46)");
+    FN2_CHECK_ARG(fl.n == img.n && fl.h == img.h && fl.w == img.w,
+                  "flow_warp: flow dims must match image (flow_warp_layer.cpp:45-48)");
+    FN2_CHECK_ARG(same_dims(img, out), "flow_warp: top must have the image's shape");
+    // 0xFFE00000 is the reference GPU NaN pattern (flow_warp_layer.cu:372-375)
+    float fill = 0.f;
+    if (fill_nan) { unsigned u = 0xFFE00000u; memcpy(&fill, &u, 4); }
+    const long long total = (long long)out.n * out.h * out.w;
+    flow_warp_fwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(img, fl, out, fill);
+    FN2_LAUNCH_CHECK();
+    return FN2_OK;
+}
+
+int fn2_flow_warp_backward(const fn2_tensor* image, const fn2_tensor* flow,
+                           const fn2_tensor* warped_diff, const fn2_tensor* image_diff,
+                           const fn2_tensor* flow_diff, void* stream) {
+    FN2_CHECK_ARG(valid(image) && valid(flow) && valid(warped_diff) && valid(image_diff) && valid(flow_diff),
+                  "flow_warp_backward: null/empty tensor");
+    T4 img = view(image), fl = view(flow), wd = view(warped_diff), id = view(image_diff), fd = view(flow_diff);
+    FN2_CHECK_ARG(fl.c == 2 && fd.c == 2 && same_dims(img, wd) && same_dims(img, id) && same_dims(fl, fd),
+                  "flow_warp_backward: shape mismatch");
+    fill_kernel<<<ew_grid(id.count(), 256), 256, 0, (cudaStream_t)stream>>>(id, 0.f);
+    FN2_LAUNCH_CHECK();
+    const long long total = (long long)img.n * img.h * img.w;
+    flow_warp_bwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(img, fl, wd, id, fd);
+    FN2_LAUNCH_CHECK();
+    return FN2_OK;
+}
+
+int fn2_resample_forward(const fn2_tensor* bottom, const fn2_tensor* top, int type, int antialias,
+                         void* stream) {
+    FN2_CHECK_ARG(valid(bottom) && valid(top), "resample: null/empty tensor");
+    T4 in = view(bottom), out = view(top);
+    FN2_CHECK_ARG(in.n == out.n && in.c == out.c,
+                  "resample: top channel count must match bottom (resample_layer.cu:143)");
+    const float fx = (float)in.w / (float)out.w;
+    const float fy = (float)in.h / (float)out.h;
+    const int isDown = (fx > 1) || (fy > 1);
+    const int aa = isDown && antialias;
+    const int grid = ew_grid(out.count(), 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (type == 1) resample_kernel<1><<<grid, 256, 0, s>>>(in, out, fx, fy, aa);
+    else if (type == 2) resample_kernel<2><<<grid, 256, 0, s>>>(in, out, fx, fy, aa);
+    else if (type == 3) resample_kernel<3><<<grid, 256, 0, s>>>(in, out, fx, fy, aa);
+    else { set_error("resample: unsupported type %d (resample_layer.cu:204)", type); return FN2_ERR_INVALID; }
+    FN2_LAUNCH_CHECK();
+    return FN2_OK;
+}
+
+int fn2_spatial_augmentation(const fn2_tensor* bottom, const fn2_tensor* top,
+                             const float* trans_mats_dev, void* stream) {
+    FN2_CHECK_ARG(valid(bottom) && valid(top) && trans_mats_dev, "spatial_augmentation: null argument");
+    T4 in = view(bottom), out = view(top);
+    FN2_CHECK_ARG(in.n == out.n && in.c == out.c, "spatial_augmentation: num/channels must match");
+    FN2_CHECK_ARG(in.w >= 2 && in.h >= 2, "spatial_augmentation: bottom must be at least 2x2");
+    const long long total = (long long)out.n * out.h * out.w;
+    spatial_aug_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, trans_mats_dev);
+    FN2_LAUNCH_CHECK();
+    return FN2_OK;
+}
+
+int fn2_color_contrast_augmentation(const fn2_tensor* data, const float* chroma_dev,
+                                    float max_multiplier, void* stream) {
+    FN2_CHECK_ARG(valid(data) && chroma_dev, "color_contrast: null argument");
+    T4 d = view(data);
+    FN2_CHECK_ARG(d.c == 3, "Chromatic augmentations only work with 3-channel input "
+                            "(data_augmentation_layer.cu:561)");
+    const long long total = (long long)d.n * d.h * d.w;
+    color_contrast_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(d, chroma_dev, max_multiplier);
+    FN2_LAUNCH_CHECK();
+    return FN2_OK;
+}
+
+int fn2_mean_update(const fn2_tensor* top, const fn2_tensor* mean_pp, float* mean_pc_dev,
+                    float num_iter, void* stream) {
+    FN2_CHECK_ARG(valid(top) && valid(mean_pp) && mean_pc_dev, "mean_update: null argument");
+    T4 t = view(top), m = view(mean_pp);
+    FN2_CHECK_ARG(m.n == 1 && m.c == t.c && m.h == t.h && m.w == t.w,
+                  "mean_update: mean blob must be (1,C,H,W) (data_augmentation_layer.cu:603)");
+    const long long total = (long long)t.c * t.h * t.w;
+    mean_update_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(t, m, num_iter);
+    FN2_LAUNCH_CHECK();
+    mean_per_channel_kernel<<<t.c, 256, 0, (cudaStream_t)stream>>>(m, mean_pc_dev);
+    FN2_LAUNCH_CHECK();
+    return FN2_OK;
+}
+
+int fn2_mean_subtract(const fn2_tensor* top, const fn2_tensor* mean_pp, const float* mean_pc_dev,
+                      int per_pixel, void* stream) {
+    FN2_CHECK_ARG(valid(top), "mean_subtract: null top");
+    T4 t = view(top), m = t;
+    if (per_pixel) {
+        FN2_CHECK_ARG(valid(mean_pp), "mean_subtract: per-pixel mean missing");
+        m = view(mean_pp);
+        FN2_CHECK_ARG(m.c == t.c && m.h == t.h && m.w == t.w, "mean_subtract: mean shape mismatch");
+    } else {
+        FN2_CHECK_ARG(mean_pc_dev, "mean_subtract: per-channel mean missing");
+    }
+    mean_subtract_kernel<<<ew_grid(t.count(), 256), 256, 0, (cudaStream_t)stream>>>(t, m, mean_pc_dev, per_pixel);
+    FN2_LAUNCH_CHECK();
+    return FN2_OK;
+}
+
+int fn2_relu_forward(const fn2_tensor* bottom, const fn2_tensor* top, float negative_slope, void* stream) {
+    FN2_CHECK_ARG(valid(bottom) && valid(top), "relu: null/empty tensor");
+    T4 in = view(bottom), out = view(top);
+    FN2_CHECK_ARG(same_dims(in, out), "relu: shape mismatch");
+    relu_kernel<<<ew_grid(out.count(), 256), 256, 0, (cudaStream_t)stream>>>(in, out, negative_slope);
+    FN2_LAUNCH_CHECK();
+    return FN2_OK;
+}
+
+int fn2_eltwise_sum(const fn2_tensor* const* bottoms, const float* coeffs, int num_bottoms,
+                    const fn2_tensor* top, void* stream) {
+    FN2_CHECK_ARG(bottoms && valid(top) && num_bottoms >= 1 && num_bottoms <= 4,
+                  "eltwise_sum: need 1..4 bottoms");
+    EltArgs a;
+    a.nb = num_bottoms;
+    T4 out = view(top);
+    for (int i = 0; i < num_bottoms; i++) {
+        FN2_CHECK_ARG(valid(bottoms[i]), "eltwise_sum: null bottom");
+        a.b[i] = view(bottoms[i]);
+        FN2_CHECK_ARG(same_dims(a.b[i], out), "eltwise_sum: shape mismatch (eltwise_layer.cpp:33)");
+        a.coeff[i] = coeffs ? coeffs[i] : 1.0f;
+    }
+    eltwise_sum_kernel<<<ew_grid(out.count(), 256), 256, 0, (cudaStream_t)stream>>>(a, out);
+    FN2_LAUNCH_CHECK();
+    return FN2_OK;
+}
+
+int fn2_channel_norm_forward(const fn2_tensor* bottom, const fn2_tensor* top, void* stream) {
+    FN2_CHECK_ARG(valid(bottom) && valid(top), "channel_norm: null/empty tensor");
+    T4 in = view(bottom), out = view(top);
+    FN2_CHECK_ARG(out.c == 1 && out.n == in.n && out.h == in.h && out.w == in.w,
+                  "channel_norm: top must be (N,1,H,W) (channel_norm_layer.cpp:29)");
+    const long long total = (long long)in.n * in.h * in.w;
+    channel_norm_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out);
+    FN2_LAUNCH_CHECK();
+    return FN2_OK;
+}
+
+int fn2_copy(const fn2_tensor* src, const fn2_tensor* dst, void* stream) {
+    FN2_CHECK_ARG(valid(src) && valid(dst), "copy: null/empty tensor");
+    T4 s = view(src), d = view(dst);
+    FN2_CHECK_ARG(same_dims(s, d), "copy: shape mismatch");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool s_cf = (s.sc == 1), d_cf = (d.sc == 1);
+    const bool s_pl = (s.sw == 1), d_pl = (d.sw == 1);
+    if (d.c >= 8 && ((s_cf && d_pl && !d_cf) || (s_pl && d_cf && !s_cf))) {
+        const long long hw = (long long)d.h * d.w;
+        dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((d.c + 31) / 32), (unsigned)d.n);
+        copy_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(s, d, s_cf ? 1 : 0);
+    } else if (d_cf || (s_cf && !d_pl)) {
+        copy_kernel<true><<<ew_grid(d.count(), 256), 256, 0, st>>>(s, d);
+    } else {
+        copy_kernel<false><<<ew_grid(d.count(), 256), 256, 0, st>>>(s, d);
+    }
+    FN2_LAUNCH_CHECK();
+    return FN2_OK;
+}
+
+int fn2_fill(const fn2_tensor* dst, float value, void* stream) {
+    FN2_CHECK_ARG(valid(dst), "fill: null/empty tensor");
+    T4 d = view(dst);
+    fill_kernel<<<ew_grid(d.count(), 256), 256, 0, (cudaStream_t)stream>>>(d, value);
+    FN2_LAUNCH_CHECK();
+    return FN2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,222 @@
+/*
+ * fn2.h -- C-ABI of libfn2.so, the Blackwell-native (sm_100a) FlowNet2 forward hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Each entry
+ * point names the reference (lmb-freiburg/flownet2 @ b92e198) function it replaces; the
+ * reference-side binding (a Caffe Layer subclass whose Forward_gpu calls the entry point)
+ * is shown in INTEGRATION.md.  The Caffe-surface C++ host (namespace caffe: Blob, Layer,
+ * LayerParameter, LayerRegistry, Net) that sits above this ABI lives in
+ * flownet2_b200/csrc/caffe/ and is itself reachable through the fn2_net_* functions below.
+ *
+ * Conventions
+ *   - All data is fp32 on the device.  Tensors are described by fn2_tensor: logical Caffe
+ *     dims (n,c,h,w) plus element strides, so both the reference's NCHW blobs
+ *     (sn=c*h*w, sc=h*w, sh=w, sw=1) and the engine's internal NHWC activations
+ *     (sc=1, sw=channel stride) and channel-offset views into concat buffers are expressible.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously.
+ *   - Return value: 0 = FN2_OK, negative = error (see fn2_status); fn2_last_error() returns a
+ *     thread-local description.  Nothing here aborts the process (the reference CHECK-fails).
+ */
+#ifndef FN2_H_
+#define FN2_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FN2_API __attribute__((visibility("default")))
+
+typedef enum fn2_status {
+    FN2_OK = 0,
+    FN2_ERR_INVALID = -1,      /* bad argument / unsupported configuration */
+    FN2_ERR_CUDA = -2,         /* CUDA runtime or driver error */
+    FN2_ERR_PARSE = -3,        /* prototxt / caffemodel parse error */
+    FN2_ERR_NOTFOUND = -4,     /* unknown blob / layer / type */
+    FN2_ERR_WORKSPACE = -5     /* workspace too small */
+} fn2_status;
+
+typedef struct fn2_tensor {
+    float* data;               /* device pointer */
+    int32_t n, c, h, w;        /* logical Caffe dims */
+    int64_t sn, sc, sh, sw;    /* element strides */
+} fn2_tensor;
+
+FN2_API const char* fn2_last_error(void);
+FN2_API const char* fn2_version(void);
+/* Number of kernels launched by this library on the calling thread since process start
+ * (bench.py's gpu_launches). */
+FN2_API uint64_t fn2_launch_count(void);
+
+/* ------------------------------------------------------------------------------------ */
+/* Correlation -- replaces CorrelationLayer::Forward_gpu / Backward_gpu                  */
+/*   reference: src/caffe/layers/correlation_layer.cu:431-504 (fwd), :508-600 (bwd),      */
+/*   shapes src/caffe/layers/correlation_layer.cpp:41-84.                                 */
+/* corr_type: 0 MULTIPLY, 1 SUBTRACT (caffe.proto:639-643).                               */
+/* ------------------------------------------------------------------------------------ */
+FN2_API int fn2_correlation_shape(int H, int W, int pad, int kernel_size, int max_displacement,
+                                  int stride1, int stride2, int* top_channels, int* top_h,
+                                  int* top_w);
+FN2_API int fn2_correlation_workspace_bytes(int N, int C, int H, int W, int pad, int kernel_size,
+                                            int max_displacement, int stride1, int stride2,
+                                            int corr_type, size_t* bytes);
+FN2_API int fn2_correlation_forward(const fn2_tensor* bottom0, const fn2_tensor* bottom1,
+                                    const fn2_tensor* top, int pad, int kernel_size,
+                                    int max_displacement, int stride1, int stride2, int corr_type,
+                                    void* workspace, size_t workspace_bytes, void* stream);
+/* MULTIPLY only.  Gradients w.r.t. both bottoms (CorrelateDataBackward0/1, :118-249). */
+FN2_API int fn2_correlation_backward(const fn2_tensor* bottom0, const fn2_tensor* bottom1,
+                                     const fn2_tensor* top_diff, const fn2_tensor* bottom0_diff,
+                                     const fn2_tensor* bottom1_diff, int pad, int kernel_size,
+                                     int max_displacement, int stride1, int stride2, void* stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* FlowWarp -- replaces FlowWarpLayer::Forward_gpu / Backward_gpu                         */
+/*   reference: src/caffe/layers/flow_warp_layer.cu:357-458, :461-514; CPU twin           */
+/*   flow_warp_layer.cpp:57-198.  fill_nan: 0 = ZERO, 1 = NOT_A_NUMBER (caffe.proto:553).  */
+/* ------------------------------------------------------------------------------------ */
+FN2_API int fn2_flow_warp_forward(const fn2_tensor* image, const fn2_tensor* flow,
+                                  const fn2_tensor* warped, int fill_nan, void* stream);
+FN2_API int fn2_flow_warp_backward(const fn2_tensor* image, const fn2_tensor* flow,
+                                   const fn2_tensor* warped_diff, const fn2_tensor* image_diff,
+                                   const fn2_tensor* flow_diff, void* stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* Resample -- replaces ResampleLayer::Forward_gpu (resample_layer.cu:128-206).           */
+/* type: 1 NEAREST, 2 LINEAR, 3 CUBIC (caffe.proto:666-671).                              */
+/* ------------------------------------------------------------------------------------ */
+FN2_API int fn2_resample_forward(const fn2_tensor* bottom, const fn2_tensor* top, int type,
+                                 int antialias, void* stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* DataAugmentation kernels -- replace the device side of                                 */
+/* DataAugmentationLayer::Forward_gpu (data_augmentation_layer.cu:321-637).               */
+/* ------------------------------------------------------------------------------------ */
+/* SpatialAugmentation (:25-70).  trans_mats: device array, 6 floats per sample in NAME order
+ * t0,t1,t2,t3,t4,t5 (xin = x*t0 + y*t2 + t4 ; yin = x*t1 + y*t3 + t5). */
+FN2_API int fn2_spatial_augmentation(const fn2_tensor* bottom, const fn2_tensor* top,
+                                     const float* trans_mats_dev, void* stream);
+/* ColorContrastAugmentation (:73-117), in place.  chroma: device array, 6 floats per sample
+ * {gamma, brightness, contrast, color0, color1, color2}. */
+FN2_API int fn2_color_contrast_augmentation(const fn2_tensor* data, const float* chroma_dev,
+                                            float max_multiplier, void* stream);
+/* Running-mean update of :600-608: mean_pp = (mean_pp*(num_iter-1) + sum_n top_n/num)/num_iter,
+ * mean_pc[c] = average of mean_pp over the area.  mean_pp is a (1,C,H,W)-shaped tensor. */
+FN2_API int fn2_mean_update(const fn2_tensor* top, const fn2_tensor* mean_pp, float* mean_pc_dev,
+                            float num_iter, void* stream);
+/* Mean subtraction :610-634: per_pixel != 0 subtracts mean_pp, else the per-channel values. */
+FN2_API int fn2_mean_subtract(const fn2_tensor* top, const fn2_tensor* mean_pp,
+                              const float* mean_pc_dev, int per_pixel, void* stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* Convolution / Deconvolution (+ fused bias and leaky ReLU)                              */
+/*   reference: conv_layer.cu:8-23, deconv_layer.cu:8-23, base_conv_layer.cpp:257-298,    */
+/*   relu_layer.cu:9-14.                                                                  */
+/* ------------------------------------------------------------------------------------ */
+typedef struct fn2_conv_desc {
+    int32_t ci, co;            /* channels in / out (group == 1 only) */
+    int32_t kh, kw, stride_h, stride_w, pad_h, pad_w;
+    int32_t deconv;            /* 0 convolution, 1 deconvolution (transposed) */
+    int32_t has_bias;
+    int32_t relu;              /* 1: apply x>0 ? x : x*negative_slope in the epilogue */
+    float negative_slope;
+    int32_t engine;            /* 0 default (tensor cores when eligible), 1 SIMT fp32, 2 tcgen05 */
+} fn2_conv_desc;
+
+/* Packed weight size (floats) and packing from Caffe layout: conv [co][ci][kh][kw]
+ * (base_conv_layer.cpp:135-140), deconv [ci][co][kh][kw] (:125-137).  Packing happens once
+ * at weight-load time.  ci_stride = padded channel count of the input tensor. */
+FN2_API int fn2_conv_packed_floats(const fn2_conv_desc* d, int ci_stride, size_t* floats);
+FN2_API int fn2_conv_pack_weights(const fn2_conv_desc* d, int ci_stride,
+                                  const float* caffe_weights_dev, float* packed_dev, void* stream);
+FN2_API int fn2_conv_out_shape(const fn2_conv_desc* d, int H, int W, int* Ho, int* Wo);
+FN2_API int fn2_conv_forward(const fn2_conv_desc* d, const fn2_tensor* bottom,
+                             const float* packed_weights_dev, const float* bias_dev,
+                             const fn2_tensor* top, void* stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* Glue: ReLU (relu_layer.cu:9-14), Eltwise SUM with coeffs (eltwise_layer.cu),           */
+/* ChannelNorm (channel_norm_layer.cu:17-30), strided copy (Concat concat_layer.cu,        */
+/* layout conversion).                                                                    */
+/* ------------------------------------------------------------------------------------ */
+FN2_API int fn2_relu_forward(const fn2_tensor* bottom, const fn2_tensor* top, float negative_slope,
+                             void* stream);
+FN2_API int fn2_eltwise_sum(const fn2_tensor* const* bottoms, const float* coeffs, int num_bottoms,
+                            const fn2_tensor* top, void* stream);
+FN2_API int fn2_channel_norm_forward(const fn2_tensor* bottom, const fn2_tensor* top, void* stream);
+FN2_API int fn2_copy(const fn2_tensor* src, const fn2_tensor* dst, void* stream);
+FN2_API int fn2_fill(const fn2_tensor* dst, float value, void* stream);
+
+/* ------------------------------------------------------------------------------------ */
+/* Net -- replaces caffe::Net<float> as used by scripts/run-flownet.py:64-98              */
+/*   (Net::Init net.cpp:40-286, CopyTrainedLayersFrom :752-802, ForwardFromTo :546-557).  */
+/* ------------------------------------------------------------------------------------ */
+typedef struct fn2_net fn2_net;
+
+/* Parse a deploy prototxt (text format, $VARS$ already substituted) and build the graph on
+ * the current CUDA device.  phase: 0 TRAIN, 1 TEST. */
+FN2_API int fn2_net_create(const char* prototxt_text, int phase, fn2_net** out);
+/* Same, overriding dim 0 of every Input shape with `batch` (> 0): the released deploy templates
+ * say `dim: 1`; frame-batch sharding runs B pairs per replica. */
+FN2_API int fn2_net_create_batch(const char* prototxt_text, int phase, int batch, fn2_net** out);
+FN2_API void fn2_net_destroy(fn2_net* net);
+/* Load weights from the bytes of a .caffemodel (binary NetParameter). */
+FN2_API int fn2_net_copy_trained_layers(fn2_net* net, const void* caffemodel, size_t bytes);
+/* Serialise current parameters as a .caffemodel.  Call with buf==NULL to query the size. */
+FN2_API int fn2_net_to_caffemodel(fn2_net* net, void* buf, size_t* bytes);
+/* Fill parameters from the prototxt's fillers (deterministic given seed); used for synthetic
+ * benchmarks where no .caffemodel exists. */
+FN2_API int fn2_net_fill_params(fn2_net* net, uint64_t seed);
+/* Contiguous device arena holding every layer parameter (for one ncclBroadcast). */
+FN2_API int fn2_net_param_arena(fn2_net* net, void** dev_ptr, size_t* bytes);
+/* Re-derive packed weights after the arena was overwritten (e.g. by a broadcast). */
+FN2_API int fn2_net_params_changed(fn2_net* net);
+
+FN2_API int fn2_net_num_inputs(fn2_net* net);
+FN2_API const char* fn2_net_input_name(fn2_net* net, int i);
+FN2_API int fn2_net_num_outputs(fn2_net* net);
+FN2_API const char* fn2_net_output_name(fn2_net* net, int i);
+FN2_API int fn2_net_num_blobs(fn2_net* net);
+FN2_API const char* fn2_net_blob_name(fn2_net* net, int i);
+FN2_API int fn2_net_num_layers(fn2_net* net);
+FN2_API const char* fn2_net_layer_name(fn2_net* net, int i);
+FN2_API const char* fn2_net_layer_type(fn2_net* net, int i);
+FN2_API int fn2_net_blob_shape(fn2_net* net, const char* blob, int shape[4]);
+
+/* Host NCHW <-> blob.  set: H2D copy + layout conversion, asynchronous on the net's stream
+ * (host buffer must stay valid until fn2_net_sync; pinned memory makes it truly async).
+ * get: device->host, synchronises. */
+FN2_API int fn2_net_set_input(fn2_net* net, const char* blob, const float* host_nchw);
+FN2_API int fn2_net_get_blob(fn2_net* net, const char* blob, float* host_nchw);
+/* Same with device NCHW buffers (no host round trip). */
+FN2_API int fn2_net_set_input_device(fn2_net* net, const char* blob, const float* dev_nchw);
+FN2_API int fn2_net_get_blob_device(fn2_net* net, const char* blob, float* dev_nchw);
+
+/* Net::Forward.  Asynchronous on the net's stream; replayed from a CUDA graph when possible. */
+FN2_API int fn2_net_forward(fn2_net* net);
+FN2_API int fn2_net_sync(fn2_net* net);
+FN2_API void* fn2_net_stream(fn2_net* net);
+/* Per-layer device time of one forward pass in the style of `caffe time`
+ * (tools/caffe.cpp:346-385).  ms must hold fn2_net_num_layers() floats. */
+FN2_API int fn2_net_time_layers(fn2_net* net, float* ms);
+/* Kernels launched by one forward pass. */
+FN2_API int fn2_net_launches_per_forward(fn2_net* net);
+
+/* Host-only parser checks (no GPU needed; used by the CPU test-suite).
+ * fn2_proto_canonical: parse a prototxt with the engine's text-format parser (after the legacy
+ * `input:` upgrade) and print it back in canonical text format.  fn2_caffemodel_summary: parse a
+ * .caffemodel and print one line per layer: name, type, then per blob shape and a checksum.
+ * Both follow the size-query convention: call with out==NULL to get the needed size in *bytes. */
+FN2_API int fn2_proto_canonical(const char* prototxt_text, char* out, size_t* bytes);
+FN2_API int fn2_caffemodel_summary(const void* caffemodel, size_t n, char* out, size_t* bytes);
+
+/* .flo files (util/output.cpp:16-64): "PIEH", int32 w, int32 h, interleaved (u,v) fp32. */
+FN2_API int fn2_write_flo(const char* path, const float* flow_nchw_2hw, int h, int w);
+FN2_API int fn2_read_flo(const char* path, float* flow_nchw_2hw, int* h, int* w, size_t capacity_floats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FN2_H_ */

@@ -1,0 +1,270 @@
+"""CPU oracle for whole-net forward passes (TEST INFRASTRUCTURE, see oracle/oracle.c header).
+
+An independent, deliberately simple restatement of the reference's graph semantics
+(src/caffe/net.cpp:40-286 in-order execution, in-place tops :394-400; weight matching by layer
+name :752-802) on top of oracle.py's per-layer functions.  It has its own prototxt text-format
+parser and its own .caffemodel wire-format reader so that nothing is shared with the product's
+C++ parsers.
+"""
+import struct
+
+import numpy as np
+
+from . import oracle as O
+
+
+# ------------------------------------------------------------------------------------------------
+# text format
+# ------------------------------------------------------------------------------------------------
+def _tokens(text):
+    i, n = 0, len(text)
+    while i < n:
+        c = text[i]
+        if c in " \t\r\n,;":
+            i += 1
+        elif c == "#":
+            while i < n and text[i] != "\n":
+                i += 1
+        elif c in "{}:<>[]":
+            yield c
+            i += 1
+        elif c in "\"'":
+            j = i + 1
+            out = []
+            while text[j] != c:
+                if text[j] == "\\":
+                    j += 1
+                out.append(text[j])
+                j += 1
+            yield ("str", "".join(out))
+            i = j + 1
+        else:
+            j = i
+            while j < n and text[j] not in " \t\r\n,;{}:<>[]#\"'":
+                j += 1
+            yield ("tok", text[i:j])
+            i = j
+
+
+def parse_prototxt(text):
+    toks = list(_tokens(text))
+    pos = [0]
+
+    def parse_msg(closer):
+        fields = []
+        while pos[0] < len(toks):
+            t = toks[pos[0]]
+            if t == closer:
+                pos[0] += 1
+                return fields
+            name = t[1]
+            pos[0] += 1
+            if toks[pos[0]] == ":":
+                pos[0] += 1
+            t = toks[pos[0]]
+            if t in ("{", "<"):
+                pos[0] += 1
+                fields.append((name, parse_msg("}" if t == "{" else ">")))
+            elif t == "[":
+                pos[0] += 1
+                while toks[pos[0]] != "]":
+                    fields.append((name, toks[pos[0]][1]))
+                    pos[0] += 1
+                pos[0] += 1
+            else:
+                fields.append((name, t[1]))
+                pos[0] += 1
+        assert closer is None, "unbalanced braces"
+        return fields
+
+    return parse_msg(None)
+
+
+def getall(msg, name):
+    return [v for k, v in msg if k == name]
+
+
+def get(msg, name, default=None):
+    v = getall(msg, name)
+    return v[0] if v else default
+
+
+# ------------------------------------------------------------------------------------------------
+# wire format (.caffemodel): NetParameter.layer=100 -> name=1, type=2, blobs=7 -> shape=7{dim=1},
+# data=5 (packed float), legacy num/channels/height/width = 1..4   (caffe.proto:10-22,94,313-331)
+# ------------------------------------------------------------------------------------------------
+def _varint(b, i):
+    v, s = 0, 0
+    while True:
+        x = b[i]
+        i += 1
+        v |= (x & 0x7F) << s
+        if not x & 0x80:
+            return v, i
+        s += 7
+
+
+def _fields(b):
+    i = 0
+    while i < len(b):
+        key, i = _varint(b, i)
+        fn, wt = key >> 3, key & 7
+        if wt == 0:
+            v, i = _varint(b, i)
+        elif wt == 2:
+            ln, i = _varint(b, i)
+            v = b[i:i + ln]
+            i += ln
+        elif wt == 5:
+            v = b[i:i + 4]
+            i += 4
+        elif wt == 1:
+            v = b[i:i + 8]
+            i += 8
+        else:
+            raise ValueError("wire type %d" % wt)
+        yield fn, wt, v
+
+
+def parse_caffemodel(data):
+    layers = {}
+    for fn, wt, v in _fields(memoryview(data)):
+        if fn != 100:
+            continue
+        name, blobs = None, []
+        for f2, w2, v2 in _fields(v):
+            if f2 == 1:
+                name = bytes(v2).decode()
+            elif f2 == 7:
+                shape, legacy, arr = None, {}, None
+                for f3, w3, v3 in _fields(v2):
+                    if f3 == 7:
+                        for f4, w4, v4 in _fields(v3):
+                            if f4 == 1 and w4 == 2:
+                                shape, j = [], 0
+                                while j < len(v4):
+                                    d, j = _varint(v4, j)
+                                    shape.append(d)
+                    elif f3 == 5 and w3 == 2:
+                        arr = np.frombuffer(v3, dtype="<f4").copy()
+                    elif f3 in (1, 2, 3, 4) and w3 == 0:
+                        legacy[f3] = v3
+                if shape is None:
+                    shape = [legacy.get(k, 1) for k in (1, 2, 3, 4)]
+                blobs.append(arr.reshape(shape))
+        layers[name] = blobs
+    return layers
+
+
+# ------------------------------------------------------------------------------------------------
+# forward
+# ------------------------------------------------------------------------------------------------
+def _hw(msg, rep, h, w, default):
+    if get(msg, h) is not None or get(msg, w) is not None:
+        return int(get(msg, h, default)), int(get(msg, w, default))
+    v = [int(x) for x in getall(msg, rep)]
+    if not v:
+        return default, default
+    return (v[0], v[0]) if len(v) == 1 else (v[0], v[1])
+
+
+class OracleNet(object):
+    def __init__(self, prototxt_text, caffemodel_bytes, batch=0, f64acc=False):
+        self.root = parse_prototxt(prototxt_text)
+        self.weights = parse_caffemodel(caffemodel_bytes)
+        self.f64acc = f64acc
+        self.input_names = getall(self.root, "input")
+        self.input_shapes = [[int(d) for d in getall(s, "dim")] for s in getall(self.root, "input_shape")]
+        self.layers = getall(self.root, "layer")
+        for l in self.layers:
+            if get(l, "type") == "Input":
+                self.input_names += getall(l, "top")
+                self.input_shapes += [[int(d) for d in getall(s, "dim")] for s in getall(get(l, "input_param", []), "shape")]
+        if batch:
+            for s in self.input_shapes:
+                s[0] = batch
+        self.blobs = {}
+
+    def forward(self, **inputs):
+        B = self.blobs = {}
+        for n, s in zip(self.input_names, self.input_shapes):
+            a = np.ascontiguousarray(inputs[n], np.float32)
+            assert list(a.shape) == s, (n, a.shape, s)
+            B[n] = a
+        for l in self.layers:
+            typ, name = get(l, "type"), get(l, "name")
+            bots = [B[b] for b in getall(l, "bottom")]
+            tops = getall(l, "top")
+            if typ == "Input":
+                continue
+            elif typ == "Eltwise":
+                ep = get(l, "eltwise_param", [])
+                assert get(ep, "operation", "SUM") == "SUM"
+                B[tops[0]] = O.eltwise_sum(bots, [float(c) for c in getall(ep, "coeff")])
+            elif typ == "DataAugmentation":
+                B[tops[0]] = self._aug(l, name, bots[0])
+            elif typ == "Resample":
+                rp = get(l, "resample_param", [])
+                if len(bots) == 2:
+                    oh, ow = bots[1].shape[2], bots[1].shape[3]
+                else:
+                    oh, ow = int(get(rp, "height")), int(get(rp, "width"))
+                rtype = {"NEAREST": 1, "LINEAR": 2, "CUBIC": 3}[get(rp, "type", "LINEAR")]
+                B[tops[0]] = O.resample_fwd(bots[0], oh, ow, rtype, get(rp, "antialias", "true") == "true")
+            elif typ in ("Convolution", "Deconvolution"):
+                cp = get(l, "convolution_param")
+                kh, kw = _hw(cp, "kernel_size", "kernel_h", "kernel_w", 0)
+                sh, sw = _hw(cp, "stride", "stride_h", "stride_w", 1)
+                ph, pw = _hw(cp, "pad", "pad_h", "pad_w", 0)
+                has_bias = get(cp, "bias_term", "true") == "true"
+                w = self.weights[name][0]
+                b = self.weights[name][1].reshape(-1) if has_bias else None
+                for bot, top in zip(bots, tops):
+                    if typ == "Convolution":
+                        B[top] = O.conv_fwd(bot, w, b, (sh, sw), (ph, pw), f64acc=self.f64acc)
+                    else:
+                        B[top] = O.deconv_fwd(bot, w, b, (sh, sw), (ph, pw), f64acc=self.f64acc)
+            elif typ == "ReLU":
+                B[tops[0]] = O.relu(bots[0], float(get(get(l, "relu_param", []), "negative_slope", 0)))
+            elif typ == "Concat":
+                B[tops[0]] = np.concatenate(bots, axis=1)
+            elif typ == "Correlation":
+                cp = get(l, "correlation_param")
+                B[tops[0]] = O.correlation_fwd(bots[0], bots[1], int(get(cp, "pad", 0)), int(get(cp, "kernel_size")),
+                                               int(get(cp, "max_displacement")), int(get(cp, "stride_1", 1)),
+                                               int(get(cp, "stride_2", 1)),
+                                               {"MULTIPLY": 0, "SUBTRACT": 1}[get(cp, "correlation_type", "MULTIPLY")],
+                                               exact_order=not self.f64acc)
+            elif typ == "FlowWarp":
+                fp = get(l, "flow_warp_param", [])
+                B[tops[0]] = O.flow_warp_fwd(bots[0], bots[1], get(fp, "fill_value", "ZERO") == "NOT_A_NUMBER")
+            elif typ == "ChannelNorm":
+                B[tops[0]] = O.channel_norm(bots[0])
+            else:
+                raise NotImplementedError(typ)
+        return B
+
+    def _aug(self, l, name, x):
+        ap = get(l, "augmentation_param")
+        N, C, H, W = x.shape
+        cw, ch = get(ap, "crop_width"), get(ap, "crop_height")
+        if cw is not None and ch is not None:
+            cw, ch = int(cw), int(ch)
+            mats = np.stack([O.transmat_from_coeff(cw, ch, W, H)] * N)
+            top = O.spatial_augmentation(x, mats, ch, cw)
+        else:
+            top = x.copy()
+        rm = int(get(ap, "recompute_mean", 0))
+        mpp_flag = get(ap, "mean_per_pixel", "true") == "true"
+        if rm > 0:
+            st = self.weights[name]
+            st[0] = np.float32(int(st[0].reshape(-1)[0]) + 1).reshape(st[0].shape)     # :353-354
+            num_iter = float(st[0].reshape(-1)[0])
+            top, mpp, mpc = O.mean_subtract(top, 0, num_iter, rm, mpp_flag, st[1].reshape(top.shape[1:]),
+                                            st[2].reshape(-1))
+            st[1], st[2] = mpp.reshape(st[1].shape), mpc.reshape(st[2].shape)
+        else:
+            means = [float(m) for m in getall(ap, "mean")]
+            if len(means) == 3 and not mpp_flag:
+                top, _, _ = O.mean_subtract(top, 1, mean_pc=np.array(means, np.float32))
+        return top
