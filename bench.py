@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Benchmark of the FlowNet2 forward hot path (BASELINE.json metric: frame-pairs/s, FlowNet2 forward
+@1024x436; correlation-layer HBM GB/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+ours:       one process per GPU; full FlowNet2 (CSS + SD + fusion) deploy net through the Caffe-surface
+            engine (fn2_net_* C-ABI), B pairs per GPU (weak scaling: config 4 = 32 pairs over 8 GPUs).
+            Weights are filled on rank 0 and sent with ONE NCCL broadcast of the parameter arena; every step
+            ends with a gather of the flow fields to rank 0.  `value` times K steps with inputs resident in
+            HBM; `e2e` times the same K steps with pinned-host inputs (H2D inside) and the flows read back
+            to the host (D2H inside).
+reference:  the CPU oracle (oracle/, a restatement of the reference arithmetic -- the reference's own CPU
+            path cannot be built and does not exist for Correlation/Resample/DataAugmentation) on all host
+            cores, each step a bounded spatial tile of one 1024x436 pair, scaled by the pixel ratio.
+Prints exactly one JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "frame-pairs/sec FlowNet2 forward @1024x436"
+UNIT = "frame-pairs/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="FlowNet2")
+    ap.add_argument("--width", type=int, default=1024)
+    ap.add_argument("--height", type=int, default=436)
+    ap.add_argument("--batch", type=int, default=4, help="frame pairs per GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def config(args, n_gpus):
+    return {"workload": "%s deploy forward, %dx%d synthetic pairs (adapted to /64), fp32" % (args.model, args.width, args.height),
+            "model": args.model, "width": args.width, "height": args.height, "pairs_per_gpu": args.batch,
+            "global_batch": args.batch * n_gpus, "parallelism": "frame-batch sharding x%d (1 NCCL weight broadcast, flow gather)" % n_gpus,
+            "l2": "working set (weights ~650 MB + activations) exceeds the 126 MB L2; no explicit flush"}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arm (oracle port): used for cpu_baseline (N=1, rank 0) and for --impl reference
+# ----------------------------------------------------------------------------------------------------------
+def cpu_tile_run(args, tile_w, tile_h, reps):
+    import flownet2_b200 as F
+    from oracle.net import OracleNet
+    proto = F.fill_template(F.model_template(args.model), tile_w, tile_h)
+    net = OracleNet(proto, None, batch=1, synth_seed=1701)
+    r = np.random.default_rng(3)
+    a = np.round(r.uniform(0, 255, (1, 3, tile_h, tile_w))).astype(np.float32)
+    b = np.clip(a + np.round(r.normal(0, 3, a.shape)), 0, 255).astype(np.float32)
+    net.forward(img0=a, img1=b)            # builds the synthetic weights, warms the library
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        net.forward(img0=a, img1=b)
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def cpu_pick_tile(args, budget_s):
+    """Largest /64 tile of the workload whose forward fits the per-step budget (calibrated on 128x64)."""
+    t = min(cpu_tile_run(args, 128, 64, 1))
+    per_px = t / (128.0 * 64.0)
+    full_w = (args.width + 63) // 64 * 64
+    full_h = (args.height + 63) // 64 * 64
+    best = (128, 64)
+    for th in range(64, full_h + 1, 64):
+        for tw in range(128, full_w + 1, 64):
+            if per_px * tw * th <= budget_s and tw * th > best[0] * best[1]:
+                best = (tw, th)
+    return best
+
+
+def cpu_result(args, tile, times):
+    frac = (tile[0] * tile[1]) / float(args.width * args.height)
+    mean = float(np.mean(times))
+    return frac / mean, mean
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    tile = cpu_pick_tile(args, budget)
+    times = cpu_tile_run(args, tile[0], tile[1], args.steps + args.warmup)[args.warmup:]
+    value, mean = cpu_result(args, tile, times)
+    sample = "one %dx%d tile of a %dx%d pair per step, scaled by pixel ratio" % (tile[0], tile[1], args.width, args.height)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config(args, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------
+class _DevPtr(object):
+    def __init__(self, ptr, nfloats):
+        self.__cuda_array_interface__ = {"shape": (nfloats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def clocks_sampler_start(dev_index):
+    q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    try:
+        return subprocess.Popen(["nvidia-smi", "-i", str(dev_index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except Exception:
+        return None
+
+
+def clocks_sampler_stop(p):
+    if p is None:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    p.terminate()
+    try:
+        out, _ = p.communicate(timeout=5)
+    except Exception:
+        p.kill()
+        out = ""
+    sm, mx, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for line in out.strip().splitlines():
+        f = [x.strip() for x in line.split(",")]
+        if len(f) < 7:
+            continue
+        try:
+            sm.append(float(f[0])); mx.append(float(f[1]))
+        except ValueError:
+            continue
+        for nm, v in zip(names, f[3:7]):
+            if v.lower().startswith("active"):
+                reasons.add(nm)
+    if not sm:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+    # median over the samples taken under load (upper half)
+    sm_sorted = sorted(sm)
+    load = sm_sorted[len(sm_sorted) // 2:]
+    return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import flownet2_b200 as F
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun (WORLD_SIZE=%d)" % (args.gpus, world))
+    assert torch.cuda.is_available(), "bench.py needs a GPU; there is no CPU fallback for the product path"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    B, H, W = args.batch, args.height, args.width
+    proto = F.fill_template(F.model_template(args.model), W, H)
+    net = F.Net(proto, None, F.TEST, batch=B)
+    stream = torch.cuda.ExternalStream(net.stream)
+
+    # ---- weights: rank 0 fills, one NCCL broadcast of the contiguous parameter arena -------------------------
+    ptr, nbytes = net.param_arena()
+    if rank == 0:
+        net.fill_params(1701)
+    if world > 1:
+        arena = torch.as_tensor(_DevPtr(ptr, nbytes // 4), device="cuda")
+        torch.cuda.synchronize()
+        dist.broadcast(arena, src=0)
+        torch.cuda.synchronize()
+        net.params_changed()
+
+    # ---- synthetic inputs (uint8-valued BGR floats as scripts/run-flownet.py:30-35 feeds them) ---------------
+    r = np.random.default_rng(1000 + rank)
+    img0 = np.round(r.uniform(0, 255, (B, 3, H, W))).astype(np.float32)
+    img1 = np.clip(img0 + np.round(r.normal(0, 4, img0.shape)), 0, 255).astype(np.float32)
+    pin0, pin1 = torch.from_numpy(img0).pin_memory(), torch.from_numpy(img1).pin_memory()
+    dev0, dev1 = pin0.cuda(), pin1.cuda()
+    flow_dev = torch.empty((B, 2, H, W), device="cuda", dtype=torch.float32)
+    flow_all = torch.empty((world * B, 2, H, W), device="cuda", dtype=torch.float32) if world > 1 else flow_dev
+    flow_host = torch.empty((world * B, 2, H, W), dtype=torch.float32).pin_memory() if rank == 0 else None
+
+    def step_device():
+        net.set_input_device("img0", dev0.data_ptr())
+        net.set_input_device("img1", dev1.data_ptr())
+        net.forward_async()
+        net.get_blob_device("predict_flow_final", flow_dev.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(flow_all, flow_dev)
+
+    def step_e2e():
+        net.set_input_ptr("img0", pin0.data_ptr())       # cudaMemcpyAsync H2D from pinned memory + layout kernel
+        net.set_input_ptr("img1", pin1.data_ptr())
+        net.forward_async()
+        net.get_blob_device("predict_flow_final", flow_dev.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(flow_all, flow_dev)
+        if rank == 0:
+            flow_host.copy_(flow_all, non_blocking=True)  # D2H of every pair's flow field
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step, K):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        barrier()
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            step_device()
+        barrier()
+        launches0 = F.launch_count()
+        sampler = clocks_sampler_start(local) if rank == 0 else None
+        ms = timed(step_device, args.steps)
+        clocks = clocks_sampler_stop(sampler) if rank == 0 else None
+        # graph replays do not go through the launch counter: count = kernels per forward + layout copies
+        per_step_launches = net.launches_per_forward + 3
+        for _ in range(2):
+            step_e2e()
+        ms_e2e = timed(step_e2e, args.steps)
+        finite = bool(torch.isfinite(flow_dev).all().item())
+
+    pairs = world * B * args.steps
+    value = pairs / (ms * 1e-3)
+    e2e_value = pairs / (ms_e2e * 1e-3)
+    line = None
+    if rank == 0:
+        pk = peaks()
+        # per-layer device times (CUDA events on the net's stream, eager pass) -> roofline of the kernels
+        with torch.cuda.stream(stream):
+            net.time_layers()
+            lt = net.time_layers()
+        work = net.layer_work()
+        conv_ms = sum(t for (_, ty, t) in lt if ty in ("Convolution", "Deconvolution"))
+        conv_fl = sum(f for (_, ty, f, _) in work if ty in ("Convolution", "Deconvolution"))
+        corr = [(t, w) for (n, ty, t), w in zip(lt, work) if ty == "Correlation"]
+        total_ms = sum(t for (_, _, t) in lt)
+        conv_tf = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        roofline = {"kernel": "conv/deconv stack (implicit GEMM, fused bias+ReLU)", "bound": "tensor", "achieved": conv_tf,
+                    "peak": pk["bf16_tflops_sustained"] or pk["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": conv_tf / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"]), "traffic": None,
+                    "peak_source": pk["source"] + ", sustained bf16 dense (kernel timed inside a long step)",
+                    "share_of_step": conv_ms / total_ms if total_ms else None,
+                    "algorithmic_gflop_per_step": conv_fl / 1e9}
+        rc = None
+        if corr:
+            t_ms = sum(t for t, _ in corr)
+            by = sum(w[3] for _, w in corr)
+            fl = sum(w[2] for _, w in corr)
+            gbs = by / (t_ms * 1e-3) / 1e9
+            rc = {"kernel": "Correlation d=21 k=1 s2=2 C=256", "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                  "frac": gbs / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                  "algorithmic_bytes_per_launch": by / len(corr), "ms_per_launch": t_ms / len(corr),
+                  "fp32_tflops": fl / (t_ms * 1e-3) / 1e12, "share_of_step": t_ms / total_ms if total_ms else None}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config(args, world), "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(world * 2 * B * 3 * H * W * 4),
+                        "d2h_bytes_per_step": int(world * B * 2 * H * W * 4), "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(per_step_launches * args.steps), "launches_per_step": int(per_step_launches),
+                "output_finite": finite, "roofline": roofline, "roofline_correlation": rc,
+                "layer_ms": {"total": total_ms, "conv_deconv": conv_ms, "correlation": sum(t for t, _ in corr) if corr else 0.0}}
+        if world == 1 and not args.no_cpu_baseline:
+            tile = cpu_pick_tile(args, args.cpu_seconds)
+            times = cpu_tile_run(args, tile[0], tile[1], 1)
+            v, mean = cpu_result(args, tile, times)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                    "sample": "one %dx%d tile of one %dx%d pair (%.1f s), scaled by pixel ratio; oracle/ C port, OpenMP"
+                                              % (tile[0], tile[1], W, H, mean)}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

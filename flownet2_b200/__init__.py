@@ -72,6 +72,7 @@ def lib():
         for name in ("fn2_net_set_input", "fn2_net_get_blob", "fn2_net_set_input_device", "fn2_net_get_blob_device"):
             getattr(l, name).argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
         l.fn2_net_time_layers.argtypes = [C.c_void_p, C.c_void_p]
+        l.fn2_net_layer_work.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         T = C.POINTER(fn2_tensor)
         l.fn2_correlation_forward.argtypes = [T, T, T, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                               C.c_void_p, C.c_size_t, C.c_void_p]
@@ -273,6 +274,15 @@ class Net(object):
         ms = (C.c_float * len(self.layer_names))()
         check(lib().fn2_net_time_layers(self._h, ms))
         return list(zip(self.layer_names, self.layer_types, [float(x) for x in ms]))
+
+    def layer_work(self):
+        """[(name, type, algorithmic flops, algorithmic bytes)] per layer."""
+        out = []
+        for i, (n, t) in enumerate(zip(self.layer_names, self.layer_types)):
+            f, b = C.c_double(), C.c_double()
+            check(lib().fn2_net_layer_work(self._h, i, C.byref(f), C.byref(b)))
+            out.append((n, t, f.value, b.value))
+        return out
 
     @property
     def launches_per_forward(self):

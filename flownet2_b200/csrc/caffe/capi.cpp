@@ -180,6 +180,15 @@ int fn2_net_time_layers(fn2_net* net, float* ms) {
 }
 int fn2_net_launches_per_forward(fn2_net* net) { return net ? net->net->launches_per_forward() : 0; }
 
+int fn2_net_layer_work(fn2_net* net, int layer, double* flops, double* bytes) {
+    if (!net || !flops || !bytes || layer < 0 || layer >= (int)net->net->layers().size()) {
+        fn2::set_error("layer_work: bad argument");
+        return FN2_ERR_INVALID;
+    }
+    net->net->LayerWork(layer, flops, bytes);
+    return FN2_OK;
+}
+
 static int emit_string(const std::string& s, char* out, size_t* bytes) {
     if (!bytes) { fn2::set_error("null size pointer"); return FN2_ERR_INVALID; }
     if (!out) { *bytes = s.size() + 1; return FN2_OK; }

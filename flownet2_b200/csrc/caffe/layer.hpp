@@ -58,6 +58,15 @@ class Layer {
     virtual void FillParams(uint64_t seed) {}
     // Conv/Deconv: fuse an in-place ReLU that directly follows top[i].
     virtual bool FuseReLU(int top_index, float negative_slope) { return false; }
+    // Algorithmic work of one Forward (for roofline reporting): flops and bytes moved if every
+    // bottom were read once and every top written once.
+    virtual void WorkEstimate(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top,
+                              double* flops, double* bytes) const {
+        double b = 0;
+        for (auto* x : bottom) b += 4.0 * x->count();
+        for (auto* x : top) b += 4.0 * x->count();
+        *flops = 0; *bytes = b;
+    }
     // Preferred device layout of tops created by this layer.
     virtual typename Blob<Dtype>::Layout TopLayout() const { return Blob<Dtype>::NHWC; }
 

@@ -398,6 +398,12 @@ class CorrelationLayer : public Layer<Dtype> {
         FN2_CALL(fn2_correlation_forward(&b0, &b1, &t, pad_size_, kernel_size_, max_displacement_, stride1_,
                                          stride2_, corr_type_, ws_, ws_bytes_, S()));
     }
+    void WorkEstimate(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top, double* flops,
+                      double* bytes) const override {
+        // bytes = read both maps once + write top once; flops = 2*D^2*k^2*C per output pixel
+        *bytes = 4.0 * (bottom[0]->count() + bottom[1]->count() + top[0]->count());
+        *flops = 2.0 * top[0]->count() * (double)kernel_size_ * kernel_size_ * bottom[0]->channels();
+    }
     int kernel_size_ = 0, max_displacement_ = 0, pad_size_ = 0, stride1_ = 1, stride2_ = 1, corr_type_ = 0;
     void* ws_ = nullptr;
     size_t ws_bytes_ = 0;
@@ -474,6 +480,17 @@ class BaseConvolutionLayer : public Layer<Dtype> {
             packed_floats_ = floats;
         }
         FN2_CALL(fn2_conv_pack_weights(&d_, cis, this->blobs_[0]->gpu_data(), packed_, S()));
+    }
+    void WorkEstimate(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top, double* flops,
+                      double* bytes) const override {
+        double f = 0, b = 4.0 * this->blobs_[0]->count();
+        for (size_t i = 0; i < bottom.size(); i++) {
+            // conv: 2*N*Co*Ho*Wo*Ci*kh*kw ; deconv: 2*N*Ci*H*W*Co*kh*kw (every input pixel x every tap)
+            const Blob<Dtype>* px = deconv_ ? bottom[i] : top[i];
+            f += 2.0 * px->num() * px->height() * px->width() * (double)d_.ci * d_.co * d_.kh * d_.kw;
+            b += 4.0 * (bottom[i]->count() + top[i]->count());
+        }
+        *flops = f; *bytes = b;
     }
     bool FuseReLU(int top_index, float negative_slope) override {
         if (top_index < 0 || top_index >= (int)relu_.size() || relu_[top_index]) return false;

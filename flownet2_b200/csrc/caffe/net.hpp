@@ -41,6 +41,7 @@ class Net {
     void GetBlobDevice(const string& blob, Dtype* dev_nchw);
 
     void TimeLayers(float* ms);
+    void LayerWork(int i, double* flops, double* bytes) const { layers_[i]->WorkEstimate(bottom_vecs_[i], top_vecs_[i], flops, bytes); }
     int launches_per_forward() const { return launches_per_forward_; }
 
  private:

@@ -201,6 +201,8 @@ FN2_API void* fn2_net_stream(fn2_net* net);
 /* Per-layer device time of one forward pass in the style of `caffe time`
  * (tools/caffe.cpp:346-385).  ms must hold fn2_net_num_layers() floats. */
 FN2_API int fn2_net_time_layers(fn2_net* net, float* ms);
+/* Algorithmic flops / bytes of one layer's forward (roofline reporting). */
+FN2_API int fn2_net_layer_work(fn2_net* net, int layer, double* flops, double* bytes);
 /* Kernels launched by one forward pass. */
 FN2_API int fn2_net_launches_per_forward(fn2_net* net);
 

@@ -147,6 +147,8 @@ def parse_caffemodel(data):
                                     shape.append(d)
                     elif f3 == 5 and w3 == 2:
                         arr = np.frombuffer(v3, dtype="<f4").copy()
+                    elif f3 == 8 and w3 == 2 and arr is None:      # double_data (blob.cpp:472-476)
+                        arr = np.frombuffer(v3, dtype="<f8").astype(np.float32)
                     elif f3 in (1, 2, 3, 4) and w3 == 0:
                         legacy[f3] = v3
                 if shape is None:
@@ -169,9 +171,10 @@ def _hw(msg, rep, h, w, default):
 
 
 class OracleNet(object):
-    def __init__(self, prototxt_text, caffemodel_bytes, batch=0, f64acc=False):
+    def __init__(self, prototxt_text, caffemodel_bytes, batch=0, f64acc=False, synth_seed=None):
         self.root = parse_prototxt(prototxt_text)
-        self.weights = parse_caffemodel(caffemodel_bytes)
+        self.weights = parse_caffemodel(caffemodel_bytes) if caffemodel_bytes else {}
+        self.synth_seed = synth_seed
         self.f64acc = f64acc
         self.input_names = getall(self.root, "input")
         self.input_shapes = [[int(d) for d in getall(s, "dim")] for s in getall(self.root, "input_shape")]
@@ -217,6 +220,13 @@ class OracleNet(object):
                 sh, sw = _hw(cp, "stride", "stride_h", "stride_w", 1)
                 ph, pw = _hw(cp, "pad", "pad_h", "pad_w", 0)
                 has_bias = get(cp, "bias_term", "true") == "true"
+                if name not in self.weights:           # synthetic weights (timing-only runs)
+                    assert self.synth_seed is not None, "no weights for layer " + name
+                    co, ci = int(get(cp, "num_output")), bots[0].shape[1]
+                    r = np.random.default_rng(self.synth_seed + len(self.weights))
+                    shp = (co, ci, kh, kw) if typ == "Convolution" else (ci, co, kh, kw)
+                    self.weights[name] = [(r.standard_normal(shp) * np.sqrt(2.0 / (ci * kh * kw))).astype(np.float32),
+                                          np.zeros(co, np.float32)]
                 w = self.weights[name][0]
                 b = self.weights[name][1].reshape(-1) if has_bias else None
                 for bot, top in zip(bots, tops):
@@ -257,6 +267,11 @@ class OracleNet(object):
         rm = int(get(ap, "recompute_mean", 0))
         mpp_flag = get(ap, "mean_per_pixel", "true") == "true"
         if rm > 0:
+            if name not in self.weights:
+                assert self.synth_seed is not None, "no weights for layer " + name
+                self.weights[name] = [np.full((1, 1, 1, 1), rm + 1, np.float32),
+                                      np.full((1,) + top.shape[1:], 0.4, np.float32),
+                                      np.full((1, top.shape[1], 1, 1), 0.4, np.float32)]
             st = self.weights[name]
             st[0] = np.float32(int(st[0].reshape(-1)[0]) + 1).reshape(st[0].shape)     # :353-354
             num_iter = float(st[0].reshape(-1)[0])

@@ -611,6 +611,37 @@ FN2O_API int fn2o_conv_fwd(const float* in, const float* weight, const float* bi
     if (!col) return -2;
     for (int n = 0; n < N; n++) {
         im2col(in + (size_t)n * Ci * H * W, Ci, H, W, kh, kw, ph, pw, sh, sw, dh, dw, col);
+        if (!f64acc && group == 1) {
+            /* Same arithmetic as the plain loop below (each output accumulates its products in
+             * k-ascending order, then + bias), blocked 8 output channels x 1024 pixels so that a
+             * col row is read once per 8 outputs; only there to make the CPU baseline less slow. */
+            const int CB = 8;
+            const size_t PB = 1024;
+            const int ncb = (Co + CB - 1) / CB;
+            const int npb = (int)((P + PB - 1) / PB);
+#pragma omp parallel for collapse(2) schedule(dynamic, 1)
+            for (int cb = 0; cb < ncb; cb++)
+                for (int pb = 0; pb < npb; pb++) {
+                    const int co0 = cb * CB, nco = imin(CB, Co - co0);
+                    const size_t p0 = (size_t)pb * PB, np_ = (P - p0 < PB) ? (P - p0) : PB;
+                    float acc[8][1024];
+                    for (int j = 0; j < nco; j++) for (size_t p = 0; p < np_; p++) acc[j][p] = 0.f;
+                    for (size_t k = 0; k < K; k++) {
+                        const float* cr = col + k * P + p0;
+                        for (int j = 0; j < nco; j++) {
+                            const float wv = weight[(size_t)(co0 + j) * K + k];
+                            float* a = acc[j];
+                            for (size_t p = 0; p < np_; p++) { float pr = wv * cr[p]; a[p] = a[p] + pr; }
+                        }
+                    }
+                    for (int j = 0; j < nco; j++) {
+                        float* o = out + ((size_t)n * Co + co0 + j) * P + p0;
+                        if (bias) for (size_t p = 0; p < np_; p++) o[p] = acc[j][p] + bias[co0 + j];
+                        else      for (size_t p = 0; p < np_; p++) o[p] = acc[j][p];
+                    }
+                }
+            continue;
+        }
 #pragma omp parallel for schedule(dynamic, 1)
         for (int co = 0; co < Co; co++) {
             int g = co / Cog;

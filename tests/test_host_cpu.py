@@ -1,0 +1,170 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/fn2.h declares,
+and the engine's prototxt / caffemodel parsers agree with the REFERENCE's own protobuf schema (fixtures
+produced with python/caffe/proto/caffe_pb2.py by tests/golden/make_golden.py).  No compute calls."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import net as onet
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "fn2.h")).read()
+    return sorted(set(re.findall(r"FN2_API\s+[\w\s\*]+?\b(fn2_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(fn2):
+    lib = fn2.lib()
+    syms = declared_symbols()
+    assert len(syms) >= 50
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    assert b"sm_100a" in lib.fn2_version()
+
+
+def test_library_is_sm100a_only():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "--list-elf", os.path.join(ROOT, "flownet2_b200", "libfn2.so")],
+                         capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def canonical(fn2, text):
+    lib = fn2.lib()
+    n = C.c_size_t()
+    rc = lib.fn2_proto_canonical(text.encode(), None, C.byref(n))
+    if rc:
+        raise fn2.Fn2Error(lib.fn2_last_error().decode())
+    buf = C.create_string_buffer(n.value)
+    assert lib.fn2_proto_canonical(text.encode(), buf, C.byref(n)) == 0
+    return buf.value.decode()
+
+
+@pytest.mark.parametrize("model", ["FlowNet2-S", "FlowNet2-C", "FlowNet2-CSS", "FlowNet2-SD", "FlowNet2"])
+def test_prototxt_parser_matches_reference_protobuf(fn2, model):
+    ref = json.load(open(os.path.join(GOLD, "ref_pb2_prototxt.json")))[model]
+    text = fn2.fill_template(fn2.model_template(model), 1024, 436)
+    # engine parser -> canonical text -> (independent) oracle parser -> structure
+    msg = onet.parse_prototxt(canonical(fn2, text))
+    layers = onet.getall(msg, "layer")
+    # legacy `input:` fields become one Input layer named "input" placed first (upgrade_proto.cpp:953-992)
+    assert onet.get(layers[0], "type") == "Input" and onet.get(layers[0], "name") == "input"
+    assert onet.getall(layers[0], "top") == ref["inputs"]
+    shapes = [[int(d) for d in onet.getall(s, "dim")] for s in onet.getall(onet.get(layers[0], "input_param"), "shape")]
+    assert shapes == ref["input_shape"]
+    layers = layers[1:]
+    assert len(layers) == len(ref["layers"])
+    for got, want in zip(layers, ref["layers"]):
+        assert onet.get(got, "name") == want["name"] and onet.get(got, "type") == want["type"]
+        assert onet.getall(got, "bottom") == want["bottom"] and onet.getall(got, "top") == want["top"]
+        if "conv" in want:
+            cp = onet.get(got, "convolution_param")
+            assert [int(onet.get(cp, "num_output")), [int(v) for v in onet.getall(cp, "kernel_size")],
+                    [int(v) for v in onet.getall(cp, "stride")], [int(v) for v in onet.getall(cp, "pad")],
+                    onet.get(cp, "bias_term", "true") == "true"] == want["conv"]
+        if "corr" in want:
+            cp = onet.get(got, "correlation_param")
+            assert [int(onet.get(cp, k)) for k in ("pad", "kernel_size", "max_displacement", "stride_1", "stride_2")] + [0] == want["corr"]
+        if "resample" in want and want["resample"][0]:
+            rp = onet.get(got, "resample_param")
+            assert [int(onet.get(rp, "width")), int(onet.get(rp, "height"))] == want["resample"][:2]
+        if "coeff" in want:
+            got_c = [float(c) for c in onet.getall(onet.get(got, "eltwise_param"), "coeff")]
+            assert np.allclose(got_c, want["coeff"], rtol=1e-6)
+
+
+def test_prototxt_text_format_quirks(fn2):
+    text = '''
+    name: 'quirks'  # comment
+    layer { name: "a" type: "Input" top: "x" input_param { shape: { dim: [1, 3, 8, 8] } } }
+    layer <
+      name: "c" type: "Convolution" bottom: "x" top: "y";
+      convolution_param { num_output: 4, kernel_h: 3 kernel_w: 1 pad_h: 1 stride: 2
+                          weight_filler { type: "gaussian" std: 1e-2 } }
+      param { lr_mult: .5 }
+    >
+    layer { name: "s\\"q" type: "ReLU" bottom: "y" top: "y" relu_param { negative_slope: 1e-1 } }
+    '''
+    out = canonical(fn2, text)
+    msg = onet.parse_prototxt(out)
+    ls = onet.getall(msg, "layer")
+    assert [onet.get(l, "name") for l in ls] == ["a", "c", 's"q']
+    assert onet.getall(onet.get(onet.get(ls[0], "input_param"), "shape"), "dim") == ["1", "3", "8", "8"]
+    assert onet.get(onet.get(ls[1], "convolution_param"), "kernel_h") == "3"
+    with pytest.raises(fn2.Fn2Error, match="prototxt:"):
+        canonical(fn2, 'layer { name: "a" type: "Input" ')
+    with pytest.raises(fn2.Fn2Error):
+        canonical(fn2, 'layer { name "a" }')
+
+
+def test_caffemodel_reader_matches_reference_protobuf(fn2):
+    raw = open(os.path.join(GOLD, "ref_pb2_caffemodel.bin"), "rb").read()
+    want = json.load(open(os.path.join(GOLD, "ref_pb2_caffemodel.json")))
+    lib = fn2.lib()
+    n = C.c_size_t()
+    assert lib.fn2_caffemodel_summary(raw, len(raw), None, C.byref(n)) == 0
+    buf = C.create_string_buffer(n.value)
+    assert lib.fn2_caffemodel_summary(raw, len(raw), buf, C.byref(n)) == 0
+    lines = buf.value.decode().strip().split("\n")
+    assert len(lines) == len(want)
+    for line, w in zip(lines, want):
+        parts = line.split(" ")
+        assert parts[0] == w["name"] and parts[1] == w["type"]
+        blobs = re.findall(r"\[([\d,]*)\] n=(\d+) sum=(\S+)", line)
+        assert len(blobs) == len(w["blobs"])
+        for (shape, cnt, s), wb in zip(blobs, w["blobs"]):
+            assert [int(v) for v in shape.split(",")] == wb["shape"]
+            assert int(cnt) == int(np.prod(wb["shape"])) and abs(float(s) - wb["sum"]) < 1e-5
+    # the oracle's independent reader sees the same thing (double_data blobs are engine-only)
+    layers = onet.parse_caffemodel(raw)
+    assert list(layers["conv1"][0].shape) == [4, 3, 3, 3] and list(layers["legacy_conv"][1].shape) == [1, 1, 1, 2]
+    assert abs(float(layers["conv1"][0].astype(np.float64).sum()) - want[0]["blobs"][0]["sum"]) < 1e-5
+
+
+def test_truncated_caffemodel_is_an_error_not_a_crash(fn2):
+    raw = open(os.path.join(GOLD, "ref_pb2_caffemodel.bin"), "rb").read()
+    lib = fn2.lib()
+    n = C.c_size_t()
+    assert lib.fn2_caffemodel_summary(raw[:100], 100, None, C.byref(n)) == -3      # FN2_ERR_PARSE
+    assert b"truncated" in lib.fn2_last_error()
+
+
+def test_template_vars_follow_run_flownet():
+    import flownet2_b200 as F
+    v = F.template_vars(1024, 436)        # scripts/run-flownet.py:39-48
+    assert (v["ADAPTED_WIDTH"], v["ADAPTED_HEIGHT"]) == (1024, 448)
+    assert v["SCALE_WIDTH"] == 1.0 and abs(v["SCALE_HEIGHT"] - 436 / 448.0) < 1e-12
+    assert F.template_vars(448, 320)["ADAPTED_HEIGHT"] == 320
+
+
+def test_flo_io_against_reference_file(fn2, tmp_path):
+    d = np.load(os.path.join(GOLD, "chairs_crop.npz"))
+    # first bytes of data/FlyingChairs_examples/0000000-gt.flo: tag, w, h, then (u,v) pairs
+    head = d["flo_bytes_head"].tobytes()
+    assert head[:4] == b"PIEH" and np.frombuffer(head[4:12], np.int32).tolist() == d["flo_header"].tolist() == [512, 384]
+    flow = np.ascontiguousarray(d["flow"].transpose(2, 0, 1))
+    p = str(tmp_path / "crop.flo")
+    fn2.write_flo(p, flow)
+    raw = open(p, "rb").read()
+    assert raw[:4] == b"PIEH" and np.frombuffer(raw[4:12], np.int32).tolist() == [64, 64]
+    assert np.array_equal(np.frombuffer(raw[12:], np.float32).reshape(64, 64, 2), d["flow"])
+    assert np.array_equal(fn2.read_flo(p), flow)
+    open(p, "wb").write(b"JUNK" + raw[4:])
+    with pytest.raises(fn2.Fn2Error, match="not a .flo"):
+        fn2.read_flo(p)
+
+
+def test_no_compute_without_gpu_is_loud(fn2):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(fn2.Fn2Error):
+        fn2.Net(fn2.fill_template(fn2.model_template("FlowNet2-S"), 64, 64))
