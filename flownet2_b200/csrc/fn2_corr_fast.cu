@@ -75,7 +75,7 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
 struct FastP {
     int N, C, H, W;          // bottoms
     int S;                   // stride_2
-    int Hs, Ws;              // sub-grid extent (ceil(H/S), ceil(W/S)); planes are padded to this
+    int Hs, Ws;              // sub-grid extent (ceil(H/S), ceil(W/S))
     int tiles_x, tiles_y;
 };
 
@@ -119,7 +119,7 @@ corr_fast_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 float* b_dst = a_dst + G::A_STAGE;
                 mbar_expect_tx(&full_bar[s], (uint32_t)G::STAGE_BYTES);
                 tma_load_4d(a_dst, &mapA, &full_bar[s], xs0, ys0, it * CC, nplane);
-                tma_load_4d(b_dst, &mapB, &full_bar[s], xs0 - R, ys0 - R, it * CC, nplane);
+                tma_load_4d(b_dst, &mapB, &full_bar[s], xs0 - R + (R % 4), ys0 - R, it * CC, nplane);
             }
         }
         return;
@@ -199,8 +199,26 @@ corr_fast_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 }
 
 // ---- rearrange: strided (n,c,h,w) view -> parity-planar ws[n][plane][c][Hs][Ws] ------------------------
-// channel-fast (NHWC) source: 32 channels x 32 pixels tiles through shared memory.
-__global__ void corr_rearrange_cfast_kernel(T4 in, float* __restrict__ ws, int S, int Hs, int Ws) {
+// `shift` empty columns precede every row of the map-1 planes: TMA needs the innermost start coordinate
+// of a box to be 16-byte aligned (measured: tools/tma_probe.cu), and the halo starts at xs0 - R, so the
+// planes are stored shifted by R mod 4 columns and the halo box starts at xs0 - R + shift = 0 (mod 4).
+// channel-fast (NHWC) source: 32 channels x 32 pixels tiles through shared memory (writes real pixels
+// only; corr_zero_pads_kernel clears the pad columns/rows).
+__global__ void corr_zero_pads_kernel(float* __restrict__ ws, int rows_total, int S, int C, int Hs, int Ws, int shift,
+                                      int H, int W) {
+    // one thread per plane row
+    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < rows_total; row += gridDim.x * blockDim.x) {
+        const int ys = row % Hs;
+        const int plane = (row / (Hs * C)) % (S * S);
+        const int py = plane / S, px = plane % S;
+        const int w_true = (W - px + S - 1) / S;                 // real pixels of this parity class per row
+        const bool row_real = ys * S + py < H;
+        float* r = ws + (size_t)row * Ws;
+        for (int x = 0; x < Ws; x++)
+            if (!row_real || x < shift || x >= shift + w_true) r[x] = 0.f;
+    }
+}
+__global__ void corr_rearrange_cfast_kernel(T4 in, float* __restrict__ ws, int S, int Hs, int Ws, int shift) {
     __shared__ float tile[32][33];                           // [x][c]
     const int n = blockIdx.z / in.h, y = blockIdx.z % in.h;
     const int x0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -212,12 +230,12 @@ __global__ void corr_rearrange_cfast_kernel(T4 in, float* __restrict__ ws, int S
     if (x >= in.w) return;
     const int plane = (y % S) * S + (x % S);
     const size_t plane_sz = (size_t)Hs * Ws;
-    float* dst = ws + (((size_t)n * S * S + plane) * in.c) * plane_sz + (size_t)(y / S) * Ws + (x / S);
+    float* dst = ws + (((size_t)n * S * S + plane) * in.c) * plane_sz + (size_t)(y / S) * Ws + (x / S) + shift;
     for (int jc = threadIdx.y; jc < 32; jc += blockDim.y)
         if (c0 + jc < in.c) dst[(size_t)(c0 + jc) * plane_sz] = tile[tx][jc];
 }
 // any other layout (NCHW drop-in): one thread per workspace element, x fastest.
-__global__ void corr_rearrange_generic_kernel(T4 in, float* __restrict__ ws, int S, int Hs, int Ws) {
+__global__ void corr_rearrange_generic_kernel(T4 in, float* __restrict__ ws, int S, int Hs, int Ws, int shift) {
     const long long total = (long long)in.n * S * S * in.c * Hs * Ws;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int xs = (int)(idx % Ws);
@@ -226,8 +244,8 @@ __global__ void corr_rearrange_generic_kernel(T4 in, float* __restrict__ ws, int
         const int c = (int)(r % in.c); r /= in.c;
         const int plane = (int)(r % (S * S));
         const int n = (int)(r / (S * S));
-        const int y = ys * S + plane / S, x = xs * S + plane % S;
-        ws[idx] = (y < in.h && x < in.w) ? in.p[in.off(n, c, y, x)] : 0.f;
+        const int y = ys * S + plane / S, x = (xs - shift) * S + plane % S;
+        ws[idx] = (xs >= shift && y < in.h && x < in.w) ? in.p[in.off(n, c, y, x)] : 0.f;
     }
 }
 
@@ -262,35 +280,42 @@ int make_map(CUtensorMap* m, float* base, int Ws, int Hs, int C, int NP, int bw,
 }
 
 int sub_extent(int v, int S) { return (v + S - 1) / S; }
-int ws_width(int W, int S) { return (sub_extent(W, S) + 3) / 4 * 4; }     // 16-byte row pitch for TMA
+int ws_width(int W, int S, int shift) { return (sub_extent(W, S) + shift + 3) / 4 * 4; }     // 16-byte row pitch for TMA
 
 template <int R>
 int launch(const T4& b0, const T4& b1, const T4& top, int S, float* ws, cudaStream_t st) {
     using G = Geo<R>;
     FastP p;
     p.N = b0.n; p.C = b0.c; p.H = b0.h; p.W = b0.w; p.S = S;
-    p.Hs = sub_extent(b0.h, S); p.Ws = ws_width(b0.w, S);
-    p.tiles_x = (sub_extent(b0.w, S) + TW - 1) / TW;
+    constexpr int SHIFT = R % 4;                    // see corr_zero_pads_kernel
+    p.Hs = sub_extent(b0.h, S); p.Ws = sub_extent(b0.w, S);
+    p.tiles_x = (p.Ws + TW - 1) / TW;
     p.tiles_y = (p.Hs + TH - 1) / TH;
-    const size_t map_floats = (size_t)p.N * S * S * p.C * p.Hs * p.Ws;
-    float* wsA = ws;
-    float* wsB = ws + map_floats;
-    const bool padded = (b0.w % S) || (b0.h % S) || (p.Ws != sub_extent(b0.w, S));
+    const int pitch[2] = {ws_width(b0.w, S, 0), ws_width(b0.w, S, SHIFT)};
+    const int shift[2] = {0, SHIFT};
+    const size_t rows = (size_t)p.N * S * S * p.C * p.Hs;
+    float* dst[2] = {ws, ws + rows * pitch[0]};
     const T4* src[2] = {&b0, &b1};
-    float* dst[2] = {wsA, wsB};
     for (int k = 0; k < 2; k++) {
-        if (src[k]->sc == 1 && !padded) {
+        const bool pads = (b0.w % S) || (b0.h % S) || pitch[k] != p.Ws;
+        if (src[k]->sc == 1) {
+            if (pads) {
+                corr_zero_pads_kernel<<<ew_grid((long long)rows, 256), 256, 0, st>>>(dst[k], (int)rows, S, p.C, p.Hs, pitch[k],
+                                                                                   shift[k], b0.h, b0.w);
+                FN2_LAUNCH_CHECK();
+            }
             dim3 grid((src[k]->w + 31) / 32, (src[k]->c + 31) / 32, src[k]->n * src[k]->h);
-            corr_rearrange_cfast_kernel<<<grid, dim3(32, 8), 0, st>>>(*src[k], dst[k], S, p.Hs, p.Ws);
+            corr_rearrange_cfast_kernel<<<grid, dim3(32, 8), 0, st>>>(*src[k], dst[k], S, p.Hs, pitch[k], shift[k]);
         } else {
-            corr_rearrange_generic_kernel<<<ew_grid((long long)map_floats, 256), 256, 0, st>>>(*src[k], dst[k], S, p.Hs, p.Ws);
+            corr_rearrange_generic_kernel<<<ew_grid((long long)(rows * pitch[k]), 256), 256, 0, st>>>(*src[k], dst[k], S, p.Hs,
+                                                                                                     pitch[k], shift[k]);
         }
         FN2_LAUNCH_CHECK();
     }
     CUtensorMap mapA, mapB;
-    int rc = make_map(&mapA, wsA, p.Ws, p.Hs, p.C, p.N * S * S, TW, TH);
+    int rc = make_map(&mapA, dst[0], pitch[0], p.Hs, p.C, p.N * S * S, TW, TH);
     if (rc) return rc;
-    rc = make_map(&mapB, wsB, p.Ws, p.Hs, p.C, p.N * S * S, G::BW, G::BH);
+    rc = make_map(&mapB, dst[1], pitch[1], p.Hs, p.C, p.N * S * S, G::BW, G::BH);
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
@@ -316,8 +341,8 @@ int corr_fast_eligible(const T4& b0, const T4& b1, const T4& top, int pad, int k
 }
 
 int corr_fast_workspace(int N, int C, int H, int W, int md, int s2, size_t* bytes) {
-    (void)md;
-    *bytes = 2 * (size_t)N * s2 * s2 * C * sub_extent(H, s2) * ws_width(W, s2) * sizeof(float);
+    const int R = md / s2;
+    *bytes = (size_t)N * s2 * s2 * C * sub_extent(H, s2) * (ws_width(W, s2, 0) + ws_width(W, s2, R % 4)) * sizeof(float);
     return FN2_OK;
 }
 
