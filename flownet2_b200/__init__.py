@@ -90,7 +90,8 @@ def lib():
         l.fn2_conv_packed_floats.argtypes = [D, C.c_int, C.POINTER(C.c_size_t)]
         l.fn2_conv_pack_weights.argtypes = [D, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         l.fn2_conv_out_shape.argtypes = [D, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
-        l.fn2_conv_forward.argtypes = [D, T, C.c_void_p, C.c_void_p, T, C.c_void_p]
+        l.fn2_conv_forward.argtypes = [D, T, C.c_void_p, C.c_void_p, T, C.c_void_p, C.c_size_t, C.c_void_p]
+        l.fn2_conv_workspace_bytes.argtypes = [D, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
         l.fn2_relu_forward.argtypes = [T, T, C.c_float, C.c_void_p]
         l.fn2_eltwise_sum.argtypes = [C.POINTER(T), C.POINTER(C.c_float), C.c_int, T, C.c_void_p]
         l.fn2_channel_norm_forward.argtypes = [T, T, C.c_void_p]

@@ -29,6 +29,7 @@ SOURCES = [
     ("fn2_corr.cu", []),
     ("fn2_corr_fast.cu", []),
     ("fn2_conv.cu", []),
+    ("fn2_conv_nhwc.cu", []),
     ("fn2_conv_tc.cu", []),
     ("caffe/proto.cpp", []),
     ("caffe/blob.cpp", []),

@@ -421,7 +421,7 @@ template <typename Dtype>
 class BaseConvolutionLayer : public Layer<Dtype> {
  public:
     explicit BaseConvolutionLayer(const LayerParameter& p, bool deconv) : Layer<Dtype>(p), deconv_(deconv) {}
-    ~BaseConvolutionLayer() override { if (packed_) cudaFree(packed_); }
+    ~BaseConvolutionLayer() override { if (packed_) cudaFree(packed_); if (ws_) cudaFree(ws_); }
     int MinBottomBlobs() const override { return 1; }
     int MinTopBlobs() const override { return 1; }
     bool EqualNumBottomTopBlobs() const override { return true; }
@@ -464,6 +464,13 @@ class BaseConvolutionLayer : public Layer<Dtype> {
         FN2_CALL(fn2_conv_out_shape(&d_, bottom[0]->height(), bottom[0]->width(), &Ho, &Wo));
         for (size_t i = 0; i < top.size(); ++i) top[i]->Reshape(bottom[0]->num(), d_.co, Ho, Wo);
         bottom_cstride_ = bottom[0]->channel_stride();
+        size_t need = 0;
+        FN2_CALL(fn2_conv_workspace_bytes(&d_, bottom[0]->num(), bottom[0]->height(), bottom[0]->width(), &need));
+        if (need > ws_bytes_) {
+            if (ws_) cudaFree(ws_);
+            CUDA_CHECK(cudaMalloc(&ws_, need));
+            ws_bytes_ = need;
+        }
     }
     void FillParams(uint64_t seed) override {
         ConvolutionParameter cp = this->layer_param_.convolution_param();
@@ -504,7 +511,8 @@ class BaseConvolutionLayer : public Layer<Dtype> {
             fn2_conv_desc d = d_;
             d.relu = relu_[i]; d.negative_slope = slope_[i];
             fn2_tensor b = bottom[i]->tensor(), t = top[i]->mutable_tensor();
-            FN2_CALL(fn2_conv_forward(&d, &b, packed_, d_.has_bias ? this->blobs_[1]->gpu_data() : nullptr, &t, S()));
+            FN2_CALL(fn2_conv_forward(&d, &b, packed_, d_.has_bias ? this->blobs_[1]->gpu_data() : nullptr, &t, ws_,
+                                      ws_bytes_, S()));
         }
     }
     bool deconv_;
@@ -513,6 +521,8 @@ class BaseConvolutionLayer : public Layer<Dtype> {
     vector<float> slope_;
     float* packed_ = nullptr;
     size_t packed_floats_ = 0;
+    void* ws_ = nullptr;
+    size_t ws_bytes_ = 0;
     int bottom_cstride_ = 0;
 };
 

@@ -20,6 +20,10 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
                     const T4& out, cudaStream_t st);
 int conv_tc_packed_floats(const fn2_conv_desc* d, int ci_stride, size_t* floats);
 int conv_tc_pack(const fn2_conv_desc* d, int ci_stride, const float* w, float* wp, cudaStream_t st);
+int conv_nhwc_eligible(const fn2_conv_desc* d, const T4& in, const T4& out);
+size_t conv_nhwc_workspace_floats(const fn2_conv_desc* d, int N, int Ho, int Wo);
+int conv_nhwc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const float* bias, const T4& out,
+                      float* ws, size_t ws_floats, cudaStream_t st);
 
 struct ConvP {
     int Ci, Co, kh, kw, sh, sw, ph, pw;
@@ -228,6 +232,45 @@ __global__ void __launch_bounds__(256) conv_smallco_kernel(T4 in, const float* _
     }
 }
 
+// Tiny path (Co <= 4 and Ci <= 32: flow upsamplers 2->2, full-resolution flow predictors): one thread per
+// output pixel, all weights staged in shared memory.
+template <bool DECONV>
+__global__ void __launch_bounds__(256) conv_tiny_kernel(T4 in, const float* __restrict__ wp,
+                                                        const float* __restrict__ bias, T4 out, ConvP p) {
+    extern __shared__ float wsm[];                    // [kh*kw][Ci][Co]
+    const int nw = p.kh * p.kw * p.Ci * p.Co;
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) wsm[i] = wp[i];
+    __syncthreads();
+    const long long M = (long long)p.N * p.Ho * p.Wo;
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(m % p.Wo);
+        const int oy = (int)((m / p.Wo) % p.Ho);
+        const int n = (int)(m / ((long long)p.Wo * p.Ho));
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int r = 0; r < p.kh; r++)
+            for (int s = 0; s < p.kw; s++) {
+                int iy, ix;
+                if (!in_coord<DECONV>(p, oy, ox, r, s, iy, ix)) continue;
+                const float* ip = in.p + in.off(n, 0, iy, ix);
+                const float* w = wsm + (r * p.kw + s) * p.Ci * p.Co;
+                for (int ci = 0; ci < p.Ci; ci++) {
+                    const float a = __ldg(ip + ci * in.sc);
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (j < p.Co) acc[j] = fmaf(a, w[ci * p.Co + j], acc[j]);
+                }
+            }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (j >= p.Co) break;
+            float v = acc[j];
+            if (p.has_bias) v += __ldg(bias + j);
+            if (p.relu) v = v > 0 ? v : v * p.slope;
+            out.p[out.off(n, j, oy, ox)] = v;
+        }
+    }
+}
+
 // Caffe weights -> packed [k][co].  conv: w[co][ci][r][s]; deconv: w[ci][co][r][s].
 __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ wp, int Ci, int Co,
                                     int kh, int kw, int cis, int deconv) {
@@ -303,8 +346,18 @@ int fn2_conv_pack_weights(const fn2_conv_desc* d, int ci_stride, const float* ca
     return conv_tc_pack(d, ci_stride, caffe_weights_dev, packed_dev + total, (cudaStream_t)stream);
 }
 
+int fn2_conv_workspace_bytes(const fn2_conv_desc* d, int N, int H, int W, size_t* bytes) {
+    FN2_CHECK_ARG(d && bytes, "conv_workspace_bytes: null argument");
+    int Ho, Wo;
+    int rc = fn2_conv_out_shape(d, H, W, &Ho, &Wo);
+    if (rc) return rc;
+    *bytes = conv_nhwc_workspace_floats(d, N, Ho, Wo) * sizeof(float);
+    return FN2_OK;
+}
+
 int fn2_conv_forward(const fn2_conv_desc* d, const fn2_tensor* bottom, const float* packed_weights_dev,
-                     const float* bias_dev, const fn2_tensor* top, void* stream) {
+                     const float* bias_dev, const fn2_tensor* top, void* workspace, size_t workspace_bytes,
+                     void* stream) {
     FN2_CHECK_ARG(d && valid(bottom) && valid(top) && packed_weights_dev, "conv: null argument");
     FN2_CHECK_ARG(!d->has_bias || bias_dev, "conv: bias_term set but no bias given");
     T4 in = view(bottom), out = view(top);
@@ -316,10 +369,17 @@ int fn2_conv_forward(const fn2_conv_desc* d, const fn2_tensor* bottom, const flo
     if (d->engine != 1 && conv_tc_eligible(d, in, out))
         return conv_tc_forward(d, in, packed_weights_dev + simt_floats, bias_dev, out, st);
     FN2_CHECK_ARG(d->engine != 2, "conv: tcgen05 engine requested but the shape/layout is not eligible");
+    if (conv_nhwc_eligible(d, in, out))
+        return conv_nhwc_forward(d, in, packed_weights_dev, bias_dev, out, (float*)workspace, workspace_bytes / sizeof(float), st);
     p.cis = d->ci;
     p.K = d->kh * d->kw * p.cis;
     const long long M = (long long)p.N * p.Ho * p.Wo;
-    if (d->co <= 4) {
+    if (d->co <= 4 && d->ci <= 32) {
+        const size_t smem = (size_t)p.K * p.Co * sizeof(float);
+        const int grid = ew_grid(M, 256);
+        if (d->deconv) conv_tiny_kernel<true><<<grid, 256, smem, st>>>(in, packed_weights_dev, bias_dev, out, p);
+        else           conv_tiny_kernel<false><<<grid, 256, smem, st>>>(in, packed_weights_dev, bias_dev, out, p);
+    } else if (d->co <= 4) {
         const int grid = ew_grid(M * 32, 256);
         if (d->deconv) conv_smallco_kernel<true, 4><<<grid, 256, 0, st>>>(in, packed_weights_dev, bias_dev, out, p);
         else           conv_smallco_kernel<false, 4><<<grid, 256, 0, st>>>(in, packed_weights_dev, bias_dev, out, p);

@@ -116,7 +116,8 @@ def mean_subtract(top, mean_pp=None, mean_pc=None, per_pixel=False):
     return top
 
 
-def conv2d(x, weight, bias=None, stride=1, pad=0, deconv=False, relu_slope=None, engine=0, channels_last_out=None):
+def conv2d(x, weight, bias=None, stride=1, pad=0, deconv=False, relu_slope=None, engine=0, channels_last_out=None,
+           use_workspace=True):
     """weight in Caffe layout: conv [co,ci,kh,kw], deconv [ci,co,kh,kw]."""
     l = lib()
     if deconv:
@@ -137,8 +138,12 @@ def conv2d(x, weight, bias=None, stride=1, pad=0, deconv=False, relu_slope=None,
     check(l.fn2_conv_pack_weights(C.byref(d), cis, C.c_void_p(weight.data_ptr()), C.c_void_p(packed.data_ptr()), _stream()))
     out = _empty((x.shape[0], co, ho.value, wo.value), x, channels_last_out)
     dx, do = desc(x), desc(out)
+    wsb = C.c_size_t()
+    check(l.fn2_conv_workspace_bytes(C.byref(d), x.shape[0], x.shape[2], x.shape[3], C.byref(wsb)))
+    ws = torch.empty(max(wsb.value, 4), dtype=torch.uint8, device=x.device) if use_workspace else None
     check(l.fn2_conv_forward(C.byref(d), C.byref(dx), C.c_void_p(packed.data_ptr()),
-                             C.c_void_p(bias.data_ptr()) if bias is not None else None, C.byref(do), _stream()))
+                             C.c_void_p(bias.data_ptr()) if bias is not None else None, C.byref(do),
+                             C.c_void_p(ws.data_ptr()) if ws is not None else None, wsb.value if ws is not None else 0, _stream()))
     return out
 
 

@@ -132,9 +132,12 @@ FN2_API int fn2_conv_packed_floats(const fn2_conv_desc* d, int ci_stride, size_t
 FN2_API int fn2_conv_pack_weights(const fn2_conv_desc* d, int ci_stride,
                                   const float* caffe_weights_dev, float* packed_dev, void* stream);
 FN2_API int fn2_conv_out_shape(const fn2_conv_desc* d, int H, int W, int* Ho, int* Wo);
+/* Scratch the forward may use for this shape (split-K partials of small spatial maps); may be 0.
+ * Passing a NULL / too small workspace is allowed: the kernel then runs unsplit. */
+FN2_API int fn2_conv_workspace_bytes(const fn2_conv_desc* d, int N, int H, int W, size_t* bytes);
 FN2_API int fn2_conv_forward(const fn2_conv_desc* d, const fn2_tensor* bottom,
                              const float* packed_weights_dev, const float* bias_dev,
-                             const fn2_tensor* top, void* stream);
+                             const fn2_tensor* top, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------ */
 /* Glue: ReLU (relu_layer.cu:9-14), Eltwise SUM with coeffs (eltwise_layer.cu),           */
