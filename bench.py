@@ -127,11 +127,6 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------
-class _DevPtr(object):
-    def __init__(self, ptr, nfloats):
-        self.__cuda_array_interface__ = {"shape": (nfloats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
-
-
 def clocks_sampler_start(dev_index):
     q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -194,13 +189,13 @@ def run_ours(args):
     stream = torch.cuda.ExternalStream(net.stream)
 
     # ---- weights: rank 0 fills, one NCCL broadcast of the contiguous parameter arena -------------------------
-    ptr, nbytes = net.param_arena()
+    from flownet2_b200 import parallel as P
     if rank == 0:
         net.fill_params(1701)
     if world > 1:
-        arena = torch.as_tensor(_DevPtr(ptr, nbytes // 4), device="cuda")
+        arena = P.arena_tensor(net)          # zero-copy view of the contiguous parameter arena
         torch.cuda.synchronize()
-        dist.broadcast(arena, src=0)
+        P.broadcast_arena(arena, src=0)
         torch.cuda.synchronize()
         net.params_changed()
 
