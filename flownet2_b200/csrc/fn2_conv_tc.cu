@@ -1,11 +1,493 @@
-// tcgen05 / TMEM implicit-GEMM convolution engine (placeholder until the kernel lands).
+// tcgen05 / TMEM implicit-GEMM convolution + deconvolution engine (sm_100a), FP32-faithful.
+//
+// GEMM view per CTA: D[128 pixels x NT outputs] = sum over (kernel tap, 32-channel block) A_tap[128 x 32] * W_tap[NT x 32]^T
+//   * A (activations, NHWC) : one TMA box per step straight from the activation tensor -- {32 ch, tw, th} with element
+//     strides = conv stride and out-of-bounds zero fill, so padding, stride and the channel tail cost nothing and no
+//     im2col buffer exists.  Lands as a K-major SWIZZLE_128B tile of raw FP32.
+//   * W (weights) : packed once as [hi|lo][tap][Co][Ci32] (TF32 split), TMA boxes {32, NT}, K-major SWIZZLE_128B.
+//   * 3xTF32: a = a_hi + a_lo, w = w_hi + w_lo (each rounded to TF32), D = a_hi*w_hi + a_hi*w_lo + a_lo*w_hi.
+//     The activation split is done in-kernel by 4 converter warps that read the raw tile from shared memory and write
+//     a_hi / a_lo into TENSOR MEMORY (tcgen05.st); the MMAs take A from TMEM (kind::tf32, "TS" form), which also keeps
+//     shared-memory traffic (W reads + TMA writes) near the 128 B/clk budget.
+//   * Accumulation: the B200 tensor core rounds its FP32 accumulator TOWARD ZERO (tools/tc_probe.cu: -1.7e-8 relative
+//     per chained MMA), which over K up to 9216 and ~60 layers would shrink the flow by 1e-3.  Therefore the dominant
+//     a_hi*w_hi term is accumulated in the tensor core only over short chains (KD channel blocks = 4*KD MMAs) into a
+//     double-buffered TMEM accumulator that 4 drain warps pull out (tcgen05.ld) and add into FP32 REGISTERS with
+//     round-to-nearest, applying the measured mean RZ bias of a chain of that length as a correction.  The two cross
+//     terms (2^-11 smaller) accumulate in a third TMEM accumulator for the whole K loop.
+//   * Epilogue from registers: + bias, leaky ReLU, 128-bit stores into the strided NHWC output view.
+// Warp roles (384 threads, setmaxnreg re-balances registers): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM
+// allocator, warps 4-7 converters, warps 8-11 drain + epilogue.  Deconvolution = one launch per output parity class
+// with the taps that hit it (see fn2_conv_nhwc.cu).
+#include <cuda.h>
+#include <mutex>
+
 #include "fn2_common.cuh"
+
 namespace fn2 {
-int conv_tc_eligible(const fn2_conv_desc*, const T4&, const T4&) { return 0; }
-int conv_tc_forward(const fn2_conv_desc*, const T4&, const float*, const float*, const T4&, cudaStream_t) {
-    set_error("conv_tc: not built");
-    return FN2_ERR_INVALID;
+
+namespace {
+
+constexpr int TC_THREADS = 384;
+constexpr int A_TILE_BYTES = 128 * 128;          // 128 pixels x 32 fp32
+
+struct TcParams {
+    int N, Hu, Wu, su, sv, ou, ov, oy0, ox0;      // sub-grid / mapping (see fn2_conv_nhwc.cu)
+    int Co, cblocks;                              // cblocks = ceil(Ci / 32)
+    long long out_sn, out_sh, out_sw;
+    int relu, has_bias;
+    float slope;
+    int tw, th, tiles_x, tiles_y;
+    int ntaps;
+    int kd;                                       // channel blocks per tensor-core accumulation chain
+    float comp_a, comp_b;                         // RZ bias model: shrink(n MMAs) = comp_a + comp_b * n
+    short dy[49], dx[49], widx[49];
+};
+
+__device__ __forceinline__ uint32_t su32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(su32(bar)), "r"(count));
 }
-int conv_tc_packed_floats(const fn2_conv_desc*, int, size_t* floats) { *floats = 0; return FN2_OK; }
-int conv_tc_pack(const fn2_conv_desc*, int, const float*, float*, cudaStream_t) { return FN2_OK; }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(su32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(su32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(su32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        if (++spins > (1u << 24)) __trap();       // a lost arrival becomes a launch error, never a hang
+    }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(su32(dst)), "l"(map), "r"(su32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(su32(bar)) : "memory");
+}
+// D[tmem_c] (+)= A[tmem_a] * B[desc_b]^T, kind::tf32, A from tensor memory
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_c), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+          "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+          "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+          "r"(v[30]), "r"(v[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row atoms of 1024 B (validated by tools/tc_probe.cu)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__host__ __device__ inline uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int NT> struct TcGeo {
+    static constexpr int B_TILE_BYTES = NT * 128;
+    static constexpr int STAGE_BYTES = A_TILE_BYTES + 2 * B_TILE_BYTES;
+    static constexpr int NS = NT == 128 ? 4 : 6;
+    static constexpr int SMEM = NS * STAGE_BYTES + 1024;
+    // tensor-memory columns
+    static constexpr int COL_HH0 = 0, COL_HH1 = NT, COL_X = 2 * NT, COL_A = 384;   // A slots: 384 + 64*slot (+32 for lo)
+};
+
+template <int NT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const float* __restrict__ bias,
+               float* __restrict__ out, const TcParams p) {
+    using G = TcGeo<NT>;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::NS * G::STAGE_BYTES);
+    uint64_t* full = bars;                         // [NS]
+    uint64_t* empty = bars + G::NS;                // [NS]
+    uint64_t* a_ready = bars + 2 * G::NS;          // [2]
+    uint64_t* a_free = a_ready + 2;                // [2]
+    uint64_t* acc_full = a_free + 2;               // [2]
+    uint64_t* acc_free = acc_full + 2;             // [2]
+    uint64_t* x_full = acc_free + 2;               // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // tile decode
+    int bid = blockIdx.x;
+    const int tx = bid % p.tiles_x; bid /= p.tiles_x;
+    const int ty = bid % p.tiles_y; bid /= p.tiles_y;
+    const int n = bid;
+    const int u0 = ty * p.th, v0 = tx * p.tw;
+    const int co0 = blockIdx.y * NT;
+    const int steps = p.ntaps * p.cblocks;
+
+    if (tid == 0) {
+        for (int s = 0; s < G::NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 129); }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&a_ready[s], 128); mbar_init(&a_free[s], 1);
+            mbar_init(&acc_full[s], 1); mbar_init(&acc_free[s], 128);
+        }
+        mbar_init(x_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(su32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
+        if (warp == 0 && lane == 0) {
+            // ===== TMA producer =====
+            for (int i = 0; i < steps; i++) {
+                const int s = i % G::NS;
+                const uint32_t ph = (uint32_t)(i / G::NS) & 1u;
+                const int t = i / p.cblocks, cb = i % p.cblocks;
+                mbar_wait(&empty[s], ph ^ 1u);
+                unsigned char* st = smem + (size_t)s * G::STAGE_BYTES;
+                mbar_expect_tx(&full[s], (uint32_t)G::STAGE_BYTES);
+                tma_load_4d(st, &mapA, &full[s], cb * 32, v0 * p.su + p.dx[t], u0 * p.sv + p.dy[t], n);
+                tma_load_4d(st + A_TILE_BYTES, &mapW, &full[s], cb * 32, co0, p.widx[t], 0);
+                tma_load_4d(st + A_TILE_BYTES + G::B_TILE_BYTES, &mapW, &full[s], cb * 32, co0, p.widx[t], 1);
+            }
+        } else if (warp == 1 && lane == 0) {
+            // ===== MMA issuer =====
+            const uint32_t idesc = make_idesc_tf32(128, NT);
+            for (int i = 0; i < steps; i++) {
+                const int s = i % G::NS;
+                const uint32_t ph = (uint32_t)(i / G::NS) & 1u;
+                const int as = i & 1;
+                const uint32_t pa = (uint32_t)(i >> 1) & 1u;
+                const int chunk = i / p.kd, in_chunk = i % p.kd;
+                const int buf = chunk & 1;
+                if (in_chunk == 0) mbar_wait(&acc_free[buf], ((uint32_t)(chunk >> 1) & 1u) ^ 1u);
+                mbar_wait(&full[s], ph);
+                mbar_wait(&a_ready[as], pa);
+                fence_after();
+                const uint32_t bh = su32(smem + (size_t)s * G::STAGE_BYTES + A_TILE_BYTES);
+                const uint32_t bl = bh + G::B_TILE_BYTES;
+                const uint32_t a_hi = tmem + G::COL_A + 64 * as, a_lo = a_hi + 32;
+                const uint32_t d_hh = tmem + (buf ? G::COL_HH1 : G::COL_HH0), d_x = tmem + G::COL_X;
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) {
+                    const uint64_t dbh = make_desc_sw128(bh + kk * 32), dbl = make_desc_sw128(bl + kk * 32);
+                    mma_tf32_ts(d_hh, a_hi + kk * 8, dbh, idesc, (in_chunk | kk) != 0);
+                    mma_tf32_ts(d_x, a_hi + kk * 8, dbl, idesc, (i | kk) != 0);
+                    mma_tf32_ts(d_x, a_lo + kk * 8, dbh, idesc, 1);
+                }
+                mma_commit(&empty[s]);            // W tiles of this stage consumed
+                mma_commit(&a_free[as]);          // TMEM A slot consumed
+                if (in_chunk == p.kd - 1 || i == steps - 1) mma_commit(&acc_full[buf]);
+                if (i == steps - 1) mma_commit(x_full);
+            }
+        }
+    } else if (warp < 8) {
+        // ===== converters: raw FP32 tile (smem, swizzled) -> a_hi / a_lo in tensor memory =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 112;" ::: "memory");
+        const int q = warp & 3;
+        const int m = q * 32 + lane;               // tile row == TMEM lane
+        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        for (int i = 0; i < steps; i++) {
+            const int s = i % G::NS;
+            const uint32_t ph = (uint32_t)(i / G::NS) & 1u;
+            const int as = i & 1;
+            const uint32_t pa = (uint32_t)(i >> 1) & 1u;
+            mbar_wait(&full[s], ph);
+            const float4* row = reinterpret_cast<const float4*>(smem + (size_t)s * G::STAGE_BYTES + m * 128);
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float4 v = row[j ^ (m & 7)];
+                const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const uint32_t h = to_tf32(f[e]);
+                    hi[4 * j + e] = h;
+                    lo[4 * j + e] = to_tf32(f[e] - __uint_as_float(h));
+                }
+            }
+            mbar_arrive(&empty[s]);               // raw tile consumed (registers hold it now)
+            mbar_wait(&a_free[as], pa ^ 1u);
+            fence_after();
+            tmem_st32(lane_addr + G::COL_A + 64 * as, hi);
+            tmem_st32(lane_addr + G::COL_A + 64 * as + 32, lo);
+            tmem_wait_st();
+            fence_before();
+            mbar_arrive(&a_ready[as]);
+        }
+    } else {
+        // ===== drain + epilogue: TMEM accumulators -> FP32 registers (round to nearest) -> global =====
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;" ::: "memory");
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        float acc[NT];
+#pragma unroll
+        for (int j = 0; j < NT; j++) acc[j] = 0.f;
+        const int chunks = (steps + p.kd - 1) / p.kd;
+        for (int c = 0; c < chunks; c++) {
+            const int buf = c & 1;
+            const int nsteps = min(p.kd, steps - c * p.kd);
+            const float comp = p.comp_a + p.comp_b * (float)(4 * nsteps);      // mean RZ shrink of a 4*nsteps MMA chain
+            mbar_wait(&acc_full[buf], (uint32_t)(c >> 1) & 1u);
+            fence_after();
+            const uint32_t src = lane_addr + (buf ? G::COL_HH1 : G::COL_HH0);
+#pragma unroll
+            for (int j0 = 0; j0 < NT; j0 += 64) {
+                uint32_t v0[32], v1[32];
+                tmem_ld32(src + j0, v0);
+                tmem_ld32(src + j0 + 32, v1);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const float a = __uint_as_float(v0[j]), b = __uint_as_float(v1[j]);
+                    acc[j0 + j] += fmaf(a, comp, a);
+                    acc[j0 + 32 + j] += fmaf(b, comp, b);
+                }
+            }
+            fence_before();
+            mbar_arrive(&acc_free[buf]);
+        }
+        // cross terms
+        mbar_wait(x_full, 0);
+        fence_after();
+#pragma unroll
+        for (int j0 = 0; j0 < NT; j0 += 64) {
+            uint32_t v0[32], v1[32];
+            tmem_ld32(lane_addr + G::COL_X + j0, v0);
+            tmem_ld32(lane_addr + G::COL_X + j0 + 32, v1);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; j++) { acc[j0 + j] += __uint_as_float(v0[j]); acc[j0 + 32 + j] += __uint_as_float(v1[j]); }
+        }
+        // epilogue
+        const int yy = m / p.tw, xx = m % p.tw;
+        const int u = u0 + yy, v = v0 + xx;
+        if (u < p.Hu && v < p.Wu) {
+            float* o = out + n * p.out_sn + (long long)(u * p.ou + p.oy0) * p.out_sh + (long long)(v * p.ov + p.ox0) * p.out_sw + co0;
+#pragma unroll
+            for (int j = 0; j < NT; j += 4) {
+                float r[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    float x = acc[j + e];
+                    if (p.has_bias) x += __ldg(bias + co0 + j + e);
+                    if (p.relu) x = x > 0 ? x : x * p.slope;
+                    r[e] = x;
+                }
+                *reinterpret_cast<float4*>(o + j) = make_float4(r[0], r[1], r[2], r[3]);
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+// ---- weight packing: Caffe layout -> [hi|lo][tap][Co][Ci32] with the TF32 split -------------------------------------
+__global__ void tc_pack_kernel(const float* __restrict__ w, float* __restrict__ wp, int Ci, int Co, int kh, int kw, int cip, int deconv) {
+    const long long per = (long long)kh * kw * Co * cip;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per; idx += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(idx % cip);
+        long long r_ = idx / cip;
+        const int co = (int)(r_ % Co);
+        const int t = (int)(r_ / Co);
+        const int r = t / kw, s = t % kw;
+        float v = 0.f;
+        if (ci < Ci) v = deconv ? w[(((long long)ci * Co + co) * kh + r) * kw + s] : w[(((long long)co * Ci + ci) * kh + r) * kw + s];
+        uint32_t h;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+        const float hi = __uint_as_float(h);
+        uint32_t l;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
+        wp[idx] = hi;
+        wp[per + idx] = __uint_as_float(l);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tc_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+int tc_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("FN2_TC");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v;
+}
+int tc_kd() {
+    const char* e = getenv("FN2_TC_KD");
+    int k = e ? atoi(e) : 2;
+    return k < 1 ? 1 : (k > 64 ? 64 : k);
+}
+
+}  // namespace
+
+int conv_tc_eligible(const fn2_conv_desc* d, const T4& in, const T4& out) {
+    if (!tc_enabled()) return 0;
+    if (in.sc != 1 || out.sc != 1) return 0;
+    if (d->ci < 32 || d->co % 64) return 0;
+    if (d->kh * d->kw > 49) return 0;
+    if (d->stride_h > 2 || d->stride_w > 2) return 0;
+    if (((uintptr_t)in.p & 15) || (in.sw & 3) || (in.sh & 3) || (in.sn & 3)) return 0;
+    if (((uintptr_t)out.p & 15) || (out.sw & 3) || (out.sh & 3) || (out.sn & 3)) return 0;
+    if (!tc_encode_fn()) return 0;
+    return 1;
+}
+
+int conv_tc_packed_floats(const fn2_conv_desc* d, int ci_stride, size_t* floats) {
+    (void)ci_stride;
+    const int cip = (d->ci + 31) / 32 * 32;
+    *floats = (d->ci >= 32 && d->co % 64 == 0) ? (size_t)2 * d->kh * d->kw * d->co * cip : 0;
+    return FN2_OK;
+}
+
+int conv_tc_pack(const fn2_conv_desc* d, int ci_stride, const float* w, float* wp, cudaStream_t st) {
+    size_t floats = 0;
+    conv_tc_packed_floats(d, ci_stride, &floats);
+    if (!floats) return FN2_OK;
+    const int cip = (d->ci + 31) / 32 * 32;
+    tc_pack_kernel<<<ew_grid((long long)floats / 2, 256), 256, 0, st>>>(w, wp, d->ci, d->co, d->kh, d->kw, cip, d->deconv);
+    FN2_LAUNCH_CHECK();
+    return FN2_OK;
+}
+
+static inline int floordiv_i(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const float* bias, const T4& out, cudaStream_t st) {
+    EncodeTiledFn enc = tc_encode_fn();
+    if (!enc) { set_error("conv_tc: cuTensorMapEncodeTiled unavailable"); return FN2_ERR_CUDA; }
+    const int NT = (d->co % 128 == 0) ? 128 : 64;
+    const int cip = (d->ci + 31) / 32 * 32;
+    TcParams p;
+    p.N = in.n; p.Co = d->co; p.cblocks = cip / 32;
+    p.out_sn = out.sn; p.out_sh = out.sh; p.out_sw = out.sw;
+    p.relu = d->relu; p.has_bias = d->has_bias; p.slope = d->negative_slope;
+    p.kd = tc_kd();
+    // mean round-toward-zero shrink of an n-MMA accumulation chain, measured by tools/tc_probe.cu (test3)
+    const char* nocomp = getenv("FN2_TC_COMP");
+    p.comp_a = (nocomp && nocomp[0] == '0') ? 0.f : 1.6e-8f;
+    p.comp_b = (nocomp && nocomp[0] == '0') ? 0.f : 1.64e-8f;
+
+    // weights: [2][taps][Co][cip]
+    CUtensorMap mapW;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)cip, (cuuint64_t)d->co, (cuuint64_t)(d->kh * d->kw), 2};
+        cuuint64_t strides[3] = {(cuuint64_t)cip * 4, (cuuint64_t)cip * d->co * 4, (cuuint64_t)cip * d->co * d->kh * d->kw * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)NT, 1, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = enc(&mapW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)wp, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv_tc: weight tensor map failed (%d)", (int)r); return FN2_ERR_CUDA; }
+    }
+    auto run = [&](int su, int sv) -> int {
+        // tile shape: widest power of two covering the row, 128 pixels per tile
+        int tw = 8;
+        while (tw < p.Wu && tw < 128) tw *= 2;
+        p.tw = tw; p.th = 128 / tw;
+        p.tiles_x = (p.Wu + p.tw - 1) / p.tw; p.tiles_y = (p.Hu + p.th - 1) / p.th;
+        p.su = su; p.sv = sv;
+        CUtensorMap mapA;
+        cuuint64_t dims[4] = {(cuuint64_t)in.c, (cuuint64_t)in.w, (cuuint64_t)in.h, (cuuint64_t)in.n};
+        cuuint64_t strides[3] = {(cuuint64_t)in.sw * 4, (cuuint64_t)in.sh * 4, (cuuint64_t)in.sn * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)(p.tw * su), (cuuint32_t)(p.th * sv), 1};
+        cuuint32_t es[4] = {1, (cuuint32_t)su, (cuuint32_t)sv, 1};
+        CUresult r = enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)in.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv_tc: activation tensor map failed (%d)", (int)r); return FN2_ERR_CUDA; }
+        dim3 grid((unsigned)(p.N * p.tiles_x * p.tiles_y), (unsigned)(d->co / NT));
+        if (NT == 128) {
+            static bool set128 = false;
+            if (!set128) { FN2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGeo<128>::SMEM)); set128 = true; }
+            conv_tc_kernel<128><<<grid, TC_THREADS, TcGeo<128>::SMEM, st>>>(mapA, mapW, bias, out.p, p);
+        } else {
+            static bool set64 = false;
+            if (!set64) { FN2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGeo<64>::SMEM)); set64 = true; }
+            conv_tc_kernel<64><<<grid, TC_THREADS, TcGeo<64>::SMEM, st>>>(mapA, mapW, bias, out.p, p);
+        }
+        FN2_LAUNCH_CHECK();
+        return FN2_OK;
+    };
+    if (!d->deconv) {
+        p.Hu = out.h; p.Wu = out.w; p.ou = p.ov = 1; p.oy0 = p.ox0 = 0;
+        p.ntaps = d->kh * d->kw;
+        for (int r = 0; r < d->kh; r++)
+            for (int s = 0; s < d->kw; s++) {
+                const int t = r * d->kw + s;
+                p.dy[t] = (short)(r - d->pad_h); p.dx[t] = (short)(s - d->pad_w); p.widx[t] = (short)t;
+            }
+        return run(d->stride_w, d->stride_h);
+    }
+    const int sh = d->stride_h, sw = d->stride_w;
+    for (int py = 0; py < sh; py++)
+        for (int px = 0; px < sw; px++) {
+            if (py >= out.h || px >= out.w) continue;
+            p.Hu = (out.h - py + sh - 1) / sh; p.Wu = (out.w - px + sw - 1) / sw;
+            p.ou = sh; p.ov = sw; p.oy0 = py; p.ox0 = px;
+            int nt = 0;
+            for (int r = 0; r < d->kh; r++) {
+                if (((py + d->pad_h - r) % sh + sh) % sh) continue;
+                for (int s = 0; s < d->kw; s++) {
+                    if (((px + d->pad_w - s) % sw + sw) % sw) continue;
+                    p.dy[nt] = (short)floordiv_i(py + d->pad_h - r, sh);
+                    p.dx[nt] = (short)floordiv_i(px + d->pad_w - s, sw);
+                    p.widx[nt] = (short)(r * d->kw + s);
+                    nt++;
+                }
+            }
+            if (nt == 0) { set_error("conv_tc: deconvolution parity class without taps"); return FN2_ERR_INVALID; }
+            p.ntaps = nt;
+            int rc = run(1, 1);
+            if (rc) return rc;
+        }
+    return FN2_OK;
+}
+
 }  // namespace fn2

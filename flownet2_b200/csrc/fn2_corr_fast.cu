@@ -148,7 +148,7 @@ corr_fast_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         mbar_wait(&full_bar[s], ph);
         const float* as = stage_mem + (size_t)s * (G::A_STAGE + G::B_STAGE);
         const float* bs = as + G::A_STAGE;
-#pragma unroll 1
+#pragma unroll 2
         for (int c = 0; c < CC; c++) {
             const float4 a0v = *reinterpret_cast<const float4*>(as + c * (TH * TW) + a_off0);
             const float4 a1v = *reinterpret_cast<const float4*>(as + c * (TH * TW) + a_off0 + TW);
