@@ -32,15 +32,17 @@ constexpr int TC_THREADS = 384;
 constexpr int A_TILE_BYTES = 128 * 128;          // 128 pixels x 32 fp32
 
 struct TcParams {
-    int N, Hu, Wu, su, sv, ou, ov, oy0, ox0;      // sub-grid / mapping (see fn2_conv_nhwc.cu)
+    int N, su, sv, ou, ov;                        // sub-grid / mapping (see fn2_conv_nhwc.cu)
+    int ncls;                                     // output parity classes handled by this launch (grid.z)
+    int cls_Hu[4], cls_Wu[4], cls_oy0[4], cls_ox0[4], cls_tap0[4], cls_ntaps[4];
     int Co, cblocks;                              // cblocks = ceil(Ci / 32)
     long long out_sn, out_sh, out_sw;
     int relu, has_bias;
     float slope;
     int tw, th, tiles_x, tiles_y;
-    int ntaps;
     int kd;                                       // channel blocks per tensor-core accumulation chain
     float comp_a, comp_b;                         // RZ bias model: shrink(n MMAs) = comp_a + comp_b * n
+    int dbg;                                      // FN2_TC_DBG bits: 1 skip MMAs, 2 skip conversion math, 4 skip drain loads, 8 skip TMA A
     short dy[49], dx[49], widx[49];
 };
 
@@ -63,9 +65,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (++spins > (1u << 24)) __trap();       // a lost arrival becomes a launch error, never a hang
     }
 }
+// instrumented wait: accumulates the cycles spent waiting into *acc (debug profiling, FN2_TC_DBG & 16)
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, long long* acc) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    *acc += clock64() - t0;
+}
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(su32(dst)), "l"(map), "r"(su32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.b32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -97,6 +110,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
           "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
           "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]) : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ uint32_t to_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -119,24 +138,29 @@ __host__ __device__ inline uint32_t make_idesc_tf32(int M, int N) {
 template <int NT> struct TcGeo {
     static constexpr int B_TILE_BYTES = NT * 128;
     static constexpr int STAGE_BYTES = A_TILE_BYTES + 2 * B_TILE_BYTES;
-    static constexpr int NS = NT == 128 ? 4 : 6;
+    static constexpr int NS = NT == 128 ? 4 : (NT == 64 ? 6 : 8);
     static constexpr int SMEM = NS * STAGE_BYTES + 1024;
-    // tensor-memory columns
-    static constexpr int COL_HH0 = 0, COL_HH1 = NT, COL_X = 2 * NT, COL_A = 384;   // A slots: 384 + 64*slot (+32 for lo)
+    // tensor-memory columns.  NT == 128 has no room for a separate cross-term accumulator AND a deep enough ring of
+    // A slots (the MMA <-> converter hand-off latency needs >= 4 slots in flight, see profiles/r01_prof_tc_*), so there
+    // the cross terms go into the chunk accumulators (MERGE_X) and are drained with them.
+    static constexpr bool MERGE_X = NT == 128;
+    static constexpr int COL_HH0 = 0, COL_HH1 = NT, COL_X = 2 * NT;
+    static constexpr int NSLOT = NT == 128 ? 4 : (NT == 64 ? 5 : 6);
+    static constexpr int COL_A = 512 - 64 * NSLOT;                                 // slot s: hi at COL_A + 64*s, lo at +32
 };
 
 template <int NT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const float* __restrict__ bias,
-               float* __restrict__ out, const TcParams p) {
+               float* __restrict__ out, const TcParams p, long long* __restrict__ prof) {
     using G = TcGeo<NT>;
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::NS * G::STAGE_BYTES);
     uint64_t* full = bars;                         // [NS]
     uint64_t* empty = bars + G::NS;                // [NS]
-    uint64_t* a_ready = bars + 2 * G::NS;          // [2]
-    uint64_t* a_free = a_ready + 2;                // [2]
-    uint64_t* acc_full = a_free + 2;               // [2]
+    uint64_t* a_ready = bars + 2 * G::NS;          // [NSLOT]
+    uint64_t* a_free = a_ready + G::NSLOT;         // [NSLOT]
+    uint64_t* acc_full = a_free + G::NSLOT;        // [2]
     uint64_t* acc_free = acc_full + 2;             // [2]
     uint64_t* x_full = acc_free + 2;               // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 1);
@@ -149,14 +173,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int n = bid;
     const int u0 = ty * p.th, v0 = tx * p.tw;
     const int co0 = blockIdx.y * NT;
-    const int steps = p.ntaps * p.cblocks;
+    const int cls = blockIdx.z;
+    const int Hu = p.cls_Hu[cls], Wu = p.cls_Wu[cls], tap0 = p.cls_tap0[cls];
+    if (u0 >= Hu || v0 >= Wu) return;             // tile outside this (smaller) parity class
+    const int steps = p.cls_ntaps[cls] * p.cblocks;
 
     if (tid == 0) {
         for (int s = 0; s < G::NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 129); }
-        for (int s = 0; s < 2; s++) {
-            mbar_init(&a_ready[s], 128); mbar_init(&a_free[s], 1);
-            mbar_init(&acc_full[s], 1); mbar_init(&acc_free[s], 128);
-        }
+        for (int s = 0; s < G::NSLOT; s++) { mbar_init(&a_ready[s], 128); mbar_init(&a_free[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_free[s], 128); }
         mbar_init(x_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -168,6 +193,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncthreads();
     fence_after();
     const uint32_t tmem = *tmem_slot;
+    long long w0 = 0, w1 = 0, w2 = 0;
+    const long long t_start = clock64();
 
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
@@ -176,43 +203,53 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int i = 0; i < steps; i++) {
                 const int s = i % G::NS;
                 const uint32_t ph = (uint32_t)(i / G::NS) & 1u;
-                const int t = i / p.cblocks, cb = i % p.cblocks;
-                mbar_wait(&empty[s], ph ^ 1u);
+                const int t = tap0 + i / p.cblocks, cb = i % p.cblocks;
+                mbar_wait_t(&empty[s], ph ^ 1u, &w0);
                 unsigned char* st = smem + (size_t)s * G::STAGE_BYTES;
                 mbar_expect_tx(&full[s], (uint32_t)G::STAGE_BYTES);
-                tma_load_4d(st, &mapA, &full[s], cb * 32, v0 * p.su + p.dx[t], u0 * p.sv + p.dy[t], n);
+                if (p.dbg & 8) tma_load_4d(st, &mapW, &full[s], cb * 32, co0, p.widx[t], 0);   // same bytes when NT == 128
+                else tma_load_4d(st, &mapA, &full[s], cb * 32, v0 * p.su + p.dx[t], u0 * p.sv + p.dy[t], n);
                 tma_load_4d(st + A_TILE_BYTES, &mapW, &full[s], cb * 32, co0, p.widx[t], 0);
                 tma_load_4d(st + A_TILE_BYTES + G::B_TILE_BYTES, &mapW, &full[s], cb * 32, co0, p.widx[t], 1);
             }
-        } else if (warp == 1 && lane == 0) {
-            // ===== MMA issuer =====
+        } else if (warp == 1) {
+            // ===== MMA issuer: the whole warp runs the loop convergently (so descriptors live in uniform registers),
+            // one elected lane issues the tcgen05 instructions =====
             const uint32_t idesc = make_idesc_tf32(128, NT);
             for (int i = 0; i < steps; i++) {
                 const int s = i % G::NS;
                 const uint32_t ph = (uint32_t)(i / G::NS) & 1u;
-                const int as = i & 1;
-                const uint32_t pa = (uint32_t)(i >> 1) & 1u;
+                const int as = i % G::NSLOT;
+                const uint32_t pa = (uint32_t)(i / G::NSLOT) & 1u;
                 const int chunk = i / p.kd, in_chunk = i % p.kd;
                 const int buf = chunk & 1;
-                if (in_chunk == 0) mbar_wait(&acc_free[buf], ((uint32_t)(chunk >> 1) & 1u) ^ 1u);
-                mbar_wait(&full[s], ph);
-                mbar_wait(&a_ready[as], pa);
+                if (in_chunk == 0) mbar_wait_t(&acc_free[buf], ((uint32_t)(chunk >> 1) & 1u) ^ 1u, &w0);
+                mbar_wait_t(&full[s], ph, &w1);
+                mbar_wait_t(&a_ready[as], pa, &w2);
                 fence_after();
                 const uint32_t bh = su32(smem + (size_t)s * G::STAGE_BYTES + A_TILE_BYTES);
-                const uint32_t bl = bh + G::B_TILE_BYTES;
+                const uint64_t dbh0 = make_desc_sw128(bh), dbl0 = make_desc_sw128(bh + G::B_TILE_BYTES);
                 const uint32_t a_hi = tmem + G::COL_A + 64 * as, a_lo = a_hi + 32;
-                const uint32_t d_hh = tmem + (buf ? G::COL_HH1 : G::COL_HH0), d_x = tmem + G::COL_X;
+                const uint32_t d_hh = tmem + (buf ? G::COL_HH1 : G::COL_HH0);
+                const uint32_t d_x = G::MERGE_X ? d_hh : tmem + G::COL_X;
+                const bool last = (i == steps - 1);
+                const bool chunk_end = (in_chunk == p.kd - 1) || last;
+                if (elect_one()) {
+                    if (!(p.dbg & 1)) {
 #pragma unroll
-                for (int kk = 0; kk < 4; kk++) {
-                    const uint64_t dbh = make_desc_sw128(bh + kk * 32), dbl = make_desc_sw128(bl + kk * 32);
-                    mma_tf32_ts(d_hh, a_hi + kk * 8, dbh, idesc, (in_chunk | kk) != 0);
-                    mma_tf32_ts(d_x, a_hi + kk * 8, dbl, idesc, (i | kk) != 0);
-                    mma_tf32_ts(d_x, a_lo + kk * 8, dbh, idesc, 1);
+                        for (int kk = 0; kk < 4; kk++) {
+                            // +2 in the start-address field = +32 bytes = the next 8 TF32 columns of the swizzled tile
+                            mma_tf32_ts(d_hh, a_hi + kk * 8, dbh0 + (uint64_t)(2 * kk), idesc, (in_chunk | kk) != 0);
+                            mma_tf32_ts(d_x, a_hi + kk * 8, dbl0 + (uint64_t)(2 * kk), idesc, G::MERGE_X ? 1u : (uint32_t)((i | kk) != 0));
+                            mma_tf32_ts(d_x, a_lo + kk * 8, dbh0 + (uint64_t)(2 * kk), idesc, 1);
+                        }
+                    }
+                    mma_commit(&empty[s]);            // W tiles of this stage consumed
+                    mma_commit(&a_free[as]);          // TMEM A slot consumed
+                    if (chunk_end) mma_commit(&acc_full[buf]);
+                    if (!G::MERGE_X && last) mma_commit(x_full);
                 }
-                mma_commit(&empty[s]);            // W tiles of this stage consumed
-                mma_commit(&a_free[as]);          // TMEM A slot consumed
-                if (in_chunk == p.kd - 1 || i == steps - 1) mma_commit(&acc_full[buf]);
-                if (i == steps - 1) mma_commit(x_full);
+                __syncwarp();
             }
         }
     } else if (warp < 8) {
@@ -224,11 +261,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int i = 0; i < steps; i++) {
             const int s = i % G::NS;
             const uint32_t ph = (uint32_t)(i / G::NS) & 1u;
-            const int as = i & 1;
-            const uint32_t pa = (uint32_t)(i >> 1) & 1u;
-            mbar_wait(&full[s], ph);
+            const int as = i % G::NSLOT;
+            const uint32_t pa = (uint32_t)(i / G::NSLOT) & 1u;
+            mbar_wait_t(&full[s], ph, &w0);
             const float4* row = reinterpret_cast<const float4*>(smem + (size_t)s * G::STAGE_BYTES + m * 128);
             uint32_t hi[32], lo[32];
+            if (p.dbg & 2) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) { hi[j] = 0x3f800000u; lo[j] = 0; }
+            } else
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const float4 v = row[j ^ (m & 7)];
@@ -241,7 +282,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 }
             }
             mbar_arrive(&empty[s]);               // raw tile consumed (registers hold it now)
-            mbar_wait(&a_free[as], pa ^ 1u);
+            mbar_wait_t(&a_free[as], pa ^ 1u, &w1);
             fence_after();
             tmem_st32(lane_addr + G::COL_A + 64 * as, hi);
             tmem_st32(lane_addr + G::COL_A + 64 * as + 32, lo);
@@ -262,43 +303,62 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int c = 0; c < chunks; c++) {
             const int buf = c & 1;
             const int nsteps = min(p.kd, steps - c * p.kd);
-            const float comp = p.comp_a + p.comp_b * (float)(4 * nsteps);      // mean RZ shrink of a 4*nsteps MMA chain
-            mbar_wait(&acc_full[buf], (uint32_t)(c >> 1) & 1u);
+            // mean RZ shrink of the accumulation chain of this chunk (4 MMAs per channel block, 12 when merged)
+            const float comp = p.comp_a + p.comp_b * (float)((G::MERGE_X ? 12 : 4) * nsteps);
+            mbar_wait_t(&acc_full[buf], (uint32_t)(c >> 1) & 1u, &w0);
             fence_after();
             const uint32_t src = lane_addr + (buf ? G::COL_HH1 : G::COL_HH0);
+            if (p.dbg & 4) {
+            } else if constexpr (NT >= 64) {
 #pragma unroll
-            for (int j0 = 0; j0 < NT; j0 += 64) {
-                uint32_t v0[32], v1[32];
-                tmem_ld32(src + j0, v0);
-                tmem_ld32(src + j0 + 32, v1);
+                for (int j0 = 0; j0 < NT; j0 += 64) {
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(src + j0, v0);
+                    tmem_ld32(src + j0 + 32, v1);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float a = __uint_as_float(v0[j]), b = __uint_as_float(v1[j]);
+                        acc[j0 + j] += fmaf(a, comp, a);
+                        acc[j0 + 32 + j] += fmaf(b, comp, b);
+                    }
+                }
+            } else {
+                uint32_t v0[32];
+                if constexpr (NT == 32) tmem_ld32(src, v0); else tmem_ld16(src, v0);
                 tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const float a = __uint_as_float(v0[j]), b = __uint_as_float(v1[j]);
-                    acc[j0 + j] += fmaf(a, comp, a);
-                    acc[j0 + 32 + j] += fmaf(b, comp, b);
-                }
+                for (int j = 0; j < NT; j++) { const float a = __uint_as_float(v0[j]); acc[j] += fmaf(a, comp, a); }
             }
             fence_before();
             mbar_arrive(&acc_free[buf]);
         }
         // cross terms
-        mbar_wait(x_full, 0);
-        fence_after();
+        if constexpr (!G::MERGE_X) { mbar_wait(x_full, 0); fence_after(); }
+        if constexpr (G::MERGE_X) {
+        } else if constexpr (NT >= 64) {
 #pragma unroll
-        for (int j0 = 0; j0 < NT; j0 += 64) {
-            uint32_t v0[32], v1[32];
-            tmem_ld32(lane_addr + G::COL_X + j0, v0);
-            tmem_ld32(lane_addr + G::COL_X + j0 + 32, v1);
+            for (int j0 = 0; j0 < NT; j0 += 64) {
+                uint32_t v0[32], v1[32];
+                tmem_ld32(lane_addr + G::COL_X + j0, v0);
+                tmem_ld32(lane_addr + G::COL_X + j0 + 32, v1);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; j++) { acc[j0 + j] += __uint_as_float(v0[j]); acc[j0 + 32 + j] += __uint_as_float(v1[j]); }
+            }
+        } else {
+            uint32_t v0[32];
+            if constexpr (NT == 32) tmem_ld32(lane_addr + G::COL_X, v0); else tmem_ld16(lane_addr + G::COL_X, v0);
             tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 32; j++) { acc[j0 + j] += __uint_as_float(v0[j]); acc[j0 + 32 + j] += __uint_as_float(v1[j]); }
+            for (int j = 0; j < NT; j++) acc[j] += __uint_as_float(v0[j]);
         }
         // epilogue
         const int yy = m / p.tw, xx = m % p.tw;
         const int u = u0 + yy, v = v0 + xx;
-        if (u < p.Hu && v < p.Wu) {
-            float* o = out + n * p.out_sn + (long long)(u * p.ou + p.oy0) * p.out_sh + (long long)(v * p.ov + p.ox0) * p.out_sw + co0;
+        if (u < Hu && v < Wu) {
+            float* o = out + n * p.out_sn + (long long)(u * p.ou + p.cls_oy0[cls]) * p.out_sh +
+                       (long long)(v * p.ov + p.cls_ox0[cls]) * p.out_sw + co0;
 #pragma unroll
             for (int j = 0; j < NT; j += 4) {
                 float r[4];
@@ -312,6 +372,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 *reinterpret_cast<float4*>(o + j) = make_float4(r[0], r[1], r[2], r[3]);
             }
         }
+    }
+    if (prof && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 4 || warp == 8)) {
+        long long* o = prof + (warp == 0 ? 0 : warp == 1 ? 4 : warp == 4 ? 8 : 12);
+        o[0] = clock64() - t_start; o[1] = w0; o[2] = w1; o[3] = w2;
     }
     fence_before();
     __syncthreads();
@@ -354,6 +418,14 @@ EncodeTiledFn tc_encode_fn() {
     return fn;
 }
 
+// FN2_TC_DBG & 16: per-role wait-time profile of CTA (0,0,0), printed by fn2_tc_prof_dump()
+long long* tc_prof_buffer() {
+    static long long* buf = nullptr;
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("FN2_TC_DBG"); on = (e && (atoi(e) & 16)) ? 1 : 0; if (on) { cudaMalloc(&buf, 16 * sizeof(long long)); cudaMemset(buf, 0, 16 * sizeof(long long)); } }
+    return buf;
+}
+
 int tc_enabled() {
     static int v = -1;
     if (v < 0) {
@@ -373,7 +445,8 @@ int tc_kd() {
 int conv_tc_eligible(const fn2_conv_desc* d, const T4& in, const T4& out) {
     if (!tc_enabled()) return 0;
     if (in.sc != 1 || out.sc != 1) return 0;
-    if (d->ci < 32 || d->co % 64) return 0;
+    if (d->co % 16) return 0;
+    if (d->deconv && (d->stride_h != 2 || d->stride_w != 2) && (d->stride_h != 1 || d->stride_w != 1)) return 0;
     if (d->kh * d->kw > 49) return 0;
     if (d->stride_h > 2 || d->stride_w > 2) return 0;
     if (((uintptr_t)in.p & 15) || (in.sw & 3) || (in.sh & 3) || (in.sn & 3)) return 0;
@@ -385,7 +458,7 @@ int conv_tc_eligible(const fn2_conv_desc* d, const T4& in, const T4& out) {
 int conv_tc_packed_floats(const fn2_conv_desc* d, int ci_stride, size_t* floats) {
     (void)ci_stride;
     const int cip = (d->ci + 31) / 32 * 32;
-    *floats = (d->ci >= 32 && d->co % 64 == 0) ? (size_t)2 * d->kh * d->kw * d->co * cip : 0;
+    *floats = (d->co % 16 == 0) ? (size_t)2 * d->kh * d->kw * d->co * cip : 0;
     return FN2_OK;
 }
 
@@ -404,17 +477,18 @@ static inline int floordiv_i(int a, int b) { return (a >= 0) ? a / b : -((-a + b
 int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const float* bias, const T4& out, cudaStream_t st) {
     EncodeTiledFn enc = tc_encode_fn();
     if (!enc) { set_error("conv_tc: cuTensorMapEncodeTiled unavailable"); return FN2_ERR_CUDA; }
-    const int NT = (d->co % 128 == 0) ? 128 : 64;
+    const int NT = (d->co % 128 == 0) ? 128 : (d->co % 64 == 0 ? 64 : (d->co % 32 == 0 ? 32 : 16));
     const int cip = (d->ci + 31) / 32 * 32;
     TcParams p;
     p.N = in.n; p.Co = d->co; p.cblocks = cip / 32;
     p.out_sn = out.sn; p.out_sh = out.sh; p.out_sw = out.sw;
     p.relu = d->relu; p.has_bias = d->has_bias; p.slope = d->negative_slope;
-    p.kd = tc_kd();
+    p.kd = getenv("FN2_TC_KD") ? tc_kd() : (NT == 128 ? 1 : 2);
     // mean round-toward-zero shrink of an n-MMA accumulation chain, measured by tools/tc_probe.cu (test3)
     const char* nocomp = getenv("FN2_TC_COMP");
     p.comp_a = (nocomp && nocomp[0] == '0') ? 0.f : 1.6e-8f;
     p.comp_b = (nocomp && nocomp[0] == '0') ? 0.f : 1.64e-8f;
+    { const char* e = getenv("FN2_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
 
     // weights: [2][taps][Co][cip]
     CUtensorMap mapW;
@@ -428,11 +502,13 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
         if (r != CUDA_SUCCESS) { set_error("conv_tc: weight tensor map failed (%d)", (int)r); return FN2_ERR_CUDA; }
     }
     auto run = [&](int su, int sv) -> int {
-        // tile shape: widest power of two covering the row, 128 pixels per tile
+        // tile shape: widest power of two covering the (largest) row, 128 pixels per tile
+        int Wmax = 0, Hmax = 0;
+        for (int c = 0; c < p.ncls; c++) { Wmax = max(Wmax, p.cls_Wu[c]); Hmax = max(Hmax, p.cls_Hu[c]); }
         int tw = 8;
-        while (tw < p.Wu && tw < 128) tw *= 2;
+        while (tw < Wmax && tw < 128) tw *= 2;
         p.tw = tw; p.th = 128 / tw;
-        p.tiles_x = (p.Wu + p.tw - 1) / p.tw; p.tiles_y = (p.Hu + p.th - 1) / p.th;
+        p.tiles_x = (Wmax + p.tw - 1) / p.tw; p.tiles_y = (Hmax + p.th - 1) / p.th;
         p.su = su; p.sv = sv;
         CUtensorMap mapA;
         cuuint64_t dims[4] = {(cuuint64_t)in.c, (cuuint64_t)in.w, (cuuint64_t)in.h, (cuuint64_t)in.n};
@@ -442,22 +518,28 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
         CUresult r = enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)in.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv_tc: activation tensor map failed (%d)", (int)r); return FN2_ERR_CUDA; }
-        dim3 grid((unsigned)(p.N * p.tiles_x * p.tiles_y), (unsigned)(d->co / NT));
-        if (NT == 128) {
-            static bool set128 = false;
-            if (!set128) { FN2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGeo<128>::SMEM)); set128 = true; }
-            conv_tc_kernel<128><<<grid, TC_THREADS, TcGeo<128>::SMEM, st>>>(mapA, mapW, bias, out.p, p);
-        } else {
-            static bool set64 = false;
-            if (!set64) { FN2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGeo<64>::SMEM)); set64 = true; }
-            conv_tc_kernel<64><<<grid, TC_THREADS, TcGeo<64>::SMEM, st>>>(mapA, mapW, bias, out.p, p);
+        dim3 grid((unsigned)(p.N * p.tiles_x * p.tiles_y), (unsigned)(d->co / NT), (unsigned)p.ncls);
+#define FN2_TC_LAUNCH(NTV)                                                                                              \
+        {                                                                                                               \
+            static bool attr_set = false;                                                                               \
+            if (!attr_set) {                                                                                            \
+                FN2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGeo<NTV>::SMEM)); \
+                attr_set = true;                                                                                        \
+            }                                                                                                           \
+            conv_tc_kernel<NTV><<<grid, TC_THREADS, TcGeo<NTV>::SMEM, st>>>(mapA, mapW, bias, out.p, p, tc_prof_buffer());                \
         }
+        if (NT == 128) FN2_TC_LAUNCH(128)
+        else if (NT == 64) FN2_TC_LAUNCH(64)
+        else if (NT == 32) FN2_TC_LAUNCH(32)
+        else FN2_TC_LAUNCH(16)
+#undef FN2_TC_LAUNCH
         FN2_LAUNCH_CHECK();
         return FN2_OK;
     };
     if (!d->deconv) {
-        p.Hu = out.h; p.Wu = out.w; p.ou = p.ov = 1; p.oy0 = p.ox0 = 0;
-        p.ntaps = d->kh * d->kw;
+        p.ncls = 1;
+        p.cls_Hu[0] = out.h; p.cls_Wu[0] = out.w; p.ou = p.ov = 1; p.cls_oy0[0] = p.cls_ox0[0] = 0;
+        p.cls_tap0[0] = 0; p.cls_ntaps[0] = d->kh * d->kw;
         for (int r = 0; r < d->kh; r++)
             for (int s = 0; s < d->kw; s++) {
                 const int t = r * d->kw + s;
@@ -465,13 +547,16 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
             }
         return run(d->stride_w, d->stride_h);
     }
+    // deconvolution: all output parity classes in one launch (grid.z); every kernel tap belongs to exactly one class
     const int sh = d->stride_h, sw = d->stride_w;
+    p.ou = sh; p.ov = sw; p.ncls = 0;
+    int nt = 0;
     for (int py = 0; py < sh; py++)
         for (int px = 0; px < sw; px++) {
             if (py >= out.h || px >= out.w) continue;
-            p.Hu = (out.h - py + sh - 1) / sh; p.Wu = (out.w - px + sw - 1) / sw;
-            p.ou = sh; p.ov = sw; p.oy0 = py; p.ox0 = px;
-            int nt = 0;
+            const int c = p.ncls++;
+            p.cls_Hu[c] = (out.h - py + sh - 1) / sh; p.cls_Wu[c] = (out.w - px + sw - 1) / sw;
+            p.cls_oy0[c] = py; p.cls_ox0[c] = px; p.cls_tap0[c] = nt;
             for (int r = 0; r < d->kh; r++) {
                 if (((py + d->pad_h - r) % sh + sh) % sh) continue;
                 for (int s = 0; s < d->kw; s++) {
@@ -482,12 +567,20 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
                     nt++;
                 }
             }
-            if (nt == 0) { set_error("conv_tc: deconvolution parity class without taps"); return FN2_ERR_INVALID; }
-            p.ntaps = nt;
-            int rc = run(1, 1);
-            if (rc) return rc;
+            p.cls_ntaps[c] = nt - p.cls_tap0[c];
+            if (p.cls_ntaps[c] == 0) { set_error("conv_tc: deconvolution parity class without taps"); return FN2_ERR_INVALID; }
         }
-    return FN2_OK;
+    return run(1, 1);
 }
 
 }  // namespace fn2
+
+extern "C" __attribute__((visibility("default"))) void fn2_tc_prof_dump(void) {
+    long long h[16];
+    long long* b = fn2::tc_prof_buffer();
+    if (!b) return;
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, b, sizeof(h), cudaMemcpyDeviceToHost);
+    printf("tc prof (cycles) producer: total %lld wait_empty %lld | mma: total %lld wait_acc_free %lld wait_full %lld wait_a_ready %lld | converter: total %lld wait_full %lld wait_a_free %lld | drain: total %lld wait_acc_full %lld\n",
+           h[0], h[1], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[12], h[13]);
+}

@@ -13,6 +13,12 @@ cases = [  # N, Ci, H, W, Co, k, stride, pad, deconv
     (2, 473, 10, 14, 256, 3, 1, 1, False),
     (1, 256, 6, 7, 64, 4, 2, 1, True),
     (1, 1024, 3, 4, 512, 4, 2, 1, True),
+    (2, 3, 20, 28, 64, 7, 2, 3, False),      # conv1 of FlowNetC: Ci = 3
+    (1, 12, 20, 28, 64, 7, 2, 3, False),     # conv1 of the stacked FlowNetS: Ci = 12
+    (1, 11, 18, 22, 64, 3, 1, 1, False),     # fusion conv0
+    (1, 82, 16, 24, 16, 3, 1, 1, False),     # fusion interconv0: Co = 16
+    (1, 162, 9, 12, 32, 3, 1, 1, False),     # fusion interconv1: Co = 32
+    (1, 162, 9, 11, 16, 4, 2, 1, True),      # fusion deconv0: Co = 16
 ]
 for case in cases:
     N, Ci, H, W, Co, k, s, p, dec = case
@@ -21,7 +27,7 @@ for case in cases:
     b = r.standard_normal(Co).astype(np.float32)
     fn = O.deconv_fwd if dec else O.conv_fwd
     want = O.relu(fn(x, w, b, s, p, f64acc=True), 0.1)
-    Cp = (Ci + 31) // 32 * 32       # engine blobs pad the pixel stride to a multiple of 32 channels
+    Cp = (Ci + 31) // 32 * 32 if Ci >= 32 else (Ci + 3) // 4 * 4      # engine blob padding policy
     buf = torch.zeros((N, Cp, H, W), device="cuda").contiguous(memory_format=cl)
     buf[:, :Ci] = torch.from_numpy(x).cuda()
     tx = buf[:, :Ci]
@@ -33,8 +39,9 @@ for case in cases:
     print(case, "tc err %.3e  simt err %.3e  (scale %.2f)  mean signed tc %.2e" % (np.abs(g - want).max() / sc, np.abs(simt - want).max() / sc, sc,
           float(((g - want) * np.sign(want)).mean() / np.abs(want).mean())), flush=True)
 # timing on a big layer: conv3_1-like and conv4_1-like
-for (N, Ci, H, W, Co, k, s, p) in [(4, 473, 56, 128, 256, 3, 1, 1), (4, 512, 28, 64, 512, 3, 1, 1), (4, 64, 224, 512, 128, 5, 2, 2)]:
-    Cp = (Ci + 31) // 32 * 32
+for (N, Ci, H, W, Co, k, s, p) in [(4, 473, 56, 128, 256, 3, 1, 1), (4, 64, 224, 512, 128, 5, 2, 2), (4, 12, 448, 1024, 64, 7, 2, 3),
+                                   (4, 82, 448, 1024, 16, 3, 1, 1), (4, 1024, 7, 16, 1024, 3, 1, 1)]:
+    Cp = (Ci + 31) // 32 * 32 if Ci >= 32 else (Ci + 3) // 4 * 4
     x = torch.randn(N, Cp, H, W, device="cuda").contiguous(memory_format=cl)[:, :Ci]
     w = torch.randn(Co, Ci, k, k, device="cuda") * 0.02
     b = torch.zeros(Co, device="cuda")
