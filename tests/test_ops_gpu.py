@@ -213,6 +213,43 @@ def test_conv_forward(ops, case, channels_last, engine):
     assert maxabs(got, want) <= tol * max(1.0, np.abs(want).max())
 
 
+TC_CASES = [
+    # N, Ci, H, W, Co, k, stride, pad, deconv    (tcgen05 engine: NHWC views with the engine's padded pixel stride)
+    (1, 32, 8, 16, 64, 1, 1, 0, False),
+    (2, 96, 9, 13, 128, 3, 1, 1, False),
+    (1, 64, 16, 20, 128, 5, 2, 2, False),      # stride 2 through TMA element strides
+    (2, 473, 10, 14, 256, 3, 1, 1, False),     # channel tail 473 -> zero-filled by TMA
+    (1, 256, 6, 7, 64, 4, 2, 1, True),         # deconv: 4 parity classes in one launch
+    (1, 1024, 3, 4, 512, 4, 2, 1, True),
+    (2, 3, 20, 28, 64, 7, 2, 3, False),        # Ci = 3
+    (1, 12, 20, 28, 64, 7, 2, 3, False),
+    (1, 82, 16, 24, 16, 3, 1, 1, False),       # Co = 16
+    (1, 162, 9, 12, 32, 3, 1, 1, False),       # Co = 32
+    (1, 162, 9, 11, 16, 4, 2, 1, True),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tcgen05_engine(ops, case):
+    """3xTF32 tensor-core engine (engine=2 fails loudly if the shape is not eligible): same tolerance as the FP32
+    SIMT engine, and no systematic shrink (the tensor core's round-toward-zero accumulation is drained/compensated)."""
+    N, Ci, H, W, Co, k, s, p, deconv = case
+    r = rng(hash(case) % 2**31)
+    x = r.standard_normal((N, Ci, H, W)).astype(np.float32)
+    wshape = (Ci, Co, k, k) if deconv else (Co, Ci, k, k)
+    w = (r.standard_normal(wshape) * np.sqrt(2.0 / (Ci * k * k))).astype(np.float32)
+    b = r.standard_normal(Co).astype(np.float32)
+    want = O.relu((O.deconv_fwd if deconv else O.conv_fwd)(x, w, b, s, p, f64acc=True), 0.1)
+    cp = (Ci + 31) // 32 * 32 if Ci >= 32 else (Ci + 3) // 4 * 4          # Blob::compute_cstride
+    buf = torch.zeros((N, cp, H, W), device="cuda").contiguous(memory_format=torch.channels_last)
+    buf[:, :Ci] = torch.from_numpy(x).cuda()
+    got = host(ops.conv2d(buf[:, :Ci], dev(w), torch.from_numpy(b).cuda(), s, p, deconv, 0.1, 2))
+    scale = max(1.0, np.abs(want).max())
+    assert maxabs(got, want) <= 1e-6 * scale
+    shrink = float(((got - want) * np.sign(want)).mean() / np.abs(want).mean())
+    assert abs(shrink) < 1e-7, shrink
+
+
 def test_deconv_known_answer(ops):
     # the reference's TestSimpleDeconvolution (test_deconvolution_layer.cpp:91-137): input and
     # weights all ones, bias 0.1, 3 in / 4 out channels, kernel 3 stride 2: 3.1 / 6.1 / 12.1
