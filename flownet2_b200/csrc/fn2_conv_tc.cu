@@ -42,6 +42,7 @@ struct TcParams {
     int tw, th, tiles_x, tiles_y;
     int kd;                                       // channel blocks per tensor-core accumulation chain
     float comp_a, comp_b;                         // RZ bias model: shrink(n MMAs) = comp_a + comp_b * n
+    int gcs;                                      // tap-group packing for Ci <= 16: padded channels per tap (4/8/12/16), 0 = off
     int dbg;                                      // FN2_TC_DBG bits: 1 skip MMAs, 2 skip conversion math, 4 skip drain loads, 8 skip TMA A
     short dy[49], dx[49], widx[49];
 };
@@ -135,6 +136,32 @@ __host__ __device__ inline uint32_t make_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Tap-group packing (Ci <= 16): the stage holds up to 32/CS dense boxes [128 pixels][CS floats] (one per kernel tap);
+// row m of K block = concatenation of its CS-channel slices, zero beyond the taps present.
+template <int CS>
+__device__ __forceinline__ void gather_taps(const unsigned char* base, int m, int nt, uint32_t* hi, uint32_t* lo) {
+    constexpr int GS = 32 / CS;
+#pragma unroll
+    for (int j = 0; j < 32; j++) { hi[j] = 0; lo[j] = 0; }
+#pragma unroll
+    for (int j = 0; j < GS; j++) {
+        if (j < nt) {
+            const float4* row = reinterpret_cast<const float4*>(base + (size_t)j * (128 * CS * 4) + (size_t)m * (CS * 4));
+#pragma unroll
+            for (int q4 = 0; q4 < CS / 4; q4++) {
+                const float4 v = row[q4];
+                const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const uint32_t h = to_tf32(f[e]);
+                    hi[j * CS + 4 * q4 + e] = h;
+                    lo[j * CS + 4 * q4 + e] = to_tf32(f[e] - __uint_as_float(h));
+                }
+            }
+        }
+    }
+}
+
 template <int NT> struct TcGeo {
     static constexpr int B_TILE_BYTES = NT * 128;
     static constexpr int STAGE_BYTES = A_TILE_BYTES + 2 * B_TILE_BYTES;
@@ -176,7 +203,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int cls = blockIdx.z;
     const int Hu = p.cls_Hu[cls], Wu = p.cls_Wu[cls], tap0 = p.cls_tap0[cls];
     if (u0 >= Hu || v0 >= Wu) return;             // tile outside this (smaller) parity class
-    const int steps = p.cls_ntaps[cls] * p.cblocks;
+    const int gsz = p.gcs ? 32 / p.gcs : 1;       // taps per K block when packing
+    const int steps = p.gcs ? (p.cls_ntaps[cls] + gsz - 1) / gsz : p.cls_ntaps[cls] * p.cblocks;
 
     if (tid == 0) {
         for (int s = 0; s < G::NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 129); }
@@ -203,14 +231,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int i = 0; i < steps; i++) {
                 const int s = i % G::NS;
                 const uint32_t ph = (uint32_t)(i / G::NS) & 1u;
-                const int t = tap0 + i / p.cblocks, cb = i % p.cblocks;
                 mbar_wait_t(&empty[s], ph ^ 1u, &w0);
                 unsigned char* st = smem + (size_t)s * G::STAGE_BYTES;
-                mbar_expect_tx(&full[s], (uint32_t)G::STAGE_BYTES);
-                if (p.dbg & 8) tma_load_4d(st, &mapW, &full[s], cb * 32, co0, p.widx[t], 0);   // same bytes when NT == 128
-                else tma_load_4d(st, &mapA, &full[s], cb * 32, v0 * p.su + p.dx[t], u0 * p.sv + p.dy[t], n);
-                tma_load_4d(st + A_TILE_BYTES, &mapW, &full[s], cb * 32, co0, p.widx[t], 0);
-                tma_load_4d(st + A_TILE_BYTES + G::B_TILE_BYTES, &mapW, &full[s], cb * 32, co0, p.widx[t], 1);
+                if (p.gcs) {
+                    // several taps share one 32-wide K block: one small box {gcs channels, tw, th} per tap
+                    const int t0 = i * gsz, nt = min(gsz, p.cls_ntaps[cls] - t0);
+                    const int box_bytes = 128 * p.gcs * 4;
+                    mbar_expect_tx(&full[s], (uint32_t)(nt * box_bytes + 2 * G::B_TILE_BYTES));
+                    for (int j = 0; j < nt; j++) {
+                        const int t = tap0 + t0 + j;
+                        tma_load_4d(st + j * box_bytes, &mapA, &full[s], 0, v0 * p.su + p.dx[t], u0 * p.sv + p.dy[t], n);
+                    }
+                    tma_load_4d(st + A_TILE_BYTES, &mapW, &full[s], 0, co0, i, 0);
+                    tma_load_4d(st + A_TILE_BYTES + G::B_TILE_BYTES, &mapW, &full[s], 0, co0, i, 1);
+                } else {
+                    const int t = tap0 + i / p.cblocks, cb = i % p.cblocks;
+                    mbar_expect_tx(&full[s], (uint32_t)G::STAGE_BYTES);
+                    tma_load_4d(st, &mapA, &full[s], cb * 32, v0 * p.su + p.dx[t], u0 * p.sv + p.dy[t], n);
+                    tma_load_4d(st + A_TILE_BYTES, &mapW, &full[s], cb * 32, co0, p.widx[t], 0);
+                    tma_load_4d(st + A_TILE_BYTES + G::B_TILE_BYTES, &mapW, &full[s], cb * 32, co0, p.widx[t], 1);
+                }
             }
         } else if (warp == 1) {
             // ===== MMA issuer: the whole warp runs the loop convergently (so descriptors live in uniform registers),
@@ -254,7 +294,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
     } else if (warp < 8) {
         // ===== converters: raw FP32 tile (smem, swizzled) -> a_hi / a_lo in tensor memory =====
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 112;" ::: "memory");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 136;" ::: "memory");
         const int q = warp & 3;
         const int m = q * 32 + lane;               // tile row == TMEM lane
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
@@ -266,7 +306,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             mbar_wait_t(&full[s], ph, &w0);
             const float4* row = reinterpret_cast<const float4*>(smem + (size_t)s * G::STAGE_BYTES + m * 128);
             uint32_t hi[32], lo[32];
-            if (p.dbg & 2) {
+            if (p.gcs) {
+                const int nt = min(gsz, p.cls_ntaps[cls] - i * gsz);
+                const unsigned char* base = smem + (size_t)s * G::STAGE_BYTES;
+                if (p.gcs == 4) gather_taps<4>(base, m, nt, hi, lo);
+                else if (p.gcs == 8) gather_taps<8>(base, m, nt, hi, lo);
+                else if (p.gcs == 12) gather_taps<12>(base, m, nt, hi, lo);
+                else gather_taps<16>(base, m, nt, hi, lo);
+            } else if (p.dbg & 2) {
 #pragma unroll
                 for (int j = 0; j < 32; j++) { hi[j] = 0x3f800000u; lo[j] = 0; }
             } else
@@ -403,6 +450,29 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, float* __restrict__ 
     }
 }
 
+// group-packed weights for Ci <= 16: [hi|lo][group][Co][32], K index = j*CS + ci for tap = group*(32/CS) + j
+__global__ void tc_pack_group_kernel(const float* __restrict__ w, float* __restrict__ wp, int Ci, int Co, int kh, int kw, int cs, int ngroups) {
+    const long long per = (long long)ngroups * Co * 32;
+    const int gs = 32 / cs;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per; idx += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(idx % 32);
+        long long r_ = idx / 32;
+        const int co = (int)(r_ % Co);
+        const int g = (int)(r_ / Co);
+        const int j = k / cs, ci = k % cs;
+        const int t = g * gs + j;
+        float v = 0.f;
+        if (j < gs && t < kh * kw && ci < Ci) v = w[(((long long)co * Ci + ci) * kh + t / kw) * kw + t % kw];
+        uint32_t h;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+        const float hi = __uint_as_float(h);
+        uint32_t l;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
+        wp[idx] = hi;
+        wp[per + idx] = __uint_as_float(l);
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -442,6 +512,13 @@ int tc_kd() {
 
 }  // namespace
 
+// tap-group packing applies to plain convolutions with at most 16 input channels
+static int tc_group_cs(const fn2_conv_desc* d) {
+    if (d->deconv || d->ci > 16 || d->kh * d->kw < 2) return 0;
+    if (getenv("FN2_TC_NOPACK")) return 0;
+    return (d->ci + 3) / 4 * 4;
+}
+
 int conv_tc_eligible(const fn2_conv_desc* d, const T4& in, const T4& out) {
     if (!tc_enabled()) return 0;
     if (in.sc != 1 || out.sc != 1) return 0;
@@ -458,6 +535,12 @@ int conv_tc_eligible(const fn2_conv_desc* d, const T4& in, const T4& out) {
 int conv_tc_packed_floats(const fn2_conv_desc* d, int ci_stride, size_t* floats) {
     (void)ci_stride;
     const int cip = (d->ci + 31) / 32 * 32;
+    const int gcs = tc_group_cs(d);
+    if (gcs) {
+        const int gs = 32 / gcs, ngroups = (d->kh * d->kw + gs - 1) / gs;
+        *floats = (d->co % 16 == 0) ? (size_t)2 * ngroups * d->co * 32 : 0;
+        return FN2_OK;
+    }
     *floats = (d->co % 16 == 0) ? (size_t)2 * d->kh * d->kw * d->co * cip : 0;
     return FN2_OK;
 }
@@ -467,6 +550,13 @@ int conv_tc_pack(const fn2_conv_desc* d, int ci_stride, const float* w, float* w
     conv_tc_packed_floats(d, ci_stride, &floats);
     if (!floats) return FN2_OK;
     const int cip = (d->ci + 31) / 32 * 32;
+    const int gcs = tc_group_cs(d);
+    if (gcs) {
+        const int gs = 32 / gcs, ngroups = (d->kh * d->kw + gs - 1) / gs;
+        tc_pack_group_kernel<<<ew_grid((long long)floats / 2, 256), 256, 0, st>>>(w, wp, d->ci, d->co, d->kh, d->kw, gcs, ngroups);
+        FN2_LAUNCH_CHECK();
+        return FN2_OK;
+    }
     tc_pack_kernel<<<ew_grid((long long)floats / 2, 256), 256, 0, st>>>(w, wp, d->ci, d->co, d->kh, d->kw, cip, d->deconv);
     FN2_LAUNCH_CHECK();
     return FN2_OK;
@@ -483,18 +573,24 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
     p.N = in.n; p.Co = d->co; p.cblocks = cip / 32;
     p.out_sn = out.sn; p.out_sh = out.sh; p.out_sw = out.sw;
     p.relu = d->relu; p.has_bias = d->has_bias; p.slope = d->negative_slope;
-    p.kd = getenv("FN2_TC_KD") ? tc_kd() : (NT == 128 ? 1 : 2);
+    p.kd = getenv("FN2_TC_KD") ? tc_kd() : 2;
     // mean round-toward-zero shrink of an n-MMA accumulation chain, measured by tools/tc_probe.cu (test3)
     const char* nocomp = getenv("FN2_TC_COMP");
-    p.comp_a = (nocomp && nocomp[0] == '0') ? 0.f : 1.6e-8f;
-    p.comp_b = (nocomp && nocomp[0] == '0') ? 0.f : 1.64e-8f;
+    // tools/tc_calibrate.py (B200): separate cross accumulator (NT <= 64): shrink = 2.0e-8 + 1.63e-8 * n_hh;
+    // merged (NT == 128): 5.0e-8 + 1.63e-8 * n_all   (fit error < 3 % for n = 4 .. 48)
+    p.comp_a = (nocomp && nocomp[0] == '0') ? 0.f : (NT == 128 ? 5.0e-8f : 2.0e-8f);
+    p.comp_b = (nocomp && nocomp[0] == '0') ? 0.f : 1.63e-8f;
     { const char* e = getenv("FN2_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
 
-    // weights: [2][taps][Co][cip]
+    p.gcs = tc_group_cs(d);
+    // weights: [2][taps][Co][cip]   (group mode: [2][groups][Co][32])
     CUtensorMap mapW;
     {
-        cuuint64_t dims[4] = {(cuuint64_t)cip, (cuuint64_t)d->co, (cuuint64_t)(d->kh * d->kw), 2};
-        cuuint64_t strides[3] = {(cuuint64_t)cip * 4, (cuuint64_t)cip * d->co * 4, (cuuint64_t)cip * d->co * d->kh * d->kw * 4};
+        const int gs = p.gcs ? 32 / p.gcs : 1;
+        const int kin = p.gcs ? 32 : cip;
+        const int nblk = p.gcs ? (d->kh * d->kw + gs - 1) / gs : d->kh * d->kw;
+        cuuint64_t dims[4] = {(cuuint64_t)kin, (cuuint64_t)d->co, (cuuint64_t)nblk, 2};
+        cuuint64_t strides[3] = {(cuuint64_t)kin * 4, (cuuint64_t)kin * d->co * 4, (cuuint64_t)kin * d->co * nblk * 4};
         cuuint32_t box[4] = {32, (cuuint32_t)NT, 1, 1};
         cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult r = enc(&mapW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)wp, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -513,10 +609,11 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
         CUtensorMap mapA;
         cuuint64_t dims[4] = {(cuuint64_t)in.c, (cuuint64_t)in.w, (cuuint64_t)in.h, (cuuint64_t)in.n};
         cuuint64_t strides[3] = {(cuuint64_t)in.sw * 4, (cuuint64_t)in.sh * 4, (cuuint64_t)in.sn * 4};
-        cuuint32_t box[4] = {32, (cuuint32_t)(p.tw * su), (cuuint32_t)(p.th * sv), 1};
+        cuuint32_t box[4] = {(cuuint32_t)(p.gcs ? p.gcs : 32), (cuuint32_t)(p.tw * su), (cuuint32_t)(p.th * sv), 1};
         cuuint32_t es[4] = {1, (cuuint32_t)su, (cuuint32_t)sv, 1};
         CUresult r = enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)in.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         p.gcs ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv_tc: activation tensor map failed (%d)", (int)r); return FN2_ERR_CUDA; }
         dim3 grid((unsigned)(p.N * p.tiles_x * p.tiles_y), (unsigned)(d->co / NT), (unsigned)p.ncls);
 #define FN2_TC_LAUNCH(NTV)                                                                                              \
