@@ -271,6 +271,97 @@ __global__ void __launch_bounds__(256) conv_tiny_kernel(T4 in, const float* __re
     }
 }
 
+// Flow predictors (Co == 2, NHWC input): the layers are memory bound (a few MFLOP per MB), so the kernels below read
+// every input pixel as float4 vectors and keep the [tap][ci] weight pairs in shared memory.
+//   conv_pf_thread_kernel: Ci <= 32 (full-resolution fusion predictors) -- one thread per output pixel
+//   conv_pf_warp_kernel:   larger Ci -- one warp per output pixel, lanes stride the channel vectors, shuffle reduce
+// Channels [Ci, 4*C4) are blob padding: their weights are zero (the padding itself is finite, the arena is zero-filled).
+__device__ __forceinline__ void pf_stage_weights(float2* wsm, const float* __restrict__ wp, int taps, int Ci, int C4) {
+    const int cp = C4 * 4;
+    for (int i = threadIdx.x; i < taps * cp; i += blockDim.x) {
+        const int ci = i % cp, t = i / cp;
+        wsm[i] = ci < Ci ? make_float2(wp[((long long)t * Ci + ci) * 2], wp[((long long)t * Ci + ci) * 2 + 1]) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void pf_store(const T4& out, const ConvP& p, const float* __restrict__ bias, int n, int oy, int ox, float a0, float a1) {
+    if (p.has_bias) { a0 += __ldg(bias); a1 += __ldg(bias + 1); }
+    if (p.relu) { a0 = a0 > 0 ? a0 : a0 * p.slope; a1 = a1 > 0 ? a1 : a1 * p.slope; }
+    out.p[out.off(n, 0, oy, ox)] = a0;
+    out.p[out.off(n, 1, oy, ox)] = a1;
+}
+template <int C4>
+__global__ void __launch_bounds__(256) conv_pf_thread_kernel(T4 in, const float* __restrict__ wp, const float* __restrict__ bias, T4 out, ConvP p) {
+    extern __shared__ float2 pf_wsm[];
+    pf_stage_weights(pf_wsm, wp, p.kh * p.kw, p.Ci, C4);
+    const long long M = (long long)p.N * p.Ho * p.Wo;
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(m % p.Wo);
+        const int oy = (int)((m / p.Wo) % p.Ho);
+        const int n = (int)(m / ((long long)p.Wo * p.Ho));
+        float a0 = 0.f, a1 = 0.f;
+        for (int r = 0; r < p.kh; r++) {
+            const int iy = oy * p.sh - p.ph + r;
+            if (iy < 0 || iy >= p.H) continue;
+            for (int s = 0; s < p.kw; s++) {
+                const int ix = ox * p.sw - p.pw + s;
+                if (ix < 0 || ix >= p.W) continue;
+                const float4* ip = reinterpret_cast<const float4*>(in.p + in.off(n, 0, iy, ix));
+                const float4* w = reinterpret_cast<const float4*>(pf_wsm + (r * p.kw + s) * C4 * 4);
+#pragma unroll
+                for (int q = 0; q < C4; q++) {
+                    const float4 a = __ldg(ip + q);
+                    const float4 w01 = w[2 * q], w23 = w[2 * q + 1];       // (c0.o0, c0.o1, c1.o0, c1.o1), (c2.., c3..)
+                    a0 = fmaf(a.x, w01.x, a0); a1 = fmaf(a.x, w01.y, a1);
+                    a0 = fmaf(a.y, w01.z, a0); a1 = fmaf(a.y, w01.w, a1);
+                    a0 = fmaf(a.z, w23.x, a0); a1 = fmaf(a.z, w23.y, a1);
+                    a0 = fmaf(a.w, w23.z, a0); a1 = fmaf(a.w, w23.w, a1);
+                }
+            }
+        }
+        pf_store(out, p, bias, n, oy, ox, a0, a1);
+    }
+}
+__global__ void __launch_bounds__(256) conv_pf_warp_kernel(T4 in, const float* __restrict__ wp, const float* __restrict__ bias, T4 out, ConvP p, int C4) {
+    extern __shared__ float2 pf_wsm[];
+    pf_stage_weights(pf_wsm, wp, p.kh * p.kw, p.Ci, C4);
+    const long long M = (long long)p.N * p.Ho * p.Wo;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long m = warp0; m < M; m += nwarps) {
+        const int ox = (int)(m % p.Wo);
+        const int oy = (int)((m / p.Wo) % p.Ho);
+        const int n = (int)(m / ((long long)p.Wo * p.Ho));
+        float a0 = 0.f, a1 = 0.f;
+        for (int r = 0; r < p.kh; r++) {
+            const int iy = oy * p.sh - p.ph + r;
+            if (iy < 0 || iy >= p.H) continue;
+            for (int s = 0; s < p.kw; s++) {
+                const int ix = ox * p.sw - p.pw + s;
+                if (ix < 0 || ix >= p.W) continue;
+                const float4* ip = reinterpret_cast<const float4*>(in.p + in.off(n, 0, iy, ix));
+                const float4* w = reinterpret_cast<const float4*>(pf_wsm + (long long)(r * p.kw + s) * C4 * 4);
+#pragma unroll 2
+                for (int q = lane; q < C4; q += 32) {
+                    const float4 a = __ldg(ip + q);
+                    const float4 w01 = w[2 * q], w23 = w[2 * q + 1];
+                    a0 = fmaf(a.x, w01.x, a0); a1 = fmaf(a.x, w01.y, a1);
+                    a0 = fmaf(a.y, w01.z, a0); a1 = fmaf(a.y, w01.w, a1);
+                    a0 = fmaf(a.z, w23.x, a0); a1 = fmaf(a.z, w23.y, a1);
+                    a0 = fmaf(a.w, w23.z, a0); a1 = fmaf(a.w, w23.w, a1);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        }
+        if (lane == 0) pf_store(out, p, bias, n, oy, ox, a0, a1);
+    }
+}
+
 // Caffe weights -> packed [k][co].  conv: w[co][ci][r][s]; deconv: w[ci][co][r][s].
 __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ wp, int Ci, int Co,
                                     int kh, int kw, int cis, int deconv) {
@@ -374,7 +465,29 @@ int fn2_conv_forward(const fn2_conv_desc* d, const fn2_tensor* bottom, const flo
     p.cis = d->ci;
     p.K = d->kh * d->kw * p.cis;
     const long long M = (long long)p.N * p.Ho * p.Wo;
-    if (d->co <= 4 && d->ci <= 32) {
+    const int C4 = (d->ci + 3) / 4;
+    const bool pf_ok = !d->deconv && d->co == 2 && in.sc == 1 && in.sw >= 4 * C4 && !((uintptr_t)in.p & 15) && !(in.sw & 3) &&
+                       !(in.sh & 3) && !(in.sn & 3) && (size_t)d->kh * d->kw * C4 * 4 * sizeof(float2) <= 200 * 1024;
+    if (pf_ok) {
+        const size_t smem = (size_t)d->kh * d->kw * C4 * 4 * sizeof(float2);
+        if (C4 <= 8) {
+            const int grid = (int)min((long long)148 * 8, (M + 255) / 256);
+#define FN2_PF_THREAD(C)                                                                                                   \
+            case C: conv_pf_thread_kernel<C><<<grid, 256, smem, st>>>(in, packed_weights_dev, bias_dev, out, p); break;
+            switch (C4) { FN2_PF_THREAD(1) FN2_PF_THREAD(2) FN2_PF_THREAD(3) FN2_PF_THREAD(4) FN2_PF_THREAD(5) FN2_PF_THREAD(6)
+                          FN2_PF_THREAD(7) FN2_PF_THREAD(8) }
+#undef FN2_PF_THREAD
+        } else {
+            static size_t smem_set = 0;
+            if (smem > 48 * 1024 && smem > smem_set) {
+                FN2_CUDA(cudaFuncSetAttribute(conv_pf_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+                smem_set = 200 * 1024;
+            }
+            const int per_sm = (int)max((size_t)1, min((size_t)8, (size_t)(220 * 1024) / (smem + 1024)));
+            const int grid = (int)min((long long)148 * per_sm, (M + 7) / 8);
+            conv_pf_warp_kernel<<<grid, 256, smem, st>>>(in, packed_weights_dev, bias_dev, out, p, C4);
+        }
+    } else if (d->co <= 4 && d->ci <= 32) {
         const size_t smem = (size_t)p.K * p.Co * sizeof(float);
         const int grid = ew_grid(M, 256);
         if (d->deconv) conv_tiny_kernel<true><<<grid, 256, smem, st>>>(in, packed_weights_dev, bias_dev, out, p);

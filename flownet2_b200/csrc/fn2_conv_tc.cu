@@ -41,6 +41,7 @@ struct TcParams {
     float slope;
     int tw, th, tiles_x, tiles_y;
     int kd;                                       // channel blocks per tensor-core accumulation chain
+    int cl, ntiles;                               // cluster size (W multicast), number of real tiles in grid.x
     float comp_a, comp_b;                         // RZ bias model: shrink(n MMAs) = comp_a + comp_b * n
     int gcs;                                      // tap-group packing for Ci <= 16: padded channels per tap (4/8/12/16), 0 = off
     int dbg;                                      // FN2_TC_DBG bits: 1 skip MMAs, 2 skip conversion math, 4 skip drain loads, 8 skip TMA A
@@ -76,6 +77,15 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(su32(dst)), "l"(map), "r"(su32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// the same box, delivered to the same shared-memory offset (and signalling the same barrier offset) of every CTA in cta_mask
+__device__ __forceinline__ void tma_load_4d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, uint16_t cta_mask) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+                 ::"r"(su32(dst)), "l"(map), "r"(su32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.b32 %0, 1, 0, px;\n\t}" : "=r"(pred));
@@ -87,6 +97,10 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(su32(bar)) : "memory");
+}
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(su32(bar)), "h"(cta_mask) : "memory");
 }
 // D[tmem_c] (+)= A[tmem_a] * B[desc_b]^T, kind::tf32, A from tensor memory
 __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -117,11 +131,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
           "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(taddr) : "memory");
 }
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
+// round-to-nearest (ties away) to TF32 == cvt.rna.tf32.f32 for finite inputs; ptxas expands the cvt into a 5-instruction
+// sequence with an Inf/NaN guard, which made the converter warps the slowest stage of the pipeline
+__device__ __forceinline__ uint32_t to_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row atoms of 1024 B (validated by tools/tc_probe.cu)
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -167,13 +179,19 @@ template <int NT> struct TcGeo {
     static constexpr int STAGE_BYTES = A_TILE_BYTES + 2 * B_TILE_BYTES;
     static constexpr int NS = NT == 128 ? 4 : (NT == 64 ? 6 : 8);
     static constexpr int SMEM = NS * STAGE_BYTES + 1024;
-    // tensor-memory columns.  NT == 128 has no room for a separate cross-term accumulator AND a deep enough ring of
-    // A slots (the MMA <-> converter hand-off latency needs >= 4 slots in flight, see profiles/r01_prof_tc_*), so there
-    // the cross terms go into the chunk accumulators (MERGE_X) and are drained with them.
-    static constexpr bool MERGE_X = NT == 128;
-    static constexpr int COL_HH0 = 0, COL_HH1 = NT, COL_X = 2 * NT;
-    static constexpr int NSLOT = NT == 128 ? 4 : (NT == 64 ? 5 : 6);
+    // tensor-memory columns.  Two chunk accumulators (double-buffered against the drain warps) followed by a ring of
+    // A slots (the MMA <-> converter hand-off latency needs >= 4 slots in flight, see profiles/r01_tc_prof_*).
+    // NT == 128: the three products a_hi*w_hi, a_hi*w_lo, a_lo*w_hi all accumulate into the same NT columns.
+    // NT <= 64 (WIDE): the W stage holds [w_hi rows ; w_lo rows] back to back, so ONE MMA with N = 2*NT computes
+    // a_hi*[w_hi|w_lo] into 2*NT columns and a second one adds a_lo*w_hi onto the first NT of them: 2 MMAs per K=8
+    // slice instead of 3 (with A in tensor memory an MMA costs >= 64 cycles however small N is).
+    static constexpr bool WIDE = NT <= 64;
+    static constexpr int ACCW = WIDE ? 2 * NT : NT;
+    static constexpr int MMAS_PER_STEP = WIDE ? 8 : 12;                            // length of the RZ chain per step
+    static constexpr int COL_HH0 = 0, COL_HH1 = ACCW;
+    static constexpr int NSLOT = NT >= 64 ? 4 : 6;
     static constexpr int COL_A = 512 - 64 * NSLOT;                                 // slot s: hi at COL_A + 64*s, lo at +32
+    static_assert(2 * ACCW <= COL_A, "tensor memory overflow");
 };
 
 template <int NT>
@@ -189,12 +207,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     uint64_t* a_free = a_ready + G::NSLOT;         // [NSLOT]
     uint64_t* acc_full = a_free + G::NSLOT;        // [2]
     uint64_t* acc_free = acc_full + 2;             // [2]
-    uint64_t* x_full = acc_free + 2;               // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 1);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // tile decode
+    // tile decode.  CTAs of one cluster (p.cl consecutive blockIdx.x) share co0 and the parity class, so they read the same
+    // W tiles: each loads 1/cl of the rows and multicasts it to the whole cluster (the kernel is L2 -> SM bandwidth bound:
+    // 48 KB per step per SM without sharing, see profiles/r01_prof_tc128_*).  Every CTA runs the full pipeline even when its
+    // tile lies outside the image/class (valid == false: loads are zero-filled, nothing is stored).
     int bid = blockIdx.x;
+    bool valid = bid < p.ntiles;
+    if (!valid) bid = 0;
     const int tx = bid % p.tiles_x; bid /= p.tiles_x;
     const int ty = bid % p.tiles_y; bid /= p.tiles_y;
     const int n = bid;
@@ -202,15 +224,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int co0 = blockIdx.y * NT;
     const int cls = blockIdx.z;
     const int Hu = p.cls_Hu[cls], Wu = p.cls_Wu[cls], tap0 = p.cls_tap0[cls];
-    if (u0 >= Hu || v0 >= Wu) return;             // tile outside this (smaller) parity class
+    if (u0 >= Hu || v0 >= Wu) valid = false;      // tile outside this (smaller) parity class
+    const uint32_t crank = p.cl > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << p.cl) - 1u);
+    const int wrows = NT / p.cl;                   // W rows this CTA loads per tile
     const int gsz = p.gcs ? 32 / p.gcs : 1;       // taps per K block when packing
     const int steps = p.gcs ? (p.cls_ntaps[cls] + gsz - 1) / gsz : p.cls_ntaps[cls] * p.cblocks;
 
     if (tid == 0) {
-        for (int s = 0; s < G::NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 129); }
+        for (int s = 0; s < G::NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 128 + p.cl); }
         for (int s = 0; s < G::NSLOT; s++) { mbar_init(&a_ready[s], 128); mbar_init(&a_free[s], 1); }
         for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_free[s], 128); }
-        mbar_init(x_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -219,6 +243,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     fence_before();
     __syncthreads();
+    if (p.cl > 1) cluster_sync_all();             // peers' barriers are initialised before any multicast can signal them
     fence_after();
     const uint32_t tmem = *tmem_slot;
     long long w0 = 0, w1 = 0, w2 = 0;
@@ -228,6 +253,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
         if (warp == 0 && lane == 0) {
             // ===== TMA producer =====
+            auto load_w = [&](unsigned char* st, uint64_t* bar, int c0, int blk) {
+                unsigned char* wh = st + A_TILE_BYTES + crank * wrows * 128;
+                if (p.cl > 1) {
+                    tma_load_4d_mc(wh, &mapW, bar, c0, co0 + crank * wrows, blk, 0, cmask);
+                    tma_load_4d_mc(wh + G::B_TILE_BYTES, &mapW, bar, c0, co0 + crank * wrows, blk, 1, cmask);
+                } else {
+                    tma_load_4d(wh, &mapW, bar, c0, co0, blk, 0);
+                    tma_load_4d(wh + G::B_TILE_BYTES, &mapW, bar, c0, co0, blk, 1);
+                }
+            };
             for (int i = 0; i < steps; i++) {
                 const int s = i % G::NS;
                 const uint32_t ph = (uint32_t)(i / G::NS) & 1u;
@@ -242,20 +277,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         const int t = tap0 + t0 + j;
                         tma_load_4d(st + j * box_bytes, &mapA, &full[s], 0, v0 * p.su + p.dx[t], u0 * p.sv + p.dy[t], n);
                     }
-                    tma_load_4d(st + A_TILE_BYTES, &mapW, &full[s], 0, co0, i, 0);
-                    tma_load_4d(st + A_TILE_BYTES + G::B_TILE_BYTES, &mapW, &full[s], 0, co0, i, 1);
+                    load_w(st, &full[s], 0, i);
                 } else {
                     const int t = tap0 + i / p.cblocks, cb = i % p.cblocks;
                     mbar_expect_tx(&full[s], (uint32_t)G::STAGE_BYTES);
                     tma_load_4d(st, &mapA, &full[s], cb * 32, v0 * p.su + p.dx[t], u0 * p.sv + p.dy[t], n);
-                    tma_load_4d(st + A_TILE_BYTES, &mapW, &full[s], cb * 32, co0, p.widx[t], 0);
-                    tma_load_4d(st + A_TILE_BYTES + G::B_TILE_BYTES, &mapW, &full[s], cb * 32, co0, p.widx[t], 1);
+                    load_w(st, &full[s], cb * 32, p.widx[t]);
                 }
             }
         } else if (warp == 1) {
             // ===== MMA issuer: the whole warp runs the loop convergently (so descriptors live in uniform registers),
             // one elected lane issues the tcgen05 instructions =====
-            const uint32_t idesc = make_idesc_tf32(128, NT);
+            const uint32_t idesc = make_idesc_tf32(128, NT), idesc_w = make_idesc_tf32(128, G::ACCW);
             for (int i = 0; i < steps; i++) {
                 const int s = i % G::NS;
                 const uint32_t ph = (uint32_t)(i / G::NS) & 1u;
@@ -270,8 +303,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const uint32_t bh = su32(smem + (size_t)s * G::STAGE_BYTES + A_TILE_BYTES);
                 const uint64_t dbh0 = make_desc_sw128(bh), dbl0 = make_desc_sw128(bh + G::B_TILE_BYTES);
                 const uint32_t a_hi = tmem + G::COL_A + 64 * as, a_lo = a_hi + 32;
-                const uint32_t d_hh = tmem + (buf ? G::COL_HH1 : G::COL_HH0);
-                const uint32_t d_x = G::MERGE_X ? d_hh : tmem + G::COL_X;
+                const uint32_t d = tmem + (buf ? G::COL_HH1 : G::COL_HH0);
                 const bool last = (i == steps - 1);
                 const bool chunk_end = (in_chunk == p.kd - 1) || last;
                 if (elect_one()) {
@@ -279,15 +311,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                         for (int kk = 0; kk < 4; kk++) {
                             // +2 in the start-address field = +32 bytes = the next 8 TF32 columns of the swizzled tile
-                            mma_tf32_ts(d_hh, a_hi + kk * 8, dbh0 + (uint64_t)(2 * kk), idesc, (in_chunk | kk) != 0);
-                            mma_tf32_ts(d_x, a_hi + kk * 8, dbl0 + (uint64_t)(2 * kk), idesc, G::MERGE_X ? 1u : (uint32_t)((i | kk) != 0));
-                            mma_tf32_ts(d_x, a_lo + kk * 8, dbh0 + (uint64_t)(2 * kk), idesc, 1);
+                            if constexpr (G::WIDE) {
+                                mma_tf32_ts(d, a_hi + kk * 8, dbh0 + (uint64_t)(2 * kk), idesc_w, (in_chunk | kk) != 0);
+                                mma_tf32_ts(d, a_lo + kk * 8, dbh0 + (uint64_t)(2 * kk), idesc, 1);
+                            } else {
+                                mma_tf32_ts(d, a_hi + kk * 8, dbh0 + (uint64_t)(2 * kk), idesc, (in_chunk | kk) != 0);
+                                mma_tf32_ts(d, a_hi + kk * 8, dbl0 + (uint64_t)(2 * kk), idesc, 1);
+                                mma_tf32_ts(d, a_lo + kk * 8, dbh0 + (uint64_t)(2 * kk), idesc, 1);
+                            }
                         }
                     }
-                    mma_commit(&empty[s]);            // W tiles of this stage consumed
+                    if (p.cl > 1) mma_commit_mc(&empty[s], cmask);   // W tiles of this stage consumed: tell every CTA that writes into it
+                    else mma_commit(&empty[s]);
                     mma_commit(&a_free[as]);          // TMEM A slot consumed
                     if (chunk_end) mma_commit(&acc_full[buf]);
-                    if (!G::MERGE_X && last) mma_commit(x_full);
                 }
                 __syncwarp();
             }
@@ -306,6 +343,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             mbar_wait_t(&full[s], ph, &w0);
             const float4* row = reinterpret_cast<const float4*>(smem + (size_t)s * G::STAGE_BYTES + m * 128);
             uint32_t hi[32], lo[32];
+            float4 raw[8];
+            if (!p.gcs) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) raw[j] = row[j ^ (m & 7)];
+            }
+            if (i > 0) {
+                // publish the previous step's slot: its TMEM stores had the barrier wait + the loads above to land
+                tmem_wait_st();
+                fence_before();
+                mbar_arrive(&a_ready[(i - 1) % G::NSLOT]);
+            }
             if (p.gcs) {
                 const int nt = min(gsz, p.cls_ntaps[cls] - i * gsz);
                 const unsigned char* base = smem + (size_t)s * G::STAGE_BYTES;
@@ -316,16 +364,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             } else if (p.dbg & 2) {
 #pragma unroll
                 for (int j = 0; j < 32; j++) { hi[j] = 0x3f800000u; lo[j] = 0; }
-            } else
+            } else {
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const float4 v = row[j ^ (m & 7)];
-                const float f[4] = {v.x, v.y, v.z, v.w};
+                for (int j = 0; j < 8; j++) {
+                    const float f[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
 #pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const uint32_t h = to_tf32(f[e]);
-                    hi[4 * j + e] = h;
-                    lo[4 * j + e] = to_tf32(f[e] - __uint_as_float(h));
+                    for (int e = 0; e < 4; e++) {
+                        const uint32_t h = to_tf32(f[e]);
+                        hi[4 * j + e] = h;
+                        lo[4 * j + e] = to_tf32(f[e] - __uint_as_float(h));
+                    }
                 }
             }
             mbar_arrive(&empty[s]);               // raw tile consumed (registers hold it now)
@@ -333,10 +381,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             fence_after();
             tmem_st32(lane_addr + G::COL_A + 64 * as, hi);
             tmem_st32(lane_addr + G::COL_A + 64 * as + 32, lo);
-            tmem_wait_st();
-            fence_before();
-            mbar_arrive(&a_ready[as]);
         }
+        tmem_wait_st();
+        fence_before();
+        mbar_arrive(&a_ready[(steps - 1) % G::NSLOT]);
     } else {
         // ===== drain + epilogue: TMEM accumulators -> FP32 registers (round to nearest) -> global =====
         asm volatile("setmaxnreg.inc.sync.aligned.u32 216;" ::: "memory");
@@ -350,13 +398,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int c = 0; c < chunks; c++) {
             const int buf = c & 1;
             const int nsteps = min(p.kd, steps - c * p.kd);
-            // mean RZ shrink of the accumulation chain of this chunk (4 MMAs per channel block, 12 when merged)
-            const float comp = p.comp_a + p.comp_b * (float)((G::MERGE_X ? 12 : 4) * nsteps);
+            // mean RZ shrink of the accumulation chain of this chunk
+            const float comp = p.comp_a + p.comp_b * (float)(G::MMAS_PER_STEP * nsteps);
             mbar_wait_t(&acc_full[buf], (uint32_t)(c >> 1) & 1u, &w0);
             fence_after();
             const uint32_t src = lane_addr + (buf ? G::COL_HH1 : G::COL_HH0);
             if (p.dbg & 4) {
-            } else if constexpr (NT >= 64) {
+            } else if constexpr (NT == 128) {
 #pragma unroll
                 for (int j0 = 0; j0 < NT; j0 += 64) {
                     uint32_t v0[32], v1[32];
@@ -370,40 +418,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         acc[j0 + 32 + j] += fmaf(b, comp, b);
                     }
                 }
-            } else {
-                uint32_t v0[32];
-                if constexpr (NT == 32) tmem_ld32(src, v0); else tmem_ld16(src, v0);
+            } else if constexpr (NT == 64) {
+                // columns [0,64): a_hi*w_hi + a_lo*w_hi, columns [64,128): a_hi*w_lo
+#pragma unroll
+                for (int j0 = 0; j0 < 64; j0 += 32) {
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(src + j0, v0);
+                    tmem_ld32(src + 64 + j0, v1);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float a = __uint_as_float(v0[j]);
+                        acc[j0 + j] += fmaf(a, comp, a) + __uint_as_float(v1[j]);
+                    }
+                }
+            } else if constexpr (NT == 32) {
+                uint32_t v0[32], v1[32];
+                tmem_ld32(src, v0);
+                tmem_ld32(src + 32, v1);
                 tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < NT; j++) { const float a = __uint_as_float(v0[j]); acc[j] += fmaf(a, comp, a); }
+                for (int j = 0; j < 32; j++) {
+                    const float a = __uint_as_float(v0[j]);
+                    acc[j] += fmaf(a, comp, a) + __uint_as_float(v1[j]);
+                }
+            } else {
+                uint32_t v0[32];
+                tmem_ld32(src, v0);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const float a = __uint_as_float(v0[j]);
+                    acc[j] += fmaf(a, comp, a) + __uint_as_float(v0[16 + j]);
+                }
             }
             fence_before();
             mbar_arrive(&acc_free[buf]);
         }
-        // cross terms
-        if constexpr (!G::MERGE_X) { mbar_wait(x_full, 0); fence_after(); }
-        if constexpr (G::MERGE_X) {
-        } else if constexpr (NT >= 64) {
-#pragma unroll
-            for (int j0 = 0; j0 < NT; j0 += 64) {
-                uint32_t v0[32], v1[32];
-                tmem_ld32(lane_addr + G::COL_X + j0, v0);
-                tmem_ld32(lane_addr + G::COL_X + j0 + 32, v1);
-                tmem_wait_ld();
-#pragma unroll
-                for (int j = 0; j < 32; j++) { acc[j0 + j] += __uint_as_float(v0[j]); acc[j0 + 32 + j] += __uint_as_float(v1[j]); }
-            }
-        } else {
-            uint32_t v0[32];
-            if constexpr (NT == 32) tmem_ld32(lane_addr + G::COL_X, v0); else tmem_ld16(lane_addr + G::COL_X, v0);
-            tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < NT; j++) acc[j] += __uint_as_float(v0[j]);
-        }
         // epilogue
         const int yy = m / p.tw, xx = m % p.tw;
         const int u = u0 + yy, v = v0 + xx;
-        if (u < Hu && v < Wu) {
+        if (valid && u < Hu && v < Wu) {
             float* o = out + n * p.out_sn + (long long)(u * p.ou + p.cls_oy0[cls]) * p.out_sh +
                        (long long)(v * p.ov + p.cls_ox0[cls]) * p.out_sw + co0;
 #pragma unroll
@@ -427,6 +482,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     fence_before();
     __syncthreads();
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    if (p.cl > 1) cluster_sync_all();             // no CTA leaves while a peer may still multicast into it / signal its barriers
 }
 
 // ---- weight packing: Caffe layout -> [hi|lo][tap][Co][Ci32] with the TF32 split -------------------------------------
@@ -573,16 +629,18 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
     p.N = in.n; p.Co = d->co; p.cblocks = cip / 32;
     p.out_sn = out.sn; p.out_sh = out.sh; p.out_sw = out.sw;
     p.relu = d->relu; p.has_bias = d->has_bias; p.slope = d->negative_slope;
-    p.kd = getenv("FN2_TC_KD") ? tc_kd() : 2;
+    p.kd = getenv("FN2_TC_KD") ? tc_kd() : 4;
     // mean round-toward-zero shrink of an n-MMA accumulation chain, measured by tools/tc_probe.cu (test3)
     const char* nocomp = getenv("FN2_TC_COMP");
-    // tools/tc_calibrate.py (B200): separate cross accumulator (NT <= 64): shrink = 2.0e-8 + 1.63e-8 * n_hh;
-    // merged (NT == 128): 5.0e-8 + 1.63e-8 * n_all   (fit error < 3 % for n = 4 .. 48)
-    p.comp_a = (nocomp && nocomp[0] == '0') ? 0.f : (NT == 128 ? 5.0e-8f : 2.0e-8f);
+    // tools/tc_calibrate.py (B200): shrink of one chunk = comp_a + comp_b * (MMAs chained into the accumulator)
+    p.comp_a = (nocomp && nocomp[0] == '0') ? 0.f : (NT == 128 ? 5.0e-8f : 3.0e-8f);
     p.comp_b = (nocomp && nocomp[0] == '0') ? 0.f : 1.63e-8f;
+    if (const char* e = getenv("FN2_TC_COMP_A")) p.comp_a = (float)atof(e);
+    if (const char* e = getenv("FN2_TC_COMP_B")) p.comp_b = (float)atof(e);
     { const char* e = getenv("FN2_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
 
     p.gcs = tc_group_cs(d);
+    { const char* e = getenv("FN2_TC_CL"); p.cl = e ? atoi(e) : 1; if (p.cl != 1 && p.cl != 2 && p.cl != 4) p.cl = 1; if (NT / p.cl < 8) p.cl = NT / 8; }
     // weights: [2][taps][Co][cip]   (group mode: [2][groups][Co][32])
     CUtensorMap mapW;
     {
@@ -591,7 +649,7 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
         const int nblk = p.gcs ? (d->kh * d->kw + gs - 1) / gs : d->kh * d->kw;
         cuuint64_t dims[4] = {(cuuint64_t)kin, (cuuint64_t)d->co, (cuuint64_t)nblk, 2};
         cuuint64_t strides[3] = {(cuuint64_t)kin * 4, (cuuint64_t)kin * d->co * 4, (cuuint64_t)kin * d->co * nblk * 4};
-        cuuint32_t box[4] = {32, (cuuint32_t)NT, 1, 1};
+        cuuint32_t box[4] = {32, (cuuint32_t)(NT / p.cl), 1, 1};
         cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult r = enc(&mapW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)wp, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -615,7 +673,15 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
                          p.gcs ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv_tc: activation tensor map failed (%d)", (int)r); return FN2_ERR_CUDA; }
-        dim3 grid((unsigned)(p.N * p.tiles_x * p.tiles_y), (unsigned)(d->co / NT), (unsigned)p.ncls);
+        p.ntiles = p.N * p.tiles_x * p.tiles_y;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((p.ntiles + p.cl - 1) / p.cl * p.cl), (unsigned)(d->co / NT), (unsigned)p.ncls);
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)p.cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
 #define FN2_TC_LAUNCH(NTV)                                                                                              \
         {                                                                                                               \
             static bool attr_set = false;                                                                               \
@@ -623,7 +689,8 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
                 FN2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGeo<NTV>::SMEM)); \
                 attr_set = true;                                                                                        \
             }                                                                                                           \
-            conv_tc_kernel<NTV><<<grid, TC_THREADS, TcGeo<NTV>::SMEM, st>>>(mapA, mapW, bias, out.p, p, tc_prof_buffer());                \
+            cfg.dynamicSmemBytes = TcGeo<NTV>::SMEM;                                                                    \
+            FN2_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<NTV>, mapA, mapW, bias, out.p, p, tc_prof_buffer()));      \
         }
         if (NT == 128) FN2_TC_LAUNCH(128)
         else if (NT == 64) FN2_TC_LAUNCH(64)

@@ -110,50 +110,60 @@ __device__ __forceinline__ float triangleCoeff(float x) {
     return 0;
 }
 
+// One thread per output pixel, all channels: the filter weights depend on the pixel only, and every channel accumulates
+// its taps in the reference's order (y outer, x inner), so each channel's result is bit-identical to the per-element
+// formulation.  Taps whose weight is exactly zero are skipped: sum + 0*v == sum and wsum + 0 == wsum for finite v (the
+// triangle filter of an up-sampling has 21 zero taps out of 25).
 template <int TYPE>   // 1 nearest, 2 linear(triangle), 3 cubic
 __global__ void resample_kernel(T4 in, T4 out, float fx, float fy, int antialias) {
-    const long long total = out.count();
+    const long long total = (long long)out.n * out.h * out.w;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        // decode with x fastest, then channel (so NHWC views stay roughly coalesced), then y, n
         const int x_out = (int)(idx % out.w);
-        long long r = idx / out.w;
-        const int c = (int)(r % out.c); r /= out.c;
-        const int y_out = (int)(r % out.h);
-        const int n = (int)(r / out.h);
+        const int y_out = (int)((idx / out.w) % out.h);
+        const int n = (int)(idx / ((long long)out.w * out.h));
         const float x_in = (x_out * fx + fy / 2.0f) - 0.5f;
         const float y_in = (y_out * fy + fx / 2.0f) - 0.5f;
         const int x_in_round = (int)roundf(x_in);
         const int y_in_round = (int)roundf(y_in);
-        float result;
         if (TYPE == 1) {
             // the reference does not clamp (resample_layer.cu:120-123) and can read out of
             // bounds; clamp instead (documented deviation)
             const int xr = min(max(x_in_round, 0), in.w - 1);
             const int yr = min(max(y_in_round, 0), in.h - 1);
-            result = in.p[in.off(n, c, yr, xr)];
-        } else {
-            const int kernel_width = (TYPE == 3) ? 4 : 2;
-            float sum = 0, wsum = 0;
-            const float ax = 1.0f / (antialias ? fx : 1.0f);
-            const float ay = 1.0f / (antialias ? fy : 1.0f);
-            const int rx = (fx < 1.0f) ? 2 : (int)ceilf((float)kernel_width / ax);
-            const int ry = (fy < 1.0f) ? 2 : (int)ceilf((float)kernel_width / ay);
-            for (int y = y_in_round - ry; y <= y_in_round + ry; y++)
+            for (int c = 0; c < out.c; c++) out.p[out.off(n, c, y_out, x_out)] = in.p[in.off(n, c, yr, xr)];
+            continue;
+        }
+        const int kernel_width = (TYPE == 3) ? 4 : 2;
+        const float ax = 1.0f / (antialias ? fx : 1.0f);
+        const float ay = 1.0f / (antialias ? fy : 1.0f);
+        const int rx = (fx < 1.0f) ? 2 : (int)ceilf((float)kernel_width / ax);
+        const int ry = (fy < 1.0f) ? 2 : (int)ceilf((float)kernel_width / ay);
+        for (int c0 = 0; c0 < out.c; c0 += 4) {
+            const int nc = min(4, out.c - c0);
+            float sum[4] = {0.f, 0.f, 0.f, 0.f};
+            float wsum = 0;
+            for (int y = y_in_round - ry; y <= y_in_round + ry; y++) {
+                if (y < 0 || y >= in.h) continue;
+                const float dy = y_in - y;
+                const float cy = (TYPE == 3) ? bicubicCoeff(ay * dy) : triangleCoeff(ay * dy);
                 for (int x = x_in_round - rx; x <= x_in_round + rx; x++) {
-                    if (y < 0 || x < 0) continue;
-                    if (y >= in.h || x >= in.w) continue;
+                    if (x < 0 || x >= in.w) continue;
                     const float dx = x_in - x;
-                    const float dy = y_in - y;
-                    float w;
-                    if (TYPE == 3) w = (ax * bicubicCoeff(ax * dx)) * ay * bicubicCoeff(ay * dy);
-                    else           w = (ax * triangleCoeff(ax * dx)) * ay * triangleCoeff(ay * dy);
-                    sum = sum + w * __ldg(in.p + in.off(n, c, y, x));
+                    const float cx = (TYPE == 3) ? bicubicCoeff(ax * dx) : triangleCoeff(ax * dx);
+                    const float w = (ax * cx) * ay * cy;
+                    if (w == 0.f) continue;
+                    const float* ip = in.p + in.off(n, c0, y, x);
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (j < nc) sum[j] = sum[j] + w * __ldg(ip + (long long)j * in.sc);
                     wsum += w;
                 }
-            result = (!wsum) ? 0 : (sum / wsum);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (j < nc) out.p[out.off(n, c0 + j, y_out, x_out)] = (!wsum) ? 0 : (sum[j] / wsum);
         }
-        out.p[out.off(n, c, y_out, x_out)] = result;
     }
 }
 
@@ -438,7 +448,7 @@ int fn2_resample_forward(const fn2_tensor* bottom, const fn2_tensor* top, int ty
     const float fy = (float)in.h / (float)out.h;
     const int isDown = (fx > 1) || (fy > 1);
     const int aa = isDown && antialias;
-    const int grid = ew_grid(out.count(), 256);
+    const int grid = ew_grid((long long)out.n * out.h * out.w, 256);
     cudaStream_t s = (cudaStream_t)stream;
     if (type == 1) resample_kernel<1><<<grid, 256, 0, s>>>(in, out, fx, fy, aa);
     else if (type == 2) resample_kernel<2><<<grid, 256, 0, s>>>(in, out, fx, fy, aa);

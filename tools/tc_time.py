@@ -4,7 +4,7 @@ import ctypes as C, torch
 from flownet2_b200 import ops, lib, check, fn2_conv_desc
 cl = torch.channels_last
 l = lib()
-for (N, Ci, H, W, Co, k, s, p) in [(4, 473, 56, 128, 256, 3, 1, 1), (4, 12, 448, 1024, 64, 7, 2, 3), (4, 82, 448, 1024, 16, 3, 1, 1)]:
+for (N, Ci, H, W, Co, k, s, p) in [(4, 473, 56, 128, 256, 3, 1, 1), (4, 12, 448, 1024, 64, 7, 2, 3), (4, 82, 448, 1024, 16, 3, 1, 1), (4, 64, 448, 1024, 64, 3, 2, 1), (4, 162, 224, 512, 32, 3, 1, 1)]:
     Cp = (Ci + 31) // 32 * 32 if Ci >= 32 else (Ci + 3) // 4 * 4
     x = torch.randn(N, Cp, H, W, device="cuda").contiguous(memory_format=cl)[:, :Ci]
     w = torch.randn(Co, Ci, k, k, device="cuda") * 0.02
