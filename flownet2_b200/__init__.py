@@ -33,7 +33,7 @@ class fn2_conv_desc(C.Structure):
     _fields_ = [("ci", C.c_int32), ("co", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
                 ("stride_h", C.c_int32), ("stride_w", C.c_int32), ("pad_h", C.c_int32), ("pad_w", C.c_int32),
                 ("deconv", C.c_int32), ("has_bias", C.c_int32), ("relu", C.c_int32), ("negative_slope", C.c_float),
-                ("engine", C.c_int32)]
+                ("engine", C.c_int32), ("input_guard_bytes", C.c_int32)]
 
 
 def lib_path():

@@ -6,7 +6,7 @@ namespace caffe {
 
 template <typename Dtype>
 Blob<Dtype>::~Blob() {
-    if (own_dev_ && dev_) cudaFree(dev_);
+    if (own_dev_ && dev_) cudaFree(dev_ - kGuardFloats);
 }
 
 template <typename Dtype>
@@ -29,7 +29,7 @@ void Blob<Dtype>::Reshape(const vector<int>& shape) {
     shape_ = shape;
     count_ = (int)cnt;
     cstride_ = compute_cstride();
-    if (own_dev_ && dev_) { cudaFree(dev_); }
+    if (own_dev_ && dev_) { cudaFree(dev_ - kGuardFloats); }
     if (own_dev_ || !dev_) { dev_ = nullptr; own_dev_ = false; }
     host_.clear();
     head_ = UNINIT;
@@ -67,10 +67,14 @@ void Blob<Dtype>::alloc_device() {
     if (dev_) return;
     size_t n = storage_floats();
     if (n == 0) n = 1;
-    CUDA_CHECK(cudaMalloc(&dev_, n * sizeof(Dtype)));
+    // kGuardFloats readable floats on both sides: the small-Ci tensor-core convolution fetches whole kernel rows and
+    // reaches a few pixels outside the tensor at the image corners (those values are masked, never used)
+    Dtype* base = nullptr;
+    CUDA_CHECK(cudaMalloc(&base, (n + 2 * kGuardFloats) * sizeof(Dtype)));
     // channel padding must read as zero forever (weights for padded channels are zero, but
     // 0 * NaN would poison the tensor-core path)
-    CUDA_CHECK(cudaMemset(dev_, 0, n * sizeof(Dtype)));
+    CUDA_CHECK(cudaMemset(base, 0, (n + 2 * kGuardFloats) * sizeof(Dtype)));
+    dev_ = base + kGuardFloats;
     own_dev_ = true;
 }
 
@@ -199,7 +203,7 @@ void Blob<Dtype>::AliasInto(Blob* parent, int c0) {
     CHECK(!dev_ || !own_dev_ || head_ == UNINIT) << "blob already has device data";
     CHECK(num() == parent->num() && height() == parent->height() && width() == parent->width());
     CHECK(c0 >= 0 && c0 + channels() <= parent->channels());
-    if (own_dev_ && dev_) cudaFree(dev_);
+    if (own_dev_ && dev_) cudaFree(dev_ - kGuardFloats);
     dev_ = nullptr; own_dev_ = false;
     parent_ = parent;
     parent_c0_ = c0;
@@ -210,7 +214,7 @@ template <typename Dtype>
 void Blob<Dtype>::BindExternal(Dtype* dev) {
     CHECK(layout_ == PLAIN && !parent_) << "only PLAIN blobs can be bound to the parameter arena";
     const Dtype* h = cpu_data();           // bring current contents to the host
-    if (own_dev_ && dev_) cudaFree(dev_);
+    if (own_dev_ && dev_) cudaFree(dev_ - kGuardFloats);
     dev_ = dev; own_dev_ = false;
     if (count_) CUDA_CHECK(cudaMemcpy(dev_, h, (size_t)count_ * sizeof(Dtype), cudaMemcpyHostToDevice));
     head_ = SYNCED;
@@ -221,7 +225,7 @@ void Blob<Dtype>::ShareData(Blob& other) {
     CHECK_EQ(count_, other.count_);
     CHECK(layout_ == other.layout_);
     other.gpu_data();
-    if (own_dev_ && dev_) cudaFree(dev_);
+    if (own_dev_ && dev_) cudaFree(dev_ - kGuardFloats);
     dev_ = other.dev_; own_dev_ = false;
     cstride_ = other.cstride_;
     head_ = AT_GPU;

@@ -55,6 +55,7 @@ class Blob {
 
     // Make this blob a channel-range view [c0, c0+channels) into `parent`'s NHWC storage
     // (zero-copy Concat).  The blob keeps its own logical shape.
+    static constexpr int kGuardFloats = 256;   // guard band (floats) before and after every owned device allocation
     void AliasInto(Blob* parent, int c0);
     bool is_alias() const { return parent_ != nullptr; }
     const Blob* alias_parent() const { return parent_; }

@@ -5,7 +5,9 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <random>
+#include <set>
 
 #include "layer.hpp"
 
@@ -421,7 +423,7 @@ template <typename Dtype>
 class BaseConvolutionLayer : public Layer<Dtype> {
  public:
     explicit BaseConvolutionLayer(const LayerParameter& p, bool deconv) : Layer<Dtype>(p), deconv_(deconv) {}
-    ~BaseConvolutionLayer() override { if (packed_) cudaFree(packed_); if (ws_) cudaFree(ws_); }
+    ~BaseConvolutionLayer() override { for (auto& kv : packed_) if (kv.second.p) cudaFree(kv.second.p); if (ws_) cudaFree(ws_); }
     int MinBottomBlobs() const override { return 1; }
     int MinTopBlobs() const override { return 1; }
     bool EqualNumBottomTopBlobs() const override { return true; }
@@ -444,6 +446,7 @@ class BaseConvolutionLayer : public Layer<Dtype> {
             if (!strcmp(e, "simt")) d_.engine = 1;
             else if (!strcmp(e, "tc")) d_.engine = 0;
         }
+        d_.input_guard_bytes = Blob<Dtype>::kGuardFloats * (int)sizeof(Dtype);   // every blob's device storage has it
         relu_.assign(top.size(), 0);
         slope_.assign(top.size(), 0.f);
         if (this->blobs_.size() > 0) {
@@ -463,7 +466,7 @@ class BaseConvolutionLayer : public Layer<Dtype> {
         int Ho, Wo;
         FN2_CALL(fn2_conv_out_shape(&d_, bottom[0]->height(), bottom[0]->width(), &Ho, &Wo));
         for (size_t i = 0; i < top.size(); ++i) top[i]->Reshape(bottom[0]->num(), d_.co, Ho, Wo);
-        bottom_cstride_ = bottom[0]->channel_stride();
+        bottoms_.assign(bottom.begin(), bottom.end());
         size_t need = 0;
         FN2_CALL(fn2_conv_workspace_bytes(&d_, bottom[0]->num(), bottom[0]->height(), bottom[0]->width(), &need));
         if (need > ws_bytes_) {
@@ -477,16 +480,23 @@ class BaseConvolutionLayer : public Layer<Dtype> {
         FillBlob(cp.weight_filler(), this->blobs_[0].get(), seed * 2 + 1);
         if (d_.has_bias) FillBlob(cp.bias_filler(), this->blobs_[1].get(), seed * 2 + 2);
     }
+    // The packed layout depends on the bottom's pixel stride (small-Ci packing modes), which zero-copy concat aliasing can
+    // change after Reshape and which may differ between the bottoms of one layer: one packed copy per distinct stride.
     void ParamsChanged() override {
-        size_t floats = 0;
-        const int cis = bottom_cstride_ > 0 ? bottom_cstride_ : d_.ci;
-        FN2_CALL(fn2_conv_packed_floats(&d_, cis, &floats));
-        if (floats > packed_floats_) {
-            if (packed_) cudaFree(packed_);
-            CUDA_CHECK(cudaMalloc(&packed_, floats * sizeof(float)));
-            packed_floats_ = floats;
+        std::set<int> strides;
+        for (const Blob<Dtype>* b : bottoms_) strides.insert(b->channel_stride() > 0 ? b->channel_stride() : d_.ci);
+        if (strides.empty()) strides.insert(d_.ci);
+        for (int cis : strides) {
+            size_t floats = 0;
+            FN2_CALL(fn2_conv_packed_floats(&d_, cis, &floats));
+            Packed& pk = packed_[cis];
+            if (floats > pk.floats) {
+                if (pk.p) cudaFree(pk.p);
+                CUDA_CHECK(cudaMalloc(&pk.p, floats * sizeof(float)));
+                pk.floats = floats;
+            }
+            FN2_CALL(fn2_conv_pack_weights(&d_, cis, this->blobs_[0]->gpu_data(), pk.p, S()));
         }
-        FN2_CALL(fn2_conv_pack_weights(&d_, cis, this->blobs_[0]->gpu_data(), packed_, S()));
     }
     void WorkEstimate(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top, double* flops,
                       double* bytes) const override {
@@ -506,12 +516,14 @@ class BaseConvolutionLayer : public Layer<Dtype> {
     }
  protected:
     void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
-        CHECK(packed_) << "convolution weights were never loaded/packed";
         for (size_t i = 0; i < bottom.size(); ++i) {
             fn2_conv_desc d = d_;
             d.relu = relu_[i]; d.negative_slope = slope_[i];
             fn2_tensor b = bottom[i]->tensor(), t = top[i]->mutable_tensor();
-            FN2_CALL(fn2_conv_forward(&d, &b, packed_, d_.has_bias ? this->blobs_[1]->gpu_data() : nullptr, &t, ws_,
+            auto it = packed_.find(bottom[i]->channel_stride() > 0 ? bottom[i]->channel_stride() : d_.ci);
+            CHECK(it != packed_.end() && it->second.p) << "convolution weights were never packed for this bottom layout";
+            const float* packed = it->second.p;
+            FN2_CALL(fn2_conv_forward(&d, &b, packed, d_.has_bias ? this->blobs_[1]->gpu_data() : nullptr, &t, ws_,
                                       ws_bytes_, S()));
         }
     }
@@ -519,11 +531,11 @@ class BaseConvolutionLayer : public Layer<Dtype> {
     fn2_conv_desc d_;
     vector<int> relu_;
     vector<float> slope_;
-    float* packed_ = nullptr;
-    size_t packed_floats_ = 0;
+    struct Packed { float* p = nullptr; size_t floats = 0; };
+    std::map<int, Packed> packed_;        // by bottom pixel stride
+    vector<const Blob<Dtype>*> bottoms_;
     void* ws_ = nullptr;
     size_t ws_bytes_ = 0;
-    int bottom_cstride_ = 0;
 };
 
 template <typename Dtype>

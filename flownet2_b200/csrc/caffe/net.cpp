@@ -152,6 +152,12 @@ void Net<Dtype>::AliasConcats() {
                 for (int t : top_id_vecs_[lj]) if (t == top_id_vecs_[li][0]) writes_top = true;
                 if (writes_top) ok = false;
             }
+            // a bottom that also feeds a convolution with few input channels stays dense: the tensor-core engine then
+            // fetches whole kernel rows per TMA box (and needs 16-byte aligned pixels), which beats saving this copy
+            for (size_t lj = 0; lj < layers_.size() && ok; lj++) {
+                if (string(layers_[lj]->type()) != "Convolution" || bl->channels() > 16) continue;
+                for (int bb : bottom_id_vecs_[lj]) if (bb == bid) ok = false;
+            }
             seen.insert(bid);
             if (ok) bl->AliasInto(top, c0);
             c0 += bl->channels();

@@ -44,6 +44,9 @@ struct TcParams {
     int cl, ntiles, ntiles_p, cotiles, total;     // cluster size (W multicast); pixel tiles (real / padded to cl), Co tiles, all tiles
     float comp_a, comp_b;                         // RZ bias model: shrink(n MMAs) = comp_a + comp_b * n
     int gcs;                                      // tap-group packing for Ci <= 16: padded channels per tap (4/8/12/16), 0 = off
+    // kernel-row packing for Ci <= 16 on a dense input (pixel stride == rcs floats, guard band around the blob): the kw taps
+    // of one kernel row are CONTIGUOUS in memory for every output pixel, so one K block = 32 consecutive floats of that run.
+    int rowmode, rcs, rblocks, rsteps, rkw, rpad, rW;   // rblocks = ceil(kw*rcs/32) K blocks per kernel row, rsteps = kh*rblocks
     int dbg;                                      // FN2_TC_DBG bits: 1 skip MMAs, 2 skip conversion math, 4 skip drain loads, 8 skip TMA A
     short dy[49], dx[49], widx[49];
 };
@@ -212,7 +215,7 @@ __device__ __forceinline__ TcTile tc_decode_tile(const TcParams& p, int tile) {
     t.tap0 = p.cls_tap0[t.cls]; t.ntaps = p.cls_ntaps[t.cls];
     if (t.u0 >= p.cls_Hu[t.cls] || t.v0 >= p.cls_Wu[t.cls]) t.valid = false;      // tile outside this (smaller) parity class
     const int gsz = p.gcs ? 32 / p.gcs : 1;
-    t.steps = p.gcs ? (t.ntaps + gsz - 1) / gsz : t.ntaps * p.cblocks;
+    t.steps = p.rowmode ? p.rsteps : (p.gcs ? (t.ntaps + gsz - 1) / gsz : t.ntaps * p.cblocks);
     return t;
 }
 
@@ -283,7 +286,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         tma_load_4d(wh + G::B_TILE_BYTES, &mapW, bar, c0, T.co0, blk, 1);
                     }
                 };
-                if (gcs) {
+                if (p.rowmode) {
+                    // one box per step: {32 floats of the kernel-row run, tw output pixels (stride su pixels), th rows}
+                    int r = 0, kb = 0;
+#pragma unroll 1
+                    for (int i = 0; i < T.steps; i++) {
+                        mbar_wait_t(&done[s], ph, &w0, timed);
+                        unsigned char* st = smem + (size_t)s * G::STAGE_BYTES;
+                        mbar_expect_tx(&full[s], (uint32_t)G::STAGE_BYTES);
+                        tma_load_4d(st, &mapA, &full[s], kb * 32, T.v0, cy0 + p.dy[r * p.rkw], T.n);
+                        load_w(st, &full[s], 0, i);
+                        if (++kb == p.rblocks) { kb = 0; ++r; }
+                        if (++s == G::R) { s = 0; ph ^= 1u; }
+                    }
+                } else if (gcs) {
                     // several taps share one 32-wide K block: one small box {gcs channels, tw, th} per tap
                     const int box_bytes = 128 * gcs * 4;
                     for (int i = 0, t0 = 0; i < T.steps; i++, t0 += gsz) {
@@ -398,14 +414,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                     for (int j = 0; j < 32; j++) { hi[j] = 0x3f800000u; lo[j] = 0; }
                 } else {
+                    // row mode: taps that fall outside the image row (and the K padding) hold whatever follows in memory
+                    int k_lo = 0, k_hi = 32;
+                    if (p.rowmode) {
+                        const int x0 = (T.v0 + m % p.tw) * p.su - p.rpad;            // input column of tap 0
+                        const int kb32 = (i % p.rblocks) * 32;
+                        k_lo = max(0, -x0) * p.rcs - kb32;
+                        k_hi = min(p.rkw, p.rW - x0) * p.rcs - kb32;
+                    }
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
+                        const bool keep = 4 * j >= k_lo && 4 * j < k_hi;
                         const float f[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
-                            const uint32_t h = to_tf32(f[e]);
+                            const uint32_t h = keep ? to_tf32(f[e]) : 0u;
                             hi[4 * j + e] = h;
-                            lo[4 * j + e] = to_tf32(f[e] - __uint_as_float(h));
+                            lo[4 * j + e] = keep ? to_tf32(f[e] - __uint_as_float(h)) : 0u;
                         }
                     }
                 }
@@ -573,6 +598,28 @@ __global__ void tc_pack_group_kernel(const float* __restrict__ w, float* __restr
     }
 }
 
+// row-packed weights for Ci <= 16: [hi|lo][r*rblocks + kb][Co][32], K index kb*32 + k = s*cs + ci of kernel row r
+__global__ void tc_pack_row_kernel(const float* __restrict__ w, float* __restrict__ wp, int Ci, int Co, int kh, int kw, int cs, int rblocks) {
+    const long long per = (long long)kh * rblocks * Co * 32;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per; idx += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(idx % 32);
+        long long r_ = idx / 32;
+        const int co = (int)(r_ % Co);
+        const int blk = (int)(r_ / Co);
+        const int r = blk / rblocks, kk = (blk % rblocks) * 32 + k;
+        const int sx = kk / cs, ci = kk % cs;
+        float v = 0.f;
+        if (sx < kw && ci < Ci) v = w[(((long long)co * Ci + ci) * kh + r) * kw + sx];
+        uint32_t h;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+        const float hi = __uint_as_float(h);
+        uint32_t l;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
+        wp[idx] = hi;
+        wp[per + idx] = __uint_as_float(l);
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -613,11 +660,21 @@ int tc_enabled() {
 
 }  // namespace
 
-// tap-group packing applies to plain convolutions with at most 16 input channels
-static int tc_group_cs(const fn2_conv_desc* d) {
-    if (d->deconv || d->ci > 16 || d->kh * d->kw < 2) return 0;
-    if (getenv("FN2_TC_NOPACK")) return 0;
-    return (d->ci + 3) / 4 * 4;
+// Small-Ci packing (plain convolutions with at most 16 input channels): mode 1 = tap groups (several taps share a 32-wide
+// K block, one small TMA box per tap), mode 2 = kernel rows (needs a dense input whose pixel stride equals the padded
+// channel count, and a guard band around the tensor because the row runs of the edge pixels reach a little outside it).
+struct TcSmallCi { int mode, cs, gs, ngroups, rblocks; };
+static TcSmallCi tc_small_ci(const fn2_conv_desc* d, int ci_stride) {
+    TcSmallCi m = {0, 0, 0, 0, 0};
+    if (d->deconv || d->ci > 16 || d->kh * d->kw < 2) return m;
+    if (getenv("FN2_TC_NOPACK")) return m;
+    m.cs = (d->ci + 3) / 4 * 4;
+    m.gs = 32 / m.cs;
+    m.ngroups = (d->kh * d->kw + m.gs - 1) / m.gs;
+    m.rblocks = (d->kw * m.cs + 31) / 32;
+    m.mode = 1;
+    if (d->input_guard_bytes >= 512 && ci_stride == m.cs && d->kh * m.rblocks <= m.ngroups && !getenv("FN2_TC_NOROW")) m.mode = 2;
+    return m;
 }
 
 int conv_tc_eligible(const fn2_conv_desc* d, const T4& in, const T4& out) {
@@ -634,12 +691,11 @@ int conv_tc_eligible(const fn2_conv_desc* d, const T4& in, const T4& out) {
 }
 
 int conv_tc_packed_floats(const fn2_conv_desc* d, int ci_stride, size_t* floats) {
-    (void)ci_stride;
     const int cip = (d->ci + 31) / 32 * 32;
-    const int gcs = tc_group_cs(d);
-    if (gcs) {
-        const int gs = 32 / gcs, ngroups = (d->kh * d->kw + gs - 1) / gs;
-        *floats = (d->co % 16 == 0) ? (size_t)2 * ngroups * d->co * 32 : 0;
+    const TcSmallCi sm = tc_small_ci(d, ci_stride);
+    if (sm.mode) {
+        const int nblk = sm.mode == 2 ? d->kh * sm.rblocks : sm.ngroups;
+        *floats = (d->co % 16 == 0) ? (size_t)2 * nblk * d->co * 32 : 0;
         return FN2_OK;
     }
     *floats = (d->co % 16 == 0) ? (size_t)2 * d->kh * d->kw * d->co * cip : 0;
@@ -651,10 +707,10 @@ int conv_tc_pack(const fn2_conv_desc* d, int ci_stride, const float* w, float* w
     conv_tc_packed_floats(d, ci_stride, &floats);
     if (!floats) return FN2_OK;
     const int cip = (d->ci + 31) / 32 * 32;
-    const int gcs = tc_group_cs(d);
-    if (gcs) {
-        const int gs = 32 / gcs, ngroups = (d->kh * d->kw + gs - 1) / gs;
-        tc_pack_group_kernel<<<ew_grid((long long)floats / 2, 256), 256, 0, st>>>(w, wp, d->ci, d->co, d->kh, d->kw, gcs, ngroups);
+    const TcSmallCi sm = tc_small_ci(d, ci_stride);
+    if (sm.mode) {
+        if (sm.mode == 2) tc_pack_row_kernel<<<ew_grid((long long)floats / 2, 256), 256, 0, st>>>(w, wp, d->ci, d->co, d->kh, d->kw, sm.cs, sm.rblocks);
+        else tc_pack_group_kernel<<<ew_grid((long long)floats / 2, 256), 256, 0, st>>>(w, wp, d->ci, d->co, d->kh, d->kw, sm.cs, sm.ngroups);
         FN2_LAUNCH_CHECK();
         return FN2_OK;
     }
@@ -688,14 +744,15 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
     if (const char* e = getenv("FN2_TC_COMP_B")) p.comp_b = (float)atof(e);
     { const char* e = getenv("FN2_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
 
-    p.gcs = tc_group_cs(d);
+    const TcSmallCi sm = tc_small_ci(d, (int)in.sw);
+    p.gcs = sm.mode == 1 ? sm.cs : 0;
+    p.rowmode = sm.mode == 2; p.rcs = sm.cs; p.rblocks = sm.rblocks; p.rsteps = d->kh * sm.rblocks; p.rkw = d->kw; p.rpad = d->pad_w; p.rW = in.w;
     { const char* e = getenv("FN2_TC_CL"); p.cl = e ? atoi(e) : 1; if (p.cl != 1 && p.cl != 2 && p.cl != 4) p.cl = 1; if (NT / p.cl < 8) p.cl = NT / 8; }
     // weights: [2][taps][Co][cip]   (group mode: [2][groups][Co][32])
     CUtensorMap mapW;
     {
-        const int gs = p.gcs ? 32 / p.gcs : 1;
-        const int kin = p.gcs ? 32 : cip;
-        const int nblk = p.gcs ? (d->kh * d->kw + gs - 1) / gs : d->kh * d->kw;
+        const int kin = sm.mode ? 32 : cip;
+        const int nblk = sm.mode == 2 ? p.rsteps : (sm.mode == 1 ? sm.ngroups : d->kh * d->kw);
         cuuint64_t dims[4] = {(cuuint64_t)kin, (cuuint64_t)d->co, (cuuint64_t)nblk, 2};
         cuuint64_t strides[3] = {(cuuint64_t)kin * 4, (cuuint64_t)kin * d->co * 4, (cuuint64_t)kin * d->co * nblk * 4};
         cuuint32_t box[4] = {32, (cuuint32_t)(NT / p.cl), 1, 1};
@@ -718,7 +775,16 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
         cuuint64_t strides[3] = {(cuuint64_t)in.sw * 4, (cuuint64_t)in.sh * 4, (cuuint64_t)in.sn * 4};
         cuuint32_t box[4] = {(cuuint32_t)(p.gcs ? p.gcs : 32), (cuuint32_t)(p.tw * su), (cuuint32_t)(p.th * sv), 1};
         cuuint32_t es[4] = {1, (cuuint32_t)su, (cuuint32_t)sv, 1};
-        CUresult r = enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)in.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        const float* baseA = in.p;
+        if (p.rowmode) {
+            // dim0: the run of kw*cs floats that starts pad_w pixels left of the output pixel's first tap column;
+            // dim1: output column (consecutive runs overlap: stride = su pixels); dim2: input row; dim3: sample
+            dims[0] = (cuuint64_t)p.rblocks * 32; dims[1] = (cuuint64_t)p.cls_Wu[0];
+            strides[0] = (cuuint64_t)su * p.rcs * 4;
+            box[1] = (cuuint32_t)p.tw; es[1] = 1;
+            baseA = in.p - (long long)p.rpad * p.rcs;
+        }
+        CUresult r = enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)baseA, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          p.gcs ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv_tc: activation tensor map failed (%d)", (int)r); return FN2_ERR_CUDA; }

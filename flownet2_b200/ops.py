@@ -117,7 +117,7 @@ def mean_subtract(top, mean_pp=None, mean_pc=None, per_pixel=False):
 
 
 def conv2d(x, weight, bias=None, stride=1, pad=0, deconv=False, relu_slope=None, engine=0, channels_last_out=None,
-           use_workspace=True):
+           use_workspace=True, input_guard_bytes=0):
     """weight in Caffe layout: conv [co,ci,kh,kw], deconv [ci,co,kh,kw]."""
     l = lib()
     if deconv:
@@ -127,7 +127,7 @@ def conv2d(x, weight, bias=None, stride=1, pad=0, deconv=False, relu_slope=None,
     sh, sw = (stride, stride) if isinstance(stride, int) else stride
     ph, pw = (pad, pad) if isinstance(pad, int) else pad
     d = fn2_conv_desc(ci, co, kh, kw, sh, sw, ph, pw, 1 if deconv else 0, 1 if bias is not None else 0,
-                      1 if relu_slope is not None else 0, float(relu_slope or 0.0), engine)
+                      1 if relu_slope is not None else 0, float(relu_slope or 0.0), engine, input_guard_bytes)
     ho, wo = C.c_int(), C.c_int()
     check(l.fn2_conv_out_shape(C.byref(d), x.shape[2], x.shape[3], C.byref(ho), C.byref(wo)))
     cis = x.stride(3) if x.stride(1) == 1 else ci

@@ -123,6 +123,8 @@ typedef struct fn2_conv_desc {
     int32_t relu;              /* 1: apply x>0 ? x : x*negative_slope in the epilogue */
     float negative_slope;
     int32_t engine;            /* 0 default (tensor cores when eligible), 1 SIMT fp32, 2 tcgen05 */
+    int32_t input_guard_bytes; /* readable (never used) bytes the caller guarantees before AND after the bottom tensor's
+                                * storage; >= 512 lets small-Ci convolutions fetch whole kernel rows per TMA box. 0 = none */
 } fn2_conv_desc;
 
 /* Packed weight size (floats) and packing from Caffe layout: conv [co][ci][kh][kw]

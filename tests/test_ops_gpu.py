@@ -250,6 +250,41 @@ def test_conv_tcgen05_engine(ops, case):
     assert abs(shrink) < 1e-7, shrink
 
 
+ROW_CASES = [
+    # N, Ci, H, W, Co, k, stride, pad   (dense small-Ci input + guard band -> kernel-row packing of the tcgen05 engine)
+    (2, 3, 20, 28, 64, 7, 2, 3),        # FlowNetC conv1: one 32-float K block per kernel row
+    (1, 3, 23, 37, 64, 7, 2, 3),        # odd sizes: masked taps on both image edges, partial tiles
+    (1, 12, 20, 28, 64, 7, 2, 3),       # stacked FlowNetS conv1: three K blocks per kernel row
+    (1, 6, 18, 22, 64, 3, 1, 1),        # FlowNet-SD conv0: stride 1
+    (2, 4, 9, 150, 32, 5, 1, 2),        # a row wider than one tile
+]
+
+
+@pytest.mark.parametrize("case", ROW_CASES)
+def test_conv_tcgen05_row_mode(ops, case):
+    """The guard band is filled with NaN: the row runs of edge pixels reach into it (and into the neighbouring image
+    rows), and none of that may leak into the result."""
+    N, Ci, H, W, Co, k, s, p = case
+    r = rng(hash(case) % 2**31)
+    x = r.standard_normal((N, Ci, H, W)).astype(np.float32)
+    w = (r.standard_normal((Co, Ci, k, k)) * np.sqrt(2.0 / (Ci * k * k))).astype(np.float32)
+    b = r.standard_normal(Co).astype(np.float32)
+    want = O.relu(O.conv_fwd(x, w, b, s, p, f64acc=True), 0.1)
+    cp = (Ci + 3) // 4 * 4
+    guard = 256                                                       # floats, == Blob::kGuardFloats
+    flat = torch.full((guard + N * H * W * cp + guard,), float("nan"), device="cuda")
+    body = flat[guard:guard + N * H * W * cp].view(N, H, W, cp)
+    body.zero_()
+    body[..., :Ci] = torch.from_numpy(x).cuda().permute(0, 2, 3, 1)
+    xv = body.permute(0, 3, 1, 2)[:, :Ci]                             # NCHW view of the NHWC storage
+    got = host(ops.conv2d(xv, dev(w), torch.from_numpy(b).cuda(), s, p, False, 0.1, 2, input_guard_bytes=4 * guard))
+    assert np.isfinite(got).all()
+    scale = max(1.0, np.abs(want).max())
+    assert maxabs(got, want) <= 1e-6 * scale
+    ungarded = host(ops.conv2d(xv, dev(w), torch.from_numpy(b).cuda(), s, p, False, 0.1, 2))
+    assert maxabs(ungarded, want) <= 1e-6 * scale                     # tap-group packing (no guard promised)
+
+
 def test_deconv_known_answer(ops):
     # the reference's TestSimpleDeconvolution (test_deconvolution_layer.cpp:91-137): input and
     # weights all ones, bias 0.1, 3 in / 4 out channels, kernel 3 stride 2: 3.1 / 6.1 / 12.1
