@@ -17,7 +17,8 @@ namespace fn2 {
 
 int conv_tc_eligible(const fn2_conv_desc* d, const T4& in, const T4& out);
 int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const float* bias,
-                    const T4& out, cudaStream_t st);
+                    const T4& out, float* ws, size_t ws_floats, cudaStream_t st);
+size_t conv_tc_workspace_floats(const fn2_conv_desc* d, int N, int Ho, int Wo);
 int conv_tc_packed_floats(const fn2_conv_desc* d, int ci_stride, size_t* floats);
 int conv_tc_pack(const fn2_conv_desc* d, int ci_stride, const float* w, float* wp, cudaStream_t st);
 int conv_nhwc_eligible(const fn2_conv_desc* d, const T4& in, const T4& out);
@@ -442,7 +443,7 @@ int fn2_conv_workspace_bytes(const fn2_conv_desc* d, int N, int H, int W, size_t
     int Ho, Wo;
     int rc = fn2_conv_out_shape(d, H, W, &Ho, &Wo);
     if (rc) return rc;
-    *bytes = conv_nhwc_workspace_floats(d, N, Ho, Wo) * sizeof(float);
+    *bytes = max(conv_nhwc_workspace_floats(d, N, Ho, Wo), conv_tc_workspace_floats(d, N, Ho, Wo)) * sizeof(float);
     return FN2_OK;
 }
 
@@ -458,7 +459,7 @@ int fn2_conv_forward(const fn2_conv_desc* d, const fn2_tensor* bottom, const flo
     cudaStream_t st = (cudaStream_t)stream;
     const long long simt_floats = (long long)d->kh * d->kw * d->ci * d->co;
     if (d->engine != 1 && conv_tc_eligible(d, in, out))
-        return conv_tc_forward(d, in, packed_weights_dev + simt_floats, bias_dev, out, st);
+        return conv_tc_forward(d, in, packed_weights_dev + simt_floats, bias_dev, out, (float*)workspace, workspace_bytes / sizeof(float), st);
     FN2_CHECK_ARG(d->engine != 2, "conv: tcgen05 engine requested but the shape/layout is not eligible");
     if (conv_nhwc_eligible(d, in, out))
         return conv_nhwc_forward(d, in, packed_weights_dev, bias_dev, out, (float*)workspace, workspace_bytes / sizeof(float), st);

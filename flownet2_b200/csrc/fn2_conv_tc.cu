@@ -41,6 +41,7 @@ struct TcParams {
     float slope;
     int tw, th, tiles_x, tiles_y;
     int kd;                                       // channel blocks per tensor-core accumulation chain
+    int splits, Ho, Wo;                           // split-K: K ranges per tile (partials go to the workspace), output size
     int cl, ntiles, ntiles_p, cotiles, total;     // cluster size (W multicast); pixel tiles (real / padded to cl), Co tiles, all tiles
     float comp_a, comp_b;                         // RZ bias model: shrink(n MMAs) = comp_a + comp_b * n
     int gcs;                                      // tap-group packing for Ci <= 16: padded channels per tap (4/8/12/16), 0 = off
@@ -196,11 +197,14 @@ template <int NT> struct TcGeo {
 // one output tile: 128 pixels (th x tw) of one sample and parity class, NT output channels
 struct TcTile {
     int n, u0, v0, co0, cls, tap0, ntaps, steps;
+    int k0, split;                                // first K step of this unit, split index
     bool valid;
 };
 template <int NT>
 __device__ __forceinline__ TcTile tc_decode_tile(const TcParams& p, int tile) {
     TcTile t;
+    t.split = 0;
+    if (p.splits > 1) { t.split = tile % p.splits; tile /= p.splits; }   // splits of a tile run side by side (shared A tiles in L2)
     int pix = tile % p.ntiles_p;
     int r = tile / p.ntiles_p;
     const int cot = r % p.cotiles;
@@ -216,6 +220,12 @@ __device__ __forceinline__ TcTile tc_decode_tile(const TcParams& p, int tile) {
     if (t.u0 >= p.cls_Hu[t.cls] || t.v0 >= p.cls_Wu[t.cls]) t.valid = false;      // tile outside this (smaller) parity class
     const int gsz = p.gcs ? 32 / p.gcs : 1;
     t.steps = p.rowmode ? p.rsteps : (p.gcs ? (t.ntaps + gsz - 1) / gsz : t.ntaps * p.cblocks);
+    t.k0 = 0;
+    if (p.splits > 1) {
+        const int per = (t.steps + p.splits - 1) / p.splits;
+        t.k0 = min(t.steps, t.split * per);
+        t.steps = min(t.steps, t.k0 + per) - t.k0;
+    }
     return t;
 }
 
@@ -225,7 +235,7 @@ __device__ __forceinline__ TcTile tc_decode_tile(const TcParams& p, int tile) {
 template <int NT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const float* __restrict__ bias,
-               float* __restrict__ out, const TcParams p, long long* __restrict__ prof) {
+               float* __restrict__ out, float* __restrict__ ws, const TcParams p, long long* __restrict__ prof) {
     using G = TcGeo<NT>;
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::R * G::STAGE_BYTES);
@@ -315,7 +325,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         if (++s == G::R) { s = 0; ph ^= 1u; }
                     }
                 } else {
-                    int t = T.tap0, cb = 0;
+                    int t = T.tap0 + T.k0 / cblocks, cb = T.k0 % cblocks;
                     int cx = cx0 + p.dx[t], cy = cy0 + p.dy[t], wi = p.widx[t];
 #pragma unroll 1
                     for (int i = 0; i < T.steps; i++) {
@@ -527,19 +537,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             // epilogue
             const int u = T.u0 + yy, v = T.v0 + xx;
             if (T.valid && u < p.cls_Hu[T.cls] && v < p.cls_Wu[T.cls]) {
-                float* o = out + T.n * p.out_sn + (long long)(u * p.ou + p.cls_oy0[T.cls]) * p.out_sh +
-                           (long long)(v * p.ov + p.cls_ox0[T.cls]) * p.out_sw + T.co0;
+                const int oy = u * p.ou + p.cls_oy0[T.cls], ox = v * p.ov + p.cls_ox0[T.cls];
+                if (p.splits > 1) {
+                    // raw partial sums, dense [split][n][oy][ox][Co]; bias / ReLU are applied by the fixed-order reduction
+                    float* o = ws + ((((long long)T.split * p.N + T.n) * p.Ho + oy) * p.Wo + ox) * p.Co + T.co0;
 #pragma unroll
-                for (int j = 0; j < NT; j += 4) {
-                    float r[4];
+                    for (int j = 0; j < NT; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                } else {
+                    float* o = out + T.n * p.out_sn + (long long)oy * p.out_sh + (long long)ox * p.out_sw + T.co0;
 #pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        float x = acc[j + e];
-                        if (p.has_bias) x += __ldg(bias + T.co0 + j + e);
-                        if (p.relu) x = x > 0 ? x : x * p.slope;
-                        r[e] = x;
+                    for (int j = 0; j < NT; j += 4) {
+                        float r[4];
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            float x = acc[j + e];
+                            if (p.has_bias) x += __ldg(bias + T.co0 + j + e);
+                            if (p.relu) x = x > 0 ? x : x * p.slope;
+                            r[e] = x;
+                        }
+                        *reinterpret_cast<float4*>(o + j) = make_float4(r[0], r[1], r[2], r[3]);
                     }
-                    *reinterpret_cast<float4*>(o + j) = make_float4(r[0], r[1], r[2], r[3]);
                 }
             }
         }
@@ -620,6 +637,30 @@ __global__ void tc_pack_row_kernel(const float* __restrict__ w, float* __restric
     }
 }
 
+// fixed-order sum of the split-K partials + bias + ReLU (4 channels per thread)
+__global__ void tc_splitk_reduce_kernel(const float* __restrict__ ws, const float* __restrict__ bias, float* __restrict__ out, TcParams p) {
+    const int c4 = p.Co / 4;
+    const long long per = (long long)p.N * p.Ho * p.Wo * c4;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % c4) * 4;
+        long long m = idx / c4;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int z = 0; z < p.splits; z++) {
+            const float4 v = *reinterpret_cast<const float4*>(ws + ((long long)z * p.N * p.Ho * p.Wo + m) * p.Co + c);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        if (p.has_bias) { a.x += __ldg(bias + c); a.y += __ldg(bias + c + 1); a.z += __ldg(bias + c + 2); a.w += __ldg(bias + c + 3); }
+        if (p.relu) {
+            a.x = a.x > 0 ? a.x : a.x * p.slope; a.y = a.y > 0 ? a.y : a.y * p.slope;
+            a.z = a.z > 0 ? a.z : a.z * p.slope; a.w = a.w > 0 ? a.w : a.w * p.slope;
+        }
+        const int ox = (int)(m % p.Wo); m /= p.Wo;
+        const int oy = (int)(m % p.Ho);
+        const int n = (int)(m / p.Ho);
+        *reinterpret_cast<float4*>(out + n * p.out_sn + (long long)oy * p.out_sh + (long long)ox * p.out_sw + c) = a;
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -677,6 +718,34 @@ static TcSmallCi tc_small_ci(const fn2_conv_desc* d, int ci_stride) {
     return m;
 }
 
+// Split-K plan: layers whose tile list cannot fill the GPU (the 7x16 .. 14x32 maps of conv5/conv6/deconv5 with
+// K = 9 * 1024) cut every tile's K loop into `z` ranges that run on different SMs.
+static int tc_split_plan(const fn2_conv_desc* d, int N, int Ho, int Wo) {
+    if (getenv("FN2_TC_NOSPLIT")) return 1;
+    if (!d->deconv && d->ci <= 16) return 1;                       // small-Ci packing modes do not split
+    if (d->co % 16) return 1;
+    const int NT = (d->co % 128 == 0) ? 128 : (d->co % 64 == 0 ? 64 : (d->co % 32 == 0 ? 32 : 16));
+    const int sh = d->deconv ? d->stride_h : 1, sw = d->deconv ? d->stride_w : 1;
+    const int Hu = (Ho + sh - 1) / sh, Wu = (Wo + sw - 1) / sw, ncls = min(sh, Ho) * min(sw, Wo);
+    int tw = 8;
+    while (tw < Wu && tw < 128) tw *= 2;
+    const int th = 128 / tw;
+    const long long tiles = (long long)N * ((Wu + tw - 1) / tw) * ((Hu + th - 1) / th) * (d->co / NT) * ncls;
+    const int ntaps = d->deconv ? max(1, d->kh / sh) * max(1, d->kw / sw) : d->kh * d->kw;
+    const int steps = ntaps * ((d->ci + 31) / 32);
+    const int nsm = tc_num_sms();
+    if (tiles * 2 > nsm || steps < 32) return 1;
+    int z = (int)(nsm / tiles);
+    z = min(z, steps / 16);
+    z = min(z, 8);
+    return z < 2 ? 1 : z;
+}
+
+size_t conv_tc_workspace_floats(const fn2_conv_desc* d, int N, int Ho, int Wo) {
+    const int z = tc_split_plan(d, N, Ho, Wo);
+    return z > 1 ? (size_t)z * N * Ho * Wo * d->co : 0;
+}
+
 int conv_tc_eligible(const fn2_conv_desc* d, const T4& in, const T4& out) {
     if (!tc_enabled()) return 0;
     if (in.sc != 1 || out.sc != 1) return 0;
@@ -721,13 +790,17 @@ int conv_tc_pack(const fn2_conv_desc* d, int ci_stride, const float* w, float* w
 
 static inline int floordiv_i(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
-int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const float* bias, const T4& out, cudaStream_t st) {
+int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const float* bias, const T4& out, float* ws, size_t ws_floats,
+                    cudaStream_t st) {
     EncodeTiledFn enc = tc_encode_fn();
     if (!enc) { set_error("conv_tc: cuTensorMapEncodeTiled unavailable"); return FN2_ERR_CUDA; }
     const int NT = (d->co % 128 == 0) ? 128 : (d->co % 64 == 0 ? 64 : (d->co % 32 == 0 ? 32 : 16));
     const int cip = (d->ci + 31) / 32 * 32;
     TcParams p;
     p.N = in.n; p.Co = d->co; p.cblocks = cip / 32;
+    p.Ho = out.h; p.Wo = out.w;
+    p.splits = tc_split_plan(d, in.n, out.h, out.w);
+    if (p.splits > 1 && (!ws || ws_floats < (size_t)p.splits * in.n * out.h * out.w * d->co)) p.splits = 1;
     p.out_sn = out.sn; p.out_sh = out.sh; p.out_sw = out.sw;
     p.relu = d->relu; p.has_bias = d->has_bias; p.slope = d->negative_slope;
     p.kd = NT == 128 ? 2 : 4;                     // chains of 24 resp. 16 MMAs per chunk: end-to-end flow error == FP32 SIMT engine's
@@ -748,6 +821,7 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
     p.gcs = sm.mode == 1 ? sm.cs : 0;
     p.rowmode = sm.mode == 2; p.rcs = sm.cs; p.rblocks = sm.rblocks; p.rsteps = d->kh * sm.rblocks; p.rkw = d->kw; p.rpad = d->pad_w; p.rW = in.w;
     { const char* e = getenv("FN2_TC_CL"); p.cl = e ? atoi(e) : 1; if (p.cl != 1 && p.cl != 2 && p.cl != 4) p.cl = 1; if (NT / p.cl < 8) p.cl = NT / 8; }
+    if (p.cl > 1) p.splits = 1;                   // cluster mates must walk the same K steps to share W tiles
     // weights: [2][taps][Co][cip]   (group mode: [2][groups][Co][32])
     CUtensorMap mapW;
     {
@@ -791,7 +865,7 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
         p.ntiles = p.N * p.tiles_x * p.tiles_y;
         p.ntiles_p = (p.ntiles + p.cl - 1) / p.cl * p.cl;
         p.cotiles = d->co / NT;
-        p.total = p.ntiles_p * p.cotiles * p.ncls;
+        p.total = p.ntiles_p * p.cotiles * p.ncls * p.splits;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)min(p.total, tc_num_sms() / p.cl * p.cl), 1, 1);
         cfg.blockDim = dim3(TC_THREADS);
@@ -808,7 +882,7 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
                 attr_set = true;                                                                                        \
             }                                                                                                           \
             cfg.dynamicSmemBytes = TcGeo<NTV>::SMEM;                                                                    \
-            FN2_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<NTV>, mapA, mapW, bias, out.p, p, tc_prof_buffer()));      \
+            FN2_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<NTV>, mapA, mapW, bias, out.p, ws, p, tc_prof_buffer()));      \
         }
         if (NT == 128) FN2_TC_LAUNCH(128)
         else if (NT == 64) FN2_TC_LAUNCH(64)
@@ -816,6 +890,10 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
         else FN2_TC_LAUNCH(16)
 #undef FN2_TC_LAUNCH
         FN2_LAUNCH_CHECK();
+        if (p.splits > 1) {
+            tc_splitk_reduce_kernel<<<ew_grid((long long)p.N * p.Ho * p.Wo * (p.Co / 4), 256), 256, 0, st>>>(ws, bias, out.p, p);
+            FN2_LAUNCH_CHECK();
+        }
         return FN2_OK;
     };
     if (!d->deconv) {
