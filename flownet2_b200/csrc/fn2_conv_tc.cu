@@ -180,18 +180,25 @@ template <int NT> struct TcGeo {
     // or commit -- costs the issuing thread ~64-78 cycles once the queue is full, see profiles/r01_prof_tc128_*.)
     static constexpr int R = NT >= 64 ? 4 : 6;
     static constexpr int SMEM = R * STAGE_BYTES + 1024;
-    // tensor-memory columns.  Two chunk accumulators (double-buffered against the drain warps) followed by the A slots.
-    // NT == 128: the three products a_hi*w_hi, a_hi*w_lo, a_lo*w_hi all accumulate into the same NT columns.
+    // tensor-memory columns.  Two chunk accumulators (double-buffered against the drain warps), then (NT == 128 only) the
+    // cross-term accumulator, then the A slots.  The tensor core truncates on every accumulation, proportionally to the
+    // accumulator's magnitude, so the dominant a_hi*w_hi chain is kept short (a chunk of kd steps, 4 MMAs per step) and
+    // drained to FP32 registers, while the small cross terms a_hi*w_lo + a_lo*w_hi may chain over the whole tile.
+    // NT == 128 (SEPX): cross terms in their own 128 columns (drained once per tile); only two A slots fit, which is
+    //   enough because a converter only needs the MMAs of step i-2 retired before it stores step i.
     // NT <= 64 (WIDE): the W stage holds [w_hi rows ; w_lo rows] back to back, so ONE MMA with N = 2*NT computes
-    // a_hi*[w_hi|w_lo] into 2*NT columns and a second one adds a_lo*w_hi onto the last NT of them (the small cross terms
-    // share columns, the a_hi*w_hi chain keeps its own): 2 MMAs per K=8 slice instead of 3 (with A in tensor memory an
-    // MMA costs >= 64 cycles however small N is), and only 4 truncating accumulations per step on the dominant term.
+    //   a_hi*[w_hi|w_lo] into 2*NT columns and a second one adds a_lo*w_hi onto the last NT of them: 2 MMAs per K=8
+    //   slice instead of 3 (with A in tensor memory an MMA costs >= 64 cycles however small N is).
     static constexpr bool WIDE = NT <= 64;
+    static constexpr bool SEPX = !WIDE;
     static constexpr int ACCW = WIDE ? 2 * NT : NT;
-    static constexpr int MMAS_PER_STEP = WIDE ? 4 : 12;                            // length of the RZ chain per step
+    static constexpr int MMAS_PER_STEP = 4;                                        // length of the RZ chain per step
     static constexpr int COL_HH0 = 0, COL_HH1 = ACCW;
-    static constexpr int COL_A = 512 - 64 * R;                                     // slot s: hi at COL_A + 64*s, lo at +32
-    static_assert(2 * ACCW <= COL_A, "tensor memory overflow");
+    static constexpr int COL_X = 2 * ACCW;                                         // SEPX only
+    static constexpr int NSLOTS = SEPX ? 2 : R;                                    // must divide R
+    static constexpr int COL_A = 512 - 64 * NSLOTS;                                // slot a: hi at COL_A + 64*a, lo at +32
+    static_assert(2 * ACCW + (SEPX ? NT : 0) <= COL_A, "tensor memory overflow");
+    static_assert(R % NSLOTS == 0, "slot ring must divide the stage ring");
 };
 
 // one output tile: 128 pixels (th x tw) of one sample and parity class, NT output channels
@@ -244,7 +251,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     uint64_t* done = bars + 2 * G::R;              // [R]  MMAs of the step have retired: stage + slot are free
     uint64_t* acc_full = bars + 3 * G::R;          // [2]
     uint64_t* acc_free = acc_full + 2;             // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
+    uint64_t* x_free = acc_free + 2;               // [1]  drain has read the cross-term accumulator of the previous tile
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_free + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // CTAs of one cluster (p.cl consecutive blockIdx.x) always work on tiles with the same co0 and parity class, so they
@@ -260,6 +268,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (tid == 0) {
         for (int s = 0; s < G::R; s++) { mbar_init(&full[s], 1); mbar_init(&a_ready[s], 128); mbar_init(&done[s], p.cl); }
         for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_free[s], 128); }
+        mbar_init(x_free, 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -346,10 +355,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const int kd = p.kd;
             int s = 0, buf = 0;
             uint32_t ph = 0, pacc = 1u;                 // pacc: parity to wait on acc_free[buf] (flips every second chunk)
+            uint32_t px = 1u;                           // parity to wait on x_free (one phase per tile)
             for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x) {
                 const TcTile T = tc_decode_tile<NT>(p, tile);
                 if (!T.valid && skip_invalid) continue;
                 int in_chunk = 0;
+                if (G::SEPX && T.steps > 0) { mbar_wait_t(x_free, px, &w0, timed); px ^= 1u; }
 #pragma unroll 1
                 for (int i = 0; i < T.steps; i++) {
                     if (in_chunk == 0) mbar_wait_t(&acc_free[buf], pacc, &w0, timed);
@@ -358,7 +369,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     fence_after();
                     const uint32_t bh = su32(smem + (size_t)s * G::STAGE_BYTES + A_TILE_BYTES);
                     const uint64_t dbh0 = make_desc_sw128(bh), dbl0 = make_desc_sw128(bh + G::B_TILE_BYTES);
-                    const uint32_t a_hi = tmem + G::COL_A + 64 * s, a_lo = a_hi + 32;
+                    const uint32_t a_hi = tmem + G::COL_A + 64 * (s % G::NSLOTS), a_lo = a_hi + 32;
                     const uint32_t d = tmem + (buf ? G::COL_HH1 : G::COL_HH0);
                     const bool chunk_end = (in_chunk == kd - 1) || (i == T.steps - 1);
                     if (elect_one()) {
@@ -371,8 +382,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                     mma_tf32_ts(d + NT, a_lo + kk * 8, dbh0 + (uint64_t)(2 * kk), idesc, 1);
                                 } else {
                                     mma_tf32_ts(d, a_hi + kk * 8, dbh0 + (uint64_t)(2 * kk), idesc, (in_chunk | kk) != 0);
-                                    mma_tf32_ts(d, a_hi + kk * 8, dbl0 + (uint64_t)(2 * kk), idesc, 1);
-                                    mma_tf32_ts(d, a_lo + kk * 8, dbh0 + (uint64_t)(2 * kk), idesc, 1);
+                                    mma_tf32_ts(tmem + G::COL_X, a_hi + kk * 8, dbl0 + (uint64_t)(2 * kk), idesc, (i | kk) != 0);
+                                    mma_tf32_ts(tmem + G::COL_X, a_lo + kk * 8, dbh0 + (uint64_t)(2 * kk), idesc, 1);
                                 }
                             }
                         }
@@ -444,10 +455,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         }
                     }
                 }
-                mbar_wait_t(&done[s], ph ^ 1u, &w1, timed);   // MMAs that read this A slot one ring turn ago have retired
+                // the MMAs that read this A slot NSLOTS steps ago must have retired
+                if (s >= G::NSLOTS) mbar_wait_t(&done[s - G::NSLOTS], ph, &w1, timed);
+                else mbar_wait_t(&done[s - G::NSLOTS + G::R], ph ^ 1u, &w1, timed);
                 fence_after();
-                tmem_st32(lane_addr + G::COL_A + 64 * s, hi);
-                tmem_st32(lane_addr + G::COL_A + 64 * s + 32, lo);
+                tmem_st32(lane_addr + G::COL_A + 64 * (s % G::NSLOTS), hi);
+                tmem_st32(lane_addr + G::COL_A + 64 * (s % G::NSLOTS) + 32, lo);
                 s_prev = s;
                 if (++s == G::R) { s = 0; ph ^= 1u; }
             }
@@ -533,6 +546,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 mbar_arrive(&acc_free[buf]);
                 if (buf) pfull ^= 1u;
                 buf ^= 1;
+            }
+            if constexpr (G::SEPX) {
+                // cross terms of the whole tile (the last chunk's commit also covers them)
+                if (T.steps > 0) {
+#pragma unroll
+                    for (int j0 = 0; j0 < NT; j0 += 64) {
+                        uint32_t v0[32], v1[32];
+                        tmem_ld32(lane_addr + G::COL_X + j0, v0);
+                        tmem_ld32(lane_addr + G::COL_X + j0 + 32, v1);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 32; j++) { acc[j0 + j] += __uint_as_float(v0[j]); acc[j0 + 32 + j] += __uint_as_float(v1[j]); }
+                    }
+                    fence_before();
+                    mbar_arrive(x_free);
+                }
             }
             // epilogue
             const int u = T.u0 + yy, v = T.v0 + xx;
@@ -803,16 +832,16 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
     if (p.splits > 1 && (!ws || ws_floats < (size_t)p.splits * in.n * out.h * out.w * d->co)) p.splits = 1;
     p.out_sn = out.sn; p.out_sh = out.sh; p.out_sw = out.sw;
     p.relu = d->relu; p.has_bias = d->has_bias; p.slope = d->negative_slope;
-    p.kd = NT == 128 ? 2 : 4;                     // chains of 24 resp. 16 MMAs per chunk: end-to-end flow error == FP32 SIMT engine's
+    p.kd = NT == 128 ? 6 : 4;                     // chains of 24 resp. 16 MMAs per chunk: end-to-end flow error == FP32 SIMT engine's
     if (const char* e = getenv(NT == 128 ? "FN2_TC_KD" : "FN2_TC_KDW")) { const int v = atoi(e); if (v >= 1 && v <= 1024) p.kd = v; }
     // mean round-toward-zero shrink of an n-MMA accumulation chain, measured by tools/tc_probe.cu (test3)
     const char* nocomp = getenv("FN2_TC_COMP");
     // tools/tc_calibrate2.py (B200, profiles/r01_tc_calibration.txt): mean relative loss of one chunk = comp_a + comp_b * n,
-    // n = MMAs chained into the chunk accumulator (12 per step when the three products share it, 4 per step in WIDE mode).
+    // n = MMAs chained into the chunk accumulator (4 per step: only the a_hi*w_hi product goes there).
     // A per-binade (ulp) model was measured too and is no better; the residual after removing the mean is ~half the loss
     // and grows linearly with n, which is what bounds kd.
-    p.comp_a = (nocomp && nocomp[0] == '0') ? 0.f : (NT == 128 ? 5.0e-8f : 2.0e-8f);
-    p.comp_b = (nocomp && nocomp[0] == '0') ? 0.f : (NT == 128 ? 1.61e-8f : 1.67e-8f);
+    p.comp_a = (nocomp && nocomp[0] == '0') ? 0.f : 2.0e-8f;
+    p.comp_b = (nocomp && nocomp[0] == '0') ? 0.f : 1.67e-8f;
     if (const char* e = getenv("FN2_TC_COMP_A")) p.comp_a = (float)atof(e);
     if (const char* e = getenv("FN2_TC_COMP_B")) p.comp_b = (float)atof(e);
     { const char* e = getenv("FN2_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
