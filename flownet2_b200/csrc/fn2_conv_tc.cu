@@ -434,15 +434,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 } else if (p.dbg & 2) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) { hi[j] = 0x3f800000u; lo[j] = 0; }
-                } else {
+                } else if (p.rowmode) {
                     // row mode: taps that fall outside the image row (and the K padding) hold whatever follows in memory
-                    int k_lo = 0, k_hi = 32;
-                    if (p.rowmode) {
-                        const int x0 = (T.v0 + m % p.tw) * p.su - p.rpad;            // input column of tap 0
-                        const int kb32 = (i % p.rblocks) * 32;
-                        k_lo = max(0, -x0) * p.rcs - kb32;
-                        k_hi = min(p.rkw, p.rW - x0) * p.rcs - kb32;
-                    }
+                    const int x0 = (T.v0 + m % p.tw) * p.su - p.rpad;            // input column of tap 0
+                    const int kb32 = (i % p.rblocks) * 32;
+                    const int k_lo = max(0, -x0) * p.rcs - kb32;
+                    const int k_hi = min(p.rkw, p.rW - x0) * p.rcs - kb32;
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const bool keep = 4 * j >= k_lo && 4 * j < k_hi;
@@ -452,6 +449,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             const uint32_t h = keep ? to_tf32(f[e]) : 0u;
                             hi[4 * j + e] = h;
                             lo[4 * j + e] = keep ? to_tf32(f[e] - __uint_as_float(h)) : 0u;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float f[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const uint32_t h = to_tf32(f[e]);
+                            hi[4 * j + e] = h;
+                            lo[4 * j + e] = to_tf32(f[e] - __uint_as_float(h));
                         }
                     }
                 }
