@@ -37,7 +37,7 @@ class fn2_conv_desc(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libfn2.so")
+    return os.environ.get("FN2_LIB") or os.path.join(_HERE, "libfn2.so")      # FN2_LIB: A/B a differently built library
 
 
 def lib():
