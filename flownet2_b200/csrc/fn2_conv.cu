@@ -363,6 +363,108 @@ __global__ void __launch_bounds__(256) conv_pf_warp_kernel(T4 in, const float* _
     }
 }
 
+// 3x3 / stride 1 specialisations of the two flow-predictor kernels (every predict_flow layer of FlowNet2): compile-time tap
+// loops so that the loads of a kernel row are in flight together.
+template <int C4>
+__global__ void __launch_bounds__(256) conv_pf3_thread_kernel(T4 in, const float* __restrict__ wp, const float* __restrict__ bias, T4 out, ConvP p) {
+    extern __shared__ float2 pf_wsm[];
+    pf_stage_weights(pf_wsm, wp, 9, p.Ci, C4);
+    const long long M = (long long)p.N * p.Ho * p.Wo;
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(m % p.Wo);
+        const int oy = (int)((m / p.Wo) % p.Ho);
+        const int n = (int)(m / ((long long)p.Wo * p.Ho));
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const int iy = oy - p.ph + r;
+            if (iy < 0 || iy >= p.H) continue;
+            float4 a[3][C4];
+#pragma unroll
+            for (int s = 0; s < 3; s++) {
+                const int ix = ox - p.pw + s;
+                const bool ok = ix >= 0 && ix < p.W;
+                const float4* ip = reinterpret_cast<const float4*>(in.p + in.off(n, 0, iy, ok ? ix : ox));
+#pragma unroll
+                for (int q = 0; q < C4; q++) a[s][q] = ok ? __ldg(ip + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int s = 0; s < 3; s++) {
+                const float4* w = reinterpret_cast<const float4*>(pf_wsm + (r * 3 + s) * C4 * 4);
+#pragma unroll
+                for (int q = 0; q < C4; q++) {
+                    const float4 w01 = w[2 * q], w23 = w[2 * q + 1];
+                    a0 = fmaf(a[s][q].x, w01.x, a0); a1 = fmaf(a[s][q].x, w01.y, a1);
+                    a0 = fmaf(a[s][q].y, w01.z, a0); a1 = fmaf(a[s][q].y, w01.w, a1);
+                    a0 = fmaf(a[s][q].z, w23.x, a0); a1 = fmaf(a[s][q].z, w23.y, a1);
+                    a0 = fmaf(a[s][q].w, w23.z, a0); a1 = fmaf(a[s][q].w, w23.w, a1);
+                }
+            }
+        }
+        pf_store(out, p, bias, n, oy, ox, a0, a1);
+    }
+}
+// one warp per PX = 4 consecutive output pixels of a row: the 6 input columns and the weights of a kernel row are loaded
+// once for the four of them (shared memory bandwidth for the weights was the limit of the one-pixel version)
+__global__ void __launch_bounds__(256) conv_pf3_warp_kernel(T4 in, const float* __restrict__ wp, const float* __restrict__ bias, T4 out, ConvP p, int C4) {
+    extern __shared__ float2 pf_wsm[];
+    pf_stage_weights(pf_wsm, wp, 9, p.Ci, C4);
+    constexpr int PX = 4;
+    const int gx = (p.Wo + PX - 1) / PX;
+    const long long G = (long long)p.N * p.Ho * gx;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long g = warp0; g < G; g += nwarps) {
+        const int ox0 = (int)(g % gx) * PX;
+        const int oy = (int)((g / gx) % p.Ho);
+        const int n = (int)(g / ((long long)gx * p.Ho));
+        float acc[PX][2];
+#pragma unroll
+        for (int j = 0; j < PX; j++) { acc[j][0] = 0.f; acc[j][1] = 0.f; }
+        for (int q = lane; q < C4; q += 32) {
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const int iy = oy - p.ph + r;
+                if (iy < 0 || iy >= p.H) continue;
+                float4 a[PX + 2];
+#pragma unroll
+                for (int c = 0; c < PX + 2; c++) {
+                    const int ix = ox0 - p.pw + c;
+                    const bool ok = ix >= 0 && ix < p.W;
+                    a[c] = ok ? __ldg(reinterpret_cast<const float4*>(in.p + in.off(n, 0, iy, ix)) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int s = 0; s < 3; s++) {
+                    const float4* w = reinterpret_cast<const float4*>(pf_wsm + (long long)(r * 3 + s) * C4 * 4);
+                    const float4 w01 = w[2 * q], w23 = w[2 * q + 1];
+#pragma unroll
+                    for (int j = 0; j < PX; j++) {
+                        const float4 v = a[j + s];
+                        acc[j][0] = fmaf(v.x, w01.x, acc[j][0]); acc[j][1] = fmaf(v.x, w01.y, acc[j][1]);
+                        acc[j][0] = fmaf(v.y, w01.z, acc[j][0]); acc[j][1] = fmaf(v.y, w01.w, acc[j][1]);
+                        acc[j][0] = fmaf(v.z, w23.x, acc[j][0]); acc[j][1] = fmaf(v.z, w23.y, acc[j][1]);
+                        acc[j][0] = fmaf(v.w, w23.z, acc[j][0]); acc[j][1] = fmaf(v.w, w23.w, acc[j][1]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PX; j++)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                acc[j][0] += __shfl_xor_sync(0xffffffffu, acc[j][0], o);
+                acc[j][1] += __shfl_xor_sync(0xffffffffu, acc[j][1], o);
+            }
+        if (lane < PX && ox0 + lane < p.Wo) {
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < PX; j++) if (lane == j) { a0 = acc[j][0]; a1 = acc[j][1]; }
+            pf_store(out, p, bias, n, oy, ox0 + lane, a0, a1);
+        }
+    }
+}
+
 // Caffe weights -> packed [k][co].  conv: w[co][ci][r][s]; deconv: w[ci][co][r][s].
 __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ wp, int Ci, int Co,
                                     int kh, int kw, int cis, int deconv) {
@@ -471,10 +573,13 @@ int fn2_conv_forward(const fn2_conv_desc* d, const fn2_tensor* bottom, const flo
                        !(in.sh & 3) && !(in.sn & 3) && (size_t)d->kh * d->kw * C4 * 4 * sizeof(float2) <= 200 * 1024;
     if (pf_ok) {
         const size_t smem = (size_t)d->kh * d->kw * C4 * 4 * sizeof(float2);
+        const bool k3 = d->kh == 3 && d->kw == 3 && d->stride_h == 1 && d->stride_w == 1;
         if (C4 <= 8) {
             const int grid = (int)min((long long)148 * 8, (M + 255) / 256);
 #define FN2_PF_THREAD(C)                                                                                                   \
-            case C: conv_pf_thread_kernel<C><<<grid, 256, smem, st>>>(in, packed_weights_dev, bias_dev, out, p); break;
+            case C: if (k3) conv_pf3_thread_kernel<C><<<grid, 256, smem, st>>>(in, packed_weights_dev, bias_dev, out, p);  \
+                    else conv_pf_thread_kernel<C><<<grid, 256, smem, st>>>(in, packed_weights_dev, bias_dev, out, p);      \
+                    break;
             switch (C4) { FN2_PF_THREAD(1) FN2_PF_THREAD(2) FN2_PF_THREAD(3) FN2_PF_THREAD(4) FN2_PF_THREAD(5) FN2_PF_THREAD(6)
                           FN2_PF_THREAD(7) FN2_PF_THREAD(8) }
 #undef FN2_PF_THREAD
@@ -482,11 +587,18 @@ int fn2_conv_forward(const fn2_conv_desc* d, const fn2_tensor* bottom, const flo
             static size_t smem_set = 0;
             if (smem > 48 * 1024 && smem > smem_set) {
                 FN2_CUDA(cudaFuncSetAttribute(conv_pf_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+                FN2_CUDA(cudaFuncSetAttribute(conv_pf3_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
                 smem_set = 200 * 1024;
             }
             const int per_sm = (int)max((size_t)1, min((size_t)8, (size_t)(220 * 1024) / (smem + 1024)));
-            const int grid = (int)min((long long)148 * per_sm, (M + 7) / 8);
-            conv_pf_warp_kernel<<<grid, 256, smem, st>>>(in, packed_weights_dev, bias_dev, out, p, C4);
+            if (k3) {
+                const long long groups = (long long)p.N * p.Ho * ((p.Wo + 3) / 4);
+                const int grid = (int)min((long long)148 * per_sm, (groups + 7) / 8);
+                conv_pf3_warp_kernel<<<grid, 256, smem, st>>>(in, packed_weights_dev, bias_dev, out, p, C4);
+            } else {
+                const int grid = (int)min((long long)148 * per_sm, (M + 7) / 8);
+                conv_pf_warp_kernel<<<grid, 256, smem, st>>>(in, packed_weights_dev, bias_dev, out, p, C4);
+            }
         }
     } else if (d->co <= 4 && d->ci <= 32) {
         const size_t smem = (size_t)p.K * p.Co * sizeof(float);

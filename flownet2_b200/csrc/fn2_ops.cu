@@ -139,15 +139,20 @@ __global__ void resample_kernel(T4 in, T4 out, float fx, float fy, int antialias
         const float ay = 1.0f / (antialias ? fy : 1.0f);
         const int rx = (fx < 1.0f) ? 2 : (int)ceilf((float)kernel_width / ax);
         const int ry = (fy < 1.0f) ? 2 : (int)ceilf((float)kernel_width / ay);
+        // the filters vanish outside |ax*dx| < support: only the taps of the reference's window that can carry weight are
+        // visited (every skipped tap has weight exactly 0, see above)
+        const float sup = (TYPE == 3) ? 2.0f : 1.0f;
+        const int xl = max(x_in_round - rx, (int)floorf(x_in - sup / ax)), xh = min(x_in_round + rx, (int)ceilf(x_in + sup / ax));
+        const int yl = max(y_in_round - ry, (int)floorf(y_in - sup / ay)), yh = min(y_in_round + ry, (int)ceilf(y_in + sup / ay));
         for (int c0 = 0; c0 < out.c; c0 += 4) {
             const int nc = min(4, out.c - c0);
             float sum[4] = {0.f, 0.f, 0.f, 0.f};
             float wsum = 0;
-            for (int y = y_in_round - ry; y <= y_in_round + ry; y++) {
+            for (int y = yl; y <= yh; y++) {
                 if (y < 0 || y >= in.h) continue;
                 const float dy = y_in - y;
                 const float cy = (TYPE == 3) ? bicubicCoeff(ay * dy) : triangleCoeff(ay * dy);
-                for (int x = x_in_round - rx; x <= x_in_round + rx; x++) {
+                for (int x = xl; x <= xh; x++) {
                     if (x < 0 || x >= in.w) continue;
                     const float dx = x_in - x;
                     const float cx = (TYPE == 3) ? bicubicCoeff(ax * dx) : triangleCoeff(ax * dx);
