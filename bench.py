@@ -279,12 +279,17 @@ def run_ours(args):
         corr = [(t, w) for (n, ty, t), w in zip(lt, work) if ty == "Correlation"]
         total_ms = sum(t for (_, _, t) in lt)
         conv_tf = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-        roofline = {"kernel": "conv/deconv stack (implicit GEMM, fused bias+ReLU)", "bound": "tensor", "achieved": conv_tf,
-                    "peak": pk["bf16_tflops_sustained"] or pk["bf16_tflops"], "unit": "TFLOP/s",
-                    "frac": conv_tf / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"]), "traffic": None,
+        peak_bf16 = pk["bf16_tflops_sustained"] or pk["bf16_tflops"]
+        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of the profiled conv_tc_kernel<128> launch (conv3_1 of FlowNetC,
+        # 473->256 3x3 at 56x128x4; profiles/r01_prof_tc128_raw.csv); its algorithmic bytes are 4*(in + out + weights) = 62.8 MB
+        roofline = {"kernel": "conv/deconv stack: conv_tc_kernel<NT> (tcgen05 3xTF32 implicit GEMM, fused bias+ReLU), summed over the layers",
+                    "bound": "tensor", "achieved": conv_tf, "peak": peak_bf16, "unit": "TFLOP/s", "frac": conv_tf / peak_bf16,
+                    "traffic": 92.9e6, "traffic_of": "conv3_1 launch (algorithmic 62.8e6 B)",
                     "peak_source": pk["source"] + ", sustained bf16 dense (kernel timed inside a long step)",
                     "share_of_step": conv_ms / total_ms if total_ms else None,
-                    "algorithmic_gflop_per_step": conv_fl / 1e9}
+                    "algorithmic_gflop_per_step": conv_fl / 1e9,
+                    # FP32 parity needs 3 TF32 MMAs per multiply-add; the TF32 pipe peaks at half the bf16 rate
+                    "executed_tf32_tflops": 3.0 * conv_tf, "tf32_peak": peak_bf16 / 2.0, "frac_executed": 3.0 * conv_tf / (peak_bf16 / 2.0)}
         rc = None
         if corr:
             t_ms = sum(t for t, _ in corr)
@@ -292,7 +297,7 @@ def run_ours(args):
             fl = sum(w[2] for _, w in corr)
             gbs = by / (t_ms * 1e-3) / 1e9
             rc = {"kernel": "Correlation d=21 k=1 s2=2 C=256", "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                  "frac": gbs / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                  "frac": gbs / pk["hbm_gbs"], "traffic": 40.7e6, "traffic_of": "profiles/r01_prof_corr_raw.csv (8x256x40x56 launch)", "peak_source": pk["source"],
                   "algorithmic_bytes_per_launch": by / len(corr), "ms_per_launch": t_ms / len(corr),
                   "fp32_tflops": fl / (t_ms * 1e-3) / 1e12, "share_of_step": t_ms / total_ms if total_ms else None}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -11,14 +11,16 @@
 //     shared-memory traffic (W reads + TMA writes) near the 128 B/clk budget.
 //   * Accumulation: the B200 tensor core rounds its FP32 accumulator TOWARD ZERO (tools/tc_probe.cu: -1.7e-8 relative
 //     per chained MMA), which over K up to 9216 and ~60 layers would shrink the flow by 1e-3.  Therefore the dominant
-//     a_hi*w_hi term is accumulated in the tensor core only over short chains (KD channel blocks = 4*KD MMAs) into a
+//     a_hi*w_hi term is accumulated in the tensor core only over short chains (kd K steps = 4*kd MMAs) into a
 //     double-buffered TMEM accumulator that 4 drain warps pull out (tcgen05.ld) and add into FP32 REGISTERS with
-//     round-to-nearest, applying the measured mean RZ bias of a chain of that length as a correction.  The two cross
-//     terms (2^-11 smaller) accumulate in a third TMEM accumulator for the whole K loop.
-//   * Epilogue from registers: + bias, leaky ReLU, 128-bit stores into the strided NHWC output view.
+//     round-to-nearest, applying the measured mean RZ loss of a chain of that length as a correction.  The two cross
+//     terms (2^-11 smaller) accumulate in their own TMEM columns for the whole K loop of a tile (TcGeo).
+//   * Epilogue from registers: + bias, leaky ReLU, 128-bit stores into the strided NHWC output view (or raw partials
+//     into the workspace when the K loop is split over SMs).
+// Persistent kernel, one CTA per SM walking the tile list (pixel tile x Co tile x deconv parity class x K split).
 // Warp roles (384 threads, setmaxnreg re-balances registers): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM
-// allocator, warps 4-7 converters, warps 8-11 drain + epilogue.  Deconvolution = one launch per output parity class
-// with the taps that hit it (see fn2_conv_nhwc.cu).
+// allocator, warps 4-7 converters, warps 8-11 drain + epilogue.  Small-Ci inputs use kernel-row or tap-group packing of
+// the K blocks (tc_small_ci).  DESIGN.md section 3 has the measurements behind each of these choices.
 #include <cuda.h>
 #include <mutex>
 
