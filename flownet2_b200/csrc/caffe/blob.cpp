@@ -73,7 +73,10 @@ void Blob<Dtype>::alloc_device() {
     CUDA_CHECK(cudaMalloc(&base, (n + 2 * kGuardFloats) * sizeof(Dtype)));
     // channel padding must read as zero forever (weights for padded channels are zero, but
     // 0 * NaN would poison the tensor-core path)
-    CUDA_CHECK(cudaMemset(base, 0, (n + 2 * kGuardFloats) * sizeof(Dtype)));
+    // stream-ordered: the nets run on non-blocking streams, a legacy-stream memset could land AFTER the first kernel
+    // that writes the blob
+    CUDA_CHECK(cudaMemsetAsync(base, 0, (n + 2 * kGuardFloats) * sizeof(Dtype), Caffe::stream()));
+    CUDA_CHECK(cudaStreamSynchronize(Caffe::stream()));
     dev_ = base + kGuardFloats;
     own_dev_ = true;
 }

@@ -390,7 +390,8 @@ class CorrelationLayer : public Layer<Dtype> {
         if (need > ws_bytes_) {
             if (ws_) cudaFree(ws_);
             CUDA_CHECK(cudaMalloc(&ws_, need));
-            CUDA_CHECK(cudaMemset(ws_, 0, need));
+            CUDA_CHECK(cudaMemsetAsync(ws_, 0, need, S()));
+            CUDA_CHECK(cudaStreamSynchronize(S()));
             ws_bytes_ = need;
         }
     }

@@ -174,6 +174,7 @@ void Net<Dtype>::BuildArena() {
     if (!total) return;
     CUDA_CHECK(cudaMalloc(&arena_, total * sizeof(Dtype)));
     CUDA_CHECK(cudaMemset(arena_, 0, total * sizeof(Dtype)));
+    CUDA_CHECK(cudaDeviceSynchronize());
     size_t off = 0;
     for (auto& l : layers_)
         for (auto& b : l->blobs()) {

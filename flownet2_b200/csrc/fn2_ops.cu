@@ -404,6 +404,86 @@ __global__ void fill_kernel(T4 dst, float v) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Channel-fast ("NHWC") variants of the element-wise kernels: one thread per (pixel, group of 4 channels), 128-bit
+// accesses where the view allows them.  Same per-element arithmetic as the generic kernels above (bit-identical).
+// vr: the view may be READ as float4 groups (16-byte aligned pixels; lanes beyond C are padding or a neighbour's
+// channels -- read, never used).  vw: a float4 WRITE may cover the lanes beyond C (they are this tensor's own padding).
+// ---------------------------------------------------------------------------------------------
+struct PxView { T4 t; int vr, vw; };
+static PxView px_view(const T4& t) {
+    PxView v; v.t = t;
+    v.vr = t.sc == 1 && !((uintptr_t)t.p & 15) && !(t.sw & 3) && !(t.sh & 3) && !(t.sn & 3) && t.sw >= (t.c + 3) / 4 * 4;
+    v.vw = v.vr && t.sw == (t.c + 3) / 4 * 4;
+    return v;
+}
+__device__ __forceinline__ float4 px_load(const PxView& v, long long o, int c0) {
+    if (v.vr) return *reinterpret_cast<const float4*>(v.t.p + o + c0);
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c0 + 0 < v.t.c) r.x = v.t.p[o + c0 + 0];
+    if (c0 + 1 < v.t.c) r.y = v.t.p[o + c0 + 1];
+    if (c0 + 2 < v.t.c) r.z = v.t.p[o + c0 + 2];
+    if (c0 + 3 < v.t.c) r.w = v.t.p[o + c0 + 3];
+    return r;
+}
+__device__ __forceinline__ void px_store(const PxView& v, long long o, int c0, float4 r) {
+    if (v.vr && c0 + 4 <= v.t.c) { *reinterpret_cast<float4*>(v.t.p + o + c0) = r; return; }
+    if (v.vw) {                                       // tail group of a tensor that owns its padding: keep the padding zero
+        if (c0 + 1 >= v.t.c) r.y = 0.f;
+        if (c0 + 2 >= v.t.c) r.z = 0.f;
+        if (c0 + 3 >= v.t.c) r.w = 0.f;
+        *reinterpret_cast<float4*>(v.t.p + o + c0) = r;
+        return;
+    }
+    if (c0 + 0 < v.t.c) v.t.p[o + c0 + 0] = r.x;
+    if (c0 + 1 < v.t.c) v.t.p[o + c0 + 1] = r.y;
+    if (c0 + 2 < v.t.c) v.t.p[o + c0 + 2] = r.z;
+    if (c0 + 3 < v.t.c) v.t.p[o + c0 + 3] = r.w;
+}
+#define FN2_PX_DECODE(T)                                                                       \
+        const int g = (int)(idx % G);                                                          \
+        long long r_ = idx / G;                                                                \
+        const int x = (int)(r_ % (T).w); r_ /= (T).w;                                          \
+        const int y = (int)(r_ % (T).h);                                                       \
+        const int n = (int)(r_ / (T).h);                                                       \
+        const int c0 = 4 * g;
+
+struct EltPx { PxView b[4]; float coeff[4]; int nb; };
+__global__ void eltwise_sum_px_kernel(EltPx a, PxView out) {
+    const int G = (out.t.c + 3) / 4;
+    const long long total = (long long)out.t.n * out.t.h * out.t.w * G;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        FN2_PX_DECODE(out.t)
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int b = 0; b < a.nb; b++) {
+            const float4 v = px_load(a.b[b], a.b[b].t.off(n, 0, y, x), c0);
+            acc.x = acc.x + a.coeff[b] * v.x; acc.y = acc.y + a.coeff[b] * v.y;
+            acc.z = acc.z + a.coeff[b] * v.z; acc.w = acc.w + a.coeff[b] * v.w;
+        }
+        px_store(out, out.t.off(n, 0, y, x), c0, acc);
+    }
+}
+__global__ void relu_px_kernel(PxView in, PxView out, float slope) {
+    const int G = (out.t.c + 3) / 4;
+    const long long total = (long long)out.t.n * out.t.h * out.t.w * G;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        FN2_PX_DECODE(out.t)
+        float4 v = px_load(in, in.t.off(n, 0, y, x), c0);
+        v.x = v.x > 0 ? v.x : v.x * slope; v.y = v.y > 0 ? v.y : v.y * slope;
+        v.z = v.z > 0 ? v.z : v.z * slope; v.w = v.w > 0 ? v.w : v.w * slope;
+        px_store(out, out.t.off(n, 0, y, x), c0, v);
+    }
+}
+__global__ void copy_px_kernel(PxView src, PxView dst) {
+    const int G = (dst.t.c + 3) / 4;
+    const long long total = (long long)dst.t.n * dst.t.h * dst.t.w * G;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        FN2_PX_DECODE(dst.t)
+        px_store(dst, dst.t.off(n, 0, y, x), c0, px_load(src, src.t.off(n, 0, y, x), c0));
+    }
+}
+#undef FN2_PX_DECODE
+
 }  // namespace fn2
 
 using namespace fn2;
@@ -521,6 +601,10 @@ int fn2_relu_forward(const fn2_tensor* bottom, const fn2_tensor* top, float nega
     FN2_CHECK_ARG(valid(bottom) && valid(top), "relu: null/empty tensor");
     T4 in = view(bottom), out = view(top);
     FN2_CHECK_ARG(same_dims(in, out), "relu: shape mismatch");
+    if (in.sc == 1 && out.sc == 1) {
+        const long long groups = (long long)out.n * out.h * out.w * ((out.c + 3) / 4);
+        relu_px_kernel<<<ew_grid(groups, 256), 256, 0, (cudaStream_t)stream>>>(px_view(in), px_view(out), negative_slope);
+    } else
     relu_kernel<<<ew_grid(out.count(), 256), 256, 0, (cudaStream_t)stream>>>(in, out, negative_slope);
     FN2_LAUNCH_CHECK();
     return FN2_OK;
@@ -539,6 +623,14 @@ int fn2_eltwise_sum(const fn2_tensor* const* bottoms, const float* coeffs, int n
         FN2_CHECK_ARG(same_dims(a.b[i], out), "eltwise_sum: shape mismatch (eltwise_layer.cpp:33)");
         a.coeff[i] = coeffs ? coeffs[i] : 1.0f;
     }
+    bool cfast = out.sc == 1;
+    for (int i = 0; i < num_bottoms; i++) cfast = cfast && a.b[i].sc == 1;
+    if (cfast) {
+        EltPx e; e.nb = a.nb;
+        for (int i = 0; i < a.nb; i++) { e.b[i] = px_view(a.b[i]); e.coeff[i] = a.coeff[i]; }
+        const long long groups = (long long)out.n * out.h * out.w * ((out.c + 3) / 4);
+        eltwise_sum_px_kernel<<<ew_grid(groups, 256), 256, 0, (cudaStream_t)stream>>>(e, px_view(out));
+    } else
     eltwise_sum_kernel<<<ew_grid(out.count(), 256), 256, 0, (cudaStream_t)stream>>>(a, out);
     FN2_LAUNCH_CHECK();
     return FN2_OK;
@@ -566,6 +658,9 @@ int fn2_copy(const fn2_tensor* src, const fn2_tensor* dst, void* stream) {
         const long long hw = (long long)d.h * d.w;
         dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((d.c + 31) / 32), (unsigned)d.n);
         copy_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(s, d, s_cf ? 1 : 0);
+    } else if (s_cf && d_cf) {
+        const long long groups = (long long)d.n * d.h * d.w * ((d.c + 3) / 4);
+        copy_px_kernel<<<ew_grid(groups, 256), 256, 0, st>>>(px_view(s), px_view(d));
     } else if (d_cf || (s_cf && !d_pl)) {
         copy_kernel<true><<<ew_grid(d.count(), 256), 256, 0, st>>>(s, d);
     } else {
