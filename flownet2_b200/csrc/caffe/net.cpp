@@ -26,6 +26,10 @@ Net<Dtype>::~Net() {
     blobs_.clear();
     for (auto& kv : staging_) if (kv.second.first) cudaFree(kv.second.first);
     if (arena_) cudaFree(arena_);
+    for (cudaEvent_t e : layer_event_) if (e) cudaEventDestroy(e);
+    if (fork_event_) cudaEventDestroy(fork_event_);
+    if (join_event_) cudaEventDestroy(join_event_);
+    if (stream2_) cudaStreamDestroy(stream2_);
     if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -94,6 +98,7 @@ void Net<Dtype>::Init(const NetParameter& param) {
     FuseReLUs();
     AliasConcats();
     BuildArena();
+    PlanStreams();
 }
 
 template <typename Dtype>
@@ -260,9 +265,95 @@ std::string Net<Dtype>::ToCaffemodel() {
     return SerializeCaffemodel(name_, out);
 }
 
+// Two-stream plan.  Dependencies are tracked on storage (an aliased concat bottom counts as its parent): read-after-write,
+// write-after-write and write-after-read.  Greedy list scheduling in prototxt order with a crude cost model: a layer goes
+// to the second stream only when that lets it start clearly earlier than on the main stream.
+template <typename Dtype>
+void Net<Dtype>::PlanStreams() {
+    const int L = (int)layers_.size();
+    layer_stream_.assign(L, 0); layer_wait_.assign(L, -1); layer_record_.assign(L, 0); layer_event_.assign(L, nullptr);
+    uses_stream2_ = false;
+    if (getenv("FN2_NO_STREAMS") || L == 0) return;
+    std::map<const Blob<Dtype>*, int> root_of;
+    auto root = [&](const Blob<Dtype>* b) {
+        while (b->alias_parent()) b = b->alias_parent();
+        auto it = root_of.find(b);
+        if (it == root_of.end()) it = root_of.insert({b, (int)root_of.size()}).first;
+        return it->second;
+    };
+    std::map<int, int> last_writer;                       // storage -> layer
+    std::map<int, vector<int> > readers;                  // storage -> layers that read it since the last write
+    vector<vector<int> > deps(L);
+    for (int i = 0; i < L; i++) {
+        std::set<int> d;
+        for (Blob<Dtype>* b : bottom_vecs_[i]) { const int r = root(b); if (last_writer.count(r)) d.insert(last_writer[r]); }
+        for (Blob<Dtype>* t : top_vecs_[i]) {
+            const int r = root(t);
+            if (last_writer.count(r)) d.insert(last_writer[r]);
+            for (int j : readers[r]) d.insert(j);
+        }
+        d.erase(i);
+        deps[i].assign(d.begin(), d.end());
+        for (Blob<Dtype>* b : bottom_vecs_[i]) readers[root(b)].push_back(i);
+        for (Blob<Dtype>* t : top_vecs_[i]) { const int r = root(t); last_writer[r] = i; readers[r].clear(); }
+    }
+    vector<double> finish(L, 0.0);
+    double busy[2] = {0.0, 0.0};
+    for (int i = 0; i < L; i++) {
+        double fl = 0, by = 0;
+        layers_[i]->WorkEstimate(bottom_vecs_[i], top_vecs_[i], &fl, &by);
+        const double cost = std::max(fl / 100e12, by / 1.5e12) + 4e-6;
+        double ready = 0;
+        for (int j : deps[i]) ready = std::max(ready, finish[j]);
+        const double s0 = std::max(ready, busy[0]), s1 = std::max(ready, busy[1]);
+        int s = (s1 + 30e-6 < s0) ? 1 : 0;
+        // stay with the producer when that costs nothing
+        if (s == 0 && s1 <= s0) for (int j : deps[i]) if (finish[j] == ready && layer_stream_[j] == 1 && busy[1] <= ready) s = 1;
+        layer_stream_[i] = s;
+        finish[i] = (s ? s1 : s0) + cost;
+        busy[s] = finish[i];
+        if (s) uses_stream2_ = true;
+    }
+    if (!uses_stream2_) return;
+    for (int i = 0; i < L; i++) {
+        int w = -1;
+        for (int j : deps[i]) if (layer_stream_[j] != layer_stream_[i]) w = std::max(w, j);
+        layer_wait_[i] = w;
+        if (w >= 0) layer_record_[w] = 1;
+    }
+    CUDA_CHECK(cudaStreamCreateWithFlags(&stream2_, cudaStreamNonBlocking));
+    for (int i = 0; i < L; i++) if (layer_record_[i]) CUDA_CHECK(cudaEventCreateWithFlags(&layer_event_[i], cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&fork_event_, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&join_event_, cudaEventDisableTiming));
+    if (getenv("FN2_DEBUG_STREAMS")) {
+        int n1 = 0;
+        for (int i = 0; i < L; i++) n1 += layer_stream_[i];
+        fprintf(stderr, "[fn2] %d of %d layers on the second stream:", n1, L);
+        for (int i = 0; i < L; i++) if (layer_stream_[i]) fprintf(stderr, " %s", layer_names_[i].c_str());
+        fprintf(stderr, "\n");
+    }
+}
+
 template <typename Dtype>
 void Net<Dtype>::ForwardEager() {
-    for (size_t i = 0; i < layers_.size(); ++i) layers_[i]->Forward(bottom_vecs_[i], top_vecs_[i]);
+    if (!uses_stream2_) {
+        for (size_t i = 0; i < layers_.size(); ++i) layers_[i]->Forward(bottom_vecs_[i], top_vecs_[i]);
+        return;
+    }
+    // fork: everything already queued on the main stream (input copies) precedes the second stream's work; under graph
+    // capture this is also what pulls the second stream into the capture
+    CUDA_CHECK(cudaEventRecord(fork_event_, stream_));
+    CUDA_CHECK(cudaStreamWaitEvent(stream2_, fork_event_, 0));
+    for (size_t i = 0; i < layers_.size(); ++i) {
+        cudaStream_t st = layer_stream_[i] ? stream2_ : stream_;
+        if (layer_wait_[i] >= 0) CUDA_CHECK(cudaStreamWaitEvent(st, layer_event_[layer_wait_[i]], 0));
+        Caffe::stream() = st;
+        layers_[i]->Forward(bottom_vecs_[i], top_vecs_[i]);
+        if (layer_record_[i]) CUDA_CHECK(cudaEventRecord(layer_event_[i], st));
+    }
+    Caffe::stream() = stream_;
+    CUDA_CHECK(cudaEventRecord(join_event_, stream2_));
+    CUDA_CHECK(cudaStreamWaitEvent(stream_, join_event_, 0));
 }
 
 // Net::ForwardFromTo(0, L-1), net.cpp:546-557 -- replayed from a CUDA graph once warm.

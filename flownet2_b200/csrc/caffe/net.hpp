@@ -50,6 +50,7 @@ class Net {
     void AliasConcats();
     void BuildArena();
     void ForwardEager();
+    void PlanStreams();
     Dtype* staging(const string& blob, size_t floats);
 
     Phase phase_;
@@ -65,6 +66,15 @@ class Net {
     Dtype* arena_ = nullptr;
     size_t arena_floats_ = 0;
     cudaStream_t stream_ = nullptr;
+    // second stream for layers off the critical path (FlowNet2: the FlowNet-SD branch next to the C-S-S chain), so that
+    // their tiles fill the idle SMs at the tail of the other branch's kernels
+    cudaStream_t stream2_ = nullptr;
+    vector<int> layer_stream_;                  // 0 / 1 per layer (PlanStreams)
+    vector<int> layer_wait_;                    // last layer on the OTHER stream this layer depends on, or -1
+    vector<char> layer_record_;                 // an event is recorded after this layer
+    vector<cudaEvent_t> layer_event_;
+    cudaEvent_t fork_event_ = nullptr, join_event_ = nullptr;
+    bool uses_stream2_ = false;
     cudaGraph_t graph_ = nullptr;
     cudaGraphExec_t graph_exec_ = nullptr;
     bool graph_disabled_ = false;
