@@ -33,6 +33,20 @@ namespace {
 constexpr int TC_THREADS = 384;
 constexpr int A_TILE_BYTES = 128 * 128;          // 128 pixels x 32 fp32
 
+// division by a launch constant without the ~40-instruction integer divide (the tile decode is on the critical path of the
+// single-thread producer and MMA roles once per tile): q = (umulhi(n, mul) + n) >> shift for n < 2^31
+struct FastDiv {
+    uint32_t mul, shift, d;
+    __host__ void init(int div) {
+        d = (uint32_t)div;
+        shift = 0;
+        while ((1u << shift) < d) shift++;
+        mul = (uint32_t)(((1ull << 32) * ((1ull << shift) - d)) / d + 1);
+    }
+    __device__ __forceinline__ int div(int n) const { return (int)(((uint32_t)__umulhi((uint32_t)n, mul) + (uint32_t)n) >> shift); }
+    __device__ __forceinline__ void divmod(int n, int& q, int& r) const { q = div(n); r = n - q * (int)d; }
+};
+
 struct TcParams {
     int N, su, sv, ou, ov;                        // sub-grid / mapping (see fn2_conv_nhwc.cu)
     int ncls;                                     // output parity classes handled by this launch (grid.z)
@@ -44,6 +58,10 @@ struct TcParams {
     int tw, th, tiles_x, tiles_y;
     int kd;                                       // channel blocks per tensor-core accumulation chain
     int splits, Ho, Wo;                           // split-K: K ranges per tile (partials go to the workspace), output size
+    // tail split: the tiles of the last, partial wave [tail_first, ntotal) are cut into tail_z K ranges each so that they
+    // spread over all SMs (448 tiles on 148 SMs: 3 + 1/8 rounds instead of 4); their partials are summed by a fix-up kernel
+    int tail_first, tail_z, ntotal;
+    FastDiv d_ntiles_p, d_cotiles, d_tiles_x, d_tiles_y, d_splits, d_tail_z;
     int cl, ntiles, ntiles_p, cotiles, total;     // cluster size (W multicast); pixel tiles (real / padded to cl), Co tiles, all tiles
     float comp_a, comp_b;                         // RZ bias model: shrink(n MMAs) = comp_a + comp_b * n
     int gcs;                                      // tap-group packing for Ci <= 16: padded channels per tap (4/8/12/16), 0 = off
@@ -207,22 +225,30 @@ template <int NT> struct TcGeo {
 struct TcTile {
     int n, u0, v0, co0, cls, tap0, ntaps, steps;
     int k0, split;                                // first K step of this unit, split index
+    int slot;                                     // >= 0: raw partial sums go to workspace slot `slot` (tail split)
     bool valid;
 };
 template <int NT>
 __device__ __forceinline__ TcTile tc_decode_tile(const TcParams& p, int tile) {
     TcTile t;
-    t.split = 0;
-    if (p.splits > 1) { t.split = tile % p.splits; tile /= p.splits; }   // splits of a tile run side by side (shared A tiles in L2)
-    int pix = tile % p.ntiles_p;
-    int r = tile / p.ntiles_p;
-    const int cot = r % p.cotiles;
-    t.cls = r / p.cotiles;
+    t.split = 0; t.slot = -1;
+    int tseg = 0;
+    if (p.tail_z > 1 && tile >= p.tail_first) {
+        t.slot = tile - p.tail_first;
+        int q;
+        p.d_tail_z.divmod(t.slot, q, tseg);
+        tile = p.tail_first + q;
+    }
+    if (p.splits > 1) { int q; p.d_splits.divmod(tile, q, t.split); tile = q; }   // splits of a tile run side by side (shared A tiles in L2)
+    int pix, r, cot = 0;
+    p.d_ntiles_p.divmod(tile, r, pix);
+    t.cls = 0;
+    if (r) p.d_cotiles.divmod(r, t.cls, cot);
     t.valid = pix < p.ntiles;
     if (!t.valid) pix = 0;
-    const int tx = pix % p.tiles_x; pix /= p.tiles_x;
-    const int ty = pix % p.tiles_y;
-    t.n = pix / p.tiles_y;
+    int tx, ty, q2;
+    p.d_tiles_x.divmod(pix, q2, tx);
+    p.d_tiles_y.divmod(q2, t.n, ty);
     t.u0 = ty * p.th; t.v0 = tx * p.tw;
     t.co0 = cot * NT;
     t.tap0 = p.cls_tap0[t.cls]; t.ntaps = p.cls_ntaps[t.cls];
@@ -233,6 +259,11 @@ __device__ __forceinline__ TcTile tc_decode_tile(const TcParams& p, int tile) {
     if (p.splits > 1) {
         const int per = (t.steps + p.splits - 1) / p.splits;
         t.k0 = min(t.steps, t.split * per);
+        t.steps = min(t.steps, t.k0 + per) - t.k0;
+    }
+    if (t.slot >= 0) {
+        const int per = (t.steps + p.tail_z - 1) / p.tail_z;
+        t.k0 = min(t.steps, tseg * per);
         t.steps = min(t.steps, t.k0 + per) - t.k0;
     }
     return t;
@@ -577,7 +608,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const int u = T.u0 + yy, v = T.v0 + xx;
             if (T.valid && u < p.cls_Hu[T.cls] && v < p.cls_Wu[T.cls]) {
                 const int oy = u * p.ou + p.cls_oy0[T.cls], ox = v * p.ov + p.cls_ox0[T.cls];
-                if (p.splits > 1) {
+                if (T.slot >= 0) {
+                    // tail split: raw partial sums of this K range, [slot][128 pixels][NT]
+                    float* o = ws + ((long long)T.slot * 128 + m) * NT;
+#pragma unroll
+                    for (int j = 0; j < NT; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                } else if (p.splits > 1) {
                     // raw partial sums, dense [split][n][oy][ox][Co]; bias / ReLU are applied by the fixed-order reduction
                     float* o = ws + ((((long long)T.split * p.N + T.n) * p.Ho + oy) * p.Wo + ox) * p.Co + T.co0;
 #pragma unroll
@@ -700,6 +736,36 @@ __global__ void tc_splitk_reduce_kernel(const float* __restrict__ ws, const floa
     }
 }
 
+// fix-up of the tail split: fixed-order sum of the tail_z partial tiles + bias + ReLU, one thread per (tile row, 4 channels)
+template <int NT>
+__global__ void tc_tail_reduce_kernel(const float* __restrict__ ws, const float* __restrict__ bias, float* __restrict__ out, TcParams p) {
+    const int ntail = p.ntotal - p.tail_first;
+    const long long per = (long long)ntail * 128 * (NT / 4);
+    TcParams q = p;
+    q.tail_z = 1;                                  // decode whole tiles
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % (NT / 4)) * 4;
+        const int m = (int)((idx / (NT / 4)) % 128);
+        const int t = (int)(idx / ((NT / 4) * 128));
+        const TcTile T = tc_decode_tile<NT>(q, p.tail_first + t);
+        const int u = T.u0 + m / p.tw, v = T.v0 + m % p.tw;
+        if (!T.valid || u >= p.cls_Hu[T.cls] || v >= p.cls_Wu[T.cls]) continue;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int z = 0; z < p.tail_z; z++) {
+            const float4 x = *reinterpret_cast<const float4*>(ws + (((long long)t * p.tail_z + z) * 128 + m) * NT + c);
+            a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+        }
+        const int co = T.co0 + c;
+        if (p.has_bias) { a.x += __ldg(bias + co); a.y += __ldg(bias + co + 1); a.z += __ldg(bias + co + 2); a.w += __ldg(bias + co + 3); }
+        if (p.relu) {
+            a.x = a.x > 0 ? a.x : a.x * p.slope; a.y = a.y > 0 ? a.y : a.y * p.slope;
+            a.z = a.z > 0 ? a.z : a.z * p.slope; a.w = a.w > 0 ? a.w : a.w * p.slope;
+        }
+        const int oy = u * p.ou + p.cls_oy0[T.cls], ox = v * p.ov + p.cls_ox0[T.cls];
+        *reinterpret_cast<float4*>(out + T.n * p.out_sn + (long long)oy * p.out_sh + (long long)ox * p.out_sw + co) = a;
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -759,6 +825,36 @@ static TcSmallCi tc_small_ci(const fn2_conv_desc* d, int ci_stride) {
 
 // Split-K plan: layers whose tile list cannot fill the GPU (the 7x16 .. 14x32 maps of conv5/conv6/deconv5 with
 // K = 9 * 1024) cut every tile's K loop into `z` ranges that run on different SMs.
+// tail split plan for a layer with `tiles` tile units of `steps` K steps each: returns z (1 = off) and the first tail tile
+static int tc_tail_plan(long long tiles, int steps, int* first) {
+    *first = (int)tiles;
+    if (getenv("FN2_TC_NOTAIL")) return 1;
+    const int nsm = tc_num_sms();
+    if (tiles <= nsm || steps < 16) return 1;
+    const long long full = tiles / nsm * nsm, r = tiles - full;
+    if (r == 0) return 1;
+    const int z = min(8, steps / 8);
+    if (z < 2) return 1;
+    const double now = (double)((tiles + nsm - 1) / nsm);
+    const double then = (double)(full / nsm) + (double)((r * z + nsm - 1) / nsm) / z;
+    if (then > 0.94 * now) return 1;
+    *first = (int)full;
+    return z;
+}
+// tile count / K steps of a layer (same tiling rules as conv_tc_forward)
+static void tc_layer_geometry(const fn2_conv_desc* d, int N, int Ho, int Wo, int* NTo, long long* tiles, int* steps) {
+    const int NT = (d->co % 128 == 0) ? 128 : (d->co % 64 == 0 ? 64 : (d->co % 32 == 0 ? 32 : 16));
+    const int sh = d->deconv ? d->stride_h : 1, sw = d->deconv ? d->stride_w : 1;
+    const int Hu = (Ho + sh - 1) / sh, Wu = (Wo + sw - 1) / sw, ncls = min(sh, Ho) * min(sw, Wo);
+    int tw = 8;
+    while (tw < Wu && tw < 128) tw *= 2;
+    const int th = 128 / tw;
+    *tiles = (long long)N * ((Wu + tw - 1) / tw) * ((Hu + th - 1) / th) * (d->co / NT) * ncls;
+    const int ntaps = d->deconv ? max(1, d->kh / sh) * max(1, d->kw / sw) : d->kh * d->kw;
+    *steps = ntaps * ((d->ci + 31) / 32);
+    *NTo = NT;
+}
+
 static int tc_split_plan(const fn2_conv_desc* d, int N, int Ho, int Wo) {
     if (getenv("FN2_TC_NOSPLIT")) return 1;
     if (!d->deconv && d->ci <= 16) return 1;                       // small-Ci packing modes do not split
@@ -782,7 +878,12 @@ static int tc_split_plan(const fn2_conv_desc* d, int N, int Ho, int Wo) {
 
 size_t conv_tc_workspace_floats(const fn2_conv_desc* d, int N, int Ho, int Wo) {
     const int z = tc_split_plan(d, N, Ho, Wo);
-    return z > 1 ? (size_t)z * N * Ho * Wo * d->co : 0;
+    if (z > 1) return (size_t)z * N * Ho * Wo * d->co;
+    if (d->co % 16 || (!d->deconv && d->ci <= 16)) return 0;
+    int NT, steps, first; long long tiles;
+    tc_layer_geometry(d, N, Ho, Wo, &NT, &tiles, &steps);
+    const int tz = tc_tail_plan(tiles, steps, &first);
+    return tz > 1 ? (size_t)(tiles - first) * tz * 128 * NT : 0;
 }
 
 int conv_tc_eligible(const fn2_conv_desc* d, const T4& in, const T4& out) {
@@ -905,6 +1006,18 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
         p.ntiles_p = (p.ntiles + p.cl - 1) / p.cl * p.cl;
         p.cotiles = d->co / NT;
         p.total = p.ntiles_p * p.cotiles * p.ncls * p.splits;
+        p.ntotal = p.total; p.tail_first = p.total; p.tail_z = 1;
+        p.d_ntiles_p.init(p.ntiles_p); p.d_cotiles.init(p.cotiles); p.d_tiles_x.init(p.tiles_x); p.d_tiles_y.init(p.tiles_y);
+        p.d_splits.init(max(1, p.splits)); p.d_tail_z.init(1);
+        if (p.splits == 1 && p.cl == 1 && !sm.mode && ws) {
+            int first = 0, steps_min = 1 << 30;
+            for (int c = 0; c < p.ncls; c++) steps_min = min(steps_min, p.cls_ntaps[c] * p.cblocks);
+            const int tz = tc_tail_plan(p.total, steps_min, &first);
+            if (tz > 1 && ws_floats >= (size_t)(p.total - first) * tz * 128 * NT) {
+                p.tail_first = first; p.tail_z = tz; p.d_tail_z.init(tz);
+                p.total = first + (p.ntotal - first) * tz;
+            }
+        }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)min(p.total, tc_num_sms() / p.cl * p.cl), 1, 1);
         cfg.blockDim = dim3(TC_THREADS);
@@ -929,6 +1042,14 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
         else FN2_TC_LAUNCH(16)
 #undef FN2_TC_LAUNCH
         FN2_LAUNCH_CHECK();
+        if (p.tail_z > 1) {
+            const long long work = (long long)(p.ntotal - p.tail_first) * 128 * (NT / 4);
+            if (NT == 128) tc_tail_reduce_kernel<128><<<ew_grid(work, 256), 256, 0, st>>>(ws, bias, out.p, p);
+            else if (NT == 64) tc_tail_reduce_kernel<64><<<ew_grid(work, 256), 256, 0, st>>>(ws, bias, out.p, p);
+            else if (NT == 32) tc_tail_reduce_kernel<32><<<ew_grid(work, 256), 256, 0, st>>>(ws, bias, out.p, p);
+            else tc_tail_reduce_kernel<16><<<ew_grid(work, 256), 256, 0, st>>>(ws, bias, out.p, p);
+            FN2_LAUNCH_CHECK();
+        }
         if (p.splits > 1) {
             tc_splitk_reduce_kernel<<<ew_grid((long long)p.N * p.Ho * p.Wo * (p.Co / 4), 256), 256, 0, st>>>(ws, bias, out.p, p);
             FN2_LAUNCH_CHECK();

@@ -226,6 +226,8 @@ TC_CASES = [
     (1, 82, 16, 24, 16, 3, 1, 1, False),       # Co = 16
     (1, 162, 9, 12, 32, 3, 1, 1, False),       # Co = 32
     (1, 162, 9, 11, 16, 4, 2, 1, True),
+    (1, 64, 96, 208, 128, 3, 1, 1, False),     # 156 tiles on 148 SMs: the 8 tiles of the partial wave are K-split (tail split)
+    (1, 96, 50, 200, 16, 3, 1, 1, False),      # same with NT = 16 (79 + ... tiles only when SMs < tiles; harmless otherwise)
 ]
 
 

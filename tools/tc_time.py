@@ -17,12 +17,15 @@ for (N, Ci, H, W, Co, k, s, p) in [(4, 473, 56, 128, 256, 3, 1, 1), (4, 12, 448,
     out = torch.empty(N, Co, Ho, Wo, device="cuda").contiguous(memory_format=cl)
     dx, do = ops.desc(x), ops.desc(out)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    wb = C.c_size_t(); check(l.fn2_conv_workspace_bytes(C.byref(d), N, H, W, C.byref(wb)))
+    wsbuf = torch.empty(max(wb.value, 4) // 4, device="cuda") if os.environ.get("TC_TIME_WS", "1") == "1" else None
+    wsp, wsn = (C.c_void_p(wsbuf.data_ptr()), wb.value) if wsbuf is not None else (None, 0)
     for _ in range(3):
-        check(l.fn2_conv_forward(C.byref(d), C.byref(dx), C.c_void_p(packed.data_ptr()), C.c_void_p(b.data_ptr()), C.byref(do), None, 0, st))
+        check(l.fn2_conv_forward(C.byref(d), C.byref(dx), C.c_void_p(packed.data_ptr()), C.c_void_p(b.data_ptr()), C.byref(do), wsp, wsn, st))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(10):
-        check(l.fn2_conv_forward(C.byref(d), C.byref(dx), C.c_void_p(packed.data_ptr()), C.c_void_p(b.data_ptr()), C.byref(do), None, 0, st))
+        check(l.fn2_conv_forward(C.byref(d), C.byref(dx), C.c_void_p(packed.data_ptr()), C.c_void_p(b.data_ptr()), C.byref(do), wsp, wsn, st))
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     steps = k * k * ((Ci + 31) // 32)
