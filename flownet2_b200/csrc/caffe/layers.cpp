@@ -573,11 +573,97 @@ struct TransMat {   // augmentation_layer_base.cpp:15-48, float arithmetic in th
     }
 };
 
+// AugmentationCoeff (caffe.proto:436-486) as a flat record: 42 float fields in declaration order (= protobuf descriptor
+// order, which coeff_to_array / array_to_coeff and the (N,42,1,1) parameter blob rely on) with presence bits.
+struct AugCoeff {
+    static constexpr int N = 42;
+    enum { MIRROR = 0, DX, DY, ANGLE, ZOOM_X, ZOOM_Y, GAMMA, BRIGHTNESS, CONTRAST, COLOR1, COLOR2, COLOR3,
+           POW_NOMEAN0, POW_NOMEAN1, POW_NOMEAN2, ADD_NOMEAN0, ADD_NOMEAN1, ADD_NOMEAN2, MULT_NOMEAN0, MULT_NOMEAN1, MULT_NOMEAN2,
+           POW_WITHMEAN0, POW_WITHMEAN1, POW_WITHMEAN2, ADD_WITHMEAN0, ADD_WITHMEAN1, ADD_WITHMEAN2, MULT_WITHMEAN0, MULT_WITHMEAN1,
+           MULT_WITHMEAN2, LMULT_POW, LMULT_ADD, LMULT_MULT, COL_ANGLE, FOG_AMOUNT, FOG_SIZE, MOTION_BLUR_ANGLE, MOTION_BLUR_SIZE,
+           SHADOW_ANGLE, SHADOW_DISTANCE, SHADOW_STRENGTH, NOISE };
+    static float def(int f) {
+        static const float d[N] = {0, 0, 0, 0, 1, 1,   1, 0, 1, 1, 1, 1,   1, 1, 1, 0, 0, 0, 1, 1, 1, 1, 1, 1, 0, 0, 0, 1, 1, 1, 1, 0, 1, 0,
+                                   0, 0, 0, 0, 0, 0, 0, 0};
+        return d[f];
+    }
+    float v[N];
+    bool has[N];
+    AugCoeff() { clear_all(); }
+    void clear(int f) { v[f] = def(f); has[f] = false; }
+    void clear_all() { for (int f = 0; f < N; f++) clear(f); }            // augmentation_layer_base.cpp:186-249
+    void set(int f, float x) { v[f] = x; has[f] = true; }
+    float get(int f) const { return v[f]; }
+    // augmentation_layer_base.cpp:352-365: fields whose default is 0 are stored as is, the others as their logarithm
+    void to_array(float* out) const {
+        for (int f = 0; f < N; f++) out[f] = (std::fabs(def(f)) < 1e-3) ? v[f] : (float)std::log(v[f]);
+    }
+    void from_array(const float* in) {                                     // :368-379
+        for (int f = 0; f < N; f++) set(f, (std::fabs(def(f)) < 1e-3) ? in[f] : (float)std::exp(in[f]));
+    }
+    void clear_defaults() {                                                // :339-349
+        for (int f = 0; f < N; f++) if (std::fabs(def(f) - v[f]) < 1e-3) clear(f);
+    }
+};
+
+// caffe_rng_generate, util/rng.cpp:8-114.  The reference draws from boost::mt19937 through boost's uniform_real /
+// normal_distribution / bernoulli_distribution of an unpinned boost version: the random STREAM is unpinned, the
+// distributions are restated (uniform on [mean-spread, mean+spread], N(mean, spread), Bernoulli(prob)).
+struct AugRng {
+    std::mt19937 gen;
+    explicit AugRng(uint32_t seed) : gen(seed) {}
+    float unit() { return (float)(gen() >> 8) * (1.0f / 16777216.0f); }                    // [0, 1)
+    float uniform(float a, float b) { return a + (b - a) * unit(); }
+    float gaussian(float mu, float sigma) {
+        const float u1 = ((float)(gen() >> 8) + 1.0f) * (1.0f / 16777216.0f), u2 = unit();
+        return mu + sigma * std::sqrt(-2.0f * std::log(u1)) * std::cos(6.28318530718f * u2);
+    }
+    int bernoulli(float p) { return unit() < p ? 1 : 0; }
+    // Randtype float; as_bool reproduces the <Dtype,bool> instantiation used for `mirror`
+    float generate(const RandomGeneratorParameter& p, float discount_coeff, float prob0_value, bool as_bool = false) {
+        const float spread = p.apply_schedule() ? p.spread() * discount_coeff : p.spread();
+        const std::string t = p.rand_type();
+        float r;
+        if (t == "uniform" || t == "gaussian") {
+            float tmp = p.mean();
+            if (spread > 0.f) tmp = (t == "uniform") ? uniform(p.mean() - spread, p.mean() + spread) : gaussian(p.mean(), spread);
+            if (p.exp()) tmp = std::exp(tmp);
+            r = tmp;
+        } else if (t == "bernoulli") {
+            r = (float)(p.prob() > 0.f ? bernoulli(p.prob()) : 0);
+        } else if (t == "uniform_bernoulli" || t == "gaussian_bernoulli") {
+            const int on = p.prob() > 0.f ? bernoulli(p.prob()) : 0;
+            float tmp;
+            if (!on) {
+                if (!std::isnan(prob0_value)) return as_bool ? (prob0_value != 0.f ? 1.f : 0.f) : prob0_value;
+                tmp = 0;
+            } else {
+                tmp = p.mean();
+                if (spread > 0.f) tmp = (t == "uniform_bernoulli") ? uniform(p.mean() - spread, p.mean() + spread) : gaussian(p.mean(), spread);
+            }
+            if (p.exp()) tmp = std::exp(tmp);
+            r = tmp;
+        } else {
+            CHECK(false) << "Unknown random type " << t;
+            r = NAN;
+        }
+        if (as_bool) r = (r != 0.f) ? 1.f : 0.f;                              // static_cast<bool>
+        if (p.discretize()) r = std::round(r);
+        r = p.multiplier() * r;
+        if (as_bool) r = (r != 0.f) ? 1.f : 0.f;
+        return r;
+    }
+};
+
 template <typename Dtype>
 class DataAugmentationLayer : public Layer<Dtype> {
  public:
-    explicit DataAugmentationLayer(const LayerParameter& p) : Layer<Dtype>(p) {}
-    ~DataAugmentationLayer() override { if (mats_dev_) cudaFree(mats_dev_); if (fixed_mean_dev_) cudaFree(fixed_mean_dev_); }
+    explicit DataAugmentationLayer(const LayerParameter& p) : Layer<Dtype>(p), rng_(seed_of(p.name())) {}
+    ~DataAugmentationLayer() override {
+        if (coef_dev_) cudaFree(coef_dev_);
+        if (fixed_mean_dev_) cudaFree(fixed_mean_dev_);
+        if (coef_host_) cudaFreeHost(coef_host_);
+    }
     const char* type() const override { return "DataAugmentation"; }
     bool AllowBackward() const override { return false; }              // data_augmentation_layer.hpp:29
     bool DoesUseCustomCopyBlobs() const override { return true; }      // data_augmentation_layer.hpp:43-46
@@ -597,11 +683,9 @@ class DataAugmentationLayer : public Layer<Dtype> {
         CHECK_LE(bottom.size(), 2u) << "Data augmentation layer takes one or two input blobs.";
         CHECK_GE(top.size(), 1u) << "Data augmentation layer outputs one or two output blobs.";
         CHECK_LE(top.size(), 2u) << "Data augmentation layer outputs one or two output blobs.";
-        CHECK(bottom.size() == 1 && top.size() == 1)
-            << "DataAugmentation: coefficient input/output blobs (training graphs) are not built yet";
+        output_params_ = top.size() > 1;                               // data_augmentation_layer.cpp:83-84
+        input_params_ = bottom.size() > 1;
         AugmentationParameter aug = this->layer_param_.augmentation_param();
-        CHECK(!(aug.has_any_generator() && (this->phase_ == TRAIN || aug.augment_during_test())))
-            << "DataAugmentation: random coefficient generators (training augmentation) are not built yet";
         const int num = bottom[0]->num(), channels = bottom[0]->channels();
         const int height = bottom[0]->height(), width = bottom[0]->width();
         do_cropping_ = aug.has_crop_width() && aug.has_crop_height();
@@ -611,18 +695,27 @@ class DataAugmentationLayer : public Layer<Dtype> {
             cropped_height_ = aug.crop_height(); CHECK_GE(height, cropped_height_) << "crop height greater than original";
         }
         top[0]->Reshape(num, channels, cropped_height_, cropped_width_);
-        // default coefficients -> one matrix per sample (data_augmentation_layer.cu:462-468)
-        vector<float> mats((size_t)num * 6);
-        for (int n = 0; n < num; n++) {
-            TransMat t; t.toIdentity();
-            t.leftMultiply(1, 0, 0, 1, -.5f * (float)cropped_width_, -.5f * (float)cropped_height_);
-            t.leftMultiply(1, 0, 0, 1, .5f * (float)width, .5f * (float)height);
-            float* m = &mats[(size_t)n * 6];
-            m[0] = t.t0; m[1] = t.t1; m[2] = t.t2; m[3] = t.t3; m[4] = t.t4; m[5] = t.t5;
+        // coefficient blob: (N, 42, 1, 1), taken from bottom[1] or created here (:103-115)
+        if (input_params_) {
+            CHECK_EQ(bottom[1]->count(), num * AugCoeff::N) << "augmentation parameter blob must be (N," << AugCoeff::N << ",1,1)";
         }
-        if (mats_dev_) cudaFree(mats_dev_);
-        CUDA_CHECK(cudaMalloc(&mats_dev_, mats.size() * sizeof(float)));
-        CUDA_CHECK(cudaMemcpy(mats_dev_, mats.data(), mats.size() * sizeof(float), cudaMemcpyHostToDevice));
+        all_coeffs_.assign((size_t)num * AugCoeff::N, 0.f);
+        if (output_params_) { top[1]->set_layout(Blob<Dtype>::PLAIN); top[1]->Reshape(num, AugCoeff::N, 1, 1); }
+        // per-batch coefficient records, one pinned host block + one device block:
+        //   [N x 6 matrices][N x 6 chromatic][N x 22 chromatic-eigen][N x 9 effects][9 eigvec][pad][32 eigenspace]
+        off_mat_ = 0; off_chroma_ = off_mat_ + 6 * num; off_eigen_ = off_chroma_ + 6 * num; off_effect_ = off_eigen_ + 22 * num;
+        off_eigvec_ = off_effect_ + 9 * num; off_space_ = (off_eigvec_ + 9 + 1) / 2 * 2; coef_floats_ = off_space_ + 32;
+        if (coef_dev_) cudaFree(coef_dev_);
+        if (coef_host_) cudaFreeHost(coef_host_);
+        CUDA_CHECK(cudaMalloc(&coef_dev_, coef_floats_ * sizeof(float)));
+        CUDA_CHECK(cudaMallocHost(&coef_host_, coef_floats_ * sizeof(float)));
+        memset(coef_host_, 0, coef_floats_ * sizeof(float));
+        for (int i = 0; i < 9 && i < aug.chromatic_eigvec_size(); i++) coef_host_[off_eigvec_ + i] = aug.chromatic_eigvec(i);
+        gen_active_ = do_cropping_ && !input_params_ && aug.has_any_generator() && (this->phase_ == TRAIN || aug.augment_during_test());
+        // default coefficients -> one matrix per sample (data_augmentation_layer.cu:462-468); constant unless coefficients
+        // are generated or received
+        prepare_records(width, height);
+        CUDA_CHECK(cudaMemcpy(coef_dev_, coef_host_, coef_floats_ * sizeof(float), cudaMemcpyHostToDevice));
         if (aug.recompute_mean()) {
             this->blobs_[1]->Reshape(1, channels, cropped_height_, cropped_width_);
             this->blobs_[2]->Reshape(1, channels, 1, 1);
@@ -646,6 +739,7 @@ class DataAugmentationLayer : public Layer<Dtype> {
                 for (int i = 0; i < area; i++) pp[(size_t)c * area + i] = pc[c];
             }
         }
+        rng_ = AugRng((uint32_t)(seed * 2654435761u) ^ seed_of(this->layer_param_.name()));
     }
     void HostTick() override {
         float& num_iter = *(this->blobs_[0]->mutable_cpu_data());
@@ -654,16 +748,212 @@ class DataAugmentationLayer : public Layer<Dtype> {
     }
     bool GraphSafe() const override {
         AugmentationParameter aug = this->layer_param_.augmentation_param();
-        // while the running mean is still being updated the launch sequence changes per call
+        // while the running mean is still being updated the launch sequence changes per call; sampled or received
+        // coefficients change the launch sequence and are uploaded from the host every call
+        if (gen_active_ || input_params_ || output_params_) return false;
         return !(aug.recompute_mean() > 0 && num_iter_ <= (float)aug.recompute_mean());
     }
 
  protected:
+    static uint32_t seed_of(const std::string& name) {
+        uint32_t h = 1701u;                                             // the reference tests' seed (test_gradient_check_util.hpp:25)
+        if (const char* e = getenv("FN2_SEED")) h = (uint32_t)strtoul(e, nullptr, 10);
+        for (char c : name) h = h * 16777619u ^ (unsigned char)c;
+        return h;
+    }
+    // generate_spatial_coeffs, augmentation_layer_base.cpp:73-99
+    void generate_spatial(const AugmentationParameter& aug, AugCoeff& c, float dc) {
+        if (aug.has("mirror")) c.set(AugCoeff::MIRROR, rng_.generate(aug.gen("mirror"), dc, AugCoeff::def(AugCoeff::MIRROR), true));
+        if (aug.has("translate")) {
+            c.set(AugCoeff::DX, rng_.generate(aug.gen("translate"), dc, 0.f));
+            c.set(AugCoeff::DY, rng_.generate(aug.gen("translate"), dc, 0.f));
+        }
+        if (aug.has("translate_x")) c.set(AugCoeff::DX, rng_.generate(aug.gen("translate_x"), dc, 0.f));
+        if (aug.has("translate_y")) c.set(AugCoeff::DY, rng_.generate(aug.gen("translate_y"), dc, 0.f));
+        if (aug.has("rotate")) c.set(AugCoeff::ANGLE, rng_.generate(aug.gen("rotate"), dc, 0.f));
+        if (aug.has("zoom")) {
+            c.set(AugCoeff::ZOOM_X, rng_.generate(aug.gen("zoom"), dc, 1.f));
+            c.set(AugCoeff::ZOOM_Y, c.get(AugCoeff::ZOOM_X));
+        }
+        if (aug.has("squeeze")) {
+            const float sq = rng_.generate(aug.gen("squeeze"), dc, 1.f);
+            c.set(AugCoeff::ZOOM_X, c.get(AugCoeff::ZOOM_X) * sq);
+            c.set(AugCoeff::ZOOM_Y, c.get(AugCoeff::ZOOM_Y) / sq);
+        }
+    }
+    // generate_valid_spatial_coeffs, augmentation_layer_base.cpp:102-169: resample until the 4 corners of the crop land
+    // inside the source image
+    void generate_valid_spatial(const AugmentationParameter& aug, AugCoeff& coeff, float dc, int width, int height, int cw, int ch,
+                                int max_num_tries = 50) {
+        float in_params[AugCoeff::N], cur[AugCoeff::N];
+        coeff.to_array(in_params);
+        int counter = 0, good = 0;
+        while (good < 4 && counter < max_num_tries) {
+            coeff.clear_all();
+            generate_spatial(aug, coeff, dc);
+            coeff.to_array(cur);
+            for (int f = 0; f < AugCoeff::N; f++) cur[f] += in_params[f];
+            coeff.from_array(cur);
+            good = 0;
+            for (int x = 0; x < cw; x += std::max(1, cw - 1))
+                for (int y = 0; y < ch; y += std::max(1, ch - 1)) {
+                    float x1, y1, x2, y2;
+                    if (coeff.get(AugCoeff::MIRROR)) { x1 = -(float)x + .5f * (float)cw; y1 = (float)y - .5f * (float)ch; }
+                    else                            { x1 = (float)x - .5f * (float)cw;  y1 = (float)y - .5f * (float)ch; }
+                    const float a = coeff.get(AugCoeff::ANGLE);
+                    x2 = std::cos(a) * x1 - std::sin(a) * y1;
+                    y2 = std::sin(a) * x1 + std::cos(a) * y1;
+                    x2 = x2 + coeff.get(AugCoeff::DX) * (float)cw;
+                    y2 = y2 + coeff.get(AugCoeff::DY) * (float)ch;
+                    x2 = x2 / coeff.get(AugCoeff::ZOOM_X);
+                    y2 = y2 / coeff.get(AugCoeff::ZOOM_Y);
+                    x2 = x2 + .5f * (float)width;
+                    y2 = y2 + .5f * (float)height;
+                    if (!(std::floor(x2) < 0 || std::floor(x2) > (float)(width - 2) || std::floor(y2) < 0 || std::floor(y2) > (float)(height - 2)))
+                        good++;
+                }
+            counter++;
+        }
+        if (counter >= max_num_tries) coeff.from_array(in_params);       // "Exceeded maximum tries in finding spatial coeffs."
+    }
+    // generate_chromatic_coeffs / _eigen_coeffs / _effect_coeffs, augmentation_layer_base.cpp:252-336
+    void generate_chromatic(const AugmentationParameter& aug, AugCoeff& c, float dc) {
+        if (aug.has("gamma")) c.set(AugCoeff::GAMMA, rng_.generate(aug.gen("gamma"), dc, NAN));
+        if (aug.has("brightness")) c.set(AugCoeff::BRIGHTNESS, rng_.generate(aug.gen("brightness"), dc, NAN));
+        if (aug.has("contrast")) c.set(AugCoeff::CONTRAST, rng_.generate(aug.gen("contrast"), dc, NAN));
+        if (aug.has("color")) for (int k = 0; k < 3; k++) c.set(AugCoeff::COLOR1 + k, rng_.generate(aug.gen("color"), dc, NAN));
+    }
+    void generate_chromatic_eigen(const AugmentationParameter& aug, AugCoeff& c, float dc) {
+        auto g = [&](const char* n) { return rng_.generate(aug.gen(n), dc, NAN); };
+        if (aug.has("ladd_pow")) c.set(AugCoeff::POW_NOMEAN0, g("ladd_pow"));
+        if (aug.has("col_pow")) { c.set(AugCoeff::POW_NOMEAN1, g("col_pow")); c.set(AugCoeff::POW_NOMEAN2, g("col_pow")); }
+        if (aug.has("ladd_add")) c.set(AugCoeff::ADD_NOMEAN0, g("ladd_add"));
+        if (aug.has("col_add")) { c.set(AugCoeff::ADD_NOMEAN1, g("col_add")); c.set(AugCoeff::ADD_NOMEAN2, g("col_add")); }
+        if (aug.has("ladd_mult")) c.set(AugCoeff::MULT_NOMEAN0, g("ladd_mult"));
+        if (aug.has("col_mult")) { c.set(AugCoeff::MULT_NOMEAN1, g("col_mult")); c.set(AugCoeff::MULT_NOMEAN2, g("col_mult")); }
+        if (aug.has("sat_pow")) { c.set(AugCoeff::POW_WITHMEAN1, g("sat_pow")); c.set(AugCoeff::POW_WITHMEAN2, c.get(AugCoeff::POW_WITHMEAN1)); }
+        if (aug.has("sat_add")) { c.set(AugCoeff::ADD_WITHMEAN1, g("sat_add")); c.set(AugCoeff::ADD_WITHMEAN2, c.get(AugCoeff::ADD_WITHMEAN1)); }
+        if (aug.has("sat_mult")) { c.set(AugCoeff::MULT_WITHMEAN1, g("sat_mult")); c.set(AugCoeff::MULT_WITHMEAN2, c.get(AugCoeff::MULT_WITHMEAN1)); }
+        if (aug.has("lmult_pow")) c.set(AugCoeff::LMULT_POW, g("lmult_pow"));
+        if (aug.has("lmult_mult")) c.set(AugCoeff::LMULT_MULT, g("lmult_mult"));
+        if (aug.has("lmult_add")) c.set(AugCoeff::LMULT_ADD, g("lmult_add"));
+        if (aug.has("col_rotate")) c.set(AugCoeff::COL_ANGLE, g("col_rotate"));
+    }
+    void generate_effect(const AugmentationParameter& aug, AugCoeff& c, float dc) {
+        if (aug.has("fog_amount") || aug.has("fog_size")) {
+            c.set(AugCoeff::FOG_AMOUNT, rng_.generate(aug.gen("fog_amount"), dc, 0.f));
+            c.set(AugCoeff::FOG_SIZE, rng_.generate(aug.gen("fog_size"), dc, 0.f));
+        }
+        if (aug.has("motion_blur_angle") || aug.has("motion_blur_size")) {
+            c.set(AugCoeff::MOTION_BLUR_ANGLE, rng_.generate(aug.gen("motion_blur_angle"), dc, 0.f));
+            c.set(AugCoeff::MOTION_BLUR_SIZE, rng_.generate(aug.gen("motion_blur_size"), dc, 0.f));
+        }
+        if (aug.has("shadow_angle") || aug.has("shadow_distance") || aug.has("shadow_strength")) {
+            c.set(AugCoeff::SHADOW_ANGLE, rng_.generate(aug.gen("shadow_angle"), dc, 0.f));
+            c.set(AugCoeff::SHADOW_DISTANCE, rng_.generate(aug.gen("shadow_distance"), dc, 0.f));
+            c.set(AugCoeff::SHADOW_STRENGTH, rng_.generate(aug.gen("shadow_strength"), dc, 0.f));
+        }
+        if (aug.has("noise")) c.set(AugCoeff::NOISE, rng_.generate(aug.gen("noise"), dc, NAN));
+    }
+    // all_coeffs_ (N x 42 array form) -> matrices / chromatic / eigen / effect records in coef_host_
+    // (data_augmentation_layer.cu:452-477; tTransMat::fromCoeff augmentation_layer_base.cpp:38-48)
+    void prepare_records(int bottomwidth, int bottomheight) {
+        const int num = (int)(all_coeffs_.size() / AugCoeff::N);
+        has_chromatic_ = has_eigen_ = has_effect_ = has_noise_ = false;
+        for (int n = 0; n < num; n++) {
+            AugCoeff c;
+            c.from_array(&all_coeffs_[(size_t)n * AugCoeff::N]);
+            c.clear_defaults();
+            TransMat t; t.toIdentity();
+            if (c.get(AugCoeff::MIRROR)) t.leftMultiply(-1, 0, 0, 1, .5f * (float)cropped_width_, -.5f * (float)cropped_height_);
+            else                         t.leftMultiply(1, 0, 0, 1, -.5f * (float)cropped_width_, -.5f * (float)cropped_height_);
+            if (c.has[AugCoeff::ANGLE]) {
+                const float a = c.get(AugCoeff::ANGLE);
+                t.leftMultiply(std::cos(a), std::sin(a), -std::sin(a), std::cos(a), 0, 0);
+            }
+            if (c.has[AugCoeff::DX] || c.has[AugCoeff::DY])
+                t.leftMultiply(1, 0, 0, 1, c.get(AugCoeff::DX) * (float)cropped_width_, c.get(AugCoeff::DY) * (float)cropped_height_);
+            if (c.has[AugCoeff::ZOOM_X] || c.has[AugCoeff::ZOOM_Y])
+                t.leftMultiply((float)(1.0 / c.get(AugCoeff::ZOOM_X)), 0, 0, (float)(1.0 / c.get(AugCoeff::ZOOM_Y)), 0, 0);
+            t.leftMultiply(1, 0, 0, 1, .5f * (float)bottomwidth, .5f * (float)bottomheight);
+            float* m = coef_host_ + off_mat_ + 6 * n;
+            m[0] = t.t0; m[1] = t.t1; m[2] = t.t2; m[3] = t.t3; m[4] = t.t4; m[5] = t.t5;
+            float* ch = coef_host_ + off_chroma_ + 6 * n;          // tChromaticCoeffs: gamma, brightness, contrast, color[3]
+            ch[0] = c.get(AugCoeff::GAMMA); ch[1] = c.get(AugCoeff::BRIGHTNESS); ch[2] = c.get(AugCoeff::CONTRAST);
+            for (int k = 0; k < 3; k++) ch[3 + k] = c.get(AugCoeff::COLOR1 + k);
+            if (ch[0] != 1 || ch[1] != 0 || ch[2] != 1 || ch[3] != 1 || ch[4] != 1 || ch[5] != 1) has_chromatic_ = true;
+            float* eg = coef_host_ + off_eigen_ + 22 * n;          // tChromaticEigenCoeffs
+            for (int k = 0; k < 22; k++) {
+                eg[k] = c.get(AugCoeff::POW_NOMEAN0 + k);
+                if (eg[k] != AugCoeff::def(AugCoeff::POW_NOMEAN0 + k)) has_eigen_ = true;
+            }
+            float* ef = coef_host_ + off_effect_ + 9 * n;          // tEffectCoeffs
+            ef[0] = c.get(AugCoeff::FOG_AMOUNT); ef[1] = c.get(AugCoeff::FOG_SIZE);
+            ef[2] = c.get(AugCoeff::MOTION_BLUR_ANGLE); ef[3] = c.get(AugCoeff::MOTION_BLUR_SIZE);
+            ef[4] = std::cos(c.get(AugCoeff::SHADOW_ANGLE)); ef[5] = std::sin(c.get(AugCoeff::SHADOW_ANGLE));
+            ef[6] = c.get(AugCoeff::SHADOW_DISTANCE); ef[7] = c.get(AugCoeff::SHADOW_STRENGTH); ef[8] = c.get(AugCoeff::NOISE);
+            if ((ef[0] != 0 && ef[1] != 0) || ef[3] > 0 || ef[7] > 0 || ef[8] > 0) has_effect_ = true;
+            if (ef[8] > 0) has_noise_ = true;
+        }
+    }
+
     void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
         AugmentationParameter aug = this->layer_param_.augmentation_param();
         fn2_tensor b = bottom[0]->tensor(), t = top[0]->mutable_tensor();
-        if (do_cropping_) FN2_CALL(fn2_spatial_augmentation(&b, &t, mats_dev_, S()));
-        else              FN2_CALL(fn2_copy(&b, &t, S()));            // data_augmentation_layer.cu:589
+        const int num = bottom[0]->num();
+        if (do_cropping_) {
+            if (gen_active_ || input_params_) {
+                if (input_params_) {
+                    const float* in = bottom[1]->cpu_data();              // "Receiving augmentation params" (:107-109)
+                    all_coeffs_.assign(in, in + (size_t)num * AugCoeff::N);
+                } else {
+                    // discount schedule, data_augmentation_layer.cu:372-374
+                    const float hl = this->layer_param_.coeff_schedule_half_life(), c0 = this->layer_param_.coeff_schedule_initial(),
+                                c1 = this->layer_param_.coeff_schedule_final();
+                    const float dc = c0 + (c1 - c0) * (2.f / (1.f + std::exp(-1.0986f * num_iter_ / hl)) - 1.f);
+                    const bool spatial = aug.has("mirror") || aug.has("rotate") || aug.has("zoom") || aug.has("translate") ||
+                                         aug.has("squeeze") || aug.has("translate_x") || aug.has("translate_y");
+                    const bool chromatic = aug.has("brightness") || aug.has("gamma") || aug.has("contrast") || aug.has("color");
+                    const bool effect = aug.has("fog_size") || aug.has("fog_amount") || aug.has("motion_blur_angle") ||
+                                        aug.has("motion_blur_size") || aug.has("shadow_angle") || aug.has("shadow_distance") ||
+                                        aug.has("shadow_strength") || aug.has("noise");
+                    const bool eigen = aug.has("lmult_pow") || aug.has("lmult_mult") || aug.has("lmult_add") || aug.has("sat_pow") ||
+                                       aug.has("sat_mult") || aug.has("sat_add") || aug.has("col_pow") || aug.has("col_mult") ||
+                                       aug.has("col_add") || aug.has("ladd_pow") || aug.has("ladd_mult") || aug.has("ladd_add") ||
+                                       aug.has("col_rotate");
+                    for (int n = 0; n < num; n++) {
+                        AugCoeff c;
+                        if (spatial) generate_valid_spatial(aug, c, dc, bottom[0]->width(), bottom[0]->height(), cropped_width_, cropped_height_);
+                        if (chromatic) generate_chromatic(aug, c, dc);
+                        if (eigen) generate_chromatic_eigen(aug, c, dc);
+                        if (effect) generate_effect(aug, c, dc);
+                        c.to_array(&all_coeffs_[(size_t)n * AugCoeff::N]);
+                    }
+                }
+                prepare_records(bottom[0]->width(), bottom[0]->height());
+                CUDA_CHECK(cudaMemcpyAsync(coef_dev_, coef_host_, (size_t)off_eigvec_ * sizeof(float), cudaMemcpyHostToDevice, S()));
+            }
+            if (output_params_) memcpy(top[1]->mutable_cpu_data(), all_coeffs_.data(), all_coeffs_.size() * sizeof(float));
+            if (has_eigen_) {
+                CHECK_EQ(bottom[0]->channels(), 3) << "Chromatic-Eigen augmentations only work with 3-channel input";
+                CHECK_EQ(aug.chromatic_eigvec_size(), 9) << "You need to specify chromatic eigenvectors for Chromatic-Eigen augmentation";
+                FN2_CALL(fn2_chromatic_eigenspace(&b, coef_dev_ + off_eigvec_, coef_dev_ + off_space_, S()));
+            }
+            FN2_CALL(fn2_spatial_augmentation(&b, &t, coef_dev_ + off_mat_, S()));
+            if (has_eigen_) FN2_CALL(fn2_chromatic_eigen_augmentation(&t, coef_dev_ + off_eigen_, coef_dev_ + off_space_, aug.max_multiplier(), S()));
+            if (has_chromatic_) {
+                CHECK_EQ(bottom[0]->channels(), 3) << "Chromatic augmentations only work with 3-channel input";
+                FN2_CALL(fn2_color_contrast_augmentation(&t, coef_dev_ + off_chroma_, aug.max_multiplier(), S()));
+            }
+            if (has_effect_) {
+                CHECK_EQ(bottom[0]->channels(), 3) << "Effect augmentations only work with 3-channel input";
+                FN2_CALL(fn2_apply_effects(&t, coef_dev_ + off_effect_, aug.max_multiplier(), (unsigned long long)rng_.gen() << 32 | rng_.gen(),
+                                           has_noise_ ? 1 : 0, S()));
+            }
+            if (gen_active_ || input_params_) CUDA_CHECK(cudaStreamSynchronize(S()));   // coef_host_ is rewritten next call
+        } else {
+            FN2_CALL(fn2_copy(&b, &t, S()));                                            // data_augmentation_layer.cu:589
+        }
         if (aug.recompute_mean() > 0) {
             fn2_tensor mpp = this->blobs_[1]->mutable_tensor();
             float* mpc = this->blobs_[2]->mutable_gpu_data();
@@ -704,11 +994,17 @@ class DataAugmentationLayer : public Layer<Dtype> {
         }
     }
 
-    bool do_cropping_ = false;
+    bool do_cropping_ = false, input_params_ = false, output_params_ = false, gen_active_ = false;
+    bool has_chromatic_ = false, has_eigen_ = false, has_effect_ = false, has_noise_ = false;
     int cropped_width_ = 0, cropped_height_ = 0;
     float num_iter_ = 0;
-    float* mats_dev_ = nullptr;
+    vector<float> all_coeffs_;                   // N x 42, array form (coeff_to_array)
+    float* coef_host_ = nullptr;                 // pinned
+    float* coef_dev_ = nullptr;
+    size_t coef_floats_ = 0;
+    int off_mat_ = 0, off_chroma_ = 0, off_eigen_ = 0, off_effect_ = 0, off_eigvec_ = 0, off_space_ = 0;
     float* fixed_mean_dev_ = nullptr;
+    AugRng rng_;
 };
 REGISTER_LAYER_CLASS(DataAugmentation);
 

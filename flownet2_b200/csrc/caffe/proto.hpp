@@ -107,6 +107,18 @@ struct ResampleParameter {                     // caffe.proto:665-677
     int type() const;                          // 1 NEAREST 2 LINEAR 3 CUBIC 4 AREA
 };
 
+struct RandomGeneratorParameter {              // caffe.proto:607-616
+    const Message* m;
+    std::string rand_type() const { return m->str_or("rand_type", "uniform"); }
+    bool exp() const { return m->b("exp", false); }
+    float mean() const { return m->f("mean", 0.f); }
+    float spread() const { return m->f("spread", 0.f); }
+    float prob() const { return m->f("prob", 1.f); }
+    bool apply_schedule() const { return m->b("apply_schedule", true); }
+    bool discretize() const { return m->b("discretize", false); }
+    float multiplier() const { return m->f("multiplier", 1.f); }
+};
+
 struct AugmentationParameter {                 // caffe.proto:489-546
     const Message* m;
     bool has_crop_width() const { return m->has("crop_width"); }
@@ -121,6 +133,10 @@ struct AugmentationParameter {                 // caffe.proto:489-546
     float mean(int i) const { return m->f("mean", 0, i); }
     // true if any RandomGeneratorParameter (spatial/chromatic/eigen/effect) is present
     bool has_any_generator() const;
+    bool has(const char* generator) const { return m->has(generator); }
+    RandomGeneratorParameter gen(const char* generator) const { return RandomGeneratorParameter{&m->msg(generator)}; }
+    int chromatic_eigvec_size() const { return m->count("chromatic_eigvec"); }
+    float chromatic_eigvec(int i) const { return m->f("chromatic_eigvec", 0, i); }
 };
 
 struct EltwiseParameter {                      // caffe.proto:1011-1023
@@ -148,6 +164,10 @@ struct LayerParameter {                        // caffe.proto:312-425
     AugmentationParameter augmentation_param() const { return AugmentationParameter{&m->msg("augmentation_param")}; }
     EltwiseParameter eltwise_param() const { return EltwiseParameter{&m->msg("eltwise_param")}; }
     float relu_negative_slope() const { return m->msg("relu_param").f("negative_slope", 0); }
+    // CoeffScheduleParameter, caffe.proto:693-697
+    float coeff_schedule_half_life() const { return m->msg("coeff_schedule_param").f("half_life", 1.f); }
+    float coeff_schedule_initial() const { return m->msg("coeff_schedule_param").f("initial_coeff", 1.f); }
+    float coeff_schedule_final() const { return m->msg("coeff_schedule_param").f("final_coeff", 1.f); }
     int concat_axis() const;                   // ConcatParameter axis / concat_dim (concat_layer.cpp:21-31)
     // phase rules (NetStateRule include/exclude, net.cpp:288-360): true if the layer is kept
     bool included_in_phase(int phase) const;

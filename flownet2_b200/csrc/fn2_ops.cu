@@ -9,6 +9,8 @@
 // All kernels take strided tensor views (fn2::T4) so the same code serves the reference's NCHW
 // blobs (drop-in use) and the engine's NHWC activations / concat views.
 #include <math.h>
+#include <cfloat>
+
 #include "fn2_common.cuh"
 
 namespace fn2 {
@@ -484,6 +486,191 @@ __global__ void copy_px_kernel(PxView src, PxView dst) {
 }
 #undef FN2_PX_DECODE
 
+// ---------------------------------------------------------------------------------------------
+// Training-time augmentations of DataAugmentation (3-channel data).  Chromatic-eigen: ComputeChromaticEigenspace
+// data_augmentation_layer.cu:148-185 + host finalisation :517-531, ChromaticEigenAugmentation :190-292; effects:
+// ApplyEffects :295-318 and the Gaussian noise of :575-583.  space = 25 floats (tChromaticEigenSpace,
+// augmentation_layer_base.hpp:117-129) followed by 3 doubles of scratch for the channel sums.
+// The reference sums the mean with float atomics (order dependent); here the per-channel sums are double atomics, whose
+// rounding is far below one float ulp.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_max_f(float* addr, float v) {       // v >= 0 or any sign: CAS loop like the reference
+    float old = *addr;
+    while (old < v) {
+        const float assumed = old;
+        old = __uint_as_float(atomicCAS(reinterpret_cast<unsigned int*>(addr), __float_as_uint(assumed), __float_as_uint(v)));
+        if (old == assumed) break;
+    }
+}
+__device__ __forceinline__ void atomic_min_f(float* addr, float v) {
+    float old = *addr;
+    while (old > v) {
+        const float assumed = old;
+        old = __uint_as_float(atomicCAS(reinterpret_cast<unsigned int*>(addr), __float_as_uint(assumed), __float_as_uint(v)));
+        if (old == assumed) break;
+    }
+}
+__global__ void eigenspace_init_kernel(float* space, const float* eigvec9) {
+    const int i = threadIdx.x;
+    if (i < 16) space[i] = (i >= 12 && i < 15) ? FLT_MAX : 0.f;
+    if (i < 9) space[16 + i] = eigvec9[i];
+    if (i < 3) reinterpret_cast<double*>(space + 26)[i] = 0.0;
+}
+__global__ void eigenspace_stats_kernel(T4 d, float* space) {
+    const long long total = (long long)d.n * d.h * d.w;
+    const float* ev = space + 16;
+    float mx_eig[3] = {0, 0, 0}, mx[3] = {0, 0, 0}, mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
+    double sum[3] = {0, 0, 0};
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % d.w);
+        const int y = (int)((idx / d.w) % d.h);
+        const int n = (int)(idx / ((long long)d.w * d.h));
+        float rgb[3];
+        for (int c = 0; c < 3; c++) rgb[c] = d.p[d.off(n, c, y, x)];
+        for (int c = 0; c < 3; c++) {
+            const float eig = ev[3 * c] * rgb[0] + ev[3 * c + 1] * rgb[1] + ev[3 * c + 2] * rgb[2];
+            mx_eig[c] = fmaxf(mx_eig[c], fabsf(eig));
+            mx[c] = fmaxf(mx[c], rgb[c]);
+            mn[c] = fminf(mn[c], rgb[c]);
+            sum[c] += rgb[c];
+        }
+    }
+    for (int c = 0; c < 3; c++) {
+        for (int o = 16; o > 0; o >>= 1) {
+            mx_eig[c] = fmaxf(mx_eig[c], __shfl_xor_sync(0xffffffffu, mx_eig[c], o));
+            mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+            mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+            sum[c] += __shfl_xor_sync(0xffffffffu, sum[c], o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomic_max_f(space + 6 + c, mx_eig[c]);
+            atomic_max_f(space + 9 + c, mx[c]);
+            atomic_min_f(space + 12 + c, mn[c]);
+            atomicAdd(reinterpret_cast<double*>(space + 26) + c, sum[c]);
+        }
+    }
+}
+__global__ void eigenspace_finish_kernel(float* space, int num, int height, int width) {
+    if (threadIdx.x || blockIdx.x) return;
+    float* mean_eig = space, *mean_rgb = space + 3, *max_abs_eig = space + 6;
+    const float* ev = space + 16;
+    const double* sum = reinterpret_cast<const double*>(space + 26);
+    for (int c = 0; c < 3; c++) {
+        mean_rgb[c] = (float)(sum[c] / (double)width / (double)height);
+        mean_rgb[c] = mean_rgb[c] / num;
+    }
+    for (int c = 0; c < 3; c++) {
+        mean_eig[c] = ev[3 * c] * mean_rgb[0] + ev[3 * c + 1] * mean_rgb[1] + ev[3 * c + 2] * mean_rgb[2];
+        if (max_abs_eig[c] > 1e-2) mean_eig[c] = mean_eig[c] / max_abs_eig[c];
+    }
+    space[15] = sqrtf(max_abs_eig[0] * max_abs_eig[0] + max_abs_eig[1] * max_abs_eig[1] + max_abs_eig[2] * max_abs_eig[2]);
+}
+__global__ void chromatic_eigen_kernel(T4 d, const float* __restrict__ coeffs, const float* __restrict__ space, float max_multiplier) {
+    const long long total = (long long)d.n * d.h * d.w;
+    const float* mean_eig = space, *mean_rgb = space + 3, *max_abs_eig = space + 6, *eigvec = space + 16;
+    const float max_l = space[15];
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % d.w);
+        const int y = (int)((idx / d.w) % d.h);
+        const int n = (int)(idx / ((long long)d.w * d.h));
+        const float* ch = coeffs + 22 * n;
+        float s, s1, l, l1 = 0.f;
+        float rgb[3], eig[3];
+        for (int c = 0; c < 3; c++) rgb[c] = d.p[d.off(n, c, y, x)] - mean_rgb[c];
+        for (int c = 0; c < 3; c++) {
+            eig[c] = eigvec[3 * c] * rgb[0] + eigvec[3 * c + 1] * rgb[1] + eigvec[3 * c + 2] * rgb[2];
+            if (max_abs_eig[c] > 1e-2f) {
+                eig[c] = eig[c] / max_abs_eig[c];
+                eig[c] = copysignf(powf(fabsf(eig[c]), ch[c]), eig[c]);
+                eig[c] = eig[c] + ch[3 + c];
+                eig[c] = eig[c] * ch[6 + c];
+            }
+        }
+        for (int c = 0; c < 3; c++) eig[c] = eig[c] + mean_eig[c];
+        if (max_abs_eig[0] > 1e-2f) {
+            eig[0] = copysignf(powf(fabsf(eig[0]), ch[9]), eig[0]);
+            eig[0] = eig[0] + ch[12];
+            eig[0] = eig[0] * ch[15];
+        }
+        s = sqrtf(eig[1] * eig[1] + eig[2] * eig[2]);
+        s1 = s;
+        if (s > 1e-2f) {
+            s1 = powf(s1, ch[10]);
+            s1 = fmaxf(s1 + ch[13], 0.f);
+            s1 = s1 * ch[16];
+        }
+        if (ch[21] != 0) {
+            const float t1 = cosf(ch[21]) * eig[1] - sinf(ch[21]) * eig[2];
+            const float t2 = sinf(ch[21]) * eig[1] + cosf(ch[21]) * eig[2];
+            eig[1] = t1; eig[2] = t2;
+        }
+        for (int c = 0; c < 3; c++) if (max_abs_eig[c] > 1e-2f) eig[c] = eig[c] * max_abs_eig[c];
+        if (max_l > 1e-2f) {
+            l1 = sqrtf(eig[0] * eig[0] + eig[1] * eig[1] + eig[2] * eig[2]);
+            l1 = l1 / max_l;
+        }
+        if (s > 1e-2f) { eig[1] = eig[1] / s * s1; eig[2] = eig[2] / s * s1; }
+        if (max_l > 1e-2f) {
+            l = sqrtf(eig[0] * eig[0] + eig[1] * eig[1] + eig[2] * eig[2]);
+            l1 = powf(l1, ch[18]);
+            l1 = fmaxf(l1 + ch[19], 0.f);
+            l1 = l1 * ch[20];
+            l1 = l1 * max_l;
+            if (l > 1e-2f)
+                for (int c = 0; c < 3; c++) {
+                    eig[c] = eig[c] / l * l1;
+                    if (eig[c] > max_abs_eig[c]) eig[c] = max_abs_eig[c];
+                }
+        }
+        for (int c = 0; c < 3; c++) {
+            float v = eigvec[c] * eig[0] + eigvec[3 + c] * eig[1] + eigvec[6 + c] * eig[2];
+            v = fminf(v, max_multiplier);
+            v = fmaxf(v, 0.f);
+            d.p[d.off(n, c, y, x)] = v;
+        }
+    }
+}
+__global__ void apply_effects_kernel(T4 d, const float* __restrict__ effects, float max_multiplier) {
+    const long long total = (long long)d.n * d.h * d.w;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % d.w);
+        const int y = (int)((idx / d.w) % d.h);
+        const int n = (int)(idx / ((long long)d.w * d.h));
+        const float* e = effects + 9 * n;
+        const bool shadow = (x - d.w / 2) * e[4] + (y - d.h / 2) * e[5] - e[6] > 0;
+        for (int c = 0; c < d.c; c++) {
+            float sample = d.p[d.off(n, c, y, x)];
+            if (shadow) sample -= e[7];
+            d.p[d.off(n, c, y, x)] = clampf(sample, 0.f, max_multiplier);
+        }
+    }
+}
+// counter-based generator (SplitMix64 of (seed, element index)) + Box-Muller.  The reference draws from cuRAND's default
+// generator with an unpinned seed/offset: the noise field is not reproducible there either, only its distribution.
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+__global__ void gaussian_noise_kernel(T4 d, const float* __restrict__ effects, unsigned long long seed) {
+    const long long total = d.count();
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % d.w);
+        long long r = idx / d.w;
+        const int y = (int)(r % d.h); r /= d.h;
+        const int c = (int)(r % d.c);
+        const int n = (int)(r / d.c);
+        const float sigma = effects[9 * n + 8];
+        if (!(sigma > 0)) continue;
+        const unsigned long long h = splitmix64(seed ^ splitmix64((unsigned long long)idx));
+        const float u1 = ((float)(h >> 40) + 1.0f) * (1.0f / 16777216.0f);                 // (0, 1]
+        const float u2 = (float)((h >> 16) & 0xffffff) * (1.0f / 16777216.0f);
+        const float g = sqrtf(-2.0f * logf(u1)) * cosf(6.28318530718f * u2);
+        d.p[d.off(n, c, y, x)] = d.p[d.off(n, c, y, x)] + sigma * g;
+    }
+}
+
 }  // namespace fn2
 
 using namespace fn2;
@@ -667,6 +854,48 @@ int fn2_copy(const fn2_tensor* src, const fn2_tensor* dst, void* stream) {
         copy_kernel<false><<<ew_grid(d.count(), 256), 256, 0, st>>>(s, d);
     }
     FN2_LAUNCH_CHECK();
+    return FN2_OK;
+}
+
+int fn2_chromatic_eigenspace(const fn2_tensor* data, const float* eigvec9_dev, float* space_dev, void* stream) {
+    FN2_CHECK_ARG(valid(data) && eigvec9_dev && space_dev, "chromatic_eigenspace: null argument");
+    T4 d = view(data);
+    FN2_CHECK_ARG(d.c == 3, "Chromatic-Eigen augmentations only work with 3-channel input (data_augmentation_layer.cu:488)");
+    FN2_CHECK_ARG(!((uintptr_t)space_dev & 7), "chromatic_eigenspace: space must be 8-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    eigenspace_init_kernel<<<1, 32, 0, st>>>(space_dev, eigvec9_dev);
+    FN2_LAUNCH_CHECK();
+    const long long total = (long long)d.n * d.h * d.w;
+    eigenspace_stats_kernel<<<ew_grid(total, 256), 256, 0, st>>>(d, space_dev);
+    FN2_LAUNCH_CHECK();
+    eigenspace_finish_kernel<<<1, 32, 0, st>>>(space_dev, d.n, d.h, d.w);
+    FN2_LAUNCH_CHECK();
+    return FN2_OK;
+}
+
+int fn2_chromatic_eigen_augmentation(const fn2_tensor* data, const float* coeffs_dev, const float* space_dev,
+                                     float max_multiplier, void* stream) {
+    FN2_CHECK_ARG(valid(data) && coeffs_dev && space_dev, "chromatic_eigen: null argument");
+    T4 d = view(data);
+    FN2_CHECK_ARG(d.c == 3, "Chromatic-Eigen augmentations only work with 3-channel input (data_augmentation_layer.cu:551)");
+    const long long total = (long long)d.n * d.h * d.w;
+    chromatic_eigen_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(d, coeffs_dev, space_dev, max_multiplier);
+    FN2_LAUNCH_CHECK();
+    return FN2_OK;
+}
+
+int fn2_apply_effects(const fn2_tensor* data, const float* effects_dev, float max_multiplier, unsigned long long noise_seed,
+                      int add_noise, void* stream) {
+    FN2_CHECK_ARG(valid(data) && effects_dev, "apply_effects: null argument");
+    T4 d = view(data);
+    FN2_CHECK_ARG(d.c == 3, "Effect augmentations only work with 3-channel input (data_augmentation_layer.cu:567)");
+    const long long total = (long long)d.n * d.h * d.w;
+    apply_effects_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(d, effects_dev, max_multiplier);
+    FN2_LAUNCH_CHECK();
+    if (add_noise) {
+        gaussian_noise_kernel<<<ew_grid(d.count(), 256), 256, 0, (cudaStream_t)stream>>>(d, effects_dev, noise_seed);
+        FN2_LAUNCH_CHECK();
+    }
     return FN2_OK;
 }
 

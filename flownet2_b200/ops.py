@@ -102,6 +102,33 @@ def color_contrast_augmentation(x, chroma, max_multiplier=1.0):
     return out
 
 
+def chromatic_eigenspace(x, eigvec9):
+    """-> 25 floats (tChromaticEigenSpace) as a device tensor of 32 (the tail is scratch)."""
+    ev = torch.as_tensor(eigvec9, dtype=torch.float32, device=x.device).reshape(9).contiguous()
+    space = torch.zeros(32, dtype=torch.float32, device=x.device)
+    dx = desc(x)
+    check(lib().fn2_chromatic_eigenspace(C.byref(dx), C.c_void_p(ev.data_ptr()), C.c_void_p(space.data_ptr()), _stream()))
+    return space
+
+
+def chromatic_eigen_augmentation(x, coeffs, space, max_multiplier=1.0):
+    out = x.clone(memory_format=torch.preserve_format)
+    coeffs = coeffs.contiguous()
+    do = desc(out)
+    check(lib().fn2_chromatic_eigen_augmentation(C.byref(do), C.c_void_p(coeffs.data_ptr()), C.c_void_p(space.data_ptr()),
+                                                 C.c_float(max_multiplier), _stream()))
+    return out
+
+
+def apply_effects(x, effects, max_multiplier=1.0, noise_seed=0, add_noise=False):
+    out = x.clone(memory_format=torch.preserve_format)
+    effects = effects.contiguous()
+    do = desc(out)
+    check(lib().fn2_apply_effects(C.byref(do), C.c_void_p(effects.data_ptr()), C.c_float(max_multiplier),
+                                  C.c_ulonglong(noise_seed), 1 if add_noise else 0, _stream()))
+    return out
+
+
 def mean_update(top, mean_pp, mean_pc, num_iter):
     dt, dm = desc(top), desc(mean_pp)
     check(lib().fn2_mean_update(C.byref(dt), C.byref(dm), C.c_void_p(mean_pc.data_ptr()), float(num_iter), _stream()))

@@ -104,6 +104,20 @@ FN2_API int fn2_color_contrast_augmentation(const fn2_tensor* data, const float*
                                             float max_multiplier, void* stream);
 /* Running-mean update of :600-608: mean_pp = (mean_pp*(num_iter-1) + sum_n top_n/num)/num_iter,
  * mean_pc[c] = average of mean_pp over the area.  mean_pp is a (1,C,H,W)-shaped tensor. */
+/* Training-time augmentations (3-channel data, in place).  Reference: ComputeChromaticEigenspace / ChromaticEigenAugmentation /
+ * ApplyEffects, data_augmentation_layer.cu:148-318 and the host-side finalisation / noise of Forward_gpu :486-583.
+ *   space_dev : 32 floats, 8-byte aligned: tChromaticEigenSpace (25 floats: mean_eig[3], mean_rgb[3], max_abs_eig[3],
+ *               max_rgb[3], min_rgb[3], max_l, eigvec[9], augmentation_layer_base.hpp:117-129) + scratch
+ *   coeffs_dev: N x 22 floats in tChromaticEigenCoeffs order (augmentation_layer_base.hpp:52-75)
+ *   effects_dev: N x 9 floats in tEffectCoeffs order (fog_amount, fog_size, motion_blur_angle, motion_blur_size,
+ *               shadow_nx, shadow_ny, shadow_distance, shadow_strength, noise); as in the reference only the shadow, the
+ *               clamp and the additive Gaussian noise act.  The noise stream is this library's own counter-based generator
+ *               (the reference's cuRAND stream is unpinned). */
+FN2_API int fn2_chromatic_eigenspace(const fn2_tensor* data, const float* eigvec9_dev, float* space_dev, void* stream);
+FN2_API int fn2_chromatic_eigen_augmentation(const fn2_tensor* data, const float* coeffs_dev, const float* space_dev,
+                                             float max_multiplier, void* stream);
+FN2_API int fn2_apply_effects(const fn2_tensor* data, const float* effects_dev, float max_multiplier,
+                              unsigned long long noise_seed, int add_noise, void* stream);
 FN2_API int fn2_mean_update(const fn2_tensor* top, const fn2_tensor* mean_pp, float* mean_pc_dev,
                             float num_iter, void* stream);
 /* Mean subtraction :610-634: per_pixel != 0 subtracts mean_pp, else the per-channel values. */

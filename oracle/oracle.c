@@ -519,6 +519,137 @@ FN2O_API int fn2o_color_contrast_augmentation(float* data, const float* chroma, 
     return 0;
 }
 
+/* Chromatic-eigen augmentation (training use of DataAugmentation).  PARITY UNPINNED: the reference has no test or CPU path
+ * for it; this restates data_augmentation_layer.cu:148-185 (ComputeChromaticEigenspace), :490-545 (host finalisation in
+ * Forward_gpu) and :190-292 (ChromaticEigenAugmentation).  The reference kernels address the plane as [x*height + y]; since
+ * every (x, y) is visited exactly once and the per-pixel arithmetic does not depend on the position, that is the plain
+ * per-pixel transform restated here.  space[25] = mean_eig[3], mean_rgb[3], max_abs_eig[3], max_rgb[3], min_rgb[3],
+ * max_l, eigvec[9] (tChromaticEigenSpace, augmentation_layer_base.hpp:117-129).  The mean is summed in double (the
+ * reference's float atomicAdd order is not reproducible). */
+FN2O_API int fn2o_chromatic_eigenspace(const float* data, int num, int height, int width, const float* eigvec9, float* space) {
+    double sum[3] = {0, 0, 0};
+    float max_abs_eig[3] = {0, 0, 0}, max_rgb[3] = {0, 0, 0}, min_rgb[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
+    const size_t plane = (size_t)height * width;
+    for (int n = 0; n < num; n++)
+        for (size_t i = 0; i < plane; i++) {
+            float rgb[3];
+            for (int c = 0; c < 3; c++) rgb[c] = data[((size_t)n * 3 + c) * plane + i];
+            for (int c = 0; c < 3; c++) {
+                float eig = eigvec9[3 * c] * rgb[0] + eigvec9[3 * c + 1] * rgb[1] + eigvec9[3 * c + 2] * rgb[2];
+                if (fabsf(eig) > max_abs_eig[c]) max_abs_eig[c] = fabsf(eig);
+                if (rgb[c] > max_rgb[c]) max_rgb[c] = rgb[c];
+                if (rgb[c] < min_rgb[c]) min_rgb[c] = rgb[c];
+                sum[c] += rgb[c];
+            }
+        }
+    float* mean_eig = space, *mean_rgb = space + 3;
+    for (int c = 0; c < 3; c++) {
+        mean_rgb[c] = (float)(sum[c] / (double)width / (double)height);
+        mean_rgb[c] = mean_rgb[c] / num;                                      /* :517-518 */
+        space[6 + c] = max_abs_eig[c]; space[9 + c] = max_rgb[c]; space[12 + c] = min_rgb[c];
+    }
+    for (int c = 0; c < 3; c++) {                                            /* :520-526 */
+        mean_eig[c] = eigvec9[3 * c] * mean_rgb[0] + eigvec9[3 * c + 1] * mean_rgb[1] + eigvec9[3 * c + 2] * mean_rgb[2];
+        if (max_abs_eig[c] > 1e-2) mean_eig[c] = mean_eig[c] / max_abs_eig[c];
+    }
+    space[15] = sqrtf(max_abs_eig[0] * max_abs_eig[0] + max_abs_eig[1] * max_abs_eig[1] + max_abs_eig[2] * max_abs_eig[2]);
+    for (int i = 0; i < 9; i++) space[16 + i] = eigvec9[i];
+    return 0;
+}
+
+/* coeffs: per sample 22 floats in tChromaticEigenCoeffs order (augmentation_layer_base.hpp:52-75). In place, (N,3,H,W). */
+FN2O_API int fn2o_chromatic_eigen_augmentation(float* data, const float* coeffs, const float* space, int num, int height,
+                                               int width, float max_multiplier) {
+    const float* mean_eig = space, *mean_rgb = space + 3, *max_abs_eig = space + 6, *eigvec = space + 16;
+    const float max_l = space[15];
+    const size_t plane = (size_t)height * width;
+#pragma omp parallel for schedule(static)
+    for (int n = 0; n < num; n++) {
+        const float* ch = coeffs + 22 * n;
+        const float pow_nomean[3] = {ch[0], ch[1], ch[2]}, add_nomean[3] = {ch[3], ch[4], ch[5]}, mult_nomean[3] = {ch[6], ch[7], ch[8]};
+        const float pow_withmean0 = ch[9], pow_withmean1 = ch[10], add_withmean0 = ch[12], add_withmean1 = ch[13];
+        const float mult_withmean0 = ch[15], mult_withmean1 = ch[16];
+        const float lmult_pow = ch[18], lmult_add = ch[19], lmult_mult = ch[20], col_angle = ch[21];
+        for (size_t i = 0; i < plane; i++) {
+            float s, s1, l, l1 = 0.f;
+            float rgb[3], eig[3];
+            for (int c = 0; c < 3; c++) rgb[c] = data[((size_t)n * 3 + c) * plane + i] - mean_rgb[c];
+            for (int c = 0; c < 3; c++) {
+                eig[c] = eigvec[3 * c] * rgb[0] + eigvec[3 * c + 1] * rgb[1] + eigvec[3 * c + 2] * rgb[2];
+                if (max_abs_eig[c] > 1e-2f) {
+                    eig[c] = eig[c] / max_abs_eig[c];
+                    eig[c] = copysignf(powf(fabsf(eig[c]), pow_nomean[c]), eig[c]);
+                    eig[c] = eig[c] + add_nomean[c];
+                    eig[c] = eig[c] * mult_nomean[c];
+                }
+            }
+            for (int c = 0; c < 3; c++) eig[c] = eig[c] + mean_eig[c];
+            if (max_abs_eig[0] > 1e-2f) {
+                eig[0] = copysignf(powf(fabsf(eig[0]), pow_withmean0), eig[0]);
+                eig[0] = eig[0] + add_withmean0;
+                eig[0] = eig[0] * mult_withmean0;
+            }
+            s = sqrtf(eig[1] * eig[1] + eig[2] * eig[2]);
+            s1 = s;
+            if (s > 1e-2f) {
+                s1 = powf(s1, pow_withmean1);
+                s1 = fmaxf(s1 + add_withmean1, 0.f);
+                s1 = s1 * mult_withmean1;
+            }
+            if (col_angle != 0) {
+                float t1 = cosf(col_angle) * eig[1] - sinf(col_angle) * eig[2];
+                float t2 = sinf(col_angle) * eig[1] + cosf(col_angle) * eig[2];
+                eig[1] = t1; eig[2] = t2;
+            }
+            for (int c = 0; c < 3; c++) if (max_abs_eig[c] > 1e-2f) eig[c] = eig[c] * max_abs_eig[c];
+            if (max_l > 1e-2f) {
+                l1 = sqrtf(eig[0] * eig[0] + eig[1] * eig[1] + eig[2] * eig[2]);
+                l1 = l1 / max_l;
+            }
+            if (s > 1e-2f) { eig[1] = eig[1] / s * s1; eig[2] = eig[2] / s * s1; }
+            if (max_l > 1e-2f) {
+                l = sqrtf(eig[0] * eig[0] + eig[1] * eig[1] + eig[2] * eig[2]);
+                l1 = powf(l1, lmult_pow);
+                l1 = fmaxf(l1 + lmult_add, 0.f);
+                l1 = l1 * lmult_mult;
+                l1 = l1 * max_l;
+                if (l > 1e-2f)
+                    for (int c = 0; c < 3; c++) {
+                        eig[c] = eig[c] / l * l1;
+                        if (eig[c] > max_abs_eig[c]) eig[c] = max_abs_eig[c];
+                    }
+            }
+            for (int c = 0; c < 3; c++) {
+                float v = eigvec[c] * eig[0] + eigvec[3 + c] * eig[1] + eigvec[6 + c] * eig[2];
+                v = fminf(v, max_multiplier);
+                v = fmaxf(v, 0.f);
+                data[((size_t)n * 3 + c) * plane + i] = v;
+            }
+        }
+    }
+    return 0;
+}
+
+/* ApplyEffects, data_augmentation_layer.cu:295-318 (only the shadow and the clamp are implemented by the reference; fog and
+ * motion blur coefficients are carried but unused; noise is added afterwards by cuRAND, :575-583 -- not restated, RNG
+ * unpinned).  effects: per sample 9 floats in tEffectCoeffs order (fog_amount, fog_size, motion_blur_angle,
+ * motion_blur_size, shadow_nx, shadow_ny, shadow_distance, shadow_strength, noise).  In place, (N,C,H,W). */
+FN2O_API int fn2o_apply_effects(float* data, const float* effects, int num, int channels, int height, int width,
+                                float max_multiplier) {
+    for (int n = 0; n < num; n++) {
+        const float* e = effects + 9 * n;
+        for (int c = 0; c < channels; c++)
+            for (int y = 0; y < height; y++)
+                for (int x = 0; x < width; x++) {
+                    float* p = data + (((size_t)n * channels + c) * height + y) * width + x;
+                    float sample = *p;
+                    if ((x - width / 2) * e[4] + (y - height / 2) * e[5] - e[6] > 0) sample -= e[7];
+                    *p = clampf(sample, 0.f, max_multiplier);
+                }
+    }
+    return 0;
+}
+
 /* Mean handling of DataAugmentationLayer::Forward_gpu, data_augmentation_layer.cu:594-634.
  * mode 0: recompute_mean>0 path.  state = {num_iter (already incremented, :353-354)},
  *         mean_pp[C*H*W], mean_pc[C] are layer blobs_[1], blobs_[2] and are UPDATED when

@@ -138,6 +138,36 @@ def color_contrast_augmentation(data, chroma, max_multiplier=1.0):
     return data
 
 
+def chromatic_eigenspace(data, eigvec9):
+    """-> 25 floats (tChromaticEigenSpace: mean_eig, mean_rgb, max_abs_eig, max_rgb, min_rgb, max_l, eigvec)."""
+    data, pd = _f(data)
+    ev, pe = _f(np.asarray(eigvec9, np.float32).reshape(9))
+    N, Cc, H, W = data.shape
+    assert Cc == 3
+    space = np.zeros(25, np.float32)
+    lib().fn2o_chromatic_eigenspace(pd, N, H, W, pe, space.ctypes.data_as(C.POINTER(C.c_float)))
+    return space
+
+
+def chromatic_eigen_augmentation(data, coeffs, space, max_multiplier=1.0):
+    data = np.array(data, np.float32, copy=True, order="C")
+    coeffs, pc = _f(coeffs)
+    space, ps = _f(space)
+    N, Cc, H, W = data.shape
+    assert Cc == 3 and coeffs.shape == (N, 22) and space.shape == (25,)
+    lib().fn2o_chromatic_eigen_augmentation(data.ctypes.data_as(C.POINTER(C.c_float)), pc, ps, N, H, W, C.c_float(max_multiplier))
+    return data
+
+
+def apply_effects(data, effects, max_multiplier=1.0):
+    data = np.array(data, np.float32, copy=True, order="C")
+    effects, pe = _f(effects)
+    N, Cc, H, W = data.shape
+    assert effects.shape == (N, 9)
+    lib().fn2o_apply_effects(data.ctypes.data_as(C.POINTER(C.c_float)), pe, N, Cc, H, W, C.c_float(max_multiplier))
+    return data
+
+
 def mean_subtract(top, mode, num_iter=0.0, recompute_mean=0, mean_per_pixel=False, mean_pp=None,
                   mean_pc=None):
     """Returns (top, mean_pp, mean_pc) after the mean step (copies; inputs untouched)."""

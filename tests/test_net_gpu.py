@@ -8,6 +8,7 @@ relative to their magnitude (1e-4) to localise a failure.
 import numpy as np
 import pytest
 
+from oracle import oracle as O
 from oracle.net import OracleNet
 from tests.util import maxabs, rng, smooth_images
 
@@ -109,3 +110,99 @@ def test_flo_roundtrip_and_reference_files(fn2, tmp_path):
     # python twin of the reference writer: (H,W,2) interleaved (scripts/run-flownet.py:117-124)
     assert np.array_equal(np.frombuffer(raw[12:], np.float32).reshape(13, 17, 2), flow.transpose(1, 2, 0))
     assert np.array_equal(fn2.read_flo(p), flow)
+
+
+AUG_PROTO = """
+name: "aug_train"
+input: "img"
+input_shape { dim: 4 dim: 3 dim: 48 dim: 64 }
+input: "img_b"
+input_shape { dim: 4 dim: 3 dim: 48 dim: 64 }
+layer {
+  name: "aug" type: "DataAugmentation" bottom: "img" top: "aug" top: "params"
+  augmentation_param {
+    augment_during_test: true crop_width: 48 crop_height: 32 max_multiplier: 1
+    mirror { rand_type: "bernoulli" prob: 0.5 }
+    translate { rand_type: "uniform_bernoulli" mean: 0 spread: 0.1 prob: 1.0 }
+    rotate { rand_type: "uniform_bernoulli" mean: 0 spread: 0.2 prob: 1.0 }
+    zoom { rand_type: "uniform_bernoulli" exp: true mean: 0.1 spread: 0.1 prob: 1.0 }
+    squeeze { rand_type: "uniform_bernoulli" exp: true mean: 0 spread: 0.1 prob: 1.0 }
+    gamma { rand_type: "gaussian_bernoulli" exp: true mean: 0 spread: 0.2 prob: 1.0 }
+    brightness { rand_type: "gaussian_bernoulli" mean: 0 spread: 0.05 prob: 1.0 }
+    contrast { rand_type: "gaussian_bernoulli" exp: true mean: 0 spread: 0.2 prob: 1.0 }
+    color { rand_type: "gaussian_bernoulli" exp: true mean: 0 spread: 0.1 prob: 1.0 }
+    lmult_pow { rand_type: "uniform_bernoulli" exp: true mean: 0 spread: 0.2 prob: 1.0 }
+    lmult_mult { rand_type: "uniform_bernoulli" exp: true mean: 0 spread: 0.2 prob: 1.0 }
+    lmult_add { rand_type: "uniform_bernoulli" mean: 0 spread: 0.03 prob: 1.0 }
+    sat_pow { rand_type: "uniform_bernoulli" exp: true mean: 0 spread: 0.2 prob: 1.0 }
+    col_rotate { rand_type: "uniform_bernoulli" mean: 0 spread: 0.5 prob: 1.0 }
+    shadow_angle { rand_type: "uniform" mean: 0 spread: 3.1 }
+    shadow_distance { rand_type: "uniform" mean: 0 spread: 5 }
+    shadow_strength { rand_type: "uniform" mean: 0.2 spread: 0.1 }
+    chromatic_eigvec: 0.51 chromatic_eigvec: 0.56 chromatic_eigvec: 0.65 chromatic_eigvec: 0.79 chromatic_eigvec: 0.01
+    chromatic_eigvec: -0.62 chromatic_eigvec: 0.35 chromatic_eigvec: -0.83 chromatic_eigvec: 0.44
+  }
+}
+layer {
+  name: "aug_b" type: "DataAugmentation" bottom: "img_b" bottom: "params" top: "aug_b"
+  augmentation_param {
+    augment_during_test: true crop_width: 48 crop_height: 32 max_multiplier: 1
+    chromatic_eigvec: 0.51 chromatic_eigvec: 0.56 chromatic_eigvec: 0.65 chromatic_eigvec: 0.79 chromatic_eigvec: 0.01
+    chromatic_eigvec: -0.62 chromatic_eigvec: 0.35 chromatic_eigvec: -0.83 chromatic_eigvec: 0.44
+  }
+}
+"""
+
+COEFF_DEFAULT = np.array([0, 0, 0, 0, 1, 1, 1, 0, 1, 1, 1, 1] + [1, 1, 1, 0, 0, 0, 1, 1, 1, 1, 1, 1, 0, 0, 0, 1, 1, 1, 1, 0, 1, 0] + [0] * 8,
+                         np.float32)
+
+
+def oracle_augment(x, params, crop_w, crop_h, eigvec, max_mult):
+    """DataAugmentationLayer::Forward_gpu given the (N,42) coefficient blob, restated with the oracle's pieces."""
+    N = x.shape[0]
+    vals = np.where(np.abs(COEFF_DEFAULT) < 1e-3, params, np.exp(params)).astype(np.float32)      # array_to_coeff
+    vals = np.where(np.abs(COEFF_DEFAULT - vals) < 1e-3, COEFF_DEFAULT, vals)                      # clear_defaults
+    mats = np.stack([O.transmat_from_coeff(crop_w, crop_h, x.shape[3], x.shape[2], mirror=float(vals[n, 0]), angle=float(vals[n, 3]),
+                                           dx=float(vals[n, 1]), dy=float(vals[n, 2]), zoom_x=float(vals[n, 4]), zoom_y=float(vals[n, 5]))
+                     for n in range(N)])
+    out = O.spatial_augmentation(x, mats, crop_h, crop_w)
+    eig = vals[:, 12:34]
+    if np.any(eig != COEFF_DEFAULT[12:34]):
+        out = O.chromatic_eigen_augmentation(out, eig, O.chromatic_eigenspace(x, eigvec), max_mult)
+    chroma = vals[:, 6:12]
+    if np.any(chroma != COEFF_DEFAULT[6:12]):
+        out = O.color_contrast_augmentation(out, chroma, max_mult)
+    eff = np.zeros((N, 9), np.float32)
+    eff[:, 0:4] = vals[:, 34:38]
+    eff[:, 4], eff[:, 5] = np.cos(vals[:, 38]), np.sin(vals[:, 38])
+    eff[:, 6:9] = vals[:, 39:42]
+    if np.any((eff[:, 0] != 0) & (eff[:, 1] != 0)) or np.any(eff[:, 3] > 0) or np.any(eff[:, 7] > 0):
+        out = O.apply_effects(out, eff, max_mult)
+    return out, vals
+
+
+def test_data_augmentation_training_path(fn2):
+    """Sampled coefficients (params output blob) -> spatial + chromatic-eigen + chromatic + effect kernels; a second layer
+    consumes the same coefficient blob.  The random STREAM is unpinned (boost in the reference), so the check is: whatever
+    was sampled, the images are what the reference arithmetic gives for those coefficients, and the samples lie in the
+    configured ranges."""
+    net = fn2.Net(AUG_PROTO, None, fn2.TEST)
+    r = rng(3)
+    img = r.uniform(0, 1, (4, 3, 48, 64)).astype(np.float32)
+    img_b = r.uniform(0, 1, (4, 3, 48, 64)).astype(np.float32)
+    seen = []
+    for it in range(3):
+        net.forward(img=img, img_b=img_b)
+        params = net.blobs["params"].data.reshape(4, 42).copy()
+        seen.append(params)
+        want, vals = oracle_augment(img, params, 48, 32, EIGVEC_T, 1.0)
+        assert maxabs(net.blobs["aug"].data, want) <= 2e-5
+        want_b, _ = oracle_augment(img_b, params, 48, 32, EIGVEC_T, 1.0)
+        assert maxabs(net.blobs["aug_b"].data, want_b) <= 2e-5
+        assert set(np.unique(vals[:, 0])) <= {0.0, 1.0}                                  # mirror
+        assert np.all(np.abs(vals[:, 1:3]) <= 0.1 + 1e-6) and np.all(np.abs(vals[:, 3]) <= 0.2 + 1e-6)
+        assert np.all(vals[:, 40] >= 0.1 - 1e-6) and np.all(vals[:, 40] <= 0.3 + 1e-6)  # shadow strength
+    assert not np.array_equal(seen[0], seen[1])                                          # fresh samples every forward
+
+
+EIGVEC_T = [0.51, 0.56, 0.65, 0.79, 0.01, -0.62, 0.35, -0.83, 0.44]

@@ -287,6 +287,43 @@ def test_conv_tcgen05_row_mode(ops, case):
     assert maxabs(ungarded, want) <= 1e-6 * scale                     # tap-group packing (no guard promised)
 
 
+EIGVEC = [0.51, 0.56, 0.65, 0.79, 0.01, -0.62, 0.35, -0.83, 0.44]       # the published FlowNet chromatic eigenvectors
+
+
+@pytest.mark.parametrize("cl", [False, True])
+def test_chromatic_eigen_and_effects(ops, cl):
+    """Training-time colour augmentations: parity unpinned by the reference (no test, no CPU path); checked against the
+    oracle restatement.  powf/cosf differ by a few ulp between libm and the device."""
+    r = rng(77)
+    N, H, W = 3, 20, 28
+    x = r.uniform(0, 1, (N, 3, H, W)).astype(np.float32)
+    space_want = O.chromatic_eigenspace(x, EIGVEC)
+    space = ops.chromatic_eigenspace(dev(x, cl), EIGVEC)
+    assert maxabs(space[:25].cpu().numpy(), space_want) <= 2e-6
+    coeffs = np.tile(np.array([1, 1, 1, 0, 0, 0, 1, 1, 1, 1, 1, 1, 0, 0, 0, 1, 1, 1, 1, 0, 1, 0], np.float32), (N, 1))
+    coeffs += (r.uniform(-0.2, 0.2, coeffs.shape)).astype(np.float32)
+    want = O.chromatic_eigen_augmentation(x, coeffs, space_want, 1.0)
+    got = host(ops.chromatic_eigen_augmentation(dev(x, cl), torch.from_numpy(coeffs).cuda(), space, 1.0))
+    assert maxabs(got, want) <= 1e-5
+    eff = np.zeros((N, 9), np.float32)
+    ang = r.uniform(0, 6.28, N)
+    eff[:, 4], eff[:, 5] = np.cos(ang), np.sin(ang)
+    eff[:, 6] = r.uniform(-3, 3, N)
+    eff[:, 7] = r.uniform(0.1, 0.4, N)
+    want = O.apply_effects(x, eff, 1.0)
+    got = host(ops.apply_effects(dev(x, cl), torch.from_numpy(eff).cuda(), 1.0))
+    assert maxabs(got, want) == 0.0
+    # additive noise: own counter-based generator; only the distribution is specified (sigma per sample)
+    eff[:, 8] = [0.0, 0.05, 0.2]
+    eff[:, 7] = 0.0
+    base = np.full((N, 3, 64, 64), 0.5, np.float32)
+    noisy = host(ops.apply_effects(dev(base, cl), torch.from_numpy(eff).cuda(), 10.0, noise_seed=1234, add_noise=True))
+    d = noisy - base
+    assert np.abs(d[0]).max() == 0.0
+    for n in (1, 2):
+        assert abs(d[n].std() - eff[n, 8]) < 0.03 * eff[n, 8] + 1e-4 and abs(d[n].mean()) < 0.05 * eff[n, 8]
+
+
 def test_deconv_known_answer(ops):
     # the reference's TestSimpleDeconvolution (test_deconvolution_layer.cpp:91-137): input and
     # weights all ones, bias 0.1, 3 in / 4 out channels, kernel 3 stride 2: 3.1 / 6.1 / 12.1

@@ -225,3 +225,23 @@ def test_ops_golden_fixture():
     assert eq(O.conv_fwd(g["conv_x"], g["conv_w"], g["conv_b"], 2, 1), g["conv_s2_p1"])
     assert eq(O.deconv_fwd(g["conv_x"], g["deconv_w"], g["deconv_b"], 2, 1), g["deconv_s2_p1"])
     assert eq(O.channel_norm(g["conv_x"]), g["chnorm"])
+
+
+def test_oracle_training_augmentations_identities():
+    """Chromatic-eigen with an orthonormal basis and default coefficients is the identity (up to the [0, max] clamp); the
+    shadow effect darkens exactly the half-plane (x - W/2) nx + (y - H/2) ny > distance."""
+    r = np.random.default_rng(5)
+    x = r.uniform(0.05, 0.95, (2, 3, 6, 9)).astype(np.float32)
+    q, _ = np.linalg.qr(r.standard_normal((3, 3)))
+    space = O.chromatic_eigenspace(x, q.astype(np.float32).reshape(9))
+    assert np.allclose(space[3:6], x.mean(axis=(0, 2, 3)), atol=1e-6)
+    ident = np.tile(np.array([1, 1, 1, 0, 0, 0, 1, 1, 1, 1, 1, 1, 0, 0, 0, 1, 1, 1, 1, 0, 1, 0], np.float32), (2, 1))
+    y = O.chromatic_eigen_augmentation(x, ident, space, 1.0)
+    assert np.abs(y - x).max() < 2e-6
+    eff = np.zeros((2, 9), np.float32)
+    eff[:, 4] = 1.0; eff[:, 6] = 1.5; eff[:, 7] = 0.25                 # normal (1, 0), distance 1.5, strength 0.25
+    z = O.apply_effects(x, eff, 1.0)
+    xs = np.arange(9) - 9 // 2
+    dark = xs - 1.5 > 0
+    assert np.array_equal(z[..., ~dark], x[..., ~dark])
+    assert np.allclose(z[..., dark], np.clip(x[..., dark] - 0.25, 0, 1), atol=0)
