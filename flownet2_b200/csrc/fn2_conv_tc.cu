@@ -31,6 +31,7 @@ namespace fn2 {
 namespace {
 
 constexpr int TC_THREADS = 384;
+constexpr int CORR_TR_STRIDE = 57;             // floats per pixel row of the correlation epilogue's transpose buffer (odd: no bank conflicts)
 constexpr int A_TILE_BYTES = 128 * 128;          // 128 pixels x 32 fp32
 
 // division by a launch constant without the ~40-instruction integer divide (the tile decode is on the critical path of the
@@ -62,6 +63,11 @@ struct TcParams {
     // spread over all SMs (448 tiles on 148 SMs: 3 + 1/8 rounds instead of 4); their partials are summed by a fix-up kernel
     int tail_first, tail_z, ntotal;
     FastDiv d_ntiles_p, d_cotiles, d_tiles_x, d_tiles_y, d_splits, d_tail_z;
+    // Correlation on the same pipeline (corr_tc_forward): a unit = (sample, parity plane, 128-pixel tile of map 0, block of
+    // cbw x cbh halo pixels of map 1); D[pixel][halo pixel] = <a, b> over C channels; the epilogue keeps the band that
+    // lies inside the (2R+1)^2 displacement window.  W tiles are halo-pixel tiles of the pre-split map 1.
+    int corr, cR, cS, cD, cbw, cbh, cnx, cnt;
+    float cscale;
     int cl, ntiles, ntiles_p, cotiles, total;     // cluster size (W multicast); pixel tiles (real / padded to cl), Co tiles, all tiles
     float comp_a, comp_b;                         // RZ bias model: shrink(n MMAs) = comp_a + comp_b * n
     int gcs;                                      // tap-group packing for Ci <= 16: padded channels per tap (4/8/12/16), 0 = off
@@ -232,6 +238,24 @@ template <int NT>
 __device__ __forceinline__ TcTile tc_decode_tile(const TcParams& p, int tile) {
     TcTile t;
     t.split = 0; t.slot = -1;
+    if (p.corr) {
+        // unit -> (halo block, tile x, tile y, plane, sample); co0 carries the halo block, cls the parity plane
+        int r = tile / p.cnt;
+        t.co0 = tile - r * p.cnt;
+        int q = r / p.tiles_x;
+        const int tx = r - q * p.tiles_x;
+        r = q / p.tiles_y;
+        const int ty = q - r * p.tiles_y;
+        const int planes = p.cS * p.cS;
+        t.n = r / planes;
+        t.cls = r - t.n * planes;
+        t.u0 = ty * p.th; t.v0 = tx * p.tw;
+        t.tap0 = 0; t.ntaps = 1; t.k0 = 0;
+        t.steps = p.cblocks;
+        const int py = t.cls / p.cS, px = t.cls % p.cS;
+        t.valid = t.u0 * p.cS + py < p.Ho && t.v0 * p.cS + px < p.Wo;
+        return t;
+    }
     int tseg = 0;
     if (p.tail_z > 1 && tile >= p.tail_first) {
         t.slot = tile - p.tail_first;
@@ -338,7 +362,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         tma_load_4d(wh + G::B_TILE_BYTES, &mapW, bar, c0, T.co0, blk, 1);
                     }
                 };
-                if (p.rowmode) {
+                if (p.corr) {
+                    const int py = T.cls / p.cS, px = T.cls % p.cS;
+                    const int ax = T.v0 * p.cS + px, ay = T.u0 * p.cS + py;
+                    const int bx = (T.v0 - p.cR) * p.cS + px, by = (T.u0 - p.cR + T.co0 * p.cbh) * p.cS + py;
+                    const uint32_t bbytes = (uint32_t)(p.cbw * p.cbh * 128);
+#pragma unroll 1
+                    for (int i = 0; i < T.steps; i++) {
+                        mbar_wait_t(&done[s], ph, &w0, timed);
+                        unsigned char* st = smem + (size_t)s * G::STAGE_BYTES;
+                        mbar_expect_tx(&full[s], (uint32_t)A_TILE_BYTES + 2u * bbytes);
+                        tma_load_4d(st, &mapA, &full[s], i * 32, ax, ay, T.n);
+                        tma_load_4d(st + A_TILE_BYTES, &mapW, &full[s], i * 32, bx, by, T.n);
+                        tma_load_4d(st + A_TILE_BYTES + G::B_TILE_BYTES, &mapW, &full[s], i * 32, bx, by, p.N + T.n);
+                        if (++s == G::R) { s = 0; ph ^= 1u; }
+                    }
+                } else if (p.rowmode) {
                     // one box per step: {32 floats of the kernel-row run, tw output pixels (stride su pixels), th rows}
                     int r = 0, kb = 0;
 #pragma unroll 1
@@ -384,7 +423,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         } else if (warp == 1) {
             // ===== MMA issuer: the whole warp runs the loop convergently (so descriptors live in uniform registers),
             // one elected lane issues the tcgen05 instructions =====
-            const uint32_t idesc = make_idesc_tf32(128, NT), idesc_w = make_idesc_tf32(128, G::ACCW);
+            // correlation: N = the halo block's pixel count (a multiple of 16), not the full NT
+            const uint32_t idesc = make_idesc_tf32(128, p.corr ? p.cbw * p.cbh : NT), idesc_w = make_idesc_tf32(128, G::ACCW);
             const int kd = p.kd;
             int s = 0, buf = 0;
             uint32_t ph = 0, pacc = 1u;                 // pacc: parity to wait on acc_free[buf] (flips every second chunk)
@@ -605,6 +645,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 }
             }
             // epilogue
+            if (p.corr) {
+                // A halo block = cbh full halo rows (cbw = tw + 2R pixels each): for every tile pixel it holds cbh
+                // displacement rows dy with all D = 2R+1 values of dx, i.e. runs of D consecutive output channels.  Lanes
+                // are pixels after tcgen05.ld, so the block goes through shared memory (two halves of cbh/2 halo rows) and
+                // is written with lanes = channels: one coalesced run per (pixel, dy).
+                if constexpr (NT == 128) {
+                    float* tr = reinterpret_cast<float*>(smem + G::SMEM);            // [128 pixels][CORR_TR_STRIDE]
+                    const int py = T.cls / p.cS, px = T.cls % p.cS;
+                    const int wq = warp & 3;
+                    const bool lane_on = lane < p.cD;
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+#pragma unroll
+                        for (int j = 0; j < 56; j++) tr[m * CORR_TR_STRIDE + j] = acc[h * 56 + j] * p.cscale;
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        // warp wq stores tile rows qy = wq, wq+4, ...: 8 pixels x 2 displacement rows each, lanes = dx
+                        const int dy_base = T.co0 * 4 + h * 2 - p.cR;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int qy = wq + 4 * k;
+                            const int y = (T.u0 + qy) * p.cS + py;
+                            const int dy0 = dy_base - qy, dy1 = dy0 + 1;
+                            const bool ok0 = lane_on && y < p.Ho && dy0 >= -p.cR && dy0 <= p.cR;
+                            const bool ok1 = lane_on && y < p.Ho && dy1 >= -p.cR && dy1 <= p.cR;
+                            float* o = out + T.n * p.out_sn + (long long)y * p.out_sh + (long long)(T.v0 * p.cS + px) * p.out_sw + lane;
+                            const float* t = tr + (qy * 8) * CORR_TR_STRIDE + lane;
+                            const int c0 = (dy0 + p.cR) * p.cD, c1 = (dy1 + p.cR) * p.cD;
+#pragma unroll
+                            for (int qx = 0; qx < 8; qx++) {
+                                const bool inx = (T.v0 + qx) * p.cS + px < p.Wo;
+                                const float v0 = lane_on ? t[qx * CORR_TR_STRIDE + qx] : 0.f, v1 = lane_on ? t[qx * CORR_TR_STRIDE + 28 + qx] : 0.f;
+                                if (ok0 && inx) o[(long long)qx * p.cS * p.out_sw + c0] = v0;
+                                if (ok1 && inx) o[(long long)qx * p.cS * p.out_sw + c1] = v1;
+                            }
+                        }
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                    }
+                }
+                continue;
+            }
             const int u = T.u0 + yy, v = T.v0 + xx;
             if (T.valid && u < p.cls_Hu[T.cls] && v < p.cls_Wu[T.cls]) {
                 const int oy = u * p.ou + p.cls_oy0[T.cls], ox = v * p.ov + p.cls_ox0[T.cls];
@@ -937,6 +1017,7 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
     const int NT = (d->co % 128 == 0) ? 128 : (d->co % 64 == 0 ? 64 : (d->co % 32 == 0 ? 32 : 16));
     const int cip = (d->ci + 31) / 32 * 32;
     TcParams p;
+    p.corr = 0;
     p.N = in.n; p.Co = d->co; p.cblocks = cip / 32;
     p.Ho = out.h; p.Wo = out.w;
     p.splits = tc_split_plan(d, in.n, out.h, out.w);
@@ -1030,7 +1111,8 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
         {                                                                                                               \
             static bool attr_set = false;                                                                               \
             if (!attr_set) {                                                                                            \
-                FN2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGeo<NTV>::SMEM)); \
+                FN2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize,                      \
+                                              TcGeo<NTV>::SMEM + (NTV == 128 ? 128 * CORR_TR_STRIDE * (int)sizeof(float) : 0)));     \
                 attr_set = true;                                                                                        \
             }                                                                                                           \
             cfg.dynamicSmemBytes = TcGeo<NTV>::SMEM;                                                                    \
@@ -1091,6 +1173,119 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
             if (p.cls_ntaps[c] == 0) { set_error("conv_tc: deconvolution parity class without taps"); return FN2_ERR_INVALID; }
         }
     return run(1, 1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Correlation (MULTIPLY, kernel 1, stride_1 1, pad == max_displacement) on the tensor cores.
+// stride_2 = S samples displacements that are multiples of S, so a pixel only meets map-1 pixels of its own parity plane;
+// within a plane the op is "every pixel against its (2R+1)^2 neighbours", R = md / S.  Per 8x16-pixel tile the neighbours are
+// the (8+2R) x (16+2R) halo; the kernel computes ALL tile-pixel x halo-pixel dot products as 3xTF32 GEMMs
+// D[128 x 112] = A[128 x C] * B[112 x C]^T (one unit per block of 4 full halo rows: 9 blocks for R = 10) and keeps the 441 of the
+// 1008 that lie in the window (2.3x redundant MMA work, which still beats the FP32 FMA pipe by a wide margin).
+// Map 1 is split into TF32 hi / lo once per call (workspace [2][N][H][W][C]); both maps are read through element-strided
+// TMA boxes, so the parity planes are never materialised and out-of-image neighbours are zero fill.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void corr_split_kernel(const float* __restrict__ b, long long sn, long long sh, long long sw, int N, int H, int W, int C,
+                                  float* __restrict__ hi, float* __restrict__ lo) {
+    const long long total = (long long)N * H * W * (C / 4);
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % (C / 4)) * 4;
+        long long r = idx / (C / 4);
+        const int x = (int)(r % W); r /= W;
+        const int y = (int)(r % H);
+        const int n = (int)(r / H);
+        const float4 v = *reinterpret_cast<const float4*>(b + n * sn + y * sh + x * sw + c);
+        const float f[4] = {v.x, v.y, v.z, v.w};
+        float h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const uint32_t hb = to_tf32(f[e]);
+            h[e] = __uint_as_float(hb);
+            l[e] = __uint_as_float(to_tf32(f[e] - h[e]));
+        }
+        const long long o = (((long long)n * H + y) * W + x) * C + c;
+        *reinterpret_cast<float4*>(hi + o) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(lo + o) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+int corr_tc_eligible(const T4& b0, const T4& b1, const T4& top, int md, int s2) {
+    if (!tc_enabled() || getenv("FN2_CORR_NOTC")) return 0;
+    if (s2 < 1 || s2 > 2 || md % s2 || md / s2 != 10) return 0;            // halo blocks are laid out for R = 10
+    if (b0.c % 32 || b0.sc != 1 || b1.sc != 1 || top.sc != 1) return 0;
+    if (((uintptr_t)b0.p & 15) || (b0.sw & 3) || (b0.sh & 3) || (b0.sn & 3)) return 0;
+    if (((uintptr_t)b1.p & 15) || (b1.sw & 3) || (b1.sh & 3) || (b1.sn & 3)) return 0;
+    if (!tc_encode_fn()) return 0;
+    return 1;
+}
+size_t corr_tc_workspace_floats(int N, int C, int H, int W) { return (size_t)2 * N * H * W * C; }
+
+int corr_tc_forward(const T4& b0, const T4& b1, const T4& top, int md, int s2, float* ws, size_t ws_floats, cudaStream_t st) {
+    EncodeTiledFn enc = tc_encode_fn();
+    if (!enc) { set_error("corr_tc: cuTensorMapEncodeTiled unavailable"); return FN2_ERR_CUDA; }
+    const int N = b0.n, C = b0.c, H = b0.h, W = b0.w, S = s2, R = md / s2;
+    if (!ws || ws_floats < corr_tc_workspace_floats(N, C, H, W)) { set_error("corr_tc: workspace too small"); return FN2_ERR_WORKSPACE; }
+    float* hi = ws; float* lo = ws + (size_t)N * H * W * C;
+    corr_split_kernel<<<ew_grid((long long)N * H * W * (C / 4), 256), 256, 0, st>>>(b1.p, b1.sn, b1.sh, b1.sw, N, H, W, C, hi, lo);
+    FN2_LAUNCH_CHECK();
+    constexpr int NT = 128;
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.corr = 1; p.cR = R; p.cS = S; p.cD = 2 * R + 1;
+    p.tw = 8; p.th = 16;                                                   // halo 28 x 36
+    p.cbw = p.tw + 2 * R; p.cbh = 4;                                       // block = 4 full halo rows = 112 pixels (MMA N = 112)
+    p.cnx = 1; p.cnt = (p.th + 2 * R) / p.cbh;                             // 9 blocks
+    p.cscale = 1.0f / (float)C;                                           // sumelems = k*k*C (correlation_layer.cu:108)
+    p.N = N; p.Co = NT; p.cblocks = C / 32;
+    p.Ho = H; p.Wo = W;
+    p.out_sn = top.sn; p.out_sh = top.sh; p.out_sw = top.sw;
+    p.splits = 1; p.cl = 1; p.tail_z = 1; p.su = S; p.sv = S; p.ou = p.ov = 1; p.ncls = 1;
+    p.kd = p.cblocks;                                                     // one chunk per unit: chain of 4 * C/32 MMAs
+    if (const char* e = getenv("FN2_TC_KD")) { const int v = atoi(e); if (v >= 1 && v <= 1024) p.kd = v; }
+    const char* nocomp = getenv("FN2_TC_COMP");
+    p.comp_a = (nocomp && nocomp[0] == '0') ? 0.f : 2.0e-8f;
+    p.comp_b = (nocomp && nocomp[0] == '0') ? 0.f : 1.67e-8f;
+    const int Ws = (W + S - 1) / S, Hs = (H + S - 1) / S;
+    p.tiles_x = (Ws + p.tw - 1) / p.tw; p.tiles_y = (Hs + p.th - 1) / p.th;
+    p.total = N * S * S * p.tiles_x * p.tiles_y * p.cnt;
+    p.ntotal = p.total; p.tail_first = p.total;
+    CUtensorMap mapA, mapB;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)b0.sw * 4, (cuuint64_t)b0.sh * 4, (cuuint64_t)b0.sn * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)(p.tw * S), (cuuint32_t)(p.th * S), 1};
+        cuuint32_t es[4] = {1, (cuuint32_t)S, (cuuint32_t)S, 1};
+        CUresult r = enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)b0.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("corr_tc: map-0 tensor map failed (%d)", (int)r); return FN2_ERR_CUDA; }
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)2 * N};
+        cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)(p.cbw * S), (cuuint32_t)(p.cbh * S), 1};
+        cuuint32_t es[4] = {1, (cuuint32_t)S, (cuuint32_t)S, 1};
+        CUresult r = enc(&mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)hi, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("corr_tc: map-1 tensor map failed (%d)", (int)r); return FN2_ERR_CUDA; }
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)min(p.total, tc_num_sms()), 1, 1);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const int smem_bytes = TcGeo<NT>::SMEM + 128 * CORR_TR_STRIDE * (int)sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        FN2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        attr_set = true;
+    }
+    cfg.dynamicSmemBytes = smem_bytes;
+    FN2_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<NT>, mapA, mapB, (const float*)nullptr, top.p, (float*)nullptr, p, tc_prof_buffer()));
+    FN2_LAUNCH_CHECK();
+    return FN2_OK;
 }
 
 }  // namespace fn2

@@ -16,6 +16,9 @@
 
 namespace fn2 {
 
+int corr_tc_eligible(const T4& b0, const T4& b1, const T4& top, int md, int s2);
+size_t corr_tc_workspace_floats(int N, int C, int H, int W);
+int corr_tc_forward(const T4& b0, const T4& b1, const T4& top, int md, int s2, float* ws, size_t ws_floats, cudaStream_t st);
 int corr_fast_eligible(const T4& b0, const T4& b1, const T4& top, int pad, int k, int md, int s1,
                        int s2, int type);
 int corr_fast_workspace(int N, int C, int H, int W, int md, int s2, size_t* bytes);
@@ -179,8 +182,12 @@ int fn2_correlation_workspace_bytes(int N, int C, int H, int W, int pad, int ker
     FN2_CHECK_ARG(bytes, "correlation_workspace_bytes: null out pointer");
     *bytes = 0;
     if (corr_type == 0 && kernel_size == 1 && stride1 == 1 && pad == max_displacement &&
-        stride2 >= 1 && max_displacement % stride2 == 0)
-        return corr_fast_workspace(N, C, H, W, max_displacement, stride2, bytes);
+        stride2 >= 1 && max_displacement % stride2 == 0) {
+        int rc = corr_fast_workspace(N, C, H, W, max_displacement, stride2, bytes);
+        if (rc) return rc;
+        *bytes = max(*bytes, corr_tc_workspace_floats(N, C, H, W) * sizeof(float));    // tensor-core path: TF32 hi/lo copy of map 1
+        return FN2_OK;
+    }
     return FN2_OK;
 }
 
@@ -204,6 +211,9 @@ int fn2_correlation_forward(const fn2_tensor* bottom0, const fn2_tensor* bottom1
     if (corr_fast_eligible(b0, b1, tp, pad, kernel_size, max_displacement, stride1, stride2, corr_type)) {
         size_t need = 0;
         corr_fast_workspace(b0.n, b0.c, b0.h, b0.w, max_displacement, stride2, &need);
+        if (workspace && corr_tc_eligible(b0, b1, tp, max_displacement, stride2) &&
+            workspace_bytes >= corr_tc_workspace_floats(b0.n, b0.c, b0.h, b0.w) * sizeof(float))
+            return corr_tc_forward(b0, b1, tp, max_displacement, stride2, (float*)workspace, workspace_bytes / sizeof(float), st);
         if (workspace && workspace_bytes >= need)
             return corr_fast_forward(b0, b1, tp, max_displacement, stride2, workspace, workspace_bytes, st);
         if (workspace_bytes != 0 || workspace) {
