@@ -344,8 +344,8 @@ def run_ours(args):
             by = sum(w[3] for _, w in corr)
             fl = sum(w[2] for _, w in corr)
             gbs = by / (t_ms * 1e-3) / 1e9
-            rc = {"kernel": "Correlation d=21 k=1 s2=2 C=256", "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                  "frac": gbs / pk["hbm_gbs"], "traffic": 40.7e6, "traffic_of": "profiles/r01_prof_corr_raw.csv (8x256x40x56 launch)", "peak_source": pk["source"],
+            rc = {"kernel": "Correlation d=21 k=1 s2=2 C=256: conv_tc_kernel<128> in correlation mode (3xTF32 tile x halo-block GEMMs) + hi/lo split", "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                  "frac": gbs / pk["hbm_gbs"], "traffic": 112.9e6, "traffic_of": "profiles/r01_prof_corr_raw.csv (4x256x56x128 launch of the tensor-core path; algorithmic 109.3e6 B)", "peak_source": pk["source"],
                   "algorithmic_bytes_per_launch": by / len(corr), "ms_per_launch": t_ms / len(corr),
                   "fp32_tflops": fl / (t_ms * 1e-3) / 1e12, "share_of_step": t_ms / total_ms if total_ms else None}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

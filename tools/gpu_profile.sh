@@ -11,10 +11,13 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv
     python tools/tc_time.py > $O/prof_tc128.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 29 -c 1 -f -o $O/prof_tc16 \
     python tools/tc_time.py > $O/prof_tc16.log 2>&1
-# 3. correlation fast path at the bench shape
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:corr_fast_kernel -s 3 -c 1 -f -o $O/prof_corr \
+# 3. correlation at the bench shape (4,256,56,128): the tcgen05 path (conv_tc_kernel<128> in correlation mode) and, for
+#    reference, the FP32 FMA path it replaced
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 1 -c 1 -f -o $O/prof_corr \
     python tools/profile_ops.py > $O/prof_corr.log 2>&1
-for r in prof_tc128 prof_tc16 prof_corr; do
+FN2_CORR_NOTC=1 timeout 600 ncu --set full --clock-control none -k regex:corr_fast_kernel -s 1 -c 1 -f -o $O/prof_corr_fp32 \
+    python tools/profile_ops.py > $O/prof_corr_fp32.log 2>&1
+for r in prof_tc128 prof_tc16 prof_corr prof_corr_fp32; do
     ncu -i $O/$r.ncu-rep --page raw --csv > $O/${r}_raw.csv 2>/dev/null
     ncu -i $O/$r.ncu-rep --page details > $O/${r}_details.txt 2>/dev/null
 done
