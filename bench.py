@@ -128,16 +128,18 @@ def run_reference(args):
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------
 def clocks_sampler_start(dev_index):
-    q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+    q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     try:
-        return subprocess.Popen(["nvidia-smi", "-i", str(dev_index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+        return subprocess.Popen(["nvidia-smi", "-i", str(dev_index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
     except Exception:
         return None
 
 
-def clocks_sampler_stop(p):
+def clocks_sampler_stop(p, t0=None, t1=None):
+    """Samples are taken every 20 ms from before the warm-up on (nvidia-smi needs ~0.1 s to start); only those whose
+    timestamp lies inside the timed region [t0, t1] (host clock) are used."""
     if p is None:
         return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
     p.terminate()
@@ -146,25 +148,29 @@ def clocks_sampler_stop(p):
     except Exception:
         p.kill()
         out = ""
-    sm, mx, reasons = [], [], set()
+    import datetime
+    rows = []
     names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
     for line in out.strip().splitlines():
         f = [x.strip() for x in line.split(",")]
-        if len(f) < 7:
+        if len(f) < 8:
             continue
         try:
-            sm.append(float(f[0])); mx.append(float(f[1]))
+            ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            rows.append((ts, float(f[1]), float(f[2]), [nm for nm, v in zip(names, f[4:8]) if v.lower().startswith("active")]))
         except ValueError:
             continue
-        for nm, v in zip(names, f[3:7]):
-            if v.lower().startswith("active"):
-                reasons.add(nm)
+    inside = [r for r in rows if t0 is not None and t0 - 0.01 <= r[0] <= t1 + 0.01]
+    use = inside if inside else rows[-3:]
+    sm = [r[1] for r in use]; mx = [r[2] for r in use]
+    reasons = set(x for r in use for x in r[3])
     if not sm:
         return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
     # median over the samples taken under load (upper half)
     sm_sorted = sorted(sm)
     load = sm_sorted[len(sm_sorted) // 2:]
-    return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+    return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+            "samples_in_timed_region": len(inside)}
 
 
 def run_ours(args):
@@ -292,13 +298,15 @@ def run_ours(args):
         return float(ms.item())
 
     with torch.cuda.stream(stream):
+        sampler = clocks_sampler_start(local) if rank == 0 else None       # started early: nvidia-smi takes ~0.1 s to come up
         for _ in range(max(args.warmup, 3)):
             step_device()
         barrier()
         launches0 = F.launch_count()
-        sampler = clocks_sampler_start(local) if rank == 0 else None
+        t_begin = time.time()
         ms = timed(step_device, args.steps)
-        clocks = clocks_sampler_stop(sampler) if rank == 0 else None
+        t_end = time.time()
+        clocks = clocks_sampler_stop(sampler, t_begin, t_end) if rank == 0 else None
         # graph replays do not go through the launch counter: count = kernels per forward + layout copies
         per_step_launches = net.launches_per_forward + 3
         for _ in range(2):

@@ -234,11 +234,15 @@ struct TcTile {
     int slot;                                     // >= 0: raw partial sums go to workspace slot `slot` (tail split)
     bool valid;
 };
-template <int NT>
+// MODE (compile time, so that each instantiation's role loops stay small -- the all-in-one kernel had ~1900 SASS instructions in
+// the converter loop and stalled on instruction fetch): 0 plain K blocks, 1 tap groups, 2 kernel rows, 3 correlation
+enum { TC_PLAIN = 0, TC_GROUP = 1, TC_ROW = 2, TC_CORR = 3 };
+
+template <int NT, int MODE>
 __device__ __forceinline__ TcTile tc_decode_tile(const TcParams& p, int tile) {
     TcTile t;
     t.split = 0; t.slot = -1;
-    if (p.corr) {
+    if constexpr (MODE == TC_CORR) {
         // unit -> (halo block, tile x, tile y, plane, sample); co0 carries the halo block, cls the parity plane
         int r = tile / p.cnt;
         t.co0 = tile - r * p.cnt;
@@ -277,8 +281,8 @@ __device__ __forceinline__ TcTile tc_decode_tile(const TcParams& p, int tile) {
     t.co0 = cot * NT;
     t.tap0 = p.cls_tap0[t.cls]; t.ntaps = p.cls_ntaps[t.cls];
     if (t.u0 >= p.cls_Hu[t.cls] || t.v0 >= p.cls_Wu[t.cls]) t.valid = false;      // tile outside this (smaller) parity class
-    const int gsz = p.gcs ? 32 / p.gcs : 1;
-    t.steps = p.rowmode ? p.rsteps : (p.gcs ? (t.ntaps + gsz - 1) / gsz : t.ntaps * p.cblocks);
+    const int gsz = MODE == TC_GROUP ? 32 / p.gcs : 1;
+    t.steps = MODE == TC_ROW ? p.rsteps : (MODE == TC_GROUP ? (t.ntaps + gsz - 1) / gsz : t.ntaps * p.cblocks);
     t.k0 = 0;
     if (p.splits > 1) {
         const int per = (t.steps + p.splits - 1) / p.splits;
@@ -296,7 +300,7 @@ __device__ __forceinline__ TcTile tc_decode_tile(const TcParams& p, int tile) {
 // Persistent kernel: gridDim.x CTAs (one per SM) walk the tile list with stride gridDim.x; the barrier rings and the two
 // accumulator buffers run straight through tile boundaries, so the loads / conversions / MMAs of the next tile overlap
 // the drain + epilogue of the current one.
-template <int NT>
+template <int NT, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const float* __restrict__ bias,
                float* __restrict__ out, float* __restrict__ ws, const TcParams p, long long* __restrict__ prof) {
@@ -319,7 +323,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const uint32_t crank = p.cl > 1 ? cluster_ctarank() : 0u;
     const uint16_t cmask = (uint16_t)((1u << p.cl) - 1u);
     const int wrows = NT / p.cl;                   // W rows this CTA loads per tile
-    const int gsz = p.gcs ? 32 / p.gcs : 1;       // taps per K block when packing
+    const int gsz = MODE == TC_GROUP ? 32 / p.gcs : 1;   // taps per K block when packing
     const bool skip_invalid = p.cl == 1;
 
     if (tid == 0) {
@@ -349,7 +353,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const int cblocks = p.cblocks, gcs = p.gcs;
             int s = 0; uint32_t ph = 1u;                // ph: parity to wait on done[s]
             for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x) {
-                const TcTile T = tc_decode_tile<NT>(p, tile);
+                const TcTile T = tc_decode_tile<NT, MODE>(p, tile);
                 if (!T.valid && skip_invalid) continue;
                 const int cx0 = T.v0 * p.su, cy0 = T.u0 * p.sv;
                 auto load_w = [&](unsigned char* st, uint64_t* bar, int c0, int blk) {
@@ -362,7 +366,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         tma_load_4d(wh + G::B_TILE_BYTES, &mapW, bar, c0, T.co0, blk, 1);
                     }
                 };
-                if (p.corr) {
+                if constexpr (MODE == TC_CORR) {
                     const int py = T.cls / p.cS, px = T.cls % p.cS;
                     const int ax = T.v0 * p.cS + px, ay = T.u0 * p.cS + py;
                     const int bx = (T.v0 - p.cR) * p.cS + px, by = (T.u0 - p.cR + T.co0 * p.cbh) * p.cS + py;
@@ -377,7 +381,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         tma_load_4d(st + A_TILE_BYTES + G::B_TILE_BYTES, &mapW, &full[s], i * 32, bx, by, p.N + T.n);
                         if (++s == G::R) { s = 0; ph ^= 1u; }
                     }
-                } else if (p.rowmode) {
+                } else if constexpr (MODE == TC_ROW) {
                     // one box per step: {32 floats of the kernel-row run, tw output pixels (stride su pixels), th rows}
                     int r = 0, kb = 0;
 #pragma unroll 1
@@ -390,7 +394,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         if (++kb == p.rblocks) { kb = 0; ++r; }
                         if (++s == G::R) { s = 0; ph ^= 1u; }
                     }
-                } else if (gcs) {
+                } else if constexpr (MODE == TC_GROUP) {
                     // several taps share one 32-wide K block: one small box {gcs channels, tw, th} per tap
                     const int box_bytes = 128 * gcs * 4;
                     for (int i = 0, t0 = 0; i < T.steps; i++, t0 += gsz) {
@@ -424,13 +428,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             // ===== MMA issuer: the whole warp runs the loop convergently (so descriptors live in uniform registers),
             // one elected lane issues the tcgen05 instructions =====
             // correlation: N = the halo block's pixel count (a multiple of 16), not the full NT
-            const uint32_t idesc = make_idesc_tf32(128, p.corr ? p.cbw * p.cbh : NT), idesc_w = make_idesc_tf32(128, G::ACCW);
+            const uint32_t idesc = make_idesc_tf32(128, MODE == TC_CORR ? p.cbw * p.cbh : NT), idesc_w = make_idesc_tf32(128, G::ACCW);
             const int kd = p.kd;
             int s = 0, buf = 0;
             uint32_t ph = 0, pacc = 1u;                 // pacc: parity to wait on acc_free[buf] (flips every second chunk)
             uint32_t px = 1u;                           // parity to wait on x_free (one phase per tile)
             for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x) {
-                const TcTile T = tc_decode_tile<NT>(p, tile);
+                const TcTile T = tc_decode_tile<NT, MODE>(p, tile);
                 if (!T.valid && skip_invalid) continue;
                 int in_chunk = 0;
                 if (G::SEPX && T.steps > 0) { mbar_wait_t(x_free, px, &w0, timed); px ^= 1u; }
@@ -479,7 +483,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         int s = 0, s_prev = -1;
         uint32_t ph = 0;                           // full[s] parity; done[s] is waited with ph ^ 1
         for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x) {
-            const TcTile T = tc_decode_tile<NT>(p, tile);
+            const TcTile T = tc_decode_tile<NT, MODE>(p, tile);
             if (!T.valid && skip_invalid) continue;
 #pragma unroll 1
             for (int i = 0; i < T.steps; i++) {
@@ -487,7 +491,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const float4* row = reinterpret_cast<const float4*>(smem + (size_t)s * G::STAGE_BYTES + m * 128);
                 uint32_t hi[32], lo[32];
                 float4 raw[8];
-                if (!p.gcs) {
+                if constexpr (MODE != TC_GROUP) {
 #pragma unroll
                     for (int j = 0; j < 8; j++) raw[j] = row[j ^ (m & 7)];
                 }
@@ -497,7 +501,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     fence_before();
                     mbar_arrive(&a_ready[s_prev]);
                 }
-                if (p.gcs) {
+                if constexpr (MODE == TC_GROUP) {
                     const int nt = min(gsz, T.ntaps - i * gsz);
                     const unsigned char* base = smem + (size_t)s * G::STAGE_BYTES;
                     if (p.gcs == 4) gather_taps<4>(base, m, nt, hi, lo);
@@ -507,7 +511,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 } else if (p.dbg & 2) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) { hi[j] = 0x3f800000u; lo[j] = 0; }
-                } else if (p.rowmode) {
+                } else if constexpr (MODE == TC_ROW) {
                     // row mode: taps that fall outside the image row (and the K padding) hold whatever follows in memory
                     const int x0 = (T.v0 + m % p.tw) * p.su - p.rpad;            // input column of tap 0
                     const int kb32 = (i % p.rblocks) * 32;
@@ -560,7 +564,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int yy = m / p.tw, xx = m % p.tw;
         int buf = 0; uint32_t pfull = 0;           // pfull: parity to wait on acc_full[buf]
         for (int tile = blockIdx.x; tile < p.total; tile += gridDim.x) {
-            const TcTile T = tc_decode_tile<NT>(p, tile);
+            const TcTile T = tc_decode_tile<NT, MODE>(p, tile);
             if (!T.valid && skip_invalid) continue;
             float acc[NT];
 #pragma unroll
@@ -645,7 +649,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 }
             }
             // epilogue
-            if (p.corr) {
+            if constexpr (MODE == TC_CORR) {
                 // A halo block = cbh full halo rows (cbw = tw + 2R pixels each): for every tile pixel it holds cbh
                 // displacement rows dy with all D = 2R+1 values of dx, i.e. runs of D consecutive output channels.  Lanes
                 // are pixels after tcgen05.ld, so the block goes through shared memory (two halves of cbh/2 halo rows) and
@@ -827,7 +831,7 @@ __global__ void tc_tail_reduce_kernel(const float* __restrict__ ws, const float*
         const int c = (int)(idx % (NT / 4)) * 4;
         const int m = (int)((idx / (NT / 4)) % 128);
         const int t = (int)(idx / ((NT / 4) * 128));
-        const TcTile T = tc_decode_tile<NT>(q, p.tail_first + t);
+        const TcTile T = tc_decode_tile<NT, TC_PLAIN>(q, p.tail_first + t);     // the tail split only exists in plain mode
         const int u = T.u0 + m / p.tw, v = T.v0 + m % p.tw;
         if (!T.valid || u >= p.cls_Hu[T.cls] || v >= p.cls_Wu[T.cls]) continue;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1107,21 +1111,25 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = (unsigned)p.cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-#define FN2_TC_LAUNCH(NTV)                                                                                              \
+#define FN2_TC_LAUNCH(NTV, MODEV)                                                                                       \
         {                                                                                                               \
             static bool attr_set = false;                                                                               \
             if (!attr_set) {                                                                                            \
-                FN2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize,                      \
-                                              TcGeo<NTV>::SMEM + (NTV == 128 ? 128 * CORR_TR_STRIDE * (int)sizeof(float) : 0)));     \
+                FN2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NTV, MODEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGeo<NTV>::SMEM)); \
                 attr_set = true;                                                                                        \
             }                                                                                                           \
             cfg.dynamicSmemBytes = TcGeo<NTV>::SMEM;                                                                    \
-            FN2_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<NTV>, mapA, mapW, bias, out.p, ws, p, tc_prof_buffer()));      \
+            FN2_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<NTV, MODEV>, mapA, mapW, bias, out.p, ws, p, tc_prof_buffer())); \
         }
-        if (NT == 128) FN2_TC_LAUNCH(128)
-        else if (NT == 64) FN2_TC_LAUNCH(64)
-        else if (NT == 32) FN2_TC_LAUNCH(32)
-        else FN2_TC_LAUNCH(16)
+#define FN2_TC_LAUNCH_NT(MODEV)                                                                                         \
+        if (NT == 128) FN2_TC_LAUNCH(128, MODEV)                                                                        \
+        else if (NT == 64) FN2_TC_LAUNCH(64, MODEV)                                                                     \
+        else if (NT == 32) FN2_TC_LAUNCH(32, MODEV)                                                                     \
+        else FN2_TC_LAUNCH(16, MODEV)
+        if (sm.mode == 2) { FN2_TC_LAUNCH_NT(TC_ROW) }
+        else if (sm.mode == 1) { FN2_TC_LAUNCH_NT(TC_GROUP) }
+        else { FN2_TC_LAUNCH_NT(TC_PLAIN) }
+#undef FN2_TC_LAUNCH_NT
 #undef FN2_TC_LAUNCH
         FN2_LAUNCH_CHECK();
         if (p.tail_z > 1) {
@@ -1279,11 +1287,11 @@ int corr_tc_forward(const T4& b0, const T4& b1, const T4& top, int md, int s2, f
     const int smem_bytes = TcGeo<NT>::SMEM + 128 * CORR_TR_STRIDE * (int)sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
-        FN2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        FN2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NT, TC_CORR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr_set = true;
     }
     cfg.dynamicSmemBytes = smem_bytes;
-    FN2_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<NT>, mapA, mapB, (const float*)nullptr, top.p, (float*)nullptr, p, tc_prof_buffer()));
+    FN2_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<NT, TC_CORR>, mapA, mapB, (const float*)nullptr, top.p, (float*)nullptr, p, tc_prof_buffer()));
     FN2_LAUNCH_CHECK();
     return FN2_OK;
 }
