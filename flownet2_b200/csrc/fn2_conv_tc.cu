@@ -316,6 +316,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_free + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // Programmatic dependent launch: let the next kernel of the stream be scheduled as soon as every CTA of this one is
+    // running, so that its CTAs take over SMs the moment ours exit and run their prologue (barrier init, TMEM allocation)
+    // there; it blocks in griddepcontrol.wait (below, before its first global access) until this grid has completed.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // CTAs of one cluster (p.cl consecutive blockIdx.x) always work on tiles with the same co0 and parity class, so they
     // read the same W tiles: with p.cl > 1 each loads 1/cl of the rows and multicasts it to the whole cluster.  In that
     // mode every CTA runs the full pipeline even for a tile outside the image/class (loads are zero-filled, nothing is
@@ -341,6 +345,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (p.cl > 1) cluster_sync_all();             // peers' barriers are initialised before any multicast can signal them
     fence_after();
     const uint32_t tmem = *tmem_slot;
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // no-op unless launched with programmatic stream serialization
     long long w0 = 0, w1 = 0, w2 = 0;
     const bool timed = prof != nullptr;
     const long long t_start = clock64();
@@ -866,6 +871,11 @@ EncodeTiledFn tc_encode_fn() {
 }
 
 // FN2_TC_DBG & 16: per-role wait-time profile of CTA (0,0,0), printed by fn2_tc_prof_dump()
+int tc_pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FN2_TC_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
 int tc_num_sms() {
     static int n = 0;
     if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
@@ -1107,10 +1117,12 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
         cfg.gridDim = dim3((unsigned)min(p.total, tc_num_sms() / p.cl * p.cl), 1, 1);
         cfg.blockDim = dim3(TC_THREADS);
         cfg.stream = st;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = (unsigned)p.cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = tc_pdl_enabled() ? 2 : 1;
 #define FN2_TC_LAUNCH(NTV, MODEV)                                                                                       \
         {                                                                                                               \
             static bool attr_set = false;                                                                               \

@@ -1,4 +1,4 @@
 #!/bin/bash
 cd /root/repo
-FN2_TC_DBG=16 timeout 300 python tools/corr_time.py 2>&1 | tail -7
-timeout 600 python -m pytest tests -m gpu -q -x -k "corr" 2>&1 | tail -2
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -2
+for env in "A=1" "FN2_TC_PDL=0"; do echo "== $env"; env $env python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | cut -c60-175; done
