@@ -924,7 +924,7 @@ static int tc_tail_plan(long long tiles, int steps, int* first) {
     *first = (int)tiles;
     if (getenv("FN2_TC_NOTAIL")) return 1;
     const int nsm = tc_num_sms();
-    if (tiles <= nsm || steps < 16) return 1;
+    if (steps < 16) return 1;                       // (tiles <= nsm: everything is "tail" -- 112 tiles become 896 eighths on 148 SMs)
     const long long full = tiles / nsm * nsm, r = tiles - full;
     if (r == 0) return 1;
     const int z = min(8, steps / 8);
