@@ -206,3 +206,37 @@ def test_data_augmentation_training_path(fn2):
 
 
 EIGVEC_T = [0.51, 0.56, 0.65, 0.79, 0.01, -0.62, 0.35, -0.83, 0.44]
+
+
+def test_full_size_properties(fn2, monkeypatch):
+    """BASELINE.json's configuration (FlowNet2, 1024x436, 4 pairs) is too large for the CPU oracle; checked through
+    size-independent properties instead: (1) replay determinism (eager pass == CUDA-graph replays, bit for bit),
+    (2) batch independence: sample k of a batch-4 forward equals a batch-1 forward of that pair (different tile schedules and
+    K splits, so within the flow tolerance, not bitwise), (3) the two convolution engines agree: tcgen05 3xTF32 vs exact-FP32
+    SIMT within 1e-4 of the flow scale, (4) correlation layer: tensor-core path vs FP32 path on the real conv3 features."""
+    W, H, B = 1024, 436, 4
+    proto = fn2.fill_template(fn2.model_template("FlowNet2"), W, H)
+    img0, img1 = smooth_images(rng(99), B, H, W)
+    net = fn2.Net(proto, None, fn2.TEST, batch=B)
+    net.fill_params(1701)
+    weights = net.to_caffemodel()
+    f1 = net.forward(img0=img0, img1=img1)["predict_flow_final"].copy()
+    f2 = net.forward(img0=img0, img1=img1)["predict_flow_final"].copy()      # captured into a graph here
+    f3 = net.forward(img0=img0, img1=img1)["predict_flow_final"].copy()      # graph replay
+    assert np.isfinite(f1).all() and f1.shape == (B, 2, H, W)
+    assert maxabs(f1, f2) == 0.0 and maxabs(f1, f3) == 0.0
+    scale = max(1.0, float(np.abs(f1).max()))
+    corr_tc = net.blobs["net1_corr"].data.copy() if "net1_corr" in net.blobs else None
+    del net
+    one = fn2.Net(proto, weights, fn2.TEST, batch=1)
+    g = one.forward(img0=img0[2:3], img1=img1[2:3])["predict_flow_final"]
+    assert maxabs(g, f1[2:3]) <= 1e-4 * scale, (maxabs(g, f1[2:3]), scale)
+    del one
+    monkeypatch.setenv("FN2_CONV_ENGINE", "simt")
+    monkeypatch.setenv("FN2_CORR_NOTC", "1")
+    simt = fn2.Net(proto, weights, fn2.TEST, batch=B)
+    h = simt.forward(img0=img0, img1=img1)["predict_flow_final"]
+    assert maxabs(h, f1) <= 1e-4 * scale, (maxabs(h, f1), scale)
+    if corr_tc is not None:
+        corr_fp32 = simt.blobs["net1_corr"].data
+        assert maxabs(corr_fp32, corr_tc) <= 1e-5 * max(1.0, float(np.abs(corr_fp32).max()))
