@@ -404,6 +404,55 @@ __global__ void __launch_bounds__(256) conv_pf3_thread_kernel(T4 in, const float
         pf_store(out, p, bias, n, oy, ox, a0, a1);
     }
 }
+// Shared-memory tiled variant of the thread-per-pixel predictor for Ci <= 32: a block of 256 threads produces a 32 x 8 output
+// tile from a 34 x 10 input halo that is fetched with fully coalesced 128-bit loads (the direct version reads 64..128-byte
+// pixels at a 64..128-byte lane stride: 16 L1 wavefronts per load instruction).  Same accumulation order, bit-identical.
+template <int C4>
+__global__ void __launch_bounds__(256) conv_pf3_tile_kernel(T4 in, const float* __restrict__ wp, const float* __restrict__ bias, T4 out, ConvP p) {
+    extern __shared__ float2 pf_wsm[];
+    constexpr int TW = 32, TH = 8, HW = TW + 2, HH = TH + 2, PS = C4 + 1;         // PS: pixel stride in float4 (odd: no bank conflicts)
+    float4* tile = reinterpret_cast<float4*>(pf_wsm + 9 * C4 * 4);                 // [HH][HW][PS]
+    pf_stage_weights(pf_wsm, wp, 9, p.Ci, C4);
+    const int tiles_x = (p.Wo + TW - 1) / TW, tiles_y = (p.Ho + TH - 1) / TH;
+    const int ntiles = p.N * tiles_x * tiles_y;
+    const int tx = threadIdx.x % TW, ty = threadIdx.x / TW;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int bx = t % tiles_x, by = (t / tiles_x) % tiles_y, n = t / (tiles_x * tiles_y);
+        const int x0 = bx * TW - p.pw, y0 = by * TH - p.ph;
+        __syncthreads();                                                             // previous tile fully consumed
+        for (int i = threadIdx.x; i < HH * HW * C4; i += 256) {
+            const int q = i % C4, px_ = (i / C4) % HW, py_ = i / (C4 * HW);
+            const int ix = x0 + px_, iy = y0 + py_;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ix >= 0 && ix < p.W && iy >= 0 && iy < p.H) v = __ldg(reinterpret_cast<const float4*>(in.p + in.off(n, 0, iy, ix)) + q);
+            tile[(py_ * HW + px_) * PS + q] = v;
+        }
+        __syncthreads();
+        const int ox = bx * TW + tx, oy = by * TH + ty;
+        if (ox >= p.Wo || oy >= p.Ho) continue;
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            if (oy - p.ph + r < 0 || oy - p.ph + r >= p.H) continue;                 // same skipping as the direct kernel
+#pragma unroll
+            for (int s_ = 0; s_ < 3; s_++) {
+                const float4* a = tile + ((ty + r) * HW + tx + s_) * PS;
+                const float4* w = reinterpret_cast<const float4*>(pf_wsm + (r * 3 + s_) * C4 * 4);
+#pragma unroll
+                for (int q = 0; q < C4; q++) {
+                    const float4 v = a[q];
+                    const float4 w01 = w[2 * q], w23 = w[2 * q + 1];
+                    a0 = fmaf(v.x, w01.x, a0); a1 = fmaf(v.x, w01.y, a1);
+                    a0 = fmaf(v.y, w01.z, a0); a1 = fmaf(v.y, w01.w, a1);
+                    a0 = fmaf(v.z, w23.x, a0); a1 = fmaf(v.z, w23.y, a1);
+                    a0 = fmaf(v.w, w23.z, a0); a1 = fmaf(v.w, w23.w, a1);
+                }
+            }
+        }
+        pf_store(out, p, bias, n, oy, ox, a0, a1);
+    }
+}
+
 // one warp per PX = 4 consecutive output pixels of a row: the 6 input columns and the weights of a kernel row are loaded
 // once for the four of them (shared memory bandwidth for the weights was the limit of the one-pixel version)
 __global__ void __launch_bounds__(256) conv_pf3_warp_kernel(T4 in, const float* __restrict__ wp, const float* __restrict__ bias, T4 out, ConvP p, int C4) {
@@ -461,6 +510,48 @@ __global__ void __launch_bounds__(256) conv_pf3_warp_kernel(T4 in, const float* 
 #pragma unroll
             for (int j = 0; j < PX; j++) if (lane == j) { a0 = acc[j][0]; a1 = acc[j][1]; }
             pf_store(out, p, bias, n, oy, ox0 + lane, a0, a1);
+        }
+    }
+}
+
+// Flow upsamplers (Deconvolution 4x4, stride 2, Ci, Co <= 4): an output pixel is reached by exactly the 2x2 taps whose parity
+// matches, so only those are visited (conv_tiny_kernel<true> tests all 16).  Same tap and channel order as the generic kernel,
+// hence bit-identical results.
+__global__ void __launch_bounds__(256) deconv_s2_tiny_kernel(T4 in, const float* __restrict__ wp, const float* __restrict__ bias, T4 out, ConvP p) {
+    extern __shared__ float wsm[];                    // [kh*kw][Ci][Co]
+    const int nw = p.kh * p.kw * p.Ci * p.Co;
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) wsm[i] = wp[i];
+    __syncthreads();
+    const long long M = (long long)p.N * p.Ho * p.Wo;
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(m % p.Wo);
+        const int oy = (int)((m / p.Wo) % p.Ho);
+        const int n = (int)(m / ((long long)p.Wo * p.Ho));
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const int ty = oy + p.ph, tx = ox + p.pw;
+        for (int r = ty & 1; r < p.kh; r += 2) {
+            const int iy = (ty - r) >> 1;
+            if (ty - r < 0 || iy >= p.H) continue;
+            for (int s_ = tx & 1; s_ < p.kw; s_ += 2) {
+                const int ix = (tx - s_) >> 1;
+                if (tx - s_ < 0 || ix >= p.W) continue;
+                const float* ip = in.p + in.off(n, 0, iy, ix);
+                const float* w = wsm + (r * p.kw + s_) * p.Ci * p.Co;
+                for (int ci = 0; ci < p.Ci; ci++) {
+                    const float a = __ldg(ip + ci * in.sc);
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (j < p.Co) acc[j] = fmaf(a, w[ci * p.Co + j], acc[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (j >= p.Co) break;
+            float v = acc[j];
+            if (p.has_bias) v += __ldg(bias + j);
+            if (p.relu) v = v > 0 ? v : v * p.slope;
+            out.p[out.off(n, j, oy, ox)] = v;
         }
     }
 }
@@ -577,7 +668,12 @@ int fn2_conv_forward(const fn2_conv_desc* d, const fn2_tensor* bottom, const flo
         if (C4 <= 8) {
             const int grid = (int)min((long long)148 * 8, (M + 255) / 256);
 #define FN2_PF_THREAD(C)                                                                                                   \
-            case C: if (k3) conv_pf3_thread_kernel<C><<<grid, 256, smem, st>>>(in, packed_weights_dev, bias_dev, out, p);  \
+            case C: if (k3 && d->pad_h == 1 && d->pad_w == 1 && !getenv("FN2_PF_NOTILE")) {                                \
+                        const size_t tsm = smem + (size_t)10 * 34 * (C + 1) * sizeof(float4);                               \
+                        const int tgrid = (int)min((long long)148 * 4, (long long)p.N * ((p.Wo + 31) / 32) * ((p.Ho + 7) / 8)); \
+                        if (tsm > 48 * 1024) FN2_CUDA(cudaFuncSetAttribute(conv_pf3_tile_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm)); \
+                        conv_pf3_tile_kernel<C><<<tgrid, 256, tsm, st>>>(in, packed_weights_dev, bias_dev, out, p);            \
+                    } else if (k3) conv_pf3_thread_kernel<C><<<grid, 256, smem, st>>>(in, packed_weights_dev, bias_dev, out, p);  \
                     else conv_pf_thread_kernel<C><<<grid, 256, smem, st>>>(in, packed_weights_dev, bias_dev, out, p);      \
                     break;
             switch (C4) { FN2_PF_THREAD(1) FN2_PF_THREAD(2) FN2_PF_THREAD(3) FN2_PF_THREAD(4) FN2_PF_THREAD(5) FN2_PF_THREAD(6)
@@ -603,7 +699,8 @@ int fn2_conv_forward(const fn2_conv_desc* d, const fn2_tensor* bottom, const flo
     } else if (d->co <= 4 && d->ci <= 32) {
         const size_t smem = (size_t)p.K * p.Co * sizeof(float);
         const int grid = ew_grid(M, 256);
-        if (d->deconv) conv_tiny_kernel<true><<<grid, 256, smem, st>>>(in, packed_weights_dev, bias_dev, out, p);
+        if (d->deconv && d->stride_h == 2 && d->stride_w == 2) deconv_s2_tiny_kernel<<<grid, 256, smem, st>>>(in, packed_weights_dev, bias_dev, out, p);
+        else if (d->deconv) conv_tiny_kernel<true><<<grid, 256, smem, st>>>(in, packed_weights_dev, bias_dev, out, p);
         else           conv_tiny_kernel<false><<<grid, 256, smem, st>>>(in, packed_weights_dev, bias_dev, out, p);
     } else if (d->co <= 4) {
         const int grid = ew_grid(M * 32, 256);

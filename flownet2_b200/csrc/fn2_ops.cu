@@ -20,7 +20,7 @@ namespace fn2 {
 // One thread per output pixel; the reference's NCHW->NHWC transpose pass (.cu:24-52) is not
 // needed: taps are read straight from the strided view.
 // ---------------------------------------------------------------------------------------------
-__global__ void flow_warp_fwd_kernel(T4 img, T4 flow, T4 out, float fill) {
+__global__ void flow_warp_fwd_kernel(T4 img, T4 flow, T4 out, float fill, int vec4) {
     const long long total = (long long)out.n * out.h * out.w;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -45,6 +45,17 @@ __global__ void flow_warp_fwd_kernel(T4 img, T4 flow, T4 out, float fill) {
             const float cBR = alpha * beta;
             const long long oTL = img.off(n, 0, iy2_T, ix2_L), oTR = img.off(n, 0, iy2_T, ix2_R);
             const long long oBL = img.off(n, 0, iy2_B, ix2_L), oBR = img.off(n, 0, iy2_B, ix2_R);
+            if (vec4) {
+                // channel-fast image with <= 4 channels in 16-byte pixels: one 128-bit load per tap (same arithmetic per channel)
+                const float4 TL = __ldg(reinterpret_cast<const float4*>(img.p + oTL)), TR = __ldg(reinterpret_cast<const float4*>(img.p + oTR));
+                const float4 BL = __ldg(reinterpret_cast<const float4*>(img.p + oBL)), BR = __ldg(reinterpret_cast<const float4*>(img.p + oBR));
+                const float tl[4] = {TL.x, TL.y, TL.z, TL.w}, tr[4] = {TR.x, TR.y, TR.z, TR.w};
+                const float bl[4] = {BL.x, BL.y, BL.z, BL.w}, br[4] = {BR.x, BR.y, BR.z, BR.w};
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    if (c < img.c) out.p[out.off(n, c, y, x)] = ((cTL * tl[c] + cTR * tr[c]) + cBL * bl[c]) + cBR * br[c];
+                continue;
+            }
             for (int c = 0; c < img.c; c++) {
                 const float TL = __ldg(img.p + oTL + c * img.sc);
                 const float TR = __ldg(img.p + oTR + c * img.sc);
@@ -325,7 +336,7 @@ __global__ void eltwise_sum_kernel(EltArgs a, T4 out) {
 }
 
 // ChannelNorm: channel_norm_layer.cu:17-30.
-__global__ void channel_norm_kernel(T4 in, T4 out) {
+__global__ void channel_norm_kernel(T4 in, T4 out, int vec4) {
     const long long total = (long long)in.n * in.h * in.w;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -333,9 +344,16 @@ __global__ void channel_norm_kernel(T4 in, T4 out) {
         const int y = (int)((idx / in.w) % in.h);
         const int n = (int)(idx / ((long long)in.w * in.h));
         float norm = 0;
-        for (int c = 0; c < in.c; c++) {
-            const float v = in.p[in.off(n, c, y, x)];
-            norm = norm + v * v;
+        if (vec4) {
+            const float4 q = *reinterpret_cast<const float4*>(in.p + in.off(n, 0, y, x));
+            const float v[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int c = 0; c < 4; c++) if (c < in.c) norm = norm + v[c] * v[c];
+        } else {
+            for (int c = 0; c < in.c; c++) {
+                const float v = in.p[in.off(n, c, y, x)];
+                norm = norm + v * v;
+            }
         }
         out.p[out.off(n, 0, y, x)] = sqrtf(norm);
     }
@@ -689,7 +707,8 @@ int fn2_flow_warp_forward(const fn2_tensor* image, const fn2_tensor* flow, const
     float fill = 0.f;
     if (fill_nan) { unsigned u = 0xFFE00000u; memcpy(&fill, &u, 4); }
     const long long total = (long long)out.n * out.h * out.w;
-    flow_warp_fwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(img, fl, out, fill);
+    const int vec4 = img.sc == 1 && img.c <= 4 && img.sw >= 4 && !((uintptr_t)img.p & 15) && !(img.sw & 3) && !(img.sh & 3) && !(img.sn & 3);
+    flow_warp_fwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(img, fl, out, fill, vec4);
     FN2_LAUNCH_CHECK();
     return FN2_OK;
 }
@@ -829,7 +848,8 @@ int fn2_channel_norm_forward(const fn2_tensor* bottom, const fn2_tensor* top, vo
     FN2_CHECK_ARG(out.c == 1 && out.n == in.n && out.h == in.h && out.w == in.w,
                   "channel_norm: top must be (N,1,H,W) (channel_norm_layer.cpp:29)");
     const long long total = (long long)in.n * in.h * in.w;
-    channel_norm_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out);
+    const int vec4 = in.sc == 1 && in.c <= 4 && in.sw >= 4 && !((uintptr_t)in.p & 15) && !(in.sw & 3) && !(in.sh & 3) && !(in.sn & 3);
+    channel_norm_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, vec4);
     FN2_LAUNCH_CHECK();
     return FN2_OK;
 }
