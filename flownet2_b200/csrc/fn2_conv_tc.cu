@@ -920,20 +920,26 @@ static TcSmallCi tc_small_ci(const fn2_conv_desc* d, int ci_stride) {
 // Split-K plan: layers whose tile list cannot fill the GPU (the 7x16 .. 14x32 maps of conv5/conv6/deconv5 with
 // K = 9 * 1024) cut every tile's K loop into `z` ranges that run on different SMs.
 // tail split plan for a layer with `tiles` tile units of `steps` K steps each: returns z (1 = off) and the first tail tile
-static int tc_tail_plan(long long tiles, int steps, int* first) {
+static int tc_tail_plan(long long tiles, int steps, int* first, int NT = 128) {
     *first = (int)tiles;
     if (getenv("FN2_TC_NOTAIL")) return 1;
     const int nsm = tc_num_sms();
-    if (steps < 16) return 1;                       // (tiles <= nsm: everything is "tail" -- 112 tiles become 896 eighths on 148 SMs)
+    if (steps < 16) return 1;                       // (tiles <= nsm: everything is "tail" -- 112 tiles become 560 fifths on 148 SMs)
     const long long full = tiles / nsm * nsm, r = tiles - full;
     if (r == 0) return 1;
-    const int z = min(8, steps / 8);
-    if (z < 2) return 1;
+    // cost model in units of one tile's time: rounds of whole tiles + rounds of 1/z tiles + the fix-up kernel reading r*z
+    // partial tiles (128 x NT floats each at ~3 TB/s; a tile takes ~1400 cycles per K step at 1.9 GHz)
+    const double tile_s = steps * 1400.0 / 1.9e9, part_s = 128.0 * NT * 4 / 3e12 + 2e-9;
     const double now = (double)((tiles + nsm - 1) / nsm);
-    const double then = (double)(full / nsm) + (double)((r * z + nsm - 1) / nsm) / z;
-    if (then > 0.94 * now) return 1;
+    double best = now * 0.94;
+    int bz = 1;
+    for (int z = 2; z <= min(8, steps / 8); z++) {
+        const double then = (double)(full / nsm) + (double)((r * z + nsm - 1) / nsm) / z + (r * z * part_s + 4e-6) / tile_s;
+        if (then < best) { best = then; bz = z; }
+    }
+    if (bz < 2) return 1;
     *first = (int)full;
-    return z;
+    return bz;
 }
 // tile count / K steps of a layer (same tiling rules as conv_tc_forward)
 static void tc_layer_geometry(const fn2_conv_desc* d, int N, int Ho, int Wo, int* NTo, long long* tiles, int* steps) {
@@ -976,7 +982,7 @@ size_t conv_tc_workspace_floats(const fn2_conv_desc* d, int N, int Ho, int Wo) {
     if (d->co % 16 || (!d->deconv && d->ci <= 16)) return 0;
     int NT, steps, first; long long tiles;
     tc_layer_geometry(d, N, Ho, Wo, &NT, &tiles, &steps);
-    const int tz = tc_tail_plan(tiles, steps, &first);
+    const int tz = tc_tail_plan(tiles, steps, &first, NT);
     return tz > 1 ? (size_t)(tiles - first) * tz * 128 * NT : 0;
 }
 
@@ -1107,7 +1113,7 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
         if (p.splits == 1 && p.cl == 1 && !sm.mode && ws) {
             int first = 0, steps_min = 1 << 30;
             for (int c = 0; c < p.ncls; c++) steps_min = min(steps_min, p.cls_ntaps[c] * p.cblocks);
-            const int tz = tc_tail_plan(p.total, steps_min, &first);
+            const int tz = tc_tail_plan(p.total, steps_min, &first, NT);
             if (tz > 1 && ws_floats >= (size_t)(p.total - first) * tz * 128 * NT) {
                 p.tail_first = first; p.tail_z = tz; p.d_tail_z.init(tz);
                 p.total = first + (p.ntotal - first) * tz;
