@@ -471,18 +471,27 @@ __global__ void __launch_bounds__(256) conv_pf3_warp_kernel(T4 in, const float* 
         float acc[PX][2];
 #pragma unroll
         for (int j = 0; j < PX; j++) { acc[j][0] = 0.f; acc[j][1] = 0.f; }
+        // per-row base pointers and column validity once per group (the address arithmetic used to be repeated per load)
+        const float4* rowp[3];
+        bool rowok[3], colok[PX + 2];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const int iy = oy - p.ph + r;
+            rowok[r] = iy >= 0 && iy < p.H;
+            rowp[r] = reinterpret_cast<const float4*>(in.p + in.off(n, 0, rowok[r] ? iy : 0, 0));
+        }
+#pragma unroll
+        for (int c = 0; c < PX + 2; c++) { const int ix = ox0 - p.pw + c; colok[c] = ix >= 0 && ix < p.W; }
+        const long long px4 = in.sw / 4;                                   // pixel stride in float4
+        const long long col0 = (long long)(ox0 - p.pw) * px4;
         for (int q = lane; q < C4; q += 32) {
 #pragma unroll
             for (int r = 0; r < 3; r++) {
-                const int iy = oy - p.ph + r;
-                if (iy < 0 || iy >= p.H) continue;
+                if (!rowok[r]) continue;
                 float4 a[PX + 2];
 #pragma unroll
-                for (int c = 0; c < PX + 2; c++) {
-                    const int ix = ox0 - p.pw + c;
-                    const bool ok = ix >= 0 && ix < p.W;
-                    a[c] = ok ? __ldg(reinterpret_cast<const float4*>(in.p + in.off(n, 0, iy, ix)) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                for (int c = 0; c < PX + 2; c++)
+                    a[c] = colok[c] ? __ldg(rowp[r] + col0 + c * px4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int s = 0; s < 3; s++) {
                     const float4* w = reinterpret_cast<const float4*>(pf_wsm + (long long)(r * 3 + s) * C4 * 4);

@@ -157,6 +157,19 @@ __global__ void resample_kernel(T4 in, T4 out, float fx, float fy, int antialias
         const float sup = (TYPE == 3) ? 2.0f : 1.0f;
         const int xl = max(x_in_round - rx, (int)floorf(x_in - sup / ax)), xh = min(x_in_round + rx, (int)ceilf(x_in + sup / ax));
         const int yl = max(y_in_round - ry, (int)floorf(y_in - sup / ay)), yh = min(y_in_round + ry, (int)ceilf(y_in + sup / ay));
+        // x factors ((ax * cx) * ay, the first two products of the reference's weight expression) once per pixel when the
+        // window is narrow (always, except for strong down-sampling)
+        constexpr int MAXT = 8;
+        float tx_[MAXT];
+        const bool pre = xh - xl < MAXT;
+        if (pre) {
+#pragma unroll
+            for (int k = 0; k < MAXT; k++) {
+                const float dx = x_in - (xl + k);
+                const float cx = (TYPE == 3) ? bicubicCoeff(ax * dx) : triangleCoeff(ax * dx);
+                tx_[k] = (ax * cx) * ay;
+            }
+        }
         for (int c0 = 0; c0 < out.c; c0 += 4) {
             const int nc = min(4, out.c - c0);
             float sum[4] = {0.f, 0.f, 0.f, 0.f};
@@ -165,6 +178,20 @@ __global__ void resample_kernel(T4 in, T4 out, float fx, float fy, int antialias
                 if (y < 0 || y >= in.h) continue;
                 const float dy = y_in - y;
                 const float cy = (TYPE == 3) ? bicubicCoeff(ay * dy) : triangleCoeff(ay * dy);
+#pragma unroll
+                for (int k = 0; k < MAXT; k++) {
+                    const int x = xl + k;
+                    if (!pre || x > xh) break;
+                    if (x < 0 || x >= in.w) continue;
+                    const float w = tx_[k] * cy;
+                    if (w == 0.f) continue;
+                    const float* ip = in.p + in.off(n, c0, y, x);
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (j < nc) sum[j] = sum[j] + w * __ldg(ip + (long long)j * in.sc);
+                    wsum += w;
+                }
+                if (!pre)
                 for (int x = xl; x <= xh; x++) {
                     if (x < 0 || x >= in.w) continue;
                     const float dx = x_in - x;
