@@ -19,6 +19,7 @@ int conv_tc_eligible(const fn2_conv_desc* d, const T4& in, const T4& out);
 int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const float* bias,
                     const T4& out, float* ws, size_t ws_floats, cudaStream_t st);
 size_t conv_tc_workspace_floats(const fn2_conv_desc* d, int N, int Ho, int Wo);
+int conv_tc_plan(const fn2_conv_desc* d, int N, int Ho, int Wo, int ci_stride, int* out8);
 int conv_tc_packed_floats(const fn2_conv_desc* d, int ci_stride, size_t* floats);
 int conv_tc_pack(const fn2_conv_desc* d, int ci_stride, const float* w, float* wp, cudaStream_t st);
 int conv_nhwc_eligible(const fn2_conv_desc* d, const T4& in, const T4& out);
@@ -638,6 +639,15 @@ int fn2_conv_pack_weights(const fn2_conv_desc* d, int ci_stride, const float* ca
         caffe_weights_dev, packed_dev, d->ci, d->co, d->kh, d->kw, d->ci, d->deconv);
     FN2_LAUNCH_CHECK();
     return conv_tc_pack(d, ci_stride, caffe_weights_dev, packed_dev + total, (cudaStream_t)stream);
+}
+
+int fn2_conv_plan(const fn2_conv_desc* d, int N, int H, int W, int ci_stride, int32_t* plan8) {
+    FN2_CHECK_ARG(d && plan8, "conv_plan: null argument");
+    int Ho, Wo;
+    int rc = fn2_conv_out_shape(d, H, W, &Ho, &Wo);
+    if (rc) return rc;
+    conv_tc_plan(d, N, Ho, Wo, ci_stride, plan8);
+    return FN2_OK;
 }
 
 int fn2_conv_workspace_bytes(const fn2_conv_desc* d, int N, int H, int W, size_t* bytes) {

@@ -986,6 +986,24 @@ size_t conv_tc_workspace_floats(const fn2_conv_desc* d, int N, int Ho, int Wo) {
     return tz > 1 ? (size_t)(tiles - first) * tz * 128 * NT : 0;
 }
 
+// Host-side plan of the tcgen05 engine for one layer shape (introspection for tests and tools; needs no GPU):
+// out = {NT, tile units, K steps per tile, small-Ci mode (0 plain, 1 tap groups, 2 kernel rows), uniform K splits,
+//        first tail tile, tail K ranges, 0}
+int conv_tc_plan(const fn2_conv_desc* d, int N, int Ho, int Wo, int ci_stride, int* out8) {
+    for (int i = 0; i < 8; i++) out8[i] = 0;
+    if (d->co % 16) return 0;
+    int NT, steps; long long tiles;
+    tc_layer_geometry(d, N, Ho, Wo, &NT, &tiles, &steps);
+    const TcSmallCi sm = tc_small_ci(d, ci_stride);
+    if (sm.mode == 1) steps = sm.ngroups;
+    if (sm.mode == 2) steps = d->kh * sm.rblocks;
+    out8[0] = NT; out8[1] = (int)tiles; out8[2] = steps; out8[3] = sm.mode;
+    out8[4] = tc_split_plan(d, N, Ho, Wo);
+    out8[5] = (int)tiles; out8[6] = 1;
+    if (out8[4] == 1 && !sm.mode) { int first = 0; out8[6] = tc_tail_plan(tiles, steps, &first, NT); out8[5] = first; }
+    return 1;
+}
+
 int conv_tc_eligible(const fn2_conv_desc* d, const T4& in, const T4& out) {
     if (!tc_enabled()) return 0;
     if (in.sc != 1 || out.sc != 1) return 0;

@@ -151,6 +151,10 @@ FN2_API int fn2_conv_out_shape(const fn2_conv_desc* d, int H, int W, int* Ho, in
 /* Scratch the forward may use for this shape (split-K partials of small spatial maps); may be 0.
  * Passing a NULL / too small workspace is allowed: the kernel then runs unsplit. */
 FN2_API int fn2_conv_workspace_bytes(const fn2_conv_desc* d, int N, int H, int W, size_t* bytes);
+/* Host-side plan of the tcgen05 engine for a layer shape (introspection; needs no GPU): plan8 = {NT (output channels per
+ * tile; 0 = not eligible by channel count), tile units, K steps per tile, small-Ci mode (0 plain K blocks, 1 tap groups,
+ * 2 kernel rows), uniform K splits, first tail tile, K ranges per tail tile, 0}. */
+FN2_API int fn2_conv_plan(const fn2_conv_desc* d, int N, int H, int W, int ci_stride, int32_t* plan8);
 FN2_API int fn2_conv_forward(const fn2_conv_desc* d, const fn2_tensor* bottom,
                              const float* packed_weights_dev, const float* bias_dev,
                              const fn2_tensor* top, void* workspace, size_t workspace_bytes, void* stream);

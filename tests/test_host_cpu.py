@@ -168,3 +168,44 @@ def test_no_compute_without_gpu_is_loud(fn2):
         pytest.skip("GPU present")
     with pytest.raises(fn2.Fn2Error):
         fn2.Net(fn2.fill_template(fn2.model_template("FlowNet2-S"), 64, 64))
+
+
+def test_tcgen05_engine_plan_for_flownet2_shapes(fn2):
+    """Host-side planning of the tensor-core convolution engine (no GPU needed): tile width, small-Ci packing mode, split-K for
+    the small-spatial layers and the tail split of the last partial wave, at the BASELINE shapes (4 pairs, 1024x448)."""
+    from flownet2_b200 import fn2_conv_desc
+    lib = fn2.lib()
+
+    def plan(ci, co, k, s, p, H, W, deconv=0, cis=None, guard=1024, N=4):
+        d = fn2_conv_desc(ci, co, k, k, s, s, p, p, deconv, 1, 1, 0.1, 0, guard)
+        out = (C.c_int32 * 8)()
+        assert lib.fn2_conv_plan(C.byref(d), N, H, W, cis if cis is not None else ci, out) == 0
+        ws = C.c_size_t()
+        assert lib.fn2_conv_workspace_bytes(C.byref(d), N, H, W, C.byref(ws)) == 0
+        return list(out), ws.value
+
+    # conv1 of FlowNetC on the dense 3-channel image (pixel stride 4, guard band): kernel-row packing, 7 steps of one box
+    pl, _ = plan(3, 64, 7, 2, 3, 448, 1024, cis=4)
+    assert pl[0] == 64 and pl[3] == 2 and pl[2] == 7 and pl[1] == 4 * 224 * 512 // 128
+    # the same layer on a tensor without the guard promise: tap groups (8 taps of 4 channels per K block)
+    pl, _ = plan(3, 64, 7, 2, 3, 448, 1024, cis=4, guard=0)
+    assert pl[3] == 1 and pl[2] == 7
+    # ... and as a channel-range view of a wider blob: tap groups as well
+    pl, _ = plan(3, 64, 7, 2, 3, 448, 1024, cis=12)
+    assert pl[3] == 1
+    # conv3_1: 448 tiles on 148 SMs -> the 4 tiles of the last wave are K-split, partials fit the workspace
+    pl, ws = plan(473, 256, 3, 1, 1, 56, 128)
+    assert pl[0] == 128 and pl[1] == 448 and pl[2] == 9 * 15 and pl[4] == 1
+    assert pl[5] == 444 and 2 <= pl[6] <= 8 and ws >= (448 - 444) * pl[6] * 128 * 128 * 4
+    # conv6_1: 28 tiles with K = 9*1024 -> uniform split-K over the SMs
+    pl, ws = plan(1024, 1024, 3, 1, 1, 7, 16)
+    assert pl[1] == 32 and 2 <= pl[4] <= 8 and ws >= pl[4] * 4 * 7 * 16 * 1024 * 4
+    # fusion interconv0: 16 output channels, full resolution, nothing to split
+    pl, _ = plan(82, 16, 3, 1, 1, 448, 1024, cis=96)
+    assert pl[0] == 16 and pl[3] == 0 and pl[4] == 1 and pl[2] == 27
+    # flow predictor (2 output channels) is not a tensor-core layer
+    pl, _ = plan(194, 2, 3, 1, 1, 112, 256)
+    assert pl[0] == 0
+    # deconv5: 4 parity classes of 2x2 taps
+    pl, _ = plan(1024, 512, 4, 2, 1, 7, 16, deconv=1)
+    assert pl[0] == 128 and pl[2] == 4 * 32
