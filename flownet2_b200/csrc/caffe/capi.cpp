@@ -21,6 +21,8 @@ struct fn2_net {
         return strstr(e.what(), "Unknown") ? FN2_ERR_NOTFOUND : FN2_ERR_INVALID; \
     }
 
+namespace caffe { void SampleAugmentationCoeffs(const LayerParameter& lp, uint32_t seed, int num, int width, int height, float num_iter, float* out); }
+
 extern "C" {
 
 int fn2_net_create(const char* prototxt_text, int phase, fn2_net** out) {
@@ -206,6 +208,18 @@ int fn2_proto_canonical(const char* prototxt_text, char* out, size_t* bytes) {
         if (!np.name.empty()) s += "name: \"" + np.name + "\"\n";
         for (const auto& l : np.layers) s += "layer {\n" + caffe::PrintTextFormat(*l.m, 1) + "}\n";
         return emit_string(s, out, bytes);
+    FN2_CATCH
+}
+
+int fn2_aug_sample(const char* layer_prototxt, unsigned int seed, int num, int width, int height, float num_iter, float* coeffs_out) {
+    if (!layer_prototxt || !coeffs_out || num <= 0) { fn2::set_error("aug_sample: invalid argument"); return FN2_ERR_INVALID; }
+    FN2_TRY
+        caffe::NetParameter np = caffe::NetParameter::FromText(layer_prototxt);
+        const caffe::LayerParameter* lp = nullptr;
+        for (const auto& l : np.layers) if (l.type() == "DataAugmentation") { lp = &l; break; }
+        if (!lp) { fn2::set_error("aug_sample: no DataAugmentation layer in the text"); return FN2_ERR_INVALID; }
+        caffe::SampleAugmentationCoeffs(*lp, seed, num, width, height, num_iter, coeffs_out);
+        return FN2_OK;
     FN2_CATCH
 }
 

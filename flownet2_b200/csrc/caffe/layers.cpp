@@ -655,10 +655,147 @@ struct AugRng {
     }
 };
 
+// Coefficient sampling of DataAugmentationLayer::Forward_gpu (data_augmentation_layer.cu:372-449) as a stand-alone object, so
+// that it can be exercised without a GPU (fn2_aug_sample).
+struct AugSampler {
+    AugRng rng;
+    explicit AugSampler(uint32_t seed) : rng(seed) {}
+    // generate_spatial_coeffs, augmentation_layer_base.cpp:73-99
+    void generate_spatial(const AugmentationParameter& aug, AugCoeff& c, float dc) {
+        if (aug.has("mirror")) c.set(AugCoeff::MIRROR, rng.generate(aug.gen("mirror"), dc, AugCoeff::def(AugCoeff::MIRROR), true));
+        if (aug.has("translate")) {
+            c.set(AugCoeff::DX, rng.generate(aug.gen("translate"), dc, 0.f));
+            c.set(AugCoeff::DY, rng.generate(aug.gen("translate"), dc, 0.f));
+        }
+        if (aug.has("translate_x")) c.set(AugCoeff::DX, rng.generate(aug.gen("translate_x"), dc, 0.f));
+        if (aug.has("translate_y")) c.set(AugCoeff::DY, rng.generate(aug.gen("translate_y"), dc, 0.f));
+        if (aug.has("rotate")) c.set(AugCoeff::ANGLE, rng.generate(aug.gen("rotate"), dc, 0.f));
+        if (aug.has("zoom")) {
+            c.set(AugCoeff::ZOOM_X, rng.generate(aug.gen("zoom"), dc, 1.f));
+            c.set(AugCoeff::ZOOM_Y, c.get(AugCoeff::ZOOM_X));
+        }
+        if (aug.has("squeeze")) {
+            const float sq = rng.generate(aug.gen("squeeze"), dc, 1.f);
+            c.set(AugCoeff::ZOOM_X, c.get(AugCoeff::ZOOM_X) * sq);
+            c.set(AugCoeff::ZOOM_Y, c.get(AugCoeff::ZOOM_Y) / sq);
+        }
+    }
+    // generate_valid_spatial_coeffs, augmentation_layer_base.cpp:102-169: resample until the 4 corners of the crop land
+    // inside the source image
+    void generate_valid_spatial(const AugmentationParameter& aug, AugCoeff& coeff, float dc, int width, int height, int cw, int ch,
+                                int max_num_tries = 50) {
+        float in_params[AugCoeff::N], cur[AugCoeff::N];
+        coeff.to_array(in_params);
+        int counter = 0, good = 0;
+        while (good < 4 && counter < max_num_tries) {
+            coeff.clear_all();
+            generate_spatial(aug, coeff, dc);
+            coeff.to_array(cur);
+            for (int f = 0; f < AugCoeff::N; f++) cur[f] += in_params[f];
+            coeff.from_array(cur);
+            good = 0;
+            for (int x = 0; x < cw; x += std::max(1, cw - 1))
+                for (int y = 0; y < ch; y += std::max(1, ch - 1)) {
+                    float x1, y1, x2, y2;
+                    if (coeff.get(AugCoeff::MIRROR)) { x1 = -(float)x + .5f * (float)cw; y1 = (float)y - .5f * (float)ch; }
+                    else                            { x1 = (float)x - .5f * (float)cw;  y1 = (float)y - .5f * (float)ch; }
+                    const float a = coeff.get(AugCoeff::ANGLE);
+                    x2 = std::cos(a) * x1 - std::sin(a) * y1;
+                    y2 = std::sin(a) * x1 + std::cos(a) * y1;
+                    x2 = x2 + coeff.get(AugCoeff::DX) * (float)cw;
+                    y2 = y2 + coeff.get(AugCoeff::DY) * (float)ch;
+                    x2 = x2 / coeff.get(AugCoeff::ZOOM_X);
+                    y2 = y2 / coeff.get(AugCoeff::ZOOM_Y);
+                    x2 = x2 + .5f * (float)width;
+                    y2 = y2 + .5f * (float)height;
+                    if (!(std::floor(x2) < 0 || std::floor(x2) > (float)(width - 2) || std::floor(y2) < 0 || std::floor(y2) > (float)(height - 2)))
+                        good++;
+                }
+            counter++;
+        }
+        if (counter >= max_num_tries) coeff.from_array(in_params);       // "Exceeded maximum tries in finding spatial coeffs."
+    }
+    // generate_chromatic_coeffs / _eigen_coeffs / _effect_coeffs, augmentation_layer_base.cpp:252-336
+    void generate_chromatic(const AugmentationParameter& aug, AugCoeff& c, float dc) {
+        if (aug.has("gamma")) c.set(AugCoeff::GAMMA, rng.generate(aug.gen("gamma"), dc, NAN));
+        if (aug.has("brightness")) c.set(AugCoeff::BRIGHTNESS, rng.generate(aug.gen("brightness"), dc, NAN));
+        if (aug.has("contrast")) c.set(AugCoeff::CONTRAST, rng.generate(aug.gen("contrast"), dc, NAN));
+        if (aug.has("color")) for (int k = 0; k < 3; k++) c.set(AugCoeff::COLOR1 + k, rng.generate(aug.gen("color"), dc, NAN));
+    }
+    void generate_chromatic_eigen(const AugmentationParameter& aug, AugCoeff& c, float dc) {
+        auto g = [&](const char* n) { return rng.generate(aug.gen(n), dc, NAN); };
+        if (aug.has("ladd_pow")) c.set(AugCoeff::POW_NOMEAN0, g("ladd_pow"));
+        if (aug.has("col_pow")) { c.set(AugCoeff::POW_NOMEAN1, g("col_pow")); c.set(AugCoeff::POW_NOMEAN2, g("col_pow")); }
+        if (aug.has("ladd_add")) c.set(AugCoeff::ADD_NOMEAN0, g("ladd_add"));
+        if (aug.has("col_add")) { c.set(AugCoeff::ADD_NOMEAN1, g("col_add")); c.set(AugCoeff::ADD_NOMEAN2, g("col_add")); }
+        if (aug.has("ladd_mult")) c.set(AugCoeff::MULT_NOMEAN0, g("ladd_mult"));
+        if (aug.has("col_mult")) { c.set(AugCoeff::MULT_NOMEAN1, g("col_mult")); c.set(AugCoeff::MULT_NOMEAN2, g("col_mult")); }
+        if (aug.has("sat_pow")) { c.set(AugCoeff::POW_WITHMEAN1, g("sat_pow")); c.set(AugCoeff::POW_WITHMEAN2, c.get(AugCoeff::POW_WITHMEAN1)); }
+        if (aug.has("sat_add")) { c.set(AugCoeff::ADD_WITHMEAN1, g("sat_add")); c.set(AugCoeff::ADD_WITHMEAN2, c.get(AugCoeff::ADD_WITHMEAN1)); }
+        if (aug.has("sat_mult")) { c.set(AugCoeff::MULT_WITHMEAN1, g("sat_mult")); c.set(AugCoeff::MULT_WITHMEAN2, c.get(AugCoeff::MULT_WITHMEAN1)); }
+        if (aug.has("lmult_pow")) c.set(AugCoeff::LMULT_POW, g("lmult_pow"));
+        if (aug.has("lmult_mult")) c.set(AugCoeff::LMULT_MULT, g("lmult_mult"));
+        if (aug.has("lmult_add")) c.set(AugCoeff::LMULT_ADD, g("lmult_add"));
+        if (aug.has("col_rotate")) c.set(AugCoeff::COL_ANGLE, g("col_rotate"));
+    }
+    void generate_effect(const AugmentationParameter& aug, AugCoeff& c, float dc) {
+        if (aug.has("fog_amount") || aug.has("fog_size")) {
+            c.set(AugCoeff::FOG_AMOUNT, rng.generate(aug.gen("fog_amount"), dc, 0.f));
+            c.set(AugCoeff::FOG_SIZE, rng.generate(aug.gen("fog_size"), dc, 0.f));
+        }
+        if (aug.has("motion_blur_angle") || aug.has("motion_blur_size")) {
+            c.set(AugCoeff::MOTION_BLUR_ANGLE, rng.generate(aug.gen("motion_blur_angle"), dc, 0.f));
+            c.set(AugCoeff::MOTION_BLUR_SIZE, rng.generate(aug.gen("motion_blur_size"), dc, 0.f));
+        }
+        if (aug.has("shadow_angle") || aug.has("shadow_distance") || aug.has("shadow_strength")) {
+            c.set(AugCoeff::SHADOW_ANGLE, rng.generate(aug.gen("shadow_angle"), dc, 0.f));
+            c.set(AugCoeff::SHADOW_DISTANCE, rng.generate(aug.gen("shadow_distance"), dc, 0.f));
+            c.set(AugCoeff::SHADOW_STRENGTH, rng.generate(aug.gen("shadow_strength"), dc, 0.f));
+        }
+        if (aug.has("noise")) c.set(AugCoeff::NOISE, rng.generate(aug.gen("noise"), dc, NAN));
+    }
+    // one item: which groups are sampled is decided by the presence of their generators (:383-396)
+    void sample(const AugmentationParameter& aug, float dc, int width, int height, int cw, int ch, AugCoeff& c) {
+        const bool spatial = aug.has("mirror") || aug.has("rotate") || aug.has("zoom") || aug.has("translate") ||
+                             aug.has("squeeze") || aug.has("translate_x") || aug.has("translate_y");
+        const bool chromatic = aug.has("brightness") || aug.has("gamma") || aug.has("contrast") || aug.has("color");
+        const bool effect = aug.has("fog_size") || aug.has("fog_amount") || aug.has("motion_blur_angle") ||
+                            aug.has("motion_blur_size") || aug.has("shadow_angle") || aug.has("shadow_distance") ||
+                            aug.has("shadow_strength") || aug.has("noise");
+        const bool eigen = aug.has("lmult_pow") || aug.has("lmult_mult") || aug.has("lmult_add") || aug.has("sat_pow") ||
+                           aug.has("sat_mult") || aug.has("sat_add") || aug.has("col_pow") || aug.has("col_mult") ||
+                           aug.has("col_add") || aug.has("ladd_pow") || aug.has("ladd_mult") || aug.has("ladd_add") ||
+                           aug.has("col_rotate");
+        c.clear_all();
+        if (spatial) generate_valid_spatial(aug, c, dc, width, height, cw, ch);
+        if (chromatic) generate_chromatic(aug, c, dc);
+        if (eigen) generate_chromatic_eigen(aug, c, dc);
+        if (effect) generate_effect(aug, c, dc);
+    }
+    // discount schedule, data_augmentation_layer.cu:372-374
+    static float discount(const LayerParameter& lp, float num_iter) {
+        const float hl = lp.coeff_schedule_half_life(), c0 = lp.coeff_schedule_initial(), c1 = lp.coeff_schedule_final();
+        return c0 + (c1 - c0) * (2.f / (1.f + std::exp(-1.0986f * num_iter / hl)) - 1.f);
+    }
+};
+
+// C-ABI helper (capi.cpp: fn2_aug_sample): coefficients of `num` items in array form (N x 42)
+void SampleAugmentationCoeffs(const LayerParameter& lp, uint32_t seed, int num, int width, int height, float num_iter, float* out) {
+    AugmentationParameter aug = lp.augmentation_param();
+    const int cw = aug.has_crop_width() ? aug.crop_width() : width, ch = aug.has_crop_height() ? aug.crop_height() : height;
+    AugSampler sm(seed);
+    const float dc = AugSampler::discount(lp, num_iter);
+    for (int n = 0; n < num; n++) {
+        AugCoeff c;
+        sm.sample(aug, dc, width, height, cw, ch, c);
+        c.to_array(out + (size_t)n * AugCoeff::N);
+    }
+}
+
 template <typename Dtype>
 class DataAugmentationLayer : public Layer<Dtype> {
  public:
-    explicit DataAugmentationLayer(const LayerParameter& p) : Layer<Dtype>(p), rng_(seed_of(p.name())) {}
+    explicit DataAugmentationLayer(const LayerParameter& p) : Layer<Dtype>(p), sampler_(seed_of(p.name())) {}
     ~DataAugmentationLayer() override {
         if (coef_dev_) cudaFree(coef_dev_);
         if (fixed_mean_dev_) cudaFree(fixed_mean_dev_);
@@ -739,7 +876,7 @@ class DataAugmentationLayer : public Layer<Dtype> {
                 for (int i = 0; i < area; i++) pp[(size_t)c * area + i] = pc[c];
             }
         }
-        rng_ = AugRng((uint32_t)(seed * 2654435761u) ^ seed_of(this->layer_param_.name()));
+        sampler_ = AugSampler((uint32_t)(seed * 2654435761u) ^ seed_of(this->layer_param_.name()));
     }
     void HostTick() override {
         float& num_iter = *(this->blobs_[0]->mutable_cpu_data());
@@ -760,100 +897,6 @@ class DataAugmentationLayer : public Layer<Dtype> {
         if (const char* e = getenv("FN2_SEED")) h = (uint32_t)strtoul(e, nullptr, 10);
         for (char c : name) h = h * 16777619u ^ (unsigned char)c;
         return h;
-    }
-    // generate_spatial_coeffs, augmentation_layer_base.cpp:73-99
-    void generate_spatial(const AugmentationParameter& aug, AugCoeff& c, float dc) {
-        if (aug.has("mirror")) c.set(AugCoeff::MIRROR, rng_.generate(aug.gen("mirror"), dc, AugCoeff::def(AugCoeff::MIRROR), true));
-        if (aug.has("translate")) {
-            c.set(AugCoeff::DX, rng_.generate(aug.gen("translate"), dc, 0.f));
-            c.set(AugCoeff::DY, rng_.generate(aug.gen("translate"), dc, 0.f));
-        }
-        if (aug.has("translate_x")) c.set(AugCoeff::DX, rng_.generate(aug.gen("translate_x"), dc, 0.f));
-        if (aug.has("translate_y")) c.set(AugCoeff::DY, rng_.generate(aug.gen("translate_y"), dc, 0.f));
-        if (aug.has("rotate")) c.set(AugCoeff::ANGLE, rng_.generate(aug.gen("rotate"), dc, 0.f));
-        if (aug.has("zoom")) {
-            c.set(AugCoeff::ZOOM_X, rng_.generate(aug.gen("zoom"), dc, 1.f));
-            c.set(AugCoeff::ZOOM_Y, c.get(AugCoeff::ZOOM_X));
-        }
-        if (aug.has("squeeze")) {
-            const float sq = rng_.generate(aug.gen("squeeze"), dc, 1.f);
-            c.set(AugCoeff::ZOOM_X, c.get(AugCoeff::ZOOM_X) * sq);
-            c.set(AugCoeff::ZOOM_Y, c.get(AugCoeff::ZOOM_Y) / sq);
-        }
-    }
-    // generate_valid_spatial_coeffs, augmentation_layer_base.cpp:102-169: resample until the 4 corners of the crop land
-    // inside the source image
-    void generate_valid_spatial(const AugmentationParameter& aug, AugCoeff& coeff, float dc, int width, int height, int cw, int ch,
-                                int max_num_tries = 50) {
-        float in_params[AugCoeff::N], cur[AugCoeff::N];
-        coeff.to_array(in_params);
-        int counter = 0, good = 0;
-        while (good < 4 && counter < max_num_tries) {
-            coeff.clear_all();
-            generate_spatial(aug, coeff, dc);
-            coeff.to_array(cur);
-            for (int f = 0; f < AugCoeff::N; f++) cur[f] += in_params[f];
-            coeff.from_array(cur);
-            good = 0;
-            for (int x = 0; x < cw; x += std::max(1, cw - 1))
-                for (int y = 0; y < ch; y += std::max(1, ch - 1)) {
-                    float x1, y1, x2, y2;
-                    if (coeff.get(AugCoeff::MIRROR)) { x1 = -(float)x + .5f * (float)cw; y1 = (float)y - .5f * (float)ch; }
-                    else                            { x1 = (float)x - .5f * (float)cw;  y1 = (float)y - .5f * (float)ch; }
-                    const float a = coeff.get(AugCoeff::ANGLE);
-                    x2 = std::cos(a) * x1 - std::sin(a) * y1;
-                    y2 = std::sin(a) * x1 + std::cos(a) * y1;
-                    x2 = x2 + coeff.get(AugCoeff::DX) * (float)cw;
-                    y2 = y2 + coeff.get(AugCoeff::DY) * (float)ch;
-                    x2 = x2 / coeff.get(AugCoeff::ZOOM_X);
-                    y2 = y2 / coeff.get(AugCoeff::ZOOM_Y);
-                    x2 = x2 + .5f * (float)width;
-                    y2 = y2 + .5f * (float)height;
-                    if (!(std::floor(x2) < 0 || std::floor(x2) > (float)(width - 2) || std::floor(y2) < 0 || std::floor(y2) > (float)(height - 2)))
-                        good++;
-                }
-            counter++;
-        }
-        if (counter >= max_num_tries) coeff.from_array(in_params);       // "Exceeded maximum tries in finding spatial coeffs."
-    }
-    // generate_chromatic_coeffs / _eigen_coeffs / _effect_coeffs, augmentation_layer_base.cpp:252-336
-    void generate_chromatic(const AugmentationParameter& aug, AugCoeff& c, float dc) {
-        if (aug.has("gamma")) c.set(AugCoeff::GAMMA, rng_.generate(aug.gen("gamma"), dc, NAN));
-        if (aug.has("brightness")) c.set(AugCoeff::BRIGHTNESS, rng_.generate(aug.gen("brightness"), dc, NAN));
-        if (aug.has("contrast")) c.set(AugCoeff::CONTRAST, rng_.generate(aug.gen("contrast"), dc, NAN));
-        if (aug.has("color")) for (int k = 0; k < 3; k++) c.set(AugCoeff::COLOR1 + k, rng_.generate(aug.gen("color"), dc, NAN));
-    }
-    void generate_chromatic_eigen(const AugmentationParameter& aug, AugCoeff& c, float dc) {
-        auto g = [&](const char* n) { return rng_.generate(aug.gen(n), dc, NAN); };
-        if (aug.has("ladd_pow")) c.set(AugCoeff::POW_NOMEAN0, g("ladd_pow"));
-        if (aug.has("col_pow")) { c.set(AugCoeff::POW_NOMEAN1, g("col_pow")); c.set(AugCoeff::POW_NOMEAN2, g("col_pow")); }
-        if (aug.has("ladd_add")) c.set(AugCoeff::ADD_NOMEAN0, g("ladd_add"));
-        if (aug.has("col_add")) { c.set(AugCoeff::ADD_NOMEAN1, g("col_add")); c.set(AugCoeff::ADD_NOMEAN2, g("col_add")); }
-        if (aug.has("ladd_mult")) c.set(AugCoeff::MULT_NOMEAN0, g("ladd_mult"));
-        if (aug.has("col_mult")) { c.set(AugCoeff::MULT_NOMEAN1, g("col_mult")); c.set(AugCoeff::MULT_NOMEAN2, g("col_mult")); }
-        if (aug.has("sat_pow")) { c.set(AugCoeff::POW_WITHMEAN1, g("sat_pow")); c.set(AugCoeff::POW_WITHMEAN2, c.get(AugCoeff::POW_WITHMEAN1)); }
-        if (aug.has("sat_add")) { c.set(AugCoeff::ADD_WITHMEAN1, g("sat_add")); c.set(AugCoeff::ADD_WITHMEAN2, c.get(AugCoeff::ADD_WITHMEAN1)); }
-        if (aug.has("sat_mult")) { c.set(AugCoeff::MULT_WITHMEAN1, g("sat_mult")); c.set(AugCoeff::MULT_WITHMEAN2, c.get(AugCoeff::MULT_WITHMEAN1)); }
-        if (aug.has("lmult_pow")) c.set(AugCoeff::LMULT_POW, g("lmult_pow"));
-        if (aug.has("lmult_mult")) c.set(AugCoeff::LMULT_MULT, g("lmult_mult"));
-        if (aug.has("lmult_add")) c.set(AugCoeff::LMULT_ADD, g("lmult_add"));
-        if (aug.has("col_rotate")) c.set(AugCoeff::COL_ANGLE, g("col_rotate"));
-    }
-    void generate_effect(const AugmentationParameter& aug, AugCoeff& c, float dc) {
-        if (aug.has("fog_amount") || aug.has("fog_size")) {
-            c.set(AugCoeff::FOG_AMOUNT, rng_.generate(aug.gen("fog_amount"), dc, 0.f));
-            c.set(AugCoeff::FOG_SIZE, rng_.generate(aug.gen("fog_size"), dc, 0.f));
-        }
-        if (aug.has("motion_blur_angle") || aug.has("motion_blur_size")) {
-            c.set(AugCoeff::MOTION_BLUR_ANGLE, rng_.generate(aug.gen("motion_blur_angle"), dc, 0.f));
-            c.set(AugCoeff::MOTION_BLUR_SIZE, rng_.generate(aug.gen("motion_blur_size"), dc, 0.f));
-        }
-        if (aug.has("shadow_angle") || aug.has("shadow_distance") || aug.has("shadow_strength")) {
-            c.set(AugCoeff::SHADOW_ANGLE, rng_.generate(aug.gen("shadow_angle"), dc, 0.f));
-            c.set(AugCoeff::SHADOW_DISTANCE, rng_.generate(aug.gen("shadow_distance"), dc, 0.f));
-            c.set(AugCoeff::SHADOW_STRENGTH, rng_.generate(aug.gen("shadow_strength"), dc, 0.f));
-        }
-        if (aug.has("noise")) c.set(AugCoeff::NOISE, rng_.generate(aug.gen("noise"), dc, NAN));
     }
     // all_coeffs_ (N x 42 array form) -> matrices / chromatic / eigen / effect records in coef_host_
     // (data_augmentation_layer.cu:452-477; tTransMat::fromCoeff augmentation_layer_base.cpp:38-48)
@@ -907,26 +950,10 @@ class DataAugmentationLayer : public Layer<Dtype> {
                     const float* in = bottom[1]->cpu_data();              // "Receiving augmentation params" (:107-109)
                     all_coeffs_.assign(in, in + (size_t)num * AugCoeff::N);
                 } else {
-                    // discount schedule, data_augmentation_layer.cu:372-374
-                    const float hl = this->layer_param_.coeff_schedule_half_life(), c0 = this->layer_param_.coeff_schedule_initial(),
-                                c1 = this->layer_param_.coeff_schedule_final();
-                    const float dc = c0 + (c1 - c0) * (2.f / (1.f + std::exp(-1.0986f * num_iter_ / hl)) - 1.f);
-                    const bool spatial = aug.has("mirror") || aug.has("rotate") || aug.has("zoom") || aug.has("translate") ||
-                                         aug.has("squeeze") || aug.has("translate_x") || aug.has("translate_y");
-                    const bool chromatic = aug.has("brightness") || aug.has("gamma") || aug.has("contrast") || aug.has("color");
-                    const bool effect = aug.has("fog_size") || aug.has("fog_amount") || aug.has("motion_blur_angle") ||
-                                        aug.has("motion_blur_size") || aug.has("shadow_angle") || aug.has("shadow_distance") ||
-                                        aug.has("shadow_strength") || aug.has("noise");
-                    const bool eigen = aug.has("lmult_pow") || aug.has("lmult_mult") || aug.has("lmult_add") || aug.has("sat_pow") ||
-                                       aug.has("sat_mult") || aug.has("sat_add") || aug.has("col_pow") || aug.has("col_mult") ||
-                                       aug.has("col_add") || aug.has("ladd_pow") || aug.has("ladd_mult") || aug.has("ladd_add") ||
-                                       aug.has("col_rotate");
+                    const float dc = AugSampler::discount(this->layer_param_, num_iter_);
                     for (int n = 0; n < num; n++) {
                         AugCoeff c;
-                        if (spatial) generate_valid_spatial(aug, c, dc, bottom[0]->width(), bottom[0]->height(), cropped_width_, cropped_height_);
-                        if (chromatic) generate_chromatic(aug, c, dc);
-                        if (eigen) generate_chromatic_eigen(aug, c, dc);
-                        if (effect) generate_effect(aug, c, dc);
+                        sampler_.sample(aug, dc, bottom[0]->width(), bottom[0]->height(), cropped_width_, cropped_height_, c);
                         c.to_array(&all_coeffs_[(size_t)n * AugCoeff::N]);
                     }
                 }
@@ -947,7 +974,7 @@ class DataAugmentationLayer : public Layer<Dtype> {
             }
             if (has_effect_) {
                 CHECK_EQ(bottom[0]->channels(), 3) << "Effect augmentations only work with 3-channel input";
-                FN2_CALL(fn2_apply_effects(&t, coef_dev_ + off_effect_, aug.max_multiplier(), (unsigned long long)rng_.gen() << 32 | rng_.gen(),
+                FN2_CALL(fn2_apply_effects(&t, coef_dev_ + off_effect_, aug.max_multiplier(), (unsigned long long)sampler_.rng.gen() << 32 | sampler_.rng.gen(),
                                            has_noise_ ? 1 : 0, S()));
             }
             if (gen_active_ || input_params_) CUDA_CHECK(cudaStreamSynchronize(S()));   // coef_host_ is rewritten next call
@@ -1004,7 +1031,7 @@ class DataAugmentationLayer : public Layer<Dtype> {
     size_t coef_floats_ = 0;
     int off_mat_ = 0, off_chroma_ = 0, off_eigen_ = 0, off_effect_ = 0, off_eigvec_ = 0, off_space_ = 0;
     float* fixed_mean_dev_ = nullptr;
-    AugRng rng_;
+    AugSampler sampler_;
 };
 REGISTER_LAYER_CLASS(DataAugmentation);
 

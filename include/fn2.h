@@ -235,6 +235,13 @@ FN2_API int fn2_net_launches_per_forward(fn2_net* net);
  * .caffemodel and print one line per layer: name, type, then per blob shape and a checksum.
  * Both follow the size-query convention: call with out==NULL to get the needed size in *bytes. */
 FN2_API int fn2_proto_canonical(const char* prototxt_text, char* out, size_t* bytes);
+/* Coefficient sampling of DataAugmentationLayer (host logic only, no GPU): parses a prototxt fragment that contains a
+ * DataAugmentation layer and draws the coefficients of `num` items exactly as the layer's forward does at iteration num_iter
+ * (generators, discount schedule, 4-corner validity resampling: augmentation_layer_base.cpp:73-336,
+ * data_augmentation_layer.cu:372-449).  coeffs_out: num x 42 floats in the array form of the parameter blob
+ * (fields with default 1 as logarithms, augmentation_layer_base.cpp:352-365). */
+FN2_API int fn2_aug_sample(const char* layer_prototxt, unsigned int seed, int num, int width, int height, float num_iter,
+                           float* coeffs_out);
 FN2_API int fn2_caffemodel_summary(const void* caffemodel, size_t n, char* out, size_t* bytes);
 
 /* .flo files (util/output.cpp:16-64): "PIEH", int32 w, int32 h, interleaved (u,v) fp32. */

@@ -209,3 +209,66 @@ def test_tcgen05_engine_plan_for_flownet2_shapes(fn2):
     # deconv5: 4 parity classes of 2x2 taps
     pl, _ = plan(1024, 512, 4, 2, 1, 7, 16, deconv=1)
     assert pl[0] == 128 and pl[2] == 4 * 32
+
+
+AUG_LAYER = """
+layer {
+  name: "aug" type: "DataAugmentation" bottom: "img" top: "aug"
+  coeff_schedule_param { half_life: 50000 initial_coeff: 0.5 final_coeff: 1 }
+  augmentation_param {
+    augment_during_test: true crop_width: 48 crop_height: 32
+    mirror { rand_type: "bernoulli" prob: 0.5 }
+    translate { rand_type: "uniform_bernoulli" mean: 0 spread: 0.4 prob: 1.0 }
+    rotate { rand_type: "uniform_bernoulli" mean: 0 spread: 0.4 prob: 1.0 }
+    zoom { rand_type: "uniform_bernoulli" exp: true mean: 0.2 spread: 0.4 prob: 1.0 }
+    squeeze { rand_type: "uniform_bernoulli" exp: true mean: 0 spread: 0.3 prob: 1.0 }
+    gamma { rand_type: "gaussian_bernoulli" exp: true mean: 0 spread: 0.02 prob: 1.0 apply_schedule: false }
+    brightness { rand_type: "gaussian_bernoulli" mean: 0 spread: 0.02 prob: 0.5 apply_schedule: false }
+    color { rand_type: "gaussian_bernoulli" exp: true mean: 0 spread: 0.02 prob: 0.0 }
+    noise { rand_type: "uniform_bernoulli" mean: 0.03 spread: 0.03 prob: 1.0 apply_schedule: false }
+  }
+}
+"""
+
+
+def test_augmentation_coefficient_sampling(fn2):
+    """Host logic of DataAugmentation's training use without a GPU: distributions of caffe_rng_generate (util/rng.cpp:8-114),
+    the discount schedule, and generate_valid_spatial_coeffs' guarantee that the 4 crop corners land inside the source image
+    (augmentation_layer_base.cpp:102-169).  The random stream itself is unpinned (boost in the reference)."""
+    lib = fn2.lib()
+    N, W, H, cw, ch = 4000, 64, 48, 48, 32
+    out = np.zeros((N, 42), np.float32)
+    assert lib.fn2_aug_sample(AUG_LAYER.encode(), 7, N, W, H, C.c_float(1e9), out.ctypes.data_as(C.POINTER(C.c_float))) == 0
+    default = np.array([0, 0, 0, 0, 1, 1, 1, 0, 1, 1, 1, 1] + [1, 1, 1, 0, 0, 0, 1, 1, 1, 1, 1, 1, 0, 0, 0, 1, 1, 1, 1, 0, 1, 0] + [0] * 8, np.float32)
+    v = np.where(np.abs(default) < 1e-3, out, np.exp(out))                      # array_to_coeff
+    mirror, dx, dy, ang, zx, zy = v[:, 0], v[:, 1], v[:, 2], v[:, 3], v[:, 4], v[:, 5]
+    assert set(np.unique(mirror)) <= {0.0, 1.0} and 0.4 < mirror.mean() < 0.6
+    assert np.abs(dx).max() <= 0.4 + 1e-6 and np.abs(ang).max() <= 0.4 + 1e-6
+    # every accepted sample keeps the 4 crop corners inside the source image (or is the all-default fallback after 50 tries)
+    for n in range(0, N, 7):
+        fallback = np.allclose(v[n, :6], default[:6])
+        for x in (0, cw - 1):
+            for y in (0, ch - 1):
+                x1 = (-x + .5 * cw) if mirror[n] else (x - .5 * cw)
+                y1 = y - .5 * ch
+                x2 = np.cos(ang[n]) * x1 - np.sin(ang[n]) * y1 + dx[n] * cw
+                y2 = np.sin(ang[n]) * x1 + np.cos(ang[n]) * y1 + dy[n] * ch
+                x2 = x2 / zx[n] + .5 * W
+                y2 = y2 / zy[n] + .5 * H
+                ok = 0 <= np.floor(x2) <= W - 2 and 0 <= np.floor(y2) <= H - 2
+                assert ok or fallback, (n, x, y, x2, y2)
+    gamma, bright, color, noise = v[:, 6], v[:, 7], v[:, 9:12], v[:, 41]
+    assert abs(np.log(gamma).mean()) < 2e-3 and abs(np.log(gamma).std() - 0.02) < 2e-3          # exp(N(0, 0.02))
+    on = bright != 0
+    assert 0.45 < on.mean() < 0.55 and abs(bright[on].std() - 0.02) < 3e-3                      # Bernoulli(0.5) gate
+    assert np.all(color == 1.0)                                                                # prob 0 -> tmp = 0 -> exp -> 1
+    assert noise.min() >= 0.0 and noise.max() <= 0.06 + 1e-6 and abs(noise.mean() - 0.03) < 2e-3
+    # discount schedule: at iteration 0 the scheduled spreads are halved (initial_coeff 0.5), unscheduled ones are not
+    early = np.zeros((N, 42), np.float32)
+    assert lib.fn2_aug_sample(AUG_LAYER.encode(), 7, N, W, H, C.c_float(0.0), early.ctypes.data_as(C.POINTER(C.c_float))) == 0
+    assert np.abs(early[:, 3]).max() <= 0.2 + 1e-6 and np.abs(early[:, 3]).max() > 0.15
+    assert abs(early[:, 6].std() - 0.02) < 2e-3
+    # same seed, same stream
+    again = np.zeros((N, 42), np.float32)
+    assert lib.fn2_aug_sample(AUG_LAYER.encode(), 7, N, W, H, C.c_float(1e9), again.ctypes.data_as(C.POINTER(C.c_float))) == 0
+    assert np.array_equal(again, out)
