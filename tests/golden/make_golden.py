@@ -75,6 +75,28 @@ def ops_golden():
     print("ops_golden.npz:", len(g), "arrays")
 
 
+def aug_golden():
+    """Training-time colour augmentations of DataAugmentation (oracle restatement; the reference has no vectors for them)."""
+    r = np.random.default_rng(4242)
+    g = {}
+    x = r.uniform(0, 1, (2, 3, 9, 13)).astype(np.float32)
+    ev = np.array([0.51, 0.56, 0.65, 0.79, 0.01, -0.62, 0.35, -0.83, 0.44], np.float32)
+    co = np.tile(np.array([1, 1, 1, 0, 0, 0, 1, 1, 1, 1, 1, 1, 0, 0, 0, 1, 1, 1, 1, 0, 1, 0], np.float32), (2, 1))
+    co += r.uniform(-0.25, 0.25, co.shape).astype(np.float32)
+    eff = np.zeros((2, 9), np.float32)
+    eff[:, 4], eff[:, 5] = np.cos([0.7, 2.9]), np.sin([0.7, 2.9])
+    eff[:, 6], eff[:, 7] = [1.0, -2.0], [0.3, 0.15]
+    g["x"], g["eigvec"], g["eigen_coeffs"], g["effects"] = x, ev, co, eff
+    g["space"] = O.chromatic_eigenspace(x, ev)
+    g["eigen_out"] = O.chromatic_eigen_augmentation(x, co, g["space"], 1.0)
+    g["effects_out"] = O.apply_effects(x, eff, 1.0)
+    chroma = np.array([[1.2, 0.05, 0.9, 1.1, 0.95, 1.0], [0.8, -0.03, 1.15, 0.9, 1.05, 1.1]], np.float32)
+    g["chroma"] = chroma
+    g["chroma_out"] = O.color_contrast_augmentation(x, chroma, 1.0)
+    np.savez_compressed(os.path.join(HERE, "aug_golden.npz"), **g)
+    print("aug_golden.npz:", len(g), "arrays")
+
+
 def ref_pb2():
     sys.path.insert(0, "/root/reference/python/caffe/proto")
     import caffe_pb2
@@ -171,6 +193,11 @@ def chairs():
 
 
 if __name__ == "__main__":
+    import sys
+    if "--aug-only" in sys.argv:
+        aug_golden()
+        sys.exit(0)
     ops_golden()
+    aug_golden()
     ref_pb2()
     chairs()

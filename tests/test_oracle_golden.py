@@ -245,3 +245,15 @@ def test_oracle_training_augmentations_identities():
     dark = xs - 1.5 > 0
     assert np.array_equal(z[..., ~dark], x[..., ~dark])
     assert np.allclose(z[..., dark], np.clip(x[..., dark] - 0.25, 0, 1), atol=0)
+
+
+def test_aug_golden_fixture():
+    """Regression pin of the training-time colour augmentations (generated by tests/golden/make_golden.py --aug-only); libm's
+    powf / cosf may differ in the last ulp between glibc versions, hence 1e-6."""
+    g = np.load(os.path.join(GOLD, "aug_golden.npz"))
+    x = g["x"]
+    space = O.chromatic_eigenspace(x, g["eigvec"])
+    assert maxabs(space, g["space"]) <= 1e-6
+    assert maxabs(O.chromatic_eigen_augmentation(x, g["eigen_coeffs"], g["space"], 1.0), g["eigen_out"]) <= 1e-6
+    assert maxabs(O.apply_effects(x, g["effects"], 1.0), g["effects_out"]) == 0.0
+    assert maxabs(O.color_contrast_augmentation(x, g["chroma"], 1.0), g["chroma_out"]) <= 1e-6
