@@ -324,6 +324,21 @@ def test_chromatic_eigen_and_effects(ops, cl):
         assert abs(d[n].std() - eff[n, 8]) < 0.03 * eff[n, 8] + 1e-4 and abs(d[n].mean()) < 0.05 * eff[n, 8]
 
 
+def test_training_augmentations_against_golden_fixture(ops):
+    """CUDA kernels vs the committed fixture tests/golden/aug_golden.npz (oracle outputs; generator: make_golden.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "aug_golden.npz"))
+    x = g["x"]
+    space = ops.chromatic_eigenspace(dev(x, True), g["eigvec"])
+    assert maxabs(space[:25].cpu().numpy(), g["space"]) <= 2e-6
+    got = host(ops.chromatic_eigen_augmentation(dev(x, True), torch.from_numpy(g["eigen_coeffs"]).cuda(), space, 1.0))
+    assert maxabs(got, g["eigen_out"]) <= 1e-5
+    got = host(ops.apply_effects(dev(x, True), torch.from_numpy(g["effects"]).cuda(), 1.0))
+    assert maxabs(got, g["effects_out"]) == 0.0
+    got = host(ops.color_contrast_augmentation(dev(x, True), torch.from_numpy(g["chroma"]).cuda(), 1.0))
+    assert maxabs(got, g["chroma_out"]) <= 1e-5
+
+
 def test_deconv_known_answer(ops):
     # the reference's TestSimpleDeconvolution (test_deconvolution_layer.cpp:91-137): input and
     # weights all ones, bias 0.1, 3 in / 4 out channels, kernel 3 stride 2: 3.1 / 6.1 / 12.1
