@@ -62,7 +62,8 @@ def lib():
         l.fn2_net_destroy.argtypes = [C.c_void_p]
         l.fn2_net_destroy.restype = None
         for name in ("fn2_net_num_inputs", "fn2_net_num_outputs", "fn2_net_num_blobs", "fn2_net_num_layers",
-                     "fn2_net_forward", "fn2_net_sync", "fn2_net_params_changed", "fn2_net_launches_per_forward"):
+                     "fn2_net_forward", "fn2_net_sync", "fn2_net_params_changed", "fn2_net_launches_per_forward",
+                     "fn2_net_graph_active"):
             getattr(l, name).argtypes = [C.c_void_p]
         l.fn2_net_copy_trained_layers.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         l.fn2_net_to_caffemodel.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]
@@ -284,6 +285,10 @@ class Net(object):
             check(lib().fn2_net_layer_work(self._h, i, C.byref(f), C.byref(b)))
             out.append((n, t, f.value, b.value))
         return out
+
+    @property
+    def graph_active(self):
+        return bool(lib().fn2_net_graph_active(self._h))
 
     @property
     def launches_per_forward(self):

@@ -26,6 +26,9 @@ void Blob<Dtype>::Reshape(const vector<int>& shape) {
     }
     if (shape == shape_ && count_ == (int)cnt) return;
     CHECK(!parent_) << "cannot reshape an aliased blob";
+    // externally bound storage (a slot of the Net's parameter arena, or another blob's buffer) has a fixed size
+    CHECK(own_dev_ || !dev_ || (long long)count_ == cnt)
+        << "cannot reshape a blob bound to external storage to a different count (" << count_ << " -> " << cnt << ")";
     shape_ = shape;
     count_ = (int)cnt;
     cstride_ = compute_cstride();
@@ -221,6 +224,11 @@ void Blob<Dtype>::BindExternal(Dtype* dev) {
     dev_ = dev; own_dev_ = false;
     if (count_) CUDA_CHECK(cudaMemcpy(dev_, h, (size_t)count_ * sizeof(Dtype), cudaMemcpyHostToDevice));
     head_ = SYNCED;
+}
+
+template <typename Dtype>
+void Blob<Dtype>::MarkDeviceNewer() {
+    if (dev_ || parent_) head_ = AT_GPU;
 }
 
 template <typename Dtype>

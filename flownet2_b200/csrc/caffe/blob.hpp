@@ -64,6 +64,9 @@ class Blob {
     // are copied there.
     void BindExternal(Dtype* dev);
     void ShareData(Blob& other);
+    // The device copy was written behind the blob's back (arena broadcast, CUDA-graph replay): the next cpu_data() must
+    // download it again instead of trusting the cached host copy.
+    void MarkDeviceNewer();
 
     void FromProto(const BlobProtoData& p, bool reshape = true);   // blob.cpp:436-490
     void ToProto(BlobProtoData* p);

@@ -94,7 +94,7 @@ int fn2_net_param_arena(fn2_net* net, void** dev_ptr, size_t* bytes) {
 int fn2_net_params_changed(fn2_net* net) {
     if (!net) { fn2::set_error("params_changed: null net"); return FN2_ERR_INVALID; }
     FN2_TRY
-        net->net->ParamsChanged();
+        net->net->ArenaWritten();      // the caller wrote the DEVICE arena: host caches of every param blob are stale
         return FN2_OK;
     FN2_CATCH
 }
@@ -181,6 +181,7 @@ int fn2_net_time_layers(fn2_net* net, float* ms) {
     FN2_CATCH
 }
 int fn2_net_launches_per_forward(fn2_net* net) { return net ? net->net->launches_per_forward() : 0; }
+int fn2_net_graph_active(fn2_net* net) { return net && net->net->graph_active() ? 1 : 0; }
 
 int fn2_net_layer_work(fn2_net* net, int layer, double* flops, double* bytes) {
     if (!net || !flops || !bytes || layer < 0 || layer >= (int)net->net->layers().size()) {

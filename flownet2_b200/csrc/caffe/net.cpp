@@ -163,6 +163,11 @@ void Net<Dtype>::AliasConcats() {
                 if (string(layers_[lj]->type()) != "Convolution" || bl->channels() > 16) continue;
                 for (int bb : bottom_id_vecs_[lj]) if (bb == bid) ok = false;
             }
+            // the float4 element-wise kernels (fn2_ops.cu px_store) treat a view whose pixel stride equals its own channel
+            // count rounded up to 4 as owning the lanes beyond C and zero them; for a child in the middle of the parent
+            // those lanes are a sibling's channels
+            const int cn = bl->channels();
+            if (ok && cn % 4 != 0 && c0 + cn < top->channels() && (cn + 3) / 4 * 4 == top->channel_stride()) ok = false;
             seen.insert(bid);
             if (ok) bl->AliasInto(top, c0);
             c0 += bl->channels();
@@ -197,6 +202,15 @@ void Net<Dtype>::ParamsChanged() {
     params_ready_ = true;
     if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
     if (graph_) { cudaGraphDestroy(graph_); graph_ = nullptr; }
+}
+
+// The parameter arena was overwritten on the device (ncclBroadcast from rank 0): the device is authoritative, every cached
+// host copy (conv weights, and the DataAugmentation iteration counter that HostTick reads on the host) is stale.
+template <typename Dtype>
+void Net<Dtype>::ArenaWritten() {
+    CUDA_CHECK(cudaDeviceSynchronize());
+    for (auto& l : layers_) for (auto& b : l->blobs()) b->MarkDeviceNewer();
+    ParamsChanged();
 }
 
 template <typename Dtype>
@@ -366,6 +380,7 @@ void Net<Dtype>::Forward() {
     for (auto& l : layers_) if (!l->GraphSafe()) safe = false;
     if (safe && graph_exec_) {
         CUDA_CHECK(cudaGraphLaunch(graph_exec_, stream_));
+        MarkActivationsOnDevice();
         return;
     }
     if (safe && launches_per_forward_ > 0) {
@@ -382,6 +397,7 @@ void Net<Dtype>::Forward() {
                 if (cudaGraphInstantiate(&ge, g, 0) == cudaSuccess) {
                     graph_ = g; graph_exec_ = ge;
                     CUDA_CHECK(cudaGraphLaunch(graph_exec_, stream_));
+                    MarkActivationsOnDevice();
                     return;
                 }
             }
@@ -397,6 +413,14 @@ void Net<Dtype>::Forward() {
     const uint64_t before = fn2_launch_count();
     ForwardEager();
     launches_per_forward_ = (int)(fn2_launch_count() - before);
+}
+
+// A graph replay writes every non-input activation without going through Blob::mutable_tensor: cached host copies
+// (Blob::cpu_data() after an earlier pass) are stale from here on.
+template <typename Dtype>
+void Net<Dtype>::MarkActivationsOnDevice() {
+    std::set<int> inputs(net_input_blob_indices_.begin(), net_input_blob_indices_.end());
+    for (size_t i = 0; i < blobs_.size(); i++) if (!inputs.count((int)i)) blobs_[i]->MarkDeviceNewer();
 }
 
 template <typename Dtype>

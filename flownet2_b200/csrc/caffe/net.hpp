@@ -23,6 +23,7 @@ class Net {
     std::string ToCaffemodel();
     void FillParams(uint64_t seed);
     void ParamsChanged();
+    void ArenaWritten();                               // device arena overwritten externally (broadcast)
     void ParamArena(void** dev, size_t* bytes) { *dev = arena_; *bytes = arena_floats_ * sizeof(Dtype); }
 
     const vector<string>& layer_names() const { return layer_names_; }
@@ -43,6 +44,7 @@ class Net {
     void TimeLayers(float* ms);
     void LayerWork(int i, double* flops, double* bytes) const { layers_[i]->WorkEstimate(bottom_vecs_[i], top_vecs_[i], flops, bytes); }
     int launches_per_forward() const { return launches_per_forward_; }
+    bool graph_active() const { return graph_exec_ != nullptr; }
 
  private:
     void Init(const NetParameter& param);
@@ -50,6 +52,7 @@ class Net {
     void AliasConcats();
     void BuildArena();
     void ForwardEager();
+    void MarkActivationsOnDevice();
     void PlanStreams();
     Dtype* staging(const string& blob, size_t floats);
 

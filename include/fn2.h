@@ -228,6 +228,9 @@ FN2_API int fn2_net_time_layers(fn2_net* net, float* ms);
 FN2_API int fn2_net_layer_work(fn2_net* net, int layer, double* flops, double* bytes);
 /* Kernels launched by one forward pass. */
 FN2_API int fn2_net_launches_per_forward(fn2_net* net);
+/* 1 once the forward pass is replayed from a captured CUDA graph (0 while it still runs eagerly, e.g. a DataAugmentation
+ * layer whose running mean is still being updated: data_augmentation_layer.cu:600-608). */
+FN2_API int fn2_net_graph_active(fn2_net* net);
 
 /* Host-only parser checks (no GPU needed; used by the CPU test-suite).
  * fn2_proto_canonical: parse a prototxt with the engine's text-format parser (after the legacy

@@ -158,6 +158,64 @@ def parse_caffemodel(data):
     return layers
 
 
+def _enc_varint(v):
+    out = bytearray()
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        if v:
+            out.append(b | 0x80)
+        else:
+            out.append(b)
+            return bytes(out)
+
+
+def _enc_field(fn, payload):
+    return _enc_varint((fn << 3) | 2) + _enc_varint(len(payload)) + payload
+
+
+def write_caffemodel(layers):
+    """layers: [(name, type, [ndarray, ...])] -> bytes of a binary NetParameter (inverse of parse_caffemodel; BlobProto with
+    shape=7{dim=1 packed} and data=5 packed float, caffe.proto:10-22; LayerParameter name=1 type=2 blobs=7 in NetParameter.layer=100)."""
+    out = bytearray()
+    for name, typ, blobs in layers:
+        body = _enc_field(1, name.encode()) + _enc_field(2, typ.encode())
+        for a in blobs:
+            a = np.ascontiguousarray(a, dtype="<f4")
+            dims = b"".join(_enc_varint(int(d)) for d in a.shape)
+            body += _enc_field(7, _enc_field(7, _enc_field(1, dims)) + _enc_field(5, a.tobytes()))
+        out += _enc_field(100, body)
+    return bytes(out)
+
+
+def synth_weights(prototxt_text, seed, real_prototxt=None):
+    """Deterministic synthetic weights for a deploy prototxt (He-initialised conv/deconv, zero bias, DataAugmentation state past
+    the recompute_mean threshold): {layer name: [blobs]} plus the same as caffemodel bytes.  The shapes come from one oracle
+    forward at the prototxt's own input size, so call it with a SMALL fill of the template; conv shapes do not depend on H, W.
+    real_prototxt: the fill of the same template at the size that will actually run; layers whose filler depends on the
+    template variables (the diagonal scale convolution, $SCALE_WIDTH$/$SCALE_HEIGHT$) are taken from it."""
+    net = OracleNet(prototxt_text, None, batch=1, synth_seed=seed)
+    ins = {n: np.zeros(s, np.float32) for n, s in zip(net.input_names, net.input_shapes)}
+    net.forward(**ins)
+    types = {get(l, "name"): get(l, "type") for l in net.layers}
+    ordered = [(get(l, "name"), types[get(l, "name")], net.weights[get(l, "name")]) for l in net.layers if get(l, "name") in net.weights]
+    for name, typ, blobs in ordered:
+        if typ == "DataAugmentation":          # restore the iteration counter the zero-input forward advanced; drop the sized mean
+            rm = float(blobs[0].reshape(-1)[0]) - 1
+            blobs[0] = np.full((1, 1, 1, 1), rm, np.float32)
+            blobs[1] = np.full((1, blobs[1].shape[1], 1, 1), 0.4, np.float32)
+    if real_prototxt is not None:
+        for l in getall(parse_prototxt(real_prototxt), "layer"):
+            wf = get(get(l, "convolution_param", []), "weight_filler", [])
+            if get(wf, "type") == "diagonal":
+                dv = [float(x) for x in getall(wf, "diag_val")]
+                for name, typ, blobs in ordered:
+                    if name == get(l, "name"):
+                        for i in range(min(blobs[0].shape[0], blobs[0].shape[1])):
+                            blobs[0][i, i, :, :] = dv[i] if i < len(dv) else dv[-1]
+    return {n: b for n, _, b in ordered}, write_caffemodel(ordered)
+
+
 # ------------------------------------------------------------------------------------------------
 # forward
 # ------------------------------------------------------------------------------------------------
@@ -225,8 +283,15 @@ class OracleNet(object):
                     co, ci = int(get(cp, "num_output")), bots[0].shape[1]
                     r = np.random.default_rng(self.synth_seed + len(self.weights))
                     shp = (co, ci, kh, kw) if typ == "Convolution" else (ci, co, kh, kw)
-                    self.weights[name] = [(r.standard_normal(shp) * np.sqrt(2.0 / (ci * kh * kw))).astype(np.float32),
-                                          np.zeros(co, np.float32)]
+                    wf = get(cp, "weight_filler", [])
+                    if get(wf, "type") == "diagonal":          # DiagonalFiller, filler.hpp:265-290
+                        dv = [float(x) for x in getall(wf, "diag_val")]
+                        wsyn = np.zeros(shp, np.float32)
+                        for i in range(min(shp[0], shp[1])):
+                            wsyn[i, i, :, :] = dv[i] if i < len(dv) else (dv[-1] if dv else 1.0)
+                    else:
+                        wsyn = (r.standard_normal(shp) * np.sqrt(2.0 / (ci * kh * kw))).astype(np.float32)
+                    self.weights[name] = [wsyn] + ([np.zeros(co, np.float32)] if has_bias else [])
                 w = self.weights[name][0]
                 b = self.weights[name][1].reshape(-1) if has_bias else None
                 for bot, top in zip(bots, tops):
@@ -273,6 +338,9 @@ class OracleNet(object):
                                       np.full((1,) + top.shape[1:], 0.4, np.float32),
                                       np.full((1, top.shape[1], 1, 1), 0.4, np.float32)]
             st = self.weights[name]
+            if st[1].size != top[0].size:        # adjust_blobs' size-mismatch path: channel average, replicated (.cpp:189-201)
+                pc = st[1].reshape(top.shape[1], -1).mean(axis=1, dtype=np.float64).astype(np.float32)
+                st[1] = np.broadcast_to(pc.reshape(1, -1, 1, 1), (1,) + top.shape[1:]).copy()
             st[0] = np.float32(int(st[0].reshape(-1)[0]) + 1).reshape(st[0].shape)     # :353-354
             num_iter = float(st[0].reshape(-1)[0])
             top, mpp, mpc = O.mean_subtract(top, 0, num_iter, rm, mpp_flag, st[1].reshape(top.shape[1:]),
