@@ -11,9 +11,11 @@ ours:       one process per GPU; full FlowNet2 (CSS + SD + fusion) deploy net th
             ends with a gather of the flow fields to rank 0.  `value` times K steps with inputs resident in
             HBM; `e2e` times the same K steps with pinned-host inputs (H2D inside) and the flows read back
             to the host (D2H inside).
-reference:  the CPU oracle (oracle/, a restatement of the reference arithmetic -- the reference's own CPU
-            path cannot be built and does not exist for Correlation/Resample/DataAugmentation) on all host
-            cores, each step a bounded spatial tile of one 1024x436 pair, scaled by the pixel ratio.
+reference:  the reference's own CPU forward on all host cores, ONE WHOLE 1024x436 pair per step (fixed workload, no
+            scaling): oracle/_ref (the reference's layer sources compiled unmodified) runs conv/deconv (im2col +
+            OpenBLAS sgemm), ReLU, Eltwise, Concat, FlowWarp, ChannelNorm; Correlation / Resample / DataAugmentation
+            have no CPU implementation in the reference (NOT_IMPLEMENTED / LOG(FATAL)) and run the oracle port.
+            Without oracle/_ref/libref_caffe.so the oracle port runs everything on a FIXED 256x128 tile.
 Prints exactly one JSON line on rank 0.
 """
 import argparse
@@ -46,6 +48,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=4, help="frame pairs per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config 2 / config 3 / 448x320 side measurements")
     return ap.parse_args()
 
 
@@ -62,66 +65,101 @@ def config(args, n_gpus):
     return {"workload": "%s deploy forward, %dx%d synthetic pairs (adapted to /64), fp32" % (args.model, args.width, args.height),
             "model": args.model, "width": args.width, "height": args.height, "pairs_per_gpu": args.batch,
             "global_batch": args.batch * n_gpus, "parallelism": "frame-batch sharding x%d (1 NCCL weight broadcast, flow gather)" % n_gpus,
-            "l2": "working set (weights ~650 MB + activations) exceeds the 126 MB L2; no explicit flush"}
+            "l2": "working set (weights ~650 MB + activations) exceeds the 126 MB L2; no explicit flush",
+            "cpu_arm": cpu_arm_description(args)}
 
 
 # ----------------------------------------------------------------------------------------------------------
-# CPU arm (oracle port): used for cpu_baseline (N=1, rank 0) and for --impl reference
+# CPU arm: used for cpu_baseline (N=1, rank 0) and for --impl reference.  The workload is FIXED (never picked from a
+# calibration run): one whole pair of the bench size through the reference's CPU layers, or -- only when oracle/_ref is
+# not built -- one 256x128 tile through the oracle port, scaled by the pixel ratio.
 # ----------------------------------------------------------------------------------------------------------
-def cpu_tile_run(args, tile_w, tile_h, reps):
-    import flownet2_b200 as F
-    from oracle.net import OracleNet
-    proto = F.fill_template(F.model_template(args.model), tile_w, tile_h)
-    net = OracleNet(proto, None, batch=1, synth_seed=1701)
-    r = np.random.default_rng(3)
-    a = np.round(r.uniform(0, 255, (1, 3, tile_h, tile_w))).astype(np.float32)
-    b = np.clip(a + np.round(r.normal(0, 3, a.shape)), 0, 255).astype(np.float32)
-    net.forward(img0=a, img1=b)            # builds the synthetic weights, warms the library
-    times = []
-    for _ in range(reps):
+FALLBACK_TILE = (256, 128)
+
+
+def cpu_arm_description(args):
+    """The fixed workload of the CPU legs (--impl reference, cpu_baseline); part of `config` on both arms."""
+    from oracle import ref as R
+    if R.available():
+        return ("one whole %dx%d pair per step, all host cores: reference CPU layers (oracle/_ref: im2col + OpenBLAS sgemm conv/deconv, "
+                "ReLU, Eltwise, Concat, FlowWarp, ChannelNorm) + oracle port for Correlation/Resample/DataAugmentation "
+                "(no CPU implementation in the reference)" % (args.width, args.height))
+    return "one fixed %dx%d tile of a %dx%d pair per step (oracle port, OpenMP), scaled by the pixel ratio" % (
+        FALLBACK_TILE + (args.width, args.height))
+
+
+class CpuArm(object):
+    def __init__(self, args):
+        import flownet2_b200 as F
+        from oracle import ref as R
+        self.args = args
+        r = np.random.default_rng(3)
+        if R.available():
+            self.kind, self.w, self.h, self.scale = "reference", args.width, args.height, 1.0
+            proto = F.fill_template(F.model_template(args.model), self.w, self.h)
+            self.net = R.RefCpuNet(proto, None, batch=1, synth_seed=1701)
+            self.cores = os.cpu_count()
+            self.sample = cpu_arm_description(args)
+        else:
+            from oracle.net import OracleNet
+            self.kind, (self.w, self.h) = "port", FALLBACK_TILE
+            self.scale = (self.w * self.h) / float(args.width * args.height)
+            proto = F.fill_template(F.model_template(args.model), self.w, self.h)
+            self.net = OracleNet(proto, None, batch=1, synth_seed=1701)
+            self.cores = os.cpu_count()
+            self.sample = cpu_arm_description(args)
+        self.a = np.round(r.uniform(0, 255, (1, 3, self.h, self.w))).astype(np.float32)
+        self.b = np.clip(self.a + np.round(r.normal(0, 3, self.a.shape)), 0, 255).astype(np.float32)
+
+    def step(self):
         t0 = time.perf_counter()
-        net.forward(img0=a, img1=b)
-        times.append(time.perf_counter() - t0)
-    return times
+        self.net.forward(img0=self.a, img1=self.b)
+        return time.perf_counter() - t0
 
-
-def cpu_pick_tile(args, budget_s):
-    """Largest /64 tile of the workload whose forward fits the per-step budget (calibrated on 128x64)."""
-    t = min(cpu_tile_run(args, 128, 64, 1))
-    per_px = t / (128.0 * 64.0)
-    full_w = (args.width + 63) // 64 * 64
-    full_h = (args.height + 63) // 64 * 64
-    best = (128, 64)
-    for th in range(64, full_h + 1, 64):
-        for tw in range(128, full_w + 1, 64):
-            if per_px * tw * th <= budget_s and tw * th > best[0] * best[1]:
-                best = (tw, th)
-    return best
-
-
-def cpu_result(args, tile, times):
-    frac = (tile[0] * tile[1]) / float(args.width * args.height)
-    mean = float(np.mean(times))
-    return frac / mean, mean
+    def run(self, steps, warmup):
+        for _ in range(warmup):
+            self.step()
+        times = [self.step() for _ in range(steps)]
+        mean = float(np.mean(times))
+        return self.scale / mean, mean
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count()
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    tile = cpu_pick_tile(args, budget)
-    times = cpu_tile_run(args, tile[0], tile[1], args.steps + args.warmup)[args.warmup:]
-    value, mean = cpu_result(args, tile, times)
-    sample = "one %dx%d tile of a %dx%d pair per step, scaled by pixel ratio" % (tile[0], tile[1], args.width, args.height)
+    arm = CpuArm(args)
+    value, mean = arm.run(args.steps, args.warmup)
+    cfg = config(args, args.gpus)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": config(args, args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "dtype": "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def profile_traffic(pattern):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes) of the single launch in the newest committed
+    profiles/*<pattern>*_raw.csv (`ncu --set full --csv --page raw`; row 1 = units, row 2 = values), or (None, None)."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r[0-9][0-9]_%s_raw.csv" % pattern)))
+    if not files:
+        return None, None
+    path = files[-1]
+    try:
+        rows = list(csv.reader(open(path)))
+        head, units, vals = rows[0], rows[1], rows[2]
+        mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        total = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = head.index(name)
+            total += float(vals[i]) * mult[units[i]]
+        return total, os.path.relpath(path, ROOT)
+    except Exception:
+        return None, os.path.relpath(path, ROOT)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -173,6 +211,64 @@ def clocks_sampler_stop(p, t0=None, t1=None):
             "samples_in_timed_region": len(inside)}
 
 
+def measure_tf32_peak(torch):
+    """Dense TF32 tensor-core peak of this GPU: cuBLAS GEMM 8192^3 with TF32 allowed, best of 10 (a roofline denominator,
+    measured outside every timed region)."""
+    try:
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a = torch.randn(8192, 8192, device="cuda")
+        b = torch.randn(8192, 8192, device="cuda")
+        best = 1e9
+        for _ in range(3):
+            torch.matmul(a, b)
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        torch.backends.cuda.matmul.allow_tf32 = old
+        return 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
+    except Exception:
+        return None
+
+
+def side_config(torch, F, model, w, h, batch, steps=10, warmup=3):
+    """Device-resident throughput of another BASELINE.json configuration (same engine, same step definition), N=1."""
+    proto = F.fill_template(F.model_template(model), w, h)
+    net = F.Net(proto, None, F.TEST, batch=batch)
+    net.fill_params(1701)
+    r = np.random.default_rng(7)
+    img0 = np.round(r.uniform(0, 255, (batch, 3, h, w))).astype(np.float32)
+    img1 = np.clip(img0 + np.round(r.normal(0, 4, img0.shape)), 0, 255).astype(np.float32)
+    d0, d1 = torch.from_numpy(img0).cuda(), torch.from_numpy(img1).cuda()
+    out = torch.empty((batch, 2, h, w), device="cuda")
+    stream = torch.cuda.ExternalStream(net.stream)
+    with torch.cuda.stream(stream):
+        def step():
+            net.set_input_device("img0", d0.data_ptr())
+            net.set_input_device("img1", d1.data_ptr())
+            net.forward_async()
+            net.get_blob_device("predict_flow_final", out.data_ptr())
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    res = {"workload": "%s deploy forward, %dx%d, %d pairs per step" % (model, w, h, batch), "value": batch / (ms * 1e-3), "unit": UNIT,
+           "ms_per_step": ms, "steps": steps, "warmup": warmup, "output_finite": bool(torch.isfinite(out).all().item())}
+    del net
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -211,17 +307,43 @@ def run_ours(args):
     img1 = np.clip(img0 + np.round(r.normal(0, 4, img0.shape)), 0, 255).astype(np.float32)
     pin0, pin1 = torch.from_numpy(img0).pin_memory(), torch.from_numpy(img1).pin_memory()
     dev0, dev1 = pin0.cuda(), pin1.cuda()
-    flow_dev = torch.empty((B, 2, H, W), device="cuda", dtype=torch.float32)
-    flow_all = torch.empty((world * B, 2, H, W), device="cuda", dtype=torch.float32) if world > 1 else flow_dev
+    # flow fields: double-buffered per rank; at N > 1 they are gathered to rank 0 ONLY (grouped ncclSend/ncclRecv, 1/N of an
+    # all-gather's traffic) on a side stream, so the transfer of step i overlaps the forward of step i+1
+    flow_out = [torch.empty((B, 2, H, W), device="cuda", dtype=torch.float32) for _ in range(2)]
+    flow_dev = flow_out[0]
+    flow_root = [torch.empty((world * B, 2, H, W), device="cuda", dtype=torch.float32) if (world > 1 and rank == 0) else None
+                 for _ in range(2)]
     flow_host = torch.empty((world * B, 2, H, W), dtype=torch.float32).pin_memory() if rank == 0 else None
+    gather_stream = torch.cuda.Stream() if world > 1 else None
+    ev_ready = [torch.cuda.Event() for _ in range(2)]     # flow_out[k] holds this step's flow
+    ev_sent = [torch.cuda.Event() for _ in range(2)]      # flow_out[k] has been gathered (buffer reusable)
+    dev_state = {"i": 0}
+
+    def gather_async(k):
+        with torch.cuda.stream(gather_stream):
+            gather_stream.wait_event(ev_ready[k])
+            P.gather_flows_to_root(flow_out[k], flow_root[k], dst=0)
+            ev_sent[k].record(gather_stream)
 
     def step_device():
+        k = dev_state["i"] & 1
+        dev_state["i"] += 1
+        cur = torch.cuda.current_stream()
         net.set_input_device("img0", dev0.data_ptr())
         net.set_input_device("img1", dev1.data_ptr())
         net.forward_async()
-        net.get_blob_device("predict_flow_final", flow_dev.data_ptr())
         if world > 1:
-            dist.all_gather_into_tensor(flow_all, flow_dev)
+            cur.wait_event(ev_sent[k])                    # the gather of two steps ago has released flow_out[k]
+        net.get_blob_device("predict_flow_final", flow_out[k].data_ptr())
+        if world > 1:
+            ev_ready[k].record(cur)
+            gather_async(k)
+
+    def device_finish():
+        if world > 1:
+            cur = torch.cuda.current_stream()
+            for e in ev_sent:
+                cur.wait_event(e)
 
     # End-to-end loop = what a serving caller does with the public API: every step copies its inputs from pinned host
     # memory and reads its flow back to the host.  The copies run on their own streams with double buffers, so the H2D of
@@ -229,7 +351,7 @@ def run_ours(args):
     h2d_stream, d2h_stream = torch.cuda.Stream(), torch.cuda.Stream()
     stage0 = [torch.empty_like(dev0) for _ in range(2)]
     stage1 = [torch.empty_like(dev1) for _ in range(2)]
-    flow_buf = [torch.empty_like(flow_all) for _ in range(2)]
+    flow_buf = flow_root if world > 1 else flow_out       # what rank 0 reads back to the host
     ev_h2d = [torch.cuda.Event() for _ in range(2)]
     ev_used = [torch.cuda.Event() for _ in range(2)]      # forward has consumed staging buffer k
     ev_flow = [torch.cuda.Event() for _ in range(2)]      # flow of the step is in flow_buf[k]
@@ -256,13 +378,16 @@ def run_ours(args):
         net.set_input_device("img1", stage1[k].data_ptr())
         ev_used[k].record(cur)
         net.forward_async()
-        cur.wait_event(ev_d2h[k])                         # flow_buf[k] of two steps ago has left for the host
-        net.get_blob_device("predict_flow_final", flow_dev.data_ptr())
+        cur.wait_event(ev_d2h[k])                         # flow buffers k of two steps ago have left for the host
         if world > 1:
-            dist.all_gather_into_tensor(flow_buf[k], flow_dev)
+            cur.wait_event(ev_sent[k])
+        net.get_blob_device("predict_flow_final", flow_out[k].data_ptr())
+        if world > 1:
+            ev_ready[k].record(cur)
+            gather_async(k)
+            ev_flow[k] = ev_sent[k]
         else:
-            flow_buf[k].copy_(flow_dev, non_blocking=True)
-        ev_flow[k].record(cur)
+            ev_flow[k].record(cur)
         if rank == 0:
             with torch.cuda.stream(d2h_stream):
                 d2h_stream.wait_event(ev_flow[k])
@@ -278,7 +403,7 @@ def run_ours(args):
 
     def e2e_finish():
         cur = torch.cuda.current_stream()                 # the timed region ends when the last flow has reached the host
-        for e in ev_d2h + ev_h2d:
+        for e in ev_d2h + ev_h2d + (ev_sent if world > 1 else []):
             cur.wait_event(e)
 
     def timed(step, K, finish=None):
@@ -304,7 +429,7 @@ def run_ours(args):
         barrier()
         launches0 = F.launch_count()
         t_begin = time.time()
-        ms = timed(step_device, args.steps)
+        ms = timed(step_device, args.steps, device_finish)
         t_end = time.time()
         clocks = clocks_sampler_stop(sampler, t_begin, t_end) if rank == 0 else None
         # graph replays do not go through the launch counter: count = kernels per forward + layout copies
@@ -313,11 +438,23 @@ def run_ours(args):
             step_e2e()
         torch.cuda.synchronize()
         e2e_state["i"], e2e_state["K"] = 0, args.steps
-        for e in ev_used + ev_d2h:
+        for e in ev_used + ev_d2h + ev_sent:
             e.record(torch.cuda.current_stream())
         torch.cuda.synchronize()
         ms_e2e = timed(step_e2e, args.steps, e2e_finish)
-        finite = bool(torch.isfinite(flow_dev).all().item())
+        finite = bool(torch.isfinite(flow_out[0]).all().item() and torch.isfinite(flow_out[1]).all().item())
+        # The library's own host API, no torch staging: fn2_net_set_input (pinned host NCHW -> device, layout conversion on
+        # the net's stream), fn2_net_forward, fn2_net_get_blob (device -> pinned host, synchronises).  Serial, per rank.
+        host_flow = torch.empty((B, 2, H, W), dtype=torch.float32).pin_memory()
+
+        def step_host_api():
+            net.set_input_ptr("img0", pin0.data_ptr())
+            net.set_input_ptr("img1", pin1.data_ptr())
+            net.forward_async()
+            net.get_blob_ptr("predict_flow_final", host_flow.data_ptr())
+
+        step_host_api()
+        ms_host = timed(step_host_api, args.steps)
 
     pairs = world * B * args.steps
     value = pairs / (ms * 1e-3)
@@ -336,16 +473,22 @@ def run_ours(args):
         total_ms = sum(t for (_, _, t) in lt)
         conv_tf = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         peak_bf16 = pk["bf16_tflops_sustained"] or pk["bf16_tflops"]
+        tf32_peak = measure_tf32_peak(torch) if world == 1 else None
         # traffic: dram__bytes_read.sum + dram__bytes_write.sum of the profiled conv_tc_kernel<128> launch (conv3_1 of FlowNetC,
-        # 473->256 3x3 at 56x128x4; profiles/r01_prof_tc128_raw.csv); its algorithmic bytes are 4*(in + out + weights) = 62.8 MB
+        # 473->256 3x3 at 56x128x4), read from the committed ncu capture; its algorithmic bytes are 4*(in + out + weights) = 62.8 MB
+        tc_traffic, tc_traffic_file = profile_traffic("prof_tc128")
+        corr_traffic, corr_traffic_file = profile_traffic("prof_corr")
         roofline = {"kernel": "conv/deconv stack: conv_tc_kernel<NT> (tcgen05 3xTF32 implicit GEMM, fused bias+ReLU), summed over the layers",
                     "bound": "tensor", "achieved": conv_tf, "peak": peak_bf16, "unit": "TFLOP/s", "frac": conv_tf / peak_bf16,
-                    "traffic": 92.9e6, "traffic_of": "conv3_1 launch (algorithmic 62.8e6 B)",
+                    "traffic": tc_traffic, "traffic_of": "conv3_1 launch (algorithmic 62.8e6 B), %s" % tc_traffic_file,
+                    "tf32_dense_peak_measured": tf32_peak,
                     "peak_source": pk["source"] + ", sustained bf16 dense (kernel timed inside a long step)",
                     "share_of_step": conv_ms / total_ms if total_ms else None,
                     "algorithmic_gflop_per_step": conv_fl / 1e9,
                     # FP32 parity needs 3 TF32 MMAs per multiply-add; the TF32 pipe peaks at half the bf16 rate
-                    "executed_tf32_tflops": 3.0 * conv_tf, "tf32_peak": peak_bf16 / 2.0, "frac_executed": 3.0 * conv_tf / (peak_bf16 / 2.0)}
+                    "executed_tf32_tflops": 3.0 * conv_tf, "tf32_peak": tf32_peak or peak_bf16 / 2.0,
+                    "tf32_peak_source": "cuBLAS TF32 GEMM 8192^3 measured in this run" if tf32_peak else "assumed bf16/2",
+                    "frac_executed": 3.0 * conv_tf / (tf32_peak or peak_bf16 / 2.0)}
         rc = None
         if corr:
             t_ms = sum(t for t, _ in corr)
@@ -353,7 +496,7 @@ def run_ours(args):
             fl = sum(w[2] for _, w in corr)
             gbs = by / (t_ms * 1e-3) / 1e9
             rc = {"kernel": "Correlation d=21 k=1 s2=2 C=256: conv_tc_kernel<128> in correlation mode (3xTF32 tile x halo-block GEMMs) + hi/lo split", "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                  "frac": gbs / pk["hbm_gbs"], "traffic": 112.9e6, "traffic_of": "profiles/r01_prof_corr_raw.csv (4x256x56x128 launch of the tensor-core path; algorithmic 109.3e6 B)", "peak_source": pk["source"],
+                  "frac": gbs / pk["hbm_gbs"], "traffic": corr_traffic, "traffic_of": "%s (4x256x56x128 launch; algorithmic 109.3e6 B)" % corr_traffic_file, "peak_source": pk["source"],
                   "algorithmic_bytes_per_launch": by / len(corr), "ms_per_launch": t_ms / len(corr),
                   "fp32_tflops": fl / (t_ms * 1e-3) / 1e12, "share_of_step": t_ms / total_ms if total_ms else None}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -362,16 +505,23 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(world * 2 * B * 3 * H * W * 4),
                         "d2h_bytes_per_step": int(world * B * 2 * H * W * 4), "ms_per_step": ms_e2e / args.steps,
                         "pipelined": "H2D of step i+1 and D2H of step i-1 overlap the forward of step i (copy streams, double buffers)"},
+                "e2e_host_api": {"value": world * B * args.steps / (ms_host * 1e-3), "unit": UNIT, "ms_per_step": ms_host / args.steps,
+                                 "path": "fn2_net_set_input (pinned host) -> fn2_net_forward -> fn2_net_get_blob (pinned host, synchronous); no overlap",
+                                 "h2d_bytes_per_step": int(world * 2 * B * 3 * H * W * 4), "d2h_bytes_per_step": int(world * B * 2 * H * W * 4)},
                 "gpu_launches": int(per_step_launches * args.steps), "launches_per_step": int(per_step_launches),
                 "output_finite": finite, "roofline": roofline, "roofline_correlation": rc,
                 "layer_ms": {"total": total_ms, "conv_deconv": conv_ms, "correlation": sum(t for t, _ in corr) if corr else 0.0}}
+        if world == 1 and not args.no_extra:
+            del net
+            torch.cuda.empty_cache()
+            line["extra"] = {"config2": side_config(torch, F, "FlowNet2-C", 448, 320, 8),
+                             "config3": side_config(torch, F, "FlowNet2-CSS", 768, 384, 4),
+                             "flownet2_448x320": side_config(torch, F, "FlowNet2", 448, 320, 4)}
         if world == 1 and not args.no_cpu_baseline:
-            tile = cpu_pick_tile(args, args.cpu_seconds)
-            times = cpu_tile_run(args, tile[0], tile[1], 1)
-            v, mean = cpu_result(args, tile, times)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                    "sample": "one %dx%d tile of one %dx%d pair (%.1f s), scaled by pixel ratio; oracle/ C port, OpenMP"
-                                              % (tile[0], tile[1], W, H, mean)}
+            arm = CpuArm(args)
+            v, mean = arm.run(2, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
+                                    "sample": arm.sample + "; 1 warm-up + 2 timed steps, %.1f s per step" % mean}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -163,11 +163,6 @@ void Net<Dtype>::AliasConcats() {
                 if (string(layers_[lj]->type()) != "Convolution" || bl->channels() > 16) continue;
                 for (int bb : bottom_id_vecs_[lj]) if (bb == bid) ok = false;
             }
-            // the float4 element-wise kernels (fn2_ops.cu px_store) treat a view whose pixel stride equals its own channel
-            // count rounded up to 4 as owning the lanes beyond C and zero them; for a child in the middle of the parent
-            // those lanes are a sibling's channels
-            const int cn = bl->channels();
-            if (ok && cn % 4 != 0 && c0 + cn < top->channels() && (cn + 3) / 4 * 4 == top->channel_stride()) ok = false;
             seen.insert(bid);
             if (ok) bl->AliasInto(top, c0);
             c0 += bl->channels();

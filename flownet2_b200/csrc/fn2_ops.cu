@@ -455,13 +455,14 @@ __global__ void fill_kernel(T4 dst, float v) {
 // Channel-fast ("NHWC") variants of the element-wise kernels: one thread per (pixel, group of 4 channels), 128-bit
 // accesses where the view allows them.  Same per-element arithmetic as the generic kernels above (bit-identical).
 // vr: the view may be READ as float4 groups (16-byte aligned pixels; lanes beyond C are padding or a neighbour's
-// channels -- read, never used).  vw: a float4 WRITE may cover the lanes beyond C (they are this tensor's own padding).
+// channels -- read, never used).  WRITES never touch a lane beyond C: a view cannot tell whether those lanes are its own
+// padding or a sibling's channels inside a zero-copy Concat parent (a 2-channel child of a 2+2 parent has the same strides as
+// a dense 2-channel blob), so the tail group is stored lane by lane; padding stays zero from the allocation.
 // ---------------------------------------------------------------------------------------------
-struct PxView { T4 t; int vr, vw; };
+struct PxView { T4 t; int vr; };
 static PxView px_view(const T4& t) {
     PxView v; v.t = t;
     v.vr = t.sc == 1 && !((uintptr_t)t.p & 15) && !(t.sw & 3) && !(t.sh & 3) && !(t.sn & 3) && t.sw >= (t.c + 3) / 4 * 4;
-    v.vw = v.vr && t.sw == (t.c + 3) / 4 * 4;
     return v;
 }
 __device__ __forceinline__ float4 px_load(const PxView& v, long long o, int c0) {
@@ -475,13 +476,7 @@ __device__ __forceinline__ float4 px_load(const PxView& v, long long o, int c0) 
 }
 __device__ __forceinline__ void px_store(const PxView& v, long long o, int c0, float4 r) {
     if (v.vr && c0 + 4 <= v.t.c) { *reinterpret_cast<float4*>(v.t.p + o + c0) = r; return; }
-    if (v.vw) {                                       // tail group of a tensor that owns its padding: keep the padding zero
-        if (c0 + 1 >= v.t.c) r.y = 0.f;
-        if (c0 + 2 >= v.t.c) r.z = 0.f;
-        if (c0 + 3 >= v.t.c) r.w = 0.f;
-        *reinterpret_cast<float4*>(v.t.p + o + c0) = r;
-        return;
-    }
+    if (v.vr && c0 + 2 == v.t.c) { *reinterpret_cast<float2*>(v.t.p + o + c0) = make_float2(r.x, r.y); return; }   // 2-channel flows
     if (c0 + 0 < v.t.c) v.t.p[o + c0 + 0] = r.x;
     if (c0 + 1 < v.t.c) v.t.p[o + c0 + 1] = r.y;
     if (c0 + 2 < v.t.c) v.t.p[o + c0 + 2] = r.z;

@@ -4,7 +4,9 @@ The per-pair forward does not shard; pairs do.  One process per GPU (torch.distr
 NVLink/NVSwitch on the GPU box, gloo in the CPU tests):
   * broadcast_arena : ONE broadcast of the net's contiguous parameter arena from rank 0
   * shard_bounds    : contiguous split of B pairs over the ranks (first ranks take the remainder)
-  * gather_flows    : all ranks' (b_r, 2, H, W) flow fields -> (B, 2, H, W) in global pair order
+  * gather_flows    : all ranks' (b_r, 2, H, W) flow fields -> (B, 2, H, W) in global pair order on EVERY rank
+  * gather_flows_to_root : the same, delivered to one rank only (what a serving front end needs: 1/world of the
+                      all-gather traffic, and issued on a side stream it overlaps the next step's forward)
 No collective exists inside a pair.  The reference has no inference data parallelism at all (its P2PSync
 is training-only, src/caffe/parallel.cpp:271-380).
 """
@@ -53,3 +55,22 @@ def gather_flows(local, total):
     out = local.new_empty((world * mx,) + tuple(local.shape[1:]))
     dist.all_gather_into_tensor(out, padded)
     return torch.cat([out[r * mx:r * mx + (hi - lo)] for r, (lo, hi) in enumerate(sizes)], 0)
+
+
+def gather_flows_to_root(local, out=None, dst=0):
+    """Equal shards: local (b, 2, H, W) of every rank -> out (world*b, 2, H, W) on rank `dst` only (None elsewhere).
+    One grouped send/recv (ncclSend/ncclRecv) instead of an all-gather: rank dst receives (world-1)*b flow fields, the others
+    send b and receive nothing.  Runs on the CURRENT stream's NCCL queue: call it under a side stream to overlap compute."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        if out is not None:
+            out.copy_(local)
+            return out
+        return local
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if rank == dst:
+        if out is None:
+            out = local.new_empty((world * local.shape[0],) + tuple(local.shape[1:]))
+        dist.gather(local, list(out.chunk(world)), dst=dst)
+        return out
+    dist.gather(local, None, dst=dst)
+    return None

@@ -253,71 +253,78 @@ class OracleNet(object):
             assert list(a.shape) == s, (n, a.shape, s)
             B[n] = a
         for l in self.layers:
-            typ, name = get(l, "type"), get(l, "name")
-            bots = [B[b] for b in getall(l, "bottom")]
-            tops = getall(l, "top")
-            if typ == "Input":
+            if get(l, "type") == "Input":
                 continue
-            elif typ == "Eltwise":
-                ep = get(l, "eltwise_param", [])
-                assert get(ep, "operation", "SUM") == "SUM"
-                B[tops[0]] = O.eltwise_sum(bots, [float(c) for c in getall(ep, "coeff")])
-            elif typ == "DataAugmentation":
-                B[tops[0]] = self._aug(l, name, bots[0])
-            elif typ == "Resample":
-                rp = get(l, "resample_param", [])
-                if len(bots) == 2:
-                    oh, ow = bots[1].shape[2], bots[1].shape[3]
-                else:
-                    oh, ow = int(get(rp, "height")), int(get(rp, "width"))
-                rtype = {"NEAREST": 1, "LINEAR": 2, "CUBIC": 3}[get(rp, "type", "LINEAR")]
-                B[tops[0]] = O.resample_fwd(bots[0], oh, ow, rtype, get(rp, "antialias", "true") == "true")
-            elif typ in ("Convolution", "Deconvolution"):
-                cp = get(l, "convolution_param")
-                kh, kw = _hw(cp, "kernel_size", "kernel_h", "kernel_w", 0)
-                sh, sw = _hw(cp, "stride", "stride_h", "stride_w", 1)
-                ph, pw = _hw(cp, "pad", "pad_h", "pad_w", 0)
-                has_bias = get(cp, "bias_term", "true") == "true"
-                if name not in self.weights:           # synthetic weights (timing-only runs)
-                    assert self.synth_seed is not None, "no weights for layer " + name
-                    co, ci = int(get(cp, "num_output")), bots[0].shape[1]
-                    r = np.random.default_rng(self.synth_seed + len(self.weights))
-                    shp = (co, ci, kh, kw) if typ == "Convolution" else (ci, co, kh, kw)
-                    wf = get(cp, "weight_filler", [])
-                    if get(wf, "type") == "diagonal":          # DiagonalFiller, filler.hpp:265-290
-                        dv = [float(x) for x in getall(wf, "diag_val")]
-                        wsyn = np.zeros(shp, np.float32)
-                        for i in range(min(shp[0], shp[1])):
-                            wsyn[i, i, :, :] = dv[i] if i < len(dv) else (dv[-1] if dv else 1.0)
-                    else:
-                        wsyn = (r.standard_normal(shp) * np.sqrt(2.0 / (ci * kh * kw))).astype(np.float32)
-                    self.weights[name] = [wsyn] + ([np.zeros(co, np.float32)] if has_bias else [])
-                w = self.weights[name][0]
-                b = self.weights[name][1].reshape(-1) if has_bias else None
-                for bot, top in zip(bots, tops):
-                    if typ == "Convolution":
-                        B[top] = O.conv_fwd(bot, w, b, (sh, sw), (ph, pw), f64acc=self.f64acc)
-                    else:
-                        B[top] = O.deconv_fwd(bot, w, b, (sh, sw), (ph, pw), f64acc=self.f64acc)
-            elif typ == "ReLU":
-                B[tops[0]] = O.relu(bots[0], float(get(get(l, "relu_param", []), "negative_slope", 0)))
-            elif typ == "Concat":
-                B[tops[0]] = np.concatenate(bots, axis=1)
-            elif typ == "Correlation":
-                cp = get(l, "correlation_param")
-                B[tops[0]] = O.correlation_fwd(bots[0], bots[1], int(get(cp, "pad", 0)), int(get(cp, "kernel_size")),
-                                               int(get(cp, "max_displacement")), int(get(cp, "stride_1", 1)),
-                                               int(get(cp, "stride_2", 1)),
-                                               {"MULTIPLY": 0, "SUBTRACT": 1}[get(cp, "correlation_type", "MULTIPLY")],
-                                               exact_order=not self.f64acc)
-            elif typ == "FlowWarp":
-                fp = get(l, "flow_warp_param", [])
-                B[tops[0]] = O.flow_warp_fwd(bots[0], bots[1], get(fp, "fill_value", "ZERO") == "NOT_A_NUMBER")
-            elif typ == "ChannelNorm":
-                B[tops[0]] = O.channel_norm(bots[0])
-            else:
-                raise NotImplementedError(typ)
+            bots = [B[b] for b in getall(l, "bottom")]
+            for t, v in zip(getall(l, "top"), self.run_layer(l, bots)):
+                B[t] = v
         return B
+
+    def run_layer(self, l, bots):
+        """One layer of the prototxt on numpy bottoms -> list of numpy tops (layer semantics: see the per-type comments)."""
+        typ, name = get(l, "type"), get(l, "name")
+        tops = getall(l, "top")
+        B = {}
+        if typ == "Eltwise":
+            ep = get(l, "eltwise_param", [])
+            assert get(ep, "operation", "SUM") == "SUM"
+            B[tops[0]] = O.eltwise_sum(bots, [float(c) for c in getall(ep, "coeff")])
+        elif typ == "DataAugmentation":
+            B[tops[0]] = self._aug(l, name, bots[0])
+        elif typ == "Resample":
+            rp = get(l, "resample_param", [])
+            if len(bots) == 2:
+                oh, ow = bots[1].shape[2], bots[1].shape[3]
+            else:
+                oh, ow = int(get(rp, "height")), int(get(rp, "width"))
+            rtype = {"NEAREST": 1, "LINEAR": 2, "CUBIC": 3}[get(rp, "type", "LINEAR")]
+            B[tops[0]] = O.resample_fwd(bots[0], oh, ow, rtype, get(rp, "antialias", "true") == "true")
+        elif typ in ("Convolution", "Deconvolution"):
+            cp = get(l, "convolution_param")
+            kh, kw = _hw(cp, "kernel_size", "kernel_h", "kernel_w", 0)
+            sh, sw = _hw(cp, "stride", "stride_h", "stride_w", 1)
+            ph, pw = _hw(cp, "pad", "pad_h", "pad_w", 0)
+            has_bias = get(cp, "bias_term", "true") == "true"
+            if name not in self.weights:           # synthetic weights (timing-only runs)
+                assert self.synth_seed is not None, "no weights for layer " + name
+                co, ci = int(get(cp, "num_output")), bots[0].shape[1]
+                r = np.random.default_rng(self.synth_seed + len(self.weights))
+                shp = (co, ci, kh, kw) if typ == "Convolution" else (ci, co, kh, kw)
+                wf = get(cp, "weight_filler", [])
+                if get(wf, "type") == "diagonal":          # DiagonalFiller, filler.hpp:265-290
+                    dv = [float(x) for x in getall(wf, "diag_val")]
+                    wsyn = np.zeros(shp, np.float32)
+                    for i in range(min(shp[0], shp[1])):
+                        wsyn[i, i, :, :] = dv[i] if i < len(dv) else (dv[-1] if dv else 1.0)
+                else:
+                    wsyn = (r.standard_normal(shp) * np.sqrt(2.0 / (ci * kh * kw))).astype(np.float32)
+                self.weights[name] = [wsyn] + ([np.zeros(co, np.float32)] if has_bias else [])
+            w = self.weights[name][0]
+            b = self.weights[name][1].reshape(-1) if has_bias else None
+            for bot, top in zip(bots, tops):
+                if typ == "Convolution":
+                    B[top] = O.conv_fwd(bot, w, b, (sh, sw), (ph, pw), f64acc=self.f64acc)
+                else:
+                    B[top] = O.deconv_fwd(bot, w, b, (sh, sw), (ph, pw), f64acc=self.f64acc)
+        elif typ == "ReLU":
+            B[tops[0]] = O.relu(bots[0], float(get(get(l, "relu_param", []), "negative_slope", 0)))
+        elif typ == "Concat":
+            B[tops[0]] = np.concatenate(bots, axis=1)
+        elif typ == "Correlation":
+            cp = get(l, "correlation_param")
+            B[tops[0]] = O.correlation_fwd(bots[0], bots[1], int(get(cp, "pad", 0)), int(get(cp, "kernel_size")),
+                                           int(get(cp, "max_displacement")), int(get(cp, "stride_1", 1)),
+                                           int(get(cp, "stride_2", 1)),
+                                           {"MULTIPLY": 0, "SUBTRACT": 1}[get(cp, "correlation_type", "MULTIPLY")],
+                                           exact_order=not self.f64acc)
+        elif typ == "FlowWarp":
+            fp = get(l, "flow_warp_param", [])
+            B[tops[0]] = O.flow_warp_fwd(bots[0], bots[1], get(fp, "fill_value", "ZERO") == "NOT_A_NUMBER")
+        elif typ == "ChannelNorm":
+            B[tops[0]] = O.channel_norm(bots[0])
+        else:
+            raise NotImplementedError(typ)
+        return [B[t] for t in tops]
 
     def _aug(self, l, name, x):
         ap = get(l, "augmentation_param")

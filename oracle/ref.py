@@ -320,3 +320,83 @@ class RefNet(object):
 
     def time_layers(self, iters=1):
         return [(n, t, l.time_forward(iters)) for n, t, l in self.layers]
+
+
+class _OracleLayer(object):
+    """Stand-in for the three layer types whose Forward_cpu does not exist in the reference (NOT_IMPLEMENTED / LOG(FATAL)):
+    the oracle restatement of their .cu arithmetic, exchanging data with the reference Blobs on the host."""
+
+    def __init__(self, onet, msg, bottoms, tops):
+        self.onet, self.msg, self.bottoms, self.tops = onet, msg, bottoms, tops
+        outs = onet.run_layer(msg, [np.zeros(b.shape, np.float32) for b in bottoms])       # shape inference (SetUp)
+        for t, o in zip(tops, outs):
+            t.reshape(o.shape)
+
+    def forward(self):
+        outs = self.onet.run_layer(self.msg, [b.get() for b in self.bottoms])
+        for t, o in zip(self.tops, outs):
+            t.set(o)
+
+    def time_forward(self, iters=1):
+        import time
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            self.forward()
+        return (time.perf_counter() - t0) * 1e3 / iters
+
+
+class RefCpuNet(object):
+    """The reference's CPU forward of a deploy prototxt, as far as the reference has one: conv / deconv (im2col + OpenBLAS sgemm,
+    base_conv_layer.cpp:257-298), ReLU, Eltwise, Concat, FlowWarp, ChannelNorm run the reference's own Forward_cpu; Correlation,
+    Resample and DataAugmentation -- for which the reference only has GPU code -- run the oracle port.  This is what bench.py
+    times as `--impl reference` / `cpu_baseline` (kind "reference")."""
+    ORACLE_TYPES = ("Correlation", "Resample", "DataAugmentation")
+
+    def __init__(self, prototxt_text, weights=None, batch=0, synth_seed=None):
+        from .net import OracleNet, parse_prototxt, getall, get
+        set_mode(False)
+        self.onet = OracleNet(prototxt_text, None, batch=batch, synth_seed=synth_seed)
+        if weights:
+            self.onet.weights = {k: [np.asarray(a, np.float32) for a in v] for k, v in weights.items()}
+        header, blocks = split_layers(prototxt_text)
+        self.input_names, self.input_shapes = list(self.onet.input_names), [list(s) for s in self.onet.input_shapes]
+        self.blobs, self.layers = {}, []
+        for n, s in zip(self.input_names, self.input_shapes):
+            self.blobs[n] = Blob(shape=s)
+        r = np.random.default_rng(synth_seed if synth_seed is not None else 0)
+        for blk in blocks:
+            name, typ = _names(blk, "name")[0], _names(blk, "type")[0]
+            if typ == "Input":
+                continue
+            bots = [self.blobs[b] for b in _names(blk, "bottom")]
+            tops = []
+            for t in _names(blk, "top"):
+                if t not in self.blobs:
+                    self.blobs[t] = Blob()
+                tops.append(self.blobs[t])
+            if typ in self.ORACLE_TYPES:
+                layer = _OracleLayer(self.onet, parse_prototxt(blk), bots, tops)
+            else:
+                layer = Layer(blk, 1)
+                layer.setup(bots, tops)
+                if weights and name in weights:
+                    for p, a in zip(layer.params, weights[name]):
+                        p.set(np.asarray(a, np.float32).reshape(p.shape))
+                elif synth_seed is not None and typ in ("Convolution", "Deconvolution"):
+                    ps = layer.params                      # He-initialised weights, zero bias (timing-only runs)
+                    shp = ps[0].shape
+                    fan = int(np.prod(shp[1:])) if typ == "Convolution" else shp[0] * shp[2] * shp[3]
+                    ps[0].set((r.standard_normal(shp) * np.sqrt(2.0 / fan)).astype(np.float32))
+                    if len(ps) > 1:
+                        ps[1].set(np.zeros(ps[1].shape, np.float32))
+            self.layers.append((name, typ, layer))
+
+    def forward(self, **inputs):
+        for n in self.input_names:
+            self.blobs[n].set(inputs[n])
+        for _, _, layer in self.layers:
+            layer.forward()
+        return self
+
+    def blob(self, name):
+        return self.blobs[name].get()

@@ -35,6 +35,9 @@ def _worker(rank, world, port, total, q):
         local = torch.stack([torch.full((2, 3, 4), float(i)) + torch.tensor([0.0, 0.5]).view(2, 1, 1) for i in range(lo, hi)])
         allf = P.gather_flows(local, total)
         ok_g = allf.shape == (total, 2, 3, 4) and all(float(allf[i, 0, 0, 0]) == i and float(allf[i, 1, 0, 0]) == i + 0.5 for i in range(total))
+        if total % world == 0:                      # equal shards: root-only gather (what bench.py uses at N > 1)
+            root = P.gather_flows_to_root(local)
+            ok_g = ok_g and ((root is None) if rank != 0 else bool(torch.equal(root, allf)))
         q.put((rank, ok_w, bool(ok_g)))
     finally:
         dist.destroy_process_group()
