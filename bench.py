@@ -137,7 +137,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def profile_traffic(pattern):
@@ -526,7 +526,7 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
