@@ -31,6 +31,7 @@ SOURCES = [
     ("fn2_conv.cu", []),
     ("fn2_conv_nhwc.cu", []),
     ("fn2_conv_tc.cu", []),
+    ("fn2_conv_tn.cu", []),
     ("caffe/proto.cpp", []),
     ("caffe/blob.cpp", []),
     ("caffe/layers.cpp", []),

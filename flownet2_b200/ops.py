@@ -143,8 +143,16 @@ def mean_subtract(top, mean_pp=None, mean_pc=None, per_pixel=False):
     return top
 
 
+def conv_plan(ci, co, k, stride, pad, deconv, n, h, w, ci_stride):
+    """fn2_conv_plan: the tcgen05 engines' host-side plan for a layer shape (8 ints, see include/fn2.h)."""
+    d = fn2_conv_desc(ci, co, k, k, stride, stride, pad, pad, 1 if deconv else 0, 1, 0, 0.0, 0, 0)
+    plan = (C.c_int32 * 8)()
+    check(lib().fn2_conv_plan(C.byref(d), n, h, w, ci_stride, plan))
+    return list(plan)
+
+
 def conv2d(x, weight, bias=None, stride=1, pad=0, deconv=False, relu_slope=None, engine=0, channels_last_out=None,
-           use_workspace=True, input_guard_bytes=0):
+           use_workspace=True, input_guard_bytes=0, out=None):
     """weight in Caffe layout: conv [co,ci,kh,kw], deconv [ci,co,kh,kw]."""
     l = lib()
     if deconv:
@@ -163,7 +171,8 @@ def conv2d(x, weight, bias=None, stride=1, pad=0, deconv=False, relu_slope=None,
     packed = torch.empty(max(nf.value, 1), dtype=torch.float32, device=x.device)
     weight = weight.contiguous()
     check(l.fn2_conv_pack_weights(C.byref(d), cis, C.c_void_p(weight.data_ptr()), C.c_void_p(packed.data_ptr()), _stream()))
-    out = _empty((x.shape[0], co, ho.value, wo.value), x, channels_last_out)
+    if out is None:
+        out = _empty((x.shape[0], co, ho.value, wo.value), x, channels_last_out)
     dx, do = desc(x), desc(out)
     wsb = C.c_size_t()
     check(l.fn2_conv_workspace_bytes(C.byref(d), x.shape[0], x.shape[2], x.shape[3], C.byref(wsb)))

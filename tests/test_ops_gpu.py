@@ -252,6 +252,53 @@ def test_conv_tcgen05_engine(ops, case):
     assert abs(shrink) < 1e-7, shrink
 
 
+TN_CASES = [
+    # N, Ci, H, W, Co, k, stride, pad, deconv, bias+relu      ("taps on N" engine, fn2_conv_tn.cu: Co in {16, 32}, Ci > 16)
+    (1, 82, 16, 24, 16, 3, 1, 1, False, True),        # fuse_interconv0's channels: one strip, 144 accumulator columns
+    (2, 82, 37, 70, 16, 3, 1, 1, False, True),        # odd size: 3 strips, partial last strip / tile, two samples
+    (1, 162, 21, 45, 32, 3, 1, 1, False, True),       # fuse_interconv1: two passes (5 + 4 taps), 6 K blocks
+    (1, 40, 9, 33, 16, 3, 1, 1, False, False),        # channel tail (40 of 64), no bias / ReLU, strip boundary at column 30
+    (1, 162, 9, 11, 16, 4, 2, 1, True, True),         # fuse_deconv0: 16 taps, two passes of 8
+    (2, 128, 13, 37, 32, 4, 2, 1, True, True),        # fuse_deconv1: four passes, two strips
+    (1, 64, 150, 40, 16, 3, 1, 1, False, True),       # tall: several vertical segments per strip
+    (1, 96, 70, 33, 16, 4, 2, 1, True, False),        # tall deconvolution
+    (1, 48, 20, 40, 32, 2, 1, 0, False, True),        # 2x2 kernel, no padding (output smaller than input)
+]
+
+
+@pytest.mark.parametrize("case", TN_CASES)
+def test_conv_taps_on_n_engine(ops, case):
+    """Few output channels at high resolution: GEMM over K = Ci with (tap, co) on the MMA's N side, scatter-add ("col2im") through
+    a shared-memory ring of output rows.  Same tolerance as the per-tap tcgen05 engine; the output goes into a channel slice of a
+    wider NHWC buffer (zero-copy concat child) whose other channels must stay untouched."""
+    N, Ci, H, W, Co, k, s, p, deconv, act = case
+    r = rng(hash(case) % 2**31)
+    x = r.standard_normal((N, Ci, H, W)).astype(np.float32)
+    wshape = (Ci, Co, k, k) if deconv else (Co, Ci, k, k)
+    w = (r.standard_normal(wshape) * np.sqrt(2.0 / (Ci * k * k))).astype(np.float32)
+    b = r.standard_normal(Co).astype(np.float32) if act else None
+    want = (O.deconv_fwd if deconv else O.conv_fwd)(x, w, b, s, p, f64acc=True)
+    if act:
+        want = O.relu(want, 0.1)
+    cp = (Ci + 31) // 32 * 32
+    buf = torch.zeros((N, cp, H, W), device="cuda").contiguous(memory_format=torch.channels_last)
+    buf[:, :Ci] = torch.from_numpy(x).cuda()
+    plan = ops.conv_plan(Ci, Co, k, s, p, deconv, N, H, W, cp)
+    assert plan[3] == 3, plan                                               # taps-on-N mode chosen
+    Ho, Wo = want.shape[2], want.shape[3]
+    wide = torch.full((N, Co + 32, Ho, Wo), 7.0, device="cuda").contiguous(memory_format=torch.channels_last)
+    out = wide[:, 16:16 + Co]
+    got = ops.conv2d(buf[:, :Ci], dev(w), torch.from_numpy(b).cuda() if act else None, s, p, deconv, 0.1 if act else None, 2, out=out)
+    scale = max(1.0, np.abs(want).max())
+    assert maxabs(host(got), want) <= 1e-6 * scale, maxabs(host(got), want)
+    assert float((wide[:, :16] - 7.0).abs().max()) == 0.0 and float((wide[:, 16 + Co:] - 7.0).abs().max()) == 0.0
+    shrink = float(((host(got) - want) * np.sign(want)).mean() / np.abs(want).mean())
+    print("taps-on-N case", case, "max err %.3g shrink %.3g" % (maxabs(host(got), want) / scale, shrink))
+    assert abs(shrink) < 1e-7, shrink
+    again = ops.conv2d(buf[:, :Ci], dev(w), torch.from_numpy(b).cuda() if act else None, s, p, deconv, 0.1 if act else None, 2, out=out)
+    assert torch.equal(again, got)                                          # fixed summation order
+
+
 ROW_CASES = [
     # N, Ci, H, W, Co, k, stride, pad   (dense small-Ci input + guard band -> kernel-row packing of the tcgen05 engine)
     (2, 3, 20, 28, 64, 7, 2, 3),        # FlowNetC conv1: one 32-float K block per kernel row
