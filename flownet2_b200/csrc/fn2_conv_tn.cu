@@ -49,11 +49,16 @@ struct TnParams {
     int tw, th;
     int stepx, cshift, xa;                       // strip b: input cols [b*stepx + cshift, +tw); complete outputs x = S*c0 + xa + [0, S*stepx)
     int nstrips, nseg, seg_rows;                 // segment g: output rows [g*seg_rows, min(Ho, (g+1)*seg_rows))
-    int RR, CW;                                  // ring rows; columns per (ring row, co)
+    int RR, CW, F;                               // ring rows; columns per (ring row, co); tiles between two flushes of the ring
     int npass, pass_tap0[TN_MAXPASS], pass_ntaps[TN_MAXPASS];
+    // scatter plan: every pass is a list of groups = runs of taps of ONE kernel row; inside a group, taps whose column offsets
+    // differ by a multiple of S are summed across lanes first (class cls: leader tap + partners with their lane shifts)
+    int ngrp[TN_MAXPASS];
+    struct Grp { short tl0, nrow, oyr, ncls; short ox0[2], np[2]; short ps[2][3], sh[2][3]; } grp[TN_MAXPASS][4];
     int ngmax;                                   // W tile rows in shared memory (max taps per pass * Co)
     int RA, RW, wres;                            // raw-A ring depth, W ring depth, 1 = all W stages resident in shared memory
     int total;                                   // units = N * nstrips * nseg
+    int dbg;                                     // FN2_TN_DBG bits (ablations, wrong results): 1 skip scatter, 2 skip write-out/zero, 4 skip MMAs, 8 skip conversion
     float comp;                                  // mean RZ shrink of the 12*cblocks-MMA chain
     int relu, has_bias;
     float slope;
@@ -91,6 +96,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
           "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(taddr) : "memory");
 }
 
+// named barrier of one channel half of the drain group (4 warps)
+__device__ __forceinline__ void tn_group_sync(int h) {
+    if (h) asm volatile("bar.sync 2, 128;" ::: "memory");
+    else asm volatile("bar.sync 1, 128;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr) : "memory");
@@ -104,7 +114,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
 
 // Warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4-7 converters, 8-15 drain (two warps per TMEM lane quarter, each
 // taking half of the output channels of every tap).  512 threads x 128 registers = the whole register file.
-template <int CO>
+template <int CO, int S>
 __global__ void __launch_bounds__(TN_THREADS, 1)
 conv_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const float* __restrict__ bias,
                float* __restrict__ out, const TnParams p) {
@@ -203,6 +213,7 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             if (elect_one()) {
 #pragma unroll
                                 for (int kk = 0; kk < 4; kk++) {
+                                    if (p.dbg & 4) break;
                                     mma_tf32_ts(d, a_hi + kk * 8, dbh0 + (uint64_t)(2 * kk), idesc, (cb | kk) != 0);
                                     mma_tf32_ts(d, a_hi + kk * 8, dbl0 + (uint64_t)(2 * kk), idesc, 1);
                                     mma_tf32_ts(d, a_lo + kk * 8, dbh0 + (uint64_t)(2 * kk), idesc, 1);
@@ -243,6 +254,7 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const uint32_t slot = lane_addr + TN_COL_A + 64 * (it & 1);
 #pragma unroll
                 for (int half = 0; half < 2; half++) {
+                    if (p.dbg & 8) break;
                     uint32_t hi[16], lo[16];
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
@@ -275,69 +287,141 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int rowstride = CO * p.CW;
         const int col0 = jt * p.S - p.ox_min + h * CH * p.CW;     // + ox[sx]: this thread's first element inside a ring row
         const int advance = p.th * p.S;            // output rows that leave the ring per tile
+        float bv[4] = {0.f, 0.f, 0.f, 0.f};        // bias of the 4 channels this thread writes out
+        if (p.has_bias) {
+            const int cb_ = h * CH + 4 * ((dt & 127) % (CH / 4));
+            bv[0] = __ldg(bias + cb_); bv[1] = __ldg(bias + cb_ + 1); bv[2] = __ldg(bias + cb_ + 2); bv[3] = __ldg(bias + cb_ + 3);
+        }
         int buf = 0; uint32_t pfull = 0;
+        long long tw_ = 0, ts_ = 0, tf_ = 0, tz_ = 0, tA_ = 0, tB_ = 0, tC_ = 0, tD_ = 0; int ntl_ = 0;      // FN2_TN_DBG & 16: cycles waiting / scattering / writing out / zeroing
+        const bool prof_ = (p.dbg & 16) != 0;
         for (int u = blockIdx.x; u < p.total; u += gridDim.x) {
             const TnUnit U = tn_decode(p, u);
             const int x_base = p.S * U.c0 + p.ox_min;                 // output column of ring column 0
             const int xc_lo = max(0, p.S * U.c0 + p.xa), xc_hi = min(p.Wo, p.S * U.c0 + p.xa + p.S * p.stepx);   // complete output columns
             const int ncol = xc_hi - xc_lo;
-            int prev_hi = 0;
             int rb = 0;                            // ring slot of the first row the current tile can touch
+            int flush_lo = 0, since_flush = 0;     // first row still in the ring; tiles since the last flush
             for (int k = 0; k < U.ntiles; k++) {
                 const int i0 = U.i_lo + k * p.th;
                 const int touched_lo = i0 * p.S + p.oy_min;
                 const int yrel0 = it_ * p.S - p.oy_min;            // + oy[r]: row of this lane's contribution relative to touched_lo
                 for (int ps = 0; ps < p.npass; ps++) {
+                    long long c0_ = prof_ ? clock64() : 0;
                     mbar_wait(&acc_full[buf], pfull);
                     fence_after();
+                    long long c1_ = prof_ ? clock64() : 0;
+                    tw_ += c1_ - c0_;
                     const uint32_t src = lane_addr + (uint32_t)(buf * TN_ACC_COLS + h * CH);
-                    const int t0 = p.pass_tap0[ps], nt = p.pass_ntaps[ps];
-                    int r_prev = -1;
-                    float* rowp = obuf;
+                    // Taps of one kernel row land in the same output row, a few columns apart: taps whose column offsets differ
+                    // by a multiple of S hit the column of a NEIGHBOURING lane's tap, so they are first summed across lanes with
+                    // shuffles (lane L collects what belongs to its own column) and only one read-modify-write per group reaches
+                    // shared memory.  Lanes whose neighbour lies outside the warp (= outside the tile row) produce an incomplete
+                    // sum for a column outside the strip's complete range, which is never written out.
+                    const int ng = (p.dbg & 1) ? 0 : p.ngrp[ps];
 #pragma unroll 1
-                    for (int tl = 0; tl < nt; tl++) {
-                        const int t = t0 + tl;
-                        const int r = t / p.kw, sx = t - r * p.kw;
-                        uint32_t v[CH];
-                        if constexpr (CH == 8) tmem_ld8(src + (uint32_t)(tl * CO), v);
-                        else tmem_ld16(src + (uint32_t)(tl * CO), v);
-                        if (r != r_prev) {         // next kernel row: other warps may still be adding into the rows we now target
-                            if (r_prev >= 0) asm volatile("bar.sync 1, 256;" ::: "memory");
-                            r_prev = r;
-                            int ring = rb + yrel0 + p.oy[r];
-                            if (ring >= p.RR) ring -= p.RR;
-                            rowp = obuf + ring * rowstride + col0;
-                        }
-                        tmem_wait_ld();
-                        float* o = rowp + p.ox[sx];
+                    for (int gi = 0; gi < ng; gi++) {
+                        const int tl0 = p.grp[ps][gi].tl0, nrow = p.grp[ps][gi].nrow, oyr = p.grp[ps][gi].oyr;
+                        if (gi && !(p.dbg & 128)) tn_group_sync(h);   // the other 3 warps of this channel half may still add into the rows we now target
+                        int ring = rb + yrel0 + oyr;
+                        if (ring >= p.RR) ring -= p.RR;
+                        float* rowp = obuf + ring * rowstride + col0;
+                        const int ox0 = p.grp[ps][gi].ox0[0], ox1 = p.grp[ps][gi].ox0[1];
+#pragma unroll 1
+                        for (int c0 = 0; c0 < CH; c0 += 8) {
+                            // straight-line code per (S, number of taps of this kernel row in the pass): the taps' values of lane L,
+                            // RZ-compensated; conv (S = 1): tap sa+d of lane L+d belongs to lane L's column -> shuffle down by d;
+                            // deconv (S = 2): tap sa+2 (sa+3) of lane L-1 belongs to the column of lane L's tap sa (sa+1) -> shuffle
+                            // up by 1.  Lanes without that neighbour add garbage to a column outside the strip's complete range.
+                            float a0[8], a1[8];
+                            uint32_t v0[8], v1[8], v2[8], v3[8];
+                            const uint32_t tsrc = src + (uint32_t)(tl0 * CO + c0);
+                            const long long q0_ = prof_ ? clock64() : 0;
+                            tmem_ld8(tsrc, v0);
+                            if (nrow > 1) tmem_ld8(tsrc + CO, v1);
+                            if (nrow > 2) tmem_ld8(tsrc + 2 * CO, v2);
+                            if (nrow > 3) tmem_ld8(tsrc + 3 * CO, v3);
+                            tmem_wait_ld();
+                            const long long q1_ = prof_ ? clock64() : 0;
+#define FN2_TN_COMP(x) fmaf(__uint_as_float(x), p.comp, __uint_as_float(x))
 #pragma unroll
-                        for (int c = 0; c < CH; c++) {
-                            const float a = __uint_as_float(v[c]);
-                            o[c * p.CW] += fmaf(a, p.comp, a);
+                            for (int c = 0; c < 8; c++) a0[c] = FN2_TN_COMP(v0[c]);
+                            if constexpr (S == 1) {
+                                if (nrow > 1) {
+#pragma unroll
+                                    for (int c = 0; c < 8; c++) a0[c] += __shfl_down_sync(0xffffffffu, FN2_TN_COMP(v1[c]), 1);
+                                }
+                                if (nrow > 2) {
+#pragma unroll
+                                    for (int c = 0; c < 8; c++) a0[c] += __shfl_down_sync(0xffffffffu, FN2_TN_COMP(v2[c]), 2);
+                                }
+                                if (nrow > 3) {
+#pragma unroll
+                                    for (int c = 0; c < 8; c++) a0[c] += __shfl_down_sync(0xffffffffu, FN2_TN_COMP(v3[c]), 3);
+                                }
+                            } else {
+                                if (nrow > 1) {
+#pragma unroll
+                                    for (int c = 0; c < 8; c++) a1[c] = FN2_TN_COMP(v1[c]);
+                                }
+                                if (nrow > 2) {
+#pragma unroll
+                                    for (int c = 0; c < 8; c++) a0[c] += __shfl_up_sync(0xffffffffu, FN2_TN_COMP(v2[c]), 1);
+                                }
+                                if (nrow > 3) {
+#pragma unroll
+                                    for (int c = 0; c < 8; c++) a1[c] += __shfl_up_sync(0xffffffffu, FN2_TN_COMP(v3[c]), 1);
+                                }
+                            }
+#undef FN2_TN_COMP
+                            const long long q2_ = prof_ ? clock64() : 0;
+                            // read-modify-write of 8 different channel planes: all loads first (the compiler must otherwise assume that
+                            // the store of plane c aliases the load of plane c+1 and serialises 8 shared-memory round trips)
+                            float* o = rowp + c0 * p.CW + ox0;
+                            float t_[8];
+#pragma unroll
+                            for (int c = 0; c < 8; c++) t_[c] = o[c * p.CW];
+#pragma unroll
+                            for (int c = 0; c < 8; c++) o[c * p.CW] = t_[c] + a0[c];
+                            if (S == 2 && nrow > 1) {
+                                __syncwarp();
+                                float* o1 = rowp + c0 * p.CW + ox1;
+#pragma unroll
+                                for (int c = 0; c < 8; c++) t_[c] = o1[c * p.CW];
+#pragma unroll
+                                for (int c = 0; c < 8; c++) o1[c * p.CW] = t_[c] + a1[c];
+                            }
+                            __syncwarp();
+                            if (prof_) { const long long q3_ = clock64(); tA_ += q1_ - q0_; tB_ += q2_ - q1_; tC_ += q3_ - q2_; }
                         }
-                        __syncwarp();
                     }
                     fence_before();
                     mbar_arrive(&acc_free[buf]);
                     if (buf) pfull ^= 1u;
                     buf ^= 1;
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (!(p.dbg & 128)) tn_group_sync(h);
+                    if (prof_) ts_ += clock64() - c1_;
                 }
-                // rows no later tile of this unit can touch: write them out (inside the segment / image) and clear them
-                const int lo_row = k == 0 ? touched_lo : prev_hi;
+                long long c2_ = prof_ ? clock64() : 0;
+                // rows no later tile of this unit can touch: write them out (inside the segment / image) and clear them.  The two
+                // channel halves never meet in the ring, so each group of 4 warps flushes its own half on its own barrier.
                 const int hi_row = (k == U.ntiles - 1) ? (i0 + p.th - 1) * p.S + p.oy_max + 1 : (i0 + p.th) * p.S + p.oy_min;
-                prev_hi = hi_row;
-                {
-                    constexpr int CG = CO / 4;                 // float4 groups per pixel
-                    constexpr int XPI = TN_DRAIN / CG;         // columns per iteration
-                    const int cg = dt % CG, xi0 = dt / CG;
-                    float bv[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (p.has_bias) { bv[0] = __ldg(bias + 4 * cg); bv[1] = __ldg(bias + 4 * cg + 1); bv[2] = __ldg(bias + 4 * cg + 2); bv[3] = __ldg(bias + 4 * cg + 3); }
+                if (k == 0) flush_lo = touched_lo;
+                const bool do_flush = (k == U.ntiles - 1) || (++since_flush == p.F);
+                const int lo_row = flush_lo;
+                if (do_flush) { since_flush = 0; flush_lo = hi_row; }
+                if (do_flush && !(p.dbg & 2)) {
+                    constexpr int CG = CH / 4;                 // float4 groups per pixel in this half
+                    constexpr int XPI = 128 / CG;              // columns per iteration
+                    const int d128 = dt & 127;
+                    const int cg = d128 % CG, xi0 = d128 / CG;
+                    const int cbase = h * CH + 4 * cg;
                     for (int y = max(lo_row, U.R0); y < min(hi_row, U.R1); y++) {
                         int ring = rb + (y - touched_lo);
                         if (ring >= p.RR) ring -= p.RR;
-                        const float* src_o = obuf + ring * rowstride + (4 * cg) * p.CW + (xc_lo - x_base);
-                        float* dst = out + U.n * p.out_sn + (long long)y * p.out_sh + (long long)xc_lo * p.out_sw + 4 * cg;
+                        if (ring < 0) ring += p.RR;
+                        const float* src_o = obuf + ring * rowstride + cbase * p.CW + (xc_lo - x_base);
+                        float* dst = out + U.n * p.out_sn + (long long)y * p.out_sh + (long long)xc_lo * p.out_sw + cbase;
                         for (int xi = xi0; xi < ncol; xi += XPI) {
                             float rv[4];
 #pragma unroll
@@ -350,26 +434,35 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         }
                     }
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                {
-                    const int n4 = rowstride >> 2;             // rowstride is a multiple of 4 (CW even)
+                if (do_flush && !(p.dbg & 128)) tn_group_sync(h);
+                long long c3_ = prof_ ? clock64() : 0;
+                tf_ += c3_ - c2_;
+                if (do_flush && !(p.dbg & 2)) {
+                    const int n4 = (CH * p.CW) >> 2;           // this half of a ring row, a multiple of 4 floats (CW even)
+                    const int d128 = dt & 127;
                     for (int y = lo_row; y < hi_row; y++) {
                         int ring = rb + (y - touched_lo);
                         if (ring >= p.RR) ring -= p.RR;
-                        float4* z = reinterpret_cast<float4*>(obuf + ring * rowstride);
-                        for (int e = dt; e < n4; e += TN_DRAIN) z[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ring < 0) ring += p.RR;
+                        float4* z = reinterpret_cast<float4*>(obuf + ring * rowstride + h * CH * p.CW);
+                        for (int e = d128; e < n4; e += 128) z[e] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (do_flush && !(p.dbg & 128)) tn_group_sync(h);
+                if (prof_) { tz_ += clock64() - c3_; ntl_++; }
                 rb += advance;
                 while (rb >= p.RR) rb -= p.RR;
             }
         }
+        if (prof_ && blockIdx.x == 1 && (tid == 256 || tid == 384))
+            printf("tn drain h=%d: %d tiles, per tile cycles: wait acc_full %lld, scatter %lld (tmem ld+wait %lld, comp+shuffle %lld, smem rmw %lld), write-out %lld, zero %lld\n", h, ntl_,
+                   tw_ / max(1, ntl_), ts_ / max(1, ntl_), tA_ / max(1, ntl_), tB_ / max(1, ntl_), tC_ / max(1, ntl_), tf_ / max(1, ntl_), tz_ / max(1, ntl_));
     }
     fence_before();
     __syncthreads();
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
+
 
 
 // ---- host ---------------------------------------------------------------------------------------------------------------
@@ -450,10 +543,32 @@ static bool tn_layer_plan(const fn2_conv_desc* d, TnParams* p) {
         t0 += p->pass_ntaps[i];
         p->ngmax = max(p->ngmax, p->pass_ntaps[i] * d->co);
     }
+    // scatter plan per pass
+    for (int i = 0; i < p->npass; i++) {
+        int tl = 0, ng = 0;
+        while (tl < p->pass_ntaps[i]) {
+            const int t = p->pass_tap0[i] + tl, r = t / d->kw, sa = t - r * d->kw;
+            const int nrow = min(d->kw - sa, p->pass_ntaps[i] - tl);
+            if (ng >= 4) return false;
+            TnParams::Grp& G = p->grp[i][ng++];
+            G.tl0 = (short)tl; G.nrow = (short)nrow; G.oyr = (short)p->oy[r]; G.ncls = (short)min(p->S, nrow);
+            for (int cls = 0; cls < G.ncls; cls++) {
+                G.ox0[cls] = (short)p->ox[sa + cls]; G.np[cls] = 0;
+                for (int s_ = cls + p->S; s_ < nrow; s_ += p->S) {
+                    const int k = G.np[cls]++;
+                    G.ps[cls][k] = (short)s_;
+                    G.sh[cls][k] = (short)((p->ox[sa + s_] - p->ox[sa + cls]) / p->S);
+                }
+            }
+            tl += nrow;
+        }
+        p->ngrp[i] = ng;
+    }
     // tile: one warp of the drain group = one (tw = 32) or two (tw = 16) input rows
     p->tw = 32; p->th = 4;
     p->CW = p->S * (p->tw - 1) + (ox_max - p->ox_min) + 1;
-    p->RR = (p->th - 1) * p->S + (p->oy_max - p->oy_min) + 1;
+    const int span = (p->th - 1) * p->S + (p->oy_max - p->oy_min) + 1;       // output rows one tile can touch
+    p->F = 1; p->RR = span;
     // complete output columns of a strip at c0 = 0: x such that every input column that contributes lies in [0, tw)
     int xa = 1 << 30, xb = -(1 << 30);
     for (int x = -64; x < p->S * p->tw + 64; x++) {
@@ -477,17 +592,25 @@ static bool tn_layer_plan(const fn2_conv_desc* d, TnParams* p) {
     float bm = 1.67e-8f;
     if (const char* e = getenv("FN2_TN_COMP_B")) bm = (float)atof(e);
     p->comp = (nocomp && nocomp[0] == '0') ? 0.f : (2.0e-8f + 3.f * bm * (float)((d->ci + 7) / 8));
-    // shared memory: raw-A ring + W (resident if it all fits, else a ring of 2..3 stages) + barriers + output ring
+    // shared memory: raw-A ring + W (resident if it all fits, else a ring of 2..3 stages) + barriers + output ring.  The ring is
+    // flushed (written out + cleared, two barriers) every F tiles; a larger F needs (F-1) * th * S more ring rows.
     const int wstage = 2 * p->ngmax * 128;
-    const int ring = p->RR * d->co * p->CW * 4;
-    const int budget = 227 * 1024 - ring - 1024 - 256;
-    p->RA = 4;
     const int nwall = p->npass * p->cblocks;
-    if (!getenv("FN2_TN_NORES") && p->RA * TN_A_BYTES + nwall * wstage <= budget) { p->wres = 1; p->RW = 0; return true; }
-    p->wres = 0;
-    p->RW = min(3, (budget - p->RA * TN_A_BYTES) / wstage);
-    if (p->RW < 2) { p->RA = 2; p->RW = min(3, (budget - p->RA * TN_A_BYTES) / wstage); }
-    return p->RW >= 2;
+    int fmax = 4;
+    if (const char* e = getenv("FN2_TN_F")) fmax = max(1, min(8, atoi(e)));
+    for (int F = fmax; F >= 1; F--) {
+        p->F = F; p->RR = span + (F - 1) * p->th * p->S;
+        const int ring = p->RR * d->co * p->CW * 4;
+        const int budget = 227 * 1024 - ring - 1024 - 256;
+        p->RA = 4;
+        if (!getenv("FN2_TN_NORES") && p->RA * TN_A_BYTES + nwall * wstage <= budget) { p->wres = 1; p->RW = 0; return true; }
+        p->wres = 0;
+        p->RW = min(3, (budget - p->RA * TN_A_BYTES) / wstage);
+        if (p->RW >= 3) return true;                 // a 2-deep W ring costs more than the rarer flush saves (measured)
+        if (F == 1 && p->RW >= 2) return true;
+        if (F == 1) { p->RA = 2; p->RW = min(3, (budget - p->RA * TN_A_BYTES) / wstage); return p->RW >= 2; }
+    }
+    return false;
 }
 static int tn_smem_bytes(const TnParams& p) {
     const int wstage = 2 * p.ngmax * 128;
@@ -531,6 +654,7 @@ int conv_tn_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
     TnParams p;
     if (!tn_layer_plan(d, &p)) { set_error("conv_tn: layer not eligible"); return FN2_ERR_INVALID; }
     p.N = in.n; p.Hin = in.h; p.Win = in.w; p.Ho = out.h; p.Wo = out.w;
+    { const char* e = getenv("FN2_TN_DBG"); p.dbg = e ? atoi(e) : 0; }
     p.relu = d->relu; p.has_bias = d->has_bias; p.slope = d->negative_slope;
     p.out_sn = out.sn; p.out_sh = out.sh; p.out_sw = out.sw;
     p.nstrips = (p.Wo - (p.S * p.cshift + p.xa) + p.S * p.stepx - 1) / (p.S * p.stepx);
@@ -581,15 +705,17 @@ int conv_tn_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (d->co == 16) {
-        static int set16 = 0;
-        if (set16 < smem_bytes) { FN2_CUDA(cudaFuncSetAttribute(conv_tn_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); set16 = smem_bytes; }
-        FN2_CUDA(cudaLaunchKernelEx(&cfg, conv_tn_kernel<16>, mapA, mapW, bias, out.p, p));
-    } else {
-        static int set32 = 0;
-        if (set32 < smem_bytes) { FN2_CUDA(cudaFuncSetAttribute(conv_tn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); set32 = smem_bytes; }
-        FN2_CUDA(cudaLaunchKernelEx(&cfg, conv_tn_kernel<32>, mapA, mapW, bias, out.p, p));
+#define FN2_TN_LAUNCH(COV, SV)                                                                                          \
+    {                                                                                                                   \
+        static int set_ = 0;                                                                                            \
+        if (set_ < smem_bytes) { FN2_CUDA(cudaFuncSetAttribute(conv_tn_kernel<COV, SV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); set_ = smem_bytes; } \
+        FN2_CUDA(cudaLaunchKernelEx(&cfg, conv_tn_kernel<COV, SV>, mapA, mapW, bias, out.p, p));                        \
     }
+    if (d->co == 16 && p.S == 1) FN2_TN_LAUNCH(16, 1)
+    else if (d->co == 16) FN2_TN_LAUNCH(16, 2)
+    else if (p.S == 1) FN2_TN_LAUNCH(32, 1)
+    else FN2_TN_LAUNCH(32, 2)
+#undef FN2_TN_LAUNCH
     FN2_LAUNCH_CHECK();
     return FN2_OK;
 }
