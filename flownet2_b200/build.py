@@ -28,6 +28,7 @@ SOURCES = [
     ("fn2_ops.cu", ["-fmad=false"]),        # bit-exact streaming layers, see file header
     ("fn2_corr.cu", []),
     ("fn2_corr_fast.cu", []),
+    ("fn2_corr_bwd.cu", []),
     ("fn2_conv.cu", []),
     ("fn2_conv_nhwc.cu", []),
     ("fn2_conv_tc.cu", []),

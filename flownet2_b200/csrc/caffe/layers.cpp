@@ -413,6 +413,52 @@ class CorrelationLayer : public Layer<Dtype> {
 };
 REGISTER_LAYER_CLASS(Correlation);
 
+// Correlation1D (correlation_layer1d.cpp:13-84, correlation_layer1d.cu): displacement along x only (DispNet-style nets).
+template <typename Dtype>
+class Correlation1DLayer : public Layer<Dtype> {
+ public:
+    explicit Correlation1DLayer(const LayerParameter& p) : Layer<Dtype>(p) {}
+    const char* type() const override { return "Correlation1D"; }
+    int ExactNumBottomBlobs() const override { return 2; }
+    int ExactNumTopBlobs() const override { return 1; }
+    void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        CorrelationParameter cp = this->layer_param_.correlation_param();
+        CHECK(cp.has_kernel_size()) << "Filter kernel_size is not set";
+        CHECK(cp.has_max_displacement()) << "Max displacement is required.";
+        kernel_size_ = cp.kernel_size();
+        CHECK(kernel_size_ % 2 == 1) << "Odd kernel size required";
+        max_displacement_ = cp.max_displacement();
+        pad_size_ = cp.pad();
+        stride1_ = cp.stride_1();
+        stride2_ = cp.stride_2();
+        single_direction_ = cp.single_direction();
+        CHECK(single_direction_ >= -1 && single_direction_ <= 1) << "single_direction must be -1 (left), 0 (off), or 1 (right)";
+        corr_type_ = cp.correlation_type();
+    }
+    void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        CHECK_EQ(bottom[0]->width(), bottom[1]->width()) << "Both bottom blobs must have same width";
+        CHECK_EQ(bottom[0]->height(), bottom[1]->height()) << "Both bottom blobs must have same height";
+        CHECK_EQ(bottom[0]->channels(), bottom[1]->channels()) << "Both bottom blobs must have same number of channels";
+        int tc, th, tw;
+        FN2_CALL(fn2_correlation1d_shape(bottom[0]->height(), bottom[0]->width(), pad_size_, kernel_size_, max_displacement_,
+                                         stride1_, stride2_, single_direction_, &tc, &th, &tw));
+        top[0]->Reshape(bottom[0]->num(), tc, th, tw);
+    }
+ protected:
+    void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        fn2_tensor b0 = bottom[0]->tensor(), b1 = bottom[1]->tensor(), t = top[0]->mutable_tensor();
+        FN2_CALL(fn2_correlation1d_forward(&b0, &b1, &t, pad_size_, kernel_size_, max_displacement_, stride1_, stride2_,
+                                           single_direction_, corr_type_, S()));
+    }
+    void WorkEstimate(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top, double* flops,
+                      double* bytes) const override {
+        *bytes = 4.0 * (bottom[0]->count() + bottom[1]->count() + top[0]->count());
+        *flops = 2.0 * top[0]->count() * (double)kernel_size_ * kernel_size_ * bottom[0]->channels();
+    }
+    int kernel_size_ = 0, max_displacement_ = 0, pad_size_ = 0, stride1_ = 1, stride2_ = 1, corr_type_ = 0, single_direction_ = 0;
+};
+REGISTER_LAYER_CLASS(Correlation1D);
+
 // ---------------------------------------------------------------------------------------------
 // Convolution / Deconvolution (base_conv_layer.cpp:12-254, conv_layer.cpp, deconv_layer.cpp).
 // group == 1 and dilation == 1 (all FlowNet2 layers); several bottom/top pairs share the weights

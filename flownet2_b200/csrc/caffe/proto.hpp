@@ -88,6 +88,7 @@ struct CorrelationParameter {                  // caffe.proto:628-644
     int stride_1() const { return m->i("stride_1", 1); }
     int stride_2() const { return m->i("stride_2", 1); }
     bool do_abs() const { return m->b("do_abs", false); }
+    int single_direction() const { return m->i("single_direction", 0); }   // Correlation1D: -1 left, 0 both, +1 right
     int correlation_type() const;              // 0 MULTIPLY, 1 SUBTRACT
 };
 

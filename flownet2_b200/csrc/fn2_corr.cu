@@ -10,8 +10,7 @@
 //                   the image contribute 0) and the per-displacement reduction is a warp shuffle
 //                   instead of the reference's serial lane-0 sum (:101-105, which races with the
 //                   next iteration's `sum[ch_off] = 0` on post-Volta parts).
-// Backward (MULTIPLY): gather form of CorrelateDataBackward0/1 (:118-249) with the ROUND_OFF
-// integer range arithmetic restated literally, batched over samples.
+// Backward (2-D and 1-D, MULTIPLY and SUBTRACT) and the Correlation1D forward live in fn2_corr_bwd.cu.
 #include "fn2_common.cuh"
 
 namespace fn2 {
@@ -24,6 +23,14 @@ int corr_fast_eligible(const T4& b0, const T4& b1, const T4& top, int pad, int k
 int corr_fast_workspace(int N, int C, int H, int W, int md, int s2, size_t* bytes);
 int corr_fast_forward(const T4& b0, const T4& b1, const T4& top, int md, int s2, void* ws,
                       size_t ws_bytes, cudaStream_t st);
+size_t corr_bwd_workspace_floats(int N, int C, int H, int W, int D, int k, int s1, int pad, int md, int topH, int topW, int corr_type, int one_d);
+int corr_bwd_2d(const T4& b0, const T4& b1, const T4& td, const T4& d0, const T4& d1, int pad, int k, int md, int s1, int s2, int corr_type,
+                float* ws, size_t ws_floats, cudaStream_t st);
+int corr1d_shape(int H, int W, int pad, int k, int md, int s1, int s2, int single_direction, int* tc, int* th, int* tw);
+int corr1d_forward(const T4& b0, const T4& b1, const T4& top, int pad, int k, int md, int s1, int s2, int single_direction, int corr_type,
+                   cudaStream_t st);
+int corr_bwd_1d(const T4& b0, const T4& b1, const T4& td, const T4& d0, const T4& d1, int pad, int k, int md, int s1, int s2,
+                int single_direction, int corr_type, float* ws, size_t ws_floats, cudaStream_t st);
 
 static int corr_shape(int H, int W, int pad, int k, int md, int s1, int s2, int* tc, int* th, int* tw,
                       int* gr, int* gw) {
@@ -90,72 +97,6 @@ __global__ void __launch_bounds__(128) corr_generic_kernel(T4 b0, T4 b1, T4 top,
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) top.p[top.off(n, tc, y, x)] = acc / (float)sumelems;   // :106-108
-    }
-}
-
-#define FN2_ROUND_OFF 50000   // correlation_layer.cu:13
-
-// which = 0: gradient w.r.t. bottom0 (CorrelateDataBackward0 :118-179)
-// which = 1: gradient w.r.t. bottom1 (CorrelateDataBackward1 :185-249)
-// `other` is bottom1 for which==0 and bottom0 for which==1; reads outside the image return the
-// zero of the reference's padded buffers.
-template <int WHICH>
-__global__ void corr_bwd_kernel(T4 other, T4 tdiff, T4 bdiff, CorrP p) {
-    const int C = bdiff.c, H = bdiff.h, W = bdiff.w;
-    const long long total = bdiff.count();
-    const int kr = (p.k - 1) / 2;
-    const int round_off = FN2_ROUND_OFF;
-    const int round_off_s1 = p.s1 * round_off;
-    const int sumelems = (kr * 2 + 1) * (kr * 2 + 1) * C;
-    for (long long index = blockIdx.x * (long long)blockDim.x + threadIdx.x; index < total;
-         index += (long long)gridDim.x * blockDim.x) {
-        const int n = (int)(index % C);                              // channel (:124)
-        const int l = (int)((index / C) % W) + p.pad;                // :125
-        const int m = (int)((index / C / W) % H) + p.pad;            // :126
-        const int item = (int)(index / ((long long)C * W * H));
-        float sum = 0.f;
-        if (WHICH == 0) {
-            int xmin = (l - 2 * kr - p.md + round_off_s1 - 1) / p.s1 + 1 - round_off;   // :131
-            int ymin = (m - 2 * kr - p.md + round_off_s1 - 1) / p.s1 + 1 - round_off;
-            int xmax = (l - p.md + round_off_s1) / p.s1 - round_off;                     // :135
-            int ymax = (m - p.md + round_off_s1) / p.s1 - round_off;
-            if (xmax >= 0 && ymax >= 0 && (xmin <= p.topW - 1) && (ymin <= p.topH - 1)) {
-                xmin = max(0, xmin); xmax = min(p.topW - 1, xmax);
-                ymin = max(0, ymin); ymax = min(p.topH - 1, ymax);
-                for (int pp = -p.gr; pp <= p.gr; pp++)
-                    for (int o = -p.gr; o <= p.gr; o++) {
-                        const int s2o = p.s2 * o, s2p = p.s2 * pp;
-                        const int yy = m + s2p - p.pad, xx = l + s2o - p.pad;
-                        const float bot1tmp = (yy >= 0 && yy < H && xx >= 0 && xx < W)
-                                                  ? other.p[other.off(item, n, yy, xx)] : 0.f;
-                        const int op = (pp + p.gr) * p.gw + (o + p.gr);
-                        for (int y = ymin; y <= ymax; y++)
-                            for (int x = xmin; x <= xmax; x++)
-                                sum += tdiff.p[tdiff.off(item, op, y, x)] * bot1tmp;
-                    }
-            }
-        } else {
-            for (int pp = -p.gr; pp <= p.gr; pp++)
-                for (int o = -p.gr; o <= p.gr; o++) {
-                    const int s2o = p.s2 * o, s2p = p.s2 * pp;
-                    int xmin = (l - 2 * kr - p.md - s2o + round_off_s1 - 1) / p.s1 + 1 - round_off;   // :208
-                    int ymin = (m - 2 * kr - p.md - s2p + round_off_s1 - 1) / p.s1 + 1 - round_off;
-                    int xmax = (l - p.md - s2o + round_off_s1) / p.s1 - round_off;
-                    int ymax = (m - p.md - s2p + round_off_s1) / p.s1 - round_off;
-                    if (xmax >= 0 && ymax >= 0 && (xmin <= p.topW - 1) && (ymin <= p.topH - 1)) {
-                        xmin = max(0, xmin); xmax = min(p.topW - 1, xmax);
-                        ymin = max(0, ymin); ymax = min(p.topH - 1, ymax);
-                        const int yy = m - s2p - p.pad, xx = l - s2o - p.pad;
-                        const float bot0tmp = (yy >= 0 && yy < H && xx >= 0 && xx < W)
-                                                  ? other.p[other.off(item, n, yy, xx)] : 0.f;
-                        const int op = (pp + p.gr) * p.gw + (o + p.gr);
-                        for (int y = ymin; y <= ymax; y++)
-                            for (int x = xmin; x <= xmax; x++)
-                                sum += tdiff.p[tdiff.off(item, op, y, x)] * bot0tmp;
-                    }
-                }
-        }
-        bdiff.p[bdiff.off(item, n, m - p.pad, l - p.pad)] = sum / (float)sumelems;
     }
 }
 
@@ -232,28 +173,89 @@ int fn2_correlation_forward(const fn2_tensor* bottom0, const fn2_tensor* bottom1
     return FN2_OK;
 }
 
+int fn2_correlation_backward_workspace_bytes(int N, int C, int H, int W, int pad, int kernel_size, int max_displacement,
+                                             int stride1, int stride2, int corr_type, size_t* bytes) {
+    FN2_CHECK_ARG(bytes, "correlation_backward_workspace_bytes: null out pointer");
+    int gr, gw, tc, th, tw;
+    int rc = corr_shape(H, W, pad, kernel_size, max_displacement, stride1, stride2, &tc, &th, &tw, &gr, &gw);
+    if (rc) return rc;
+    *bytes = corr_bwd_workspace_floats(N, C, H, W, tc, kernel_size, stride1, pad, max_displacement, th, tw, corr_type, 0) * sizeof(float);
+    return FN2_OK;
+}
+
 int fn2_correlation_backward(const fn2_tensor* bottom0, const fn2_tensor* bottom1,
                              const fn2_tensor* top_diff, const fn2_tensor* bottom0_diff,
                              const fn2_tensor* bottom1_diff, int pad, int kernel_size,
-                             int max_displacement, int stride1, int stride2, void* stream) {
+                             int max_displacement, int stride1, int stride2, int corr_type,
+                             void* workspace, size_t workspace_bytes, void* stream) {
     FN2_CHECK_ARG(valid(bottom0) && valid(bottom1) && valid(top_diff) && valid(bottom0_diff) && valid(bottom1_diff),
                   "correlation_backward: null/empty tensor");
     T4 b0 = view(bottom0), b1 = view(bottom1), td = view(top_diff), d0 = view(bottom0_diff), d1 = view(bottom1_diff);
     FN2_CHECK_ARG(same_dims(b0, b1) && same_dims(b0, d0) && same_dims(b0, d1), "correlation_backward: bottom shape mismatch");
+    FN2_CHECK_ARG(corr_type == 0 || corr_type == 1, "correlation_backward: unknown correlation_type %d", corr_type);
+    FN2_CHECK_ARG(corr_type == 0 || pad <= max_displacement, "correlation_backward: SUBTRACT needs pad <= max_displacement (the reference "
+                  "reads past its padded buffers otherwise)");
     CorrP p;
     int rc = corr_shape(b0.h, b0.w, pad, kernel_size, max_displacement, stride1, stride2, &p.topC,
                         &p.topH, &p.topW, &p.gr, &p.gw);
     if (rc) return rc;
     FN2_CHECK_ARG(td.n == b0.n && td.c == p.topC && td.h == p.topH && td.w == p.topW,
                   "correlation_backward: top_diff shape mismatch");
-    p.pad = pad; p.k = kernel_size; p.md = max_displacement; p.s1 = stride1; p.s2 = stride2; p.type = 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int grid = ew_grid(d0.count(), 256);
-    corr_bwd_kernel<0><<<grid, 256, 0, st>>>(b1, td, d0, p);
-    FN2_LAUNCH_CHECK();
-    corr_bwd_kernel<1><<<grid, 256, 0, st>>>(b0, td, d1, p);
-    FN2_LAUNCH_CHECK();
+    return corr_bwd_2d(b0, b1, td, d0, d1, pad, kernel_size, max_displacement, stride1, stride2, corr_type, (float*)workspace,
+                       workspace_bytes / sizeof(float), (cudaStream_t)stream);
+}
+
+/* Correlation1D (correlation_layer1d.{cpp,cu}): displacement along x only; single_direction -1 left, 0 both, +1 right. */
+int fn2_correlation1d_shape(int H, int W, int pad, int kernel_size, int max_displacement, int stride1, int stride2,
+                            int single_direction, int* top_channels, int* top_h, int* top_w) {
+    int tc, th, tw;
+    int rc = corr1d_shape(H, W, pad, kernel_size, max_displacement, stride1, stride2, single_direction, &tc, &th, &tw);
+    if (rc) return rc;
+    if (top_channels) *top_channels = tc;
+    if (top_h) *top_h = th;
+    if (top_w) *top_w = tw;
     return FN2_OK;
+}
+
+int fn2_correlation1d_forward(const fn2_tensor* bottom0, const fn2_tensor* bottom1, const fn2_tensor* top, int pad, int kernel_size,
+                              int max_displacement, int stride1, int stride2, int single_direction, int corr_type, void* stream) {
+    FN2_CHECK_ARG(valid(bottom0) && valid(bottom1) && valid(top), "correlation1d: null/empty tensor");
+    T4 b0 = view(bottom0), b1 = view(bottom1), tp = view(top);
+    FN2_CHECK_ARG(same_dims(b0, b1), "Both bottom blobs must have same shape (correlation_layer1d.cpp:44-46)");
+    FN2_CHECK_ARG(corr_type == 0 || corr_type == 1, "correlation1d: unknown correlation_type %d", corr_type);
+    int tc, th, tw;
+    int rc = corr1d_shape(b0.h, b0.w, pad, kernel_size, max_displacement, stride1, stride2, single_direction, &tc, &th, &tw);
+    if (rc) return rc;
+    FN2_CHECK_ARG(tp.n == b0.n && tp.c == tc && tp.h == th && tp.w == tw, "correlation1d: top must be (%d,%d,%d,%d)", b0.n, tc, th, tw);
+    return corr1d_forward(b0, b1, tp, pad, kernel_size, max_displacement, stride1, stride2, single_direction, corr_type, (cudaStream_t)stream);
+}
+
+int fn2_correlation1d_backward_workspace_bytes(int N, int C, int H, int W, int pad, int kernel_size, int max_displacement, int stride1,
+                                               int stride2, int single_direction, int corr_type, size_t* bytes) {
+    FN2_CHECK_ARG(bytes, "correlation1d_backward_workspace_bytes: null out pointer");
+    int tc, th, tw;
+    int rc = corr1d_shape(H, W, pad, kernel_size, max_displacement, stride1, stride2, single_direction, &tc, &th, &tw);
+    if (rc) return rc;
+    *bytes = corr_bwd_workspace_floats(N, C, H, W, tc, kernel_size, stride1, pad, max_displacement, th, tw, corr_type, 1) * sizeof(float);
+    return FN2_OK;
+}
+
+int fn2_correlation1d_backward(const fn2_tensor* bottom0, const fn2_tensor* bottom1, const fn2_tensor* top_diff,
+                               const fn2_tensor* bottom0_diff, const fn2_tensor* bottom1_diff, int pad, int kernel_size,
+                               int max_displacement, int stride1, int stride2, int single_direction, int corr_type,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+    FN2_CHECK_ARG(valid(bottom0) && valid(bottom1) && valid(top_diff) && valid(bottom0_diff) && valid(bottom1_diff),
+                  "correlation1d_backward: null/empty tensor");
+    T4 b0 = view(bottom0), b1 = view(bottom1), td = view(top_diff), d0 = view(bottom0_diff), d1 = view(bottom1_diff);
+    FN2_CHECK_ARG(same_dims(b0, b1) && same_dims(b0, d0) && same_dims(b0, d1), "correlation1d_backward: bottom shape mismatch");
+    FN2_CHECK_ARG(corr_type == 0 || corr_type == 1, "correlation1d_backward: unknown correlation_type %d", corr_type);
+    FN2_CHECK_ARG(corr_type == 0 || pad <= max_displacement, "correlation1d_backward: SUBTRACT needs pad <= max_displacement");
+    int tc, th, tw;
+    int rc = corr1d_shape(b0.h, b0.w, pad, kernel_size, max_displacement, stride1, stride2, single_direction, &tc, &th, &tw);
+    if (rc) return rc;
+    FN2_CHECK_ARG(td.n == b0.n && td.c == tc && td.h == th && td.w == tw, "correlation1d_backward: top_diff shape mismatch");
+    return corr_bwd_1d(b0, b1, td, d0, d1, pad, kernel_size, max_displacement, stride1, stride2, single_direction, corr_type,
+                       (float*)workspace, workspace_bytes / sizeof(float), (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -57,11 +57,52 @@ def correlation(b0, b1, pad, kernel_size, max_displacement, stride1, stride2, co
     return out
 
 
-def correlation_backward(b0, b1, top_diff, pad, kernel_size, max_displacement, stride1, stride2):
+def _ws(nbytes, dev):
+    return torch.zeros(max(int(nbytes), 4), dtype=torch.uint8, device=dev)
+
+
+def correlation_backward(b0, b1, top_diff, pad, kernel_size, max_displacement, stride1, stride2, corr_type=0):
     g0, g1 = torch.empty_like(b0), torch.empty_like(b1)
+    N, Cc, H, W = b0.shape
+    nb = C.c_size_t(0)
+    check(lib().fn2_correlation_backward_workspace_bytes(N, Cc, H, W, pad, kernel_size, max_displacement, stride1, stride2, corr_type,
+                                                         C.byref(nb)))
+    ws = _ws(nb.value, b0.device)
     d0, d1, dt, dg0, dg1 = desc(b0), desc(b1), desc(top_diff), desc(g0), desc(g1)
     check(lib().fn2_correlation_backward(C.byref(d0), C.byref(d1), C.byref(dt), C.byref(dg0), C.byref(dg1), pad,
-                                         kernel_size, max_displacement, stride1, stride2, _stream()))
+                                         kernel_size, max_displacement, stride1, stride2, corr_type,
+                                         C.c_void_p(ws.data_ptr()), C.c_size_t(nb.value), _stream()))
+    return g0, g1
+
+
+def correlation1d_shape(H, W, pad, kernel_size, max_displacement, stride1, stride2, single_direction=0):
+    tc, th, tw = C.c_int(), C.c_int(), C.c_int()
+    check(lib().fn2_correlation1d_shape(H, W, pad, kernel_size, max_displacement, stride1, stride2, single_direction,
+                                        C.byref(tc), C.byref(th), C.byref(tw)))
+    return tc.value, th.value, tw.value
+
+
+def correlation1d(b0, b1, pad, kernel_size, max_displacement, stride1, stride2, single_direction=0, corr_type=0):
+    N, Cc, H, W = b0.shape
+    tc, th, tw = correlation1d_shape(H, W, pad, kernel_size, max_displacement, stride1, stride2, single_direction)
+    out = _empty((N, tc, th, tw), b0)
+    d0, d1, dt = desc(b0), desc(b1), desc(out)
+    check(lib().fn2_correlation1d_forward(C.byref(d0), C.byref(d1), C.byref(dt), pad, kernel_size, max_displacement, stride1,
+                                          stride2, single_direction, corr_type, _stream()))
+    return out
+
+
+def correlation1d_backward(b0, b1, top_diff, pad, kernel_size, max_displacement, stride1, stride2, single_direction=0, corr_type=0):
+    g0, g1 = torch.empty_like(b0), torch.empty_like(b1)
+    N, Cc, H, W = b0.shape
+    nb = C.c_size_t(0)
+    check(lib().fn2_correlation1d_backward_workspace_bytes(N, Cc, H, W, pad, kernel_size, max_displacement, stride1, stride2,
+                                                           single_direction, corr_type, C.byref(nb)))
+    ws = _ws(nb.value, b0.device)
+    d0, d1, dt, dg0, dg1 = desc(b0), desc(b1), desc(top_diff), desc(g0), desc(g1)
+    check(lib().fn2_correlation1d_backward(C.byref(d0), C.byref(d1), C.byref(dt), C.byref(dg0), C.byref(dg1), pad, kernel_size,
+                                           max_displacement, stride1, stride2, single_direction, corr_type,
+                                           C.c_void_p(ws.data_ptr()), C.c_size_t(nb.value), _stream()))
     return g0, g1
 
 

@@ -66,11 +66,31 @@ FN2_API int fn2_correlation_forward(const fn2_tensor* bottom0, const fn2_tensor*
                                     const fn2_tensor* top, int pad, int kernel_size,
                                     int max_displacement, int stride1, int stride2, int corr_type,
                                     void* workspace, size_t workspace_bytes, void* stream);
-/* MULTIPLY only.  Gradients w.r.t. both bottoms (CorrelateDataBackward0/1, :118-249). */
+/* Gradients w.r.t. both bottoms: CorrelateDataBackward0/1 (:118-249), ...Subtract (:298-427), driver :508-600.  Computed through
+ * the factorisation described in flownet2_b200/csrc/fn2_corr_bwd.cu (channel-free patch sum of top_diff, then a tiled
+ * displacement-sum against the other map); needs workspace unless kernel_size 1, stride_1 1, pad == max_displacement, MULTIPLY. */
+FN2_API int fn2_correlation_backward_workspace_bytes(int N, int C, int H, int W, int pad, int kernel_size, int max_displacement,
+                                                     int stride1, int stride2, int corr_type, size_t* bytes);
 FN2_API int fn2_correlation_backward(const fn2_tensor* bottom0, const fn2_tensor* bottom1,
                                      const fn2_tensor* top_diff, const fn2_tensor* bottom0_diff,
                                      const fn2_tensor* bottom1_diff, int pad, int kernel_size,
-                                     int max_displacement, int stride1, int stride2, void* stream);
+                                     int max_displacement, int stride1, int stride2, int corr_type,
+                                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Correlation1D -- replaces Correlation1DLayer (correlation_layer1d.cpp:37-84 shapes, correlation_layer1d.cu:48-112 forward,
+ * :116-247 backward): displacement along x only, rows are not padded.  single_direction: -1 left, 0 both, +1 right
+ * (caffe.proto CorrelationParameter.single_direction); top channel tc <-> x offset (tc + x_shift) * stride_2. */
+FN2_API int fn2_correlation1d_shape(int H, int W, int pad, int kernel_size, int max_displacement, int stride1, int stride2,
+                                    int single_direction, int* top_channels, int* top_h, int* top_w);
+FN2_API int fn2_correlation1d_forward(const fn2_tensor* bottom0, const fn2_tensor* bottom1, const fn2_tensor* top, int pad,
+                                      int kernel_size, int max_displacement, int stride1, int stride2, int single_direction,
+                                      int corr_type, void* stream);
+FN2_API int fn2_correlation1d_backward_workspace_bytes(int N, int C, int H, int W, int pad, int kernel_size, int max_displacement,
+                                                       int stride1, int stride2, int single_direction, int corr_type, size_t* bytes);
+FN2_API int fn2_correlation1d_backward(const fn2_tensor* bottom0, const fn2_tensor* bottom1, const fn2_tensor* top_diff,
+                                       const fn2_tensor* bottom0_diff, const fn2_tensor* bottom1_diff, int pad, int kernel_size,
+                                       int max_displacement, int stride1, int stride2, int single_direction, int corr_type,
+                                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------ */
 /* FlowWarp -- replaces FlowWarpLayer::Forward_gpu / Backward_gpu                         */

@@ -231,6 +231,118 @@ FN2O_API int fn2o_correlation_bwd(const float* bot0, const float* bot1, const fl
     return 0;
 }
 
+/* Correlation1D and the SUBTRACT gradients: correlation_layer1d.{cpp,cu} and correlation_layer.cu:298-427.
+ * The reference indexes zero padded NHWC copies; here out-of-image taps are the same zeros by coordinate test (for
+ * single_direction = -1 the reference's x_shift = -grid_width (correlation_layer1d.cu Forward_gpu) reaches stride_2 columns
+ * past its own padding into the neighbouring row's padding -- also zeros).
+ * one_d: rows are neither padded nor displaced (ymin/ymax without max_displacement, :134,:137).
+ * corr_type 1: sign = (bot0 >= bot1) ? +1 : -1 taken AT THE DISPLACED position for both gradients (:327-329, :397-399). */
+static float tap0(const float* b, int C, int H, int W, int n, int c, int y, int x) {
+    return (y >= 0 && y < H && x >= 0 && x < W) ? b[(((size_t)n * C + c) * H + y) * W + x] : 0.f;
+}
+FN2O_API int fn2o_correlation1d_shape(int H, int W, int pad, int kernel_size, int max_disp, int stride1, int stride2,
+                                      int single_direction, int* out) {
+    if (kernel_size % 2 == 0) return -1;
+    int kr = (kernel_size - 1) / 2, border = max_disp + kr;
+    int top_w = (int)ceilf((float)(W + 2 * pad - border * 2) / (float)stride1);      /* correlation_layer1d.cpp:55 */
+    int top_h = (int)ceilf((float)(H - kr * 2) / (float)stride1);                   /* :56 */
+    if (top_w < 1 || top_h < 1) return -2;
+    int gr = max_disp / stride2;
+    int gw = single_direction != 0 ? gr + 1 : gr * 2 + 1;                            /* :64-68 */
+    int x_shift = -gr;
+    if (single_direction == -1) x_shift = -gw; else if (single_direction == 1) x_shift = 0;
+    out[0] = gw; out[1] = top_h; out[2] = top_w; out[3] = gr; out[4] = x_shift;
+    return 0;
+}
+FN2O_API int fn2o_correlation1d_fwd(const float* bot0, const float* bot1, float* top, int N, int C, int H, int W, int pad,
+                                    int kernel_size, int max_disp, int stride1, int stride2, int single_direction, int corr_type) {
+    int shp[5];
+    int rc = fn2o_correlation1d_shape(H, W, pad, kernel_size, max_disp, stride1, stride2, single_direction, shp);
+    if (rc) return rc;
+    const int topC = shp[0], topH = shp[1], topW = shp[2], x_shift = shp[4];
+    const int sumelems = kernel_size * kernel_size * C;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int n = 0; n < N; n++)
+        for (int y = 0; y < topH; y++)
+            for (int x = 0; x < topW; x++) {
+                int x1 = x * stride1 + max_disp - pad, y1 = y * stride1;               /* unpadded; correlation_layer1d.cu:56-57 */
+                for (int tc = 0; tc < topC; tc++) {
+                    int s2o = (tc + x_shift) * stride2;                                 /* :83 */
+                    double acc = 0;
+                    for (int j = 0; j < kernel_size; j++)
+                        for (int i = 0; i < kernel_size; i++)
+                            for (int ch = 0; ch < C; ch++) {
+                                float a = tap0(bot0, C, H, W, n, ch, y1 + j, x1 + i);
+                                float b = tap0(bot1, C, H, W, n, ch, y1 + j, x1 + s2o + i);
+                                acc += corr_type == 0 ? (double)a * (double)b : (double)fabsf(a - b);
+                            }
+                    top[(((size_t)n * topC + tc) * topH + y) * topW + x] = (float)(acc / (double)sumelems);
+                }
+            }
+    return 0;
+}
+FN2O_API int fn2o_correlation_bwd_ex(const float* bot0, const float* bot1, const float* topdiff, float* bot0diff, float* bot1diff,
+                                     int N, int C, int H, int W, int pad, int kernel_size, int max_disp, int stride1, int stride2,
+                                     int corr_type, int one_d, int single_direction) {
+    int shp[5];
+    int topC, topH, topW, gr, gw = 0, x_shift = 0;
+    if (one_d) {
+        int rc = fn2o_correlation1d_shape(H, W, pad, kernel_size, max_disp, stride1, stride2, single_direction, shp);
+        if (rc) return rc;
+        topC = shp[0]; topH = shp[1]; topW = shp[2]; gr = shp[3]; x_shift = shp[4];
+    } else {
+        int rc = fn2o_correlation_shape(H, W, pad, kernel_size, max_disp, stride1, stride2, shp);
+        if (rc) return rc;
+        topC = shp[0]; topH = shp[1]; topW = shp[2]; gr = shp[3]; gw = shp[4];
+    }
+    const int kr = (kernel_size - 1) / 2;
+    const int sumelems = (kr * 2 + 1) * (kr * 2 + 1) * C;
+    const int ro = FN2O_ROUND_OFF, ros1 = stride1 * FN2O_ROUND_OFF;
+    const int ypad = one_d ? 0 : pad, ymd = one_d ? 0 : max_disp;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int item = 0; item < N; item++)
+        for (int my = 0; my < H; my++)
+            for (int lx = 0; lx < W; lx++)
+                for (int n = 0; n < C; n++) {
+                    const int l = lx + pad, m = my + ypad;
+                    double s0 = 0, s1 = 0;
+                    for (int tc = 0; tc < topC; tc++) {
+                        const int s2o = one_d ? (tc + x_shift) * stride2 : (tc % gw - gr) * stride2;
+                        const int s2p = one_d ? 0 : (tc / gw - gr) * stride2;
+                        /* gradient w.r.t. bottom0: ranges without the displacement (:131-140), other map at +displacement */
+                        {
+                            int xmin = (l - 2 * kr - max_disp + ros1 - 1) / stride1 + 1 - ro, xmax = (l - max_disp + ros1) / stride1 - ro;
+                            int ymin = (m - 2 * kr - ymd + ros1 - 1) / stride1 + 1 - ro, ymax = (m - ymd + ros1) / stride1 - ro;
+                            if (xmax >= 0 && ymax >= 0 && xmin <= topW - 1 && ymin <= topH - 1) {
+                                xmin = imax(0, xmin); xmax = imin(topW - 1, xmax); ymin = imax(0, ymin); ymax = imin(topH - 1, ymax);
+                                float a = tap0(bot0, C, H, W, item, n, my + s2p, lx + s2o), b = tap0(bot1, C, H, W, item, n, my + s2p, lx + s2o);
+                                float f = corr_type == 0 ? b : (a >= b ? 1.f : -1.f);
+                                for (int y = ymin; y <= ymax; y++)
+                                    for (int x = xmin; x <= xmax; x++)
+                                        s0 += (double)topdiff[(((size_t)item * topC + tc) * topH + y) * topW + x] * (double)f;
+                            }
+                        }
+                        /* gradient w.r.t. bottom1: ranges shifted by the displacement (:208-215), other map at -displacement */
+                        {
+                            int xmin = (l - 2 * kr - max_disp - s2o + ros1 - 1) / stride1 + 1 - ro, xmax = (l - max_disp - s2o + ros1) / stride1 - ro;
+                            int ymin = (m - 2 * kr - ymd - s2p + ros1 - 1) / stride1 + 1 - ro, ymax = (m - ymd - s2p + ros1) / stride1 - ro;
+                            if (xmax >= 0 && ymax >= 0 && xmin <= topW - 1 && ymin <= topH - 1) {
+                                xmin = imax(0, xmin); xmax = imin(topW - 1, xmax); ymin = imax(0, ymin); ymax = imin(topH - 1, ymax);
+                                float a = tap0(bot0, C, H, W, item, n, my - s2p, lx - s2o), b = tap0(bot1, C, H, W, item, n, my - s2p, lx - s2o);
+                                float f = corr_type == 0 ? a : (a >= b ? -1.f : 1.f);
+                                for (int y = ymin; y <= ymax; y++)
+                                    for (int x = xmin; x <= xmax; x++)
+                                        s1 += (double)topdiff[(((size_t)item * topC + tc) * topH + y) * topW + x] * (double)f;
+                            }
+                        }
+                    }
+                    const size_t o = (((size_t)item * C + n) * H + my) * W + lx;
+                    bot0diff[o] = (float)(s0 / (double)sumelems);
+                    bot1diff[o] = (float)(s1 / (double)sumelems);
+                }
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* FlowWarp                                                                             */
 /* ------------------------------------------------------------------------------------ */

@@ -72,6 +72,41 @@ def correlation_bwd(b0, b1, topdiff, pad, kernel_size, max_disp, stride1, stride
     return d0, d1
 
 
+def correlation1d_shape(H, W, pad, kernel_size, max_disp, stride1, stride2, single_direction=0):
+    out = (C.c_int * 5)()
+    rc = lib().fn2o_correlation1d_shape(H, W, pad, kernel_size, max_disp, stride1, stride2, single_direction, out)
+    if rc:
+        raise ValueError("correlation1d: invalid configuration (rc=%d)" % rc)
+    return tuple(out)  # top_channels, top_h, top_w, grid_radius, x_shift
+
+
+def correlation1d_fwd(b0, b1, pad, kernel_size, max_disp, stride1, stride2, single_direction=0, corr_type=0):
+    b0, p0 = _f(b0)
+    b1, p1 = _f(b1)
+    N, Cc, H, W = b0.shape
+    tc, th, tw, _, _ = correlation1d_shape(H, W, pad, kernel_size, max_disp, stride1, stride2, single_direction)
+    top = np.empty((N, tc, th, tw), np.float32)
+    rc = lib().fn2o_correlation1d_fwd(p0, p1, top.ctypes.data_as(C.POINTER(C.c_float)), N, Cc, H, W, pad, kernel_size, max_disp,
+                                      stride1, stride2, single_direction, corr_type)
+    assert rc == 0
+    return top
+
+
+def correlation_bwd_ex(b0, b1, topdiff, pad, kernel_size, max_disp, stride1, stride2, corr_type=0, one_d=False, single_direction=0):
+    """Gradients of Correlation (2-D) / Correlation1D, MULTIPLY or SUBTRACT, float64 accumulation."""
+    b0, p0 = _f(b0)
+    b1, p1 = _f(b1)
+    td, ptd = _f(topdiff)
+    N, Cc, H, W = b0.shape
+    d0 = np.empty_like(b0)
+    d1 = np.empty_like(b1)
+    rc = lib().fn2o_correlation_bwd_ex(p0, p1, ptd, d0.ctypes.data_as(C.POINTER(C.c_float)), d1.ctypes.data_as(C.POINTER(C.c_float)),
+                                       N, Cc, H, W, pad, kernel_size, max_disp, stride1, stride2, corr_type, 1 if one_d else 0,
+                                       single_direction)
+    assert rc == 0
+    return d0, d1
+
+
 def flow_warp_fwd(image, flow, fill_nan=False):
     image, pi = _f(image)
     flow, pf = _f(flow)

@@ -24,6 +24,14 @@ def _corr(name, C, H, W, pad, k, md, s1, s2, typ="MULTIPLY", N=2, backward=False
                 ntop=1, backward=backward, kind="correlation", args=(pad, k, md, s1, s2, 0 if typ == "MULTIPLY" else 1))
 
 
+def _corr1d(name, C, H, W, pad, k, md, s1, s2, sd=0, typ="MULTIPLY", N=2, backward=True):
+    text = ('name: "%s" type: "Correlation1D" bottom: "a" bottom: "b" top: "t" correlation_param { pad: %d kernel_size: %d '
+            'max_displacement: %d stride_1: %d stride_2: %d single_direction: %d correlation_type: %s }' % (name, pad, k, md, s1, s2, sd, typ))
+    return dict(text=text, inputs=lambda r: [r.standard_normal((N, C, H, W)).astype(np.float32),
+                                              r.standard_normal((N, C, H, W)).astype(np.float32)],
+                ntop=1, backward=backward, kind="correlation1d", args=(pad, k, md, s1, s2, sd, 0 if typ == "MULTIPLY" else 1))
+
+
 def _resample(name, shape, oh, ow, typ, antialias=True):
     text = ('name: "%s" type: "Resample" bottom: "x" top: "y" resample_param { width: %d height: %d type: %s antialias: %s }'
             % (name, ow, oh, typ, "true" if antialias else "false"))
@@ -97,6 +105,12 @@ LAYER_CASES = {
     "corr_s2_1": _corr("corr_s2_1", 16, 9, 11, 3, 1, 3, 1, 1, backward=True),
     "corr_sub": _corr("corr_sub", 16, 9, 11, 2, 1, 2, 1, 1, typ="SUBTRACT", backward=True),
     "corr_c40": _corr("corr_c40", 40, 7, 9, 4, 1, 4, 1, 2),                        # C not a multiple of 32 (lane-strided sum)
+    # ---- Correlation1D (correlation_layer1d.cu): x displacements only; both / left / right; SUBTRACT -------------------------
+    "corr1d_both": _corr1d("corr1d_both", 16, 7, 19, 8, 1, 8, 1, 2),
+    "corr1d_left": _corr1d("corr1d_left", 16, 7, 19, 8, 1, 8, 1, 2, sd=-1),
+    "corr1d_right": _corr1d("corr1d_right", 16, 7, 19, 8, 1, 8, 1, 2, sd=1),
+    "corr1d_k3": _corr1d("corr1d_k3", 8, 11, 21, 4, 3, 4, 2, 1),
+    "corr1d_sub": _corr1d("corr1d_sub", 8, 6, 15, 3, 1, 3, 1, 1, typ="SUBTRACT"),
     # ---- Resample (resample_layer.cu:40-125,128-206) ----------------------------------------------------------------------
     "rs_lin_up": _resample("rs_lin_up", (2, 3, 13, 17), 26, 34, "LINEAR"),
     "rs_lin_flow_up": _resample("rs_lin_flow_up", (1, 2, 16, 32), 61, 128, "LINEAR"),     # 112x256 -> 436x1024 in small

@@ -21,7 +21,7 @@ from oracle import oracle as O  # noqa: E402
 GOLD = os.path.join(HERE, "golden", "ref_golden.npz")
 
 # kind -> relative tolerance (of max |reference output|) for "same arithmetic, different rounding order"
-TOL = {"correlation": 6e-7, "resample": 1.5e-6, "resample_cubic": 6e-6, "channel_norm": 4e-7, "flow_warp": 5e-7, "conv": 3e-6,
+TOL = {"correlation": 6e-7, "correlation1d": 6e-7, "resample": 1.5e-6, "resample_cubic": 6e-6, "channel_norm": 4e-7, "flow_warp": 5e-7, "conv": 3e-6,
        "aug_deploy": 6e-7, "aug_train": 3e-5, "backward": 1e-6}
 
 
@@ -91,9 +91,18 @@ def oracle_eval(name, gold=None):
     if k == "correlation":
         pad, ks, md, s1, s2, typ = c["args"]
         out["top0"] = O.correlation_fwd(bottoms[0], bottoms[1], pad, ks, md, s1, s2, typ, exact_order=True)
-        if c.get("backward") and typ == 0:
+        if c.get("backward"):
             td = r.standard_normal(out["top0"].shape).astype(np.float32)
-            out["bdiff0"], out["bdiff1"] = O.correlation_bwd(bottoms[0], bottoms[1], td, pad, ks, md, s1, s2)
+            if typ == 0:
+                out["bdiff0"], out["bdiff1"] = O.correlation_bwd(bottoms[0], bottoms[1], td, pad, ks, md, s1, s2)
+            else:
+                out["bdiff0"], out["bdiff1"] = O.correlation_bwd_ex(bottoms[0], bottoms[1], td, pad, ks, md, s1, s2, 1)
+    elif k == "correlation1d":
+        pad, ks, md, s1, s2, sd, typ = c["args"]
+        out["top0"] = O.correlation1d_fwd(bottoms[0], bottoms[1], pad, ks, md, s1, s2, sd, typ)
+        if c.get("backward"):
+            td = r.standard_normal(out["top0"].shape).astype(np.float32)
+            out["bdiff0"], out["bdiff1"] = O.correlation_bwd_ex(bottoms[0], bottoms[1], td, pad, ks, md, s1, s2, typ, True, sd)
     elif k == "resample":
         oh, ow, t, aa = c["args"]
         out["top0"] = O.resample_fwd(bottoms[0], oh, ow, t, aa)

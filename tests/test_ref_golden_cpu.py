@@ -30,10 +30,7 @@ def test_oracle_matches_reference_layer(gold, name):
             if gold[full].any():              # all zero: no chromatic-eigen coefficient was active, the statistics never ran
                 RCK.check_eigenspace(gold[full], out["space"])
             continue
-        if key not in out:
-            # SUBTRACT backward has no oracle restatement yet
-            assert RC.LAYER_CASES[name]["args"][-1] == 1 and key.startswith("bdiff"), (name, key)
-            continue
+        assert key in out, (name, key)
         err = RCK.rel_err(out[key], gold[full])
         assert err <= RCK.tol_for(name, key), (name, key, err)
 

@@ -74,9 +74,18 @@ def engine_eval(fn2, ops, name, gold, channels_last):
         a, b = dev(bottoms[0], channels_last), dev(bottoms[1], channels_last)
         top = ops.correlation(a, b, pad, ks, md, s1, s2, typ)
         out["top0"] = host(top)
-        if c.get("backward") and typ == 0:
+        if c.get("backward"):
             td = dev(r.standard_normal(top.shape).astype(np.float32), channels_last)
-            g0, g1 = ops.correlation_backward(a, b, td, pad, ks, md, s1, s2)
+            g0, g1 = ops.correlation_backward(a, b, td, pad, ks, md, s1, s2, typ)
+            out["bdiff0"], out["bdiff1"] = host(g0), host(g1)
+    elif k == "correlation1d":
+        pad, ks, md, s1, s2, sd, typ = c["args"]
+        a, b = dev(bottoms[0], channels_last), dev(bottoms[1], channels_last)
+        top = ops.correlation1d(a, b, pad, ks, md, s1, s2, sd, typ)
+        out["top0"] = host(top)
+        if c.get("backward"):
+            td = dev(r.standard_normal(top.shape).astype(np.float32), channels_last)
+            g0, g1 = ops.correlation1d_backward(a, b, td, pad, ks, md, s1, s2, sd, typ)
             out["bdiff0"], out["bdiff1"] = host(g0), host(g1)
     elif k == "resample":
         oh, ow, t, aa = c["args"]
