@@ -200,8 +200,21 @@ def test_tcgen05_engine_plan_for_flownet2_shapes(fn2):
     # conv6_1: 28 tiles with K = 9*1024 -> uniform split-K over the SMs
     pl, ws = plan(1024, 1024, 3, 1, 1, 7, 16)
     assert pl[1] == 32 and 2 <= pl[4] <= 8 and ws >= pl[4] * 4 * 7 * 16 * 1024 * 4
-    # fusion interconv0: 16 output channels, full resolution, nothing to split
-    pl, _ = plan(82, 16, 3, 1, 1, 448, 1024, cis=96)
+    # fusion interconv0: 16 output channels at full resolution -> taps-on-N engine (mode 3): one pass of 9 x 16 = 144 accumulator
+    # columns, K = 3 blocks of 32 channels, 35 strips of 30 complete columns
+    pl, ws = plan(82, 16, 3, 1, 1, 448, 1024, cis=96)
+    assert pl[3] == 3 and pl[0] == -144 and pl[2] == 3 and pl[4] == 1 and pl[5] == 35 and ws == 0
+    # fusion deconv0 (4x4 stride 2, 16 outputs): two passes of 8 taps = 128 columns, 6 K blocks
+    pl, _ = plan(162, 16, 4, 2, 1, 224, 512, deconv=1, cis=192)
+    assert pl[3] == 3 and pl[0] == -128 and pl[2] == 6 and pl[4] == 2
+    # with the taps-on-N engine switched off the per-tap engine plans 27 steps of NT = 16 (checked in a subprocess: the switch is
+    # read once per process)
+    import subprocess, sys
+    code = ("import ctypes as C, flownet2_b200 as F; from flownet2_b200 import fn2_conv_desc; "
+            "d = fn2_conv_desc(82, 16, 3, 3, 1, 1, 1, 1, 0, 1, 1, 0.1, 0, 1024); o = (C.c_int32 * 8)(); "
+            "F.lib().fn2_conv_plan(C.byref(d), 4, 448, 1024, 96, o); print(list(o))")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, FN2_TN="0"), cwd=ROOT)
+    pl = eval(out.stdout.strip().splitlines()[-1])
     assert pl[0] == 16 and pl[3] == 0 and pl[4] == 1 and pl[2] == 27
     # flow predictor (2 output channels) is not a tensor-core layer
     pl, _ = plan(194, 2, 3, 1, 1, 112, 256)
