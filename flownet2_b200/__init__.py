@@ -33,7 +33,7 @@ class fn2_conv_desc(C.Structure):
     _fields_ = [("ci", C.c_int32), ("co", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
                 ("stride_h", C.c_int32), ("stride_w", C.c_int32), ("pad_h", C.c_int32), ("pad_w", C.c_int32),
                 ("deconv", C.c_int32), ("has_bias", C.c_int32), ("relu", C.c_int32), ("negative_slope", C.c_float),
-                ("engine", C.c_int32), ("input_guard_bytes", C.c_int32)]
+                ("engine", C.c_int32), ("input_guard_bytes", C.c_int32), ("out_pad_h", C.c_int32), ("out_pad_w", C.c_int32)]
 
 
 def lib_path():
@@ -63,8 +63,14 @@ def lib():
         l.fn2_net_destroy.restype = None
         for name in ("fn2_net_num_inputs", "fn2_net_num_outputs", "fn2_net_num_blobs", "fn2_net_num_layers",
                      "fn2_net_forward", "fn2_net_sync", "fn2_net_params_changed", "fn2_net_launches_per_forward",
-                     "fn2_net_graph_active"):
+                     "fn2_net_graph_active", "fn2_net_backward", "fn2_net_clear_param_diffs", "fn2_net_launches_per_backward"):
             getattr(l, name).argtypes = [C.c_void_p]
+        l.fn2_net_param_diff_arena.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        l.fn2_net_set_diff.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+        l.fn2_net_get_diff.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+        l.fn2_net_param_shape.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int)]
+        l.fn2_net_get_param.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p]
+        l.fn2_net_layer_need_backward.argtypes = [C.c_void_p, C.c_int]
         l.fn2_net_copy_trained_layers.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         l.fn2_net_to_caffemodel.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]
         l.fn2_net_fill_params.argtypes = [C.c_void_p, C.c_uint64]
@@ -94,6 +100,12 @@ def lib():
         l.fn2_conv_forward.argtypes = [D, T, C.c_void_p, C.c_void_p, T, C.c_void_p, C.c_size_t, C.c_void_p]
         l.fn2_conv_workspace_bytes.argtypes = [D, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
         l.fn2_relu_forward.argtypes = [T, T, C.c_float, C.c_void_p]
+        l.fn2_relu_backward.argtypes = [T, T, T, C.c_float, C.c_int, C.c_void_p]
+        l.fn2_axpby.argtypes = [T, C.c_float, T, C.c_float, C.c_void_p]
+        l.fn2_conv_backward_params_workspace_bytes.argtypes = [D, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
+        l.fn2_conv_backward_params.argtypes = [D, T, T, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+        l.fn2_conv_backward_data_desc.argtypes = [D, C.c_int, C.c_int, D, C.POINTER(C.c_int)]
+        l.fn2_conv_flip_transpose_weights.argtypes = [D, C.c_void_p, C.c_void_p, C.c_void_p]
         l.fn2_eltwise_sum.argtypes = [C.POINTER(T), C.POINTER(C.c_float), C.c_int, T, C.c_void_p]
         l.fn2_channel_norm_forward.argtypes = [T, T, C.c_void_p]
         l.fn2_copy.argtypes = [T, T, C.c_void_p]
@@ -255,6 +267,52 @@ class Net(object):
 
     def forward_async(self):
         check(lib().fn2_net_forward(self._h))
+
+    # ---- gradients (pycaffe.py:127-175 Net.backward; net.cpp:640-655) ----
+    def backward_async(self):
+        check(lib().fn2_net_backward(self._h))
+
+    def clear_param_diffs(self):
+        check(lib().fn2_net_clear_param_diffs(self._h))
+
+    def set_diff(self, name, array):
+        a = np.ascontiguousarray(array, dtype=np.float32)
+        if tuple(a.shape) != self.blobs[name].shape:
+            raise Fn2Error("diff of %s has shape %s, net expects %s" % (name, a.shape, self.blobs[name].shape))
+        check(lib().fn2_net_set_diff(self._h, name.encode(), a.ctypes.data_as(C.c_void_p)))
+
+    def get_diff(self, name):
+        out = np.empty(self.blobs[name].shape, np.float32)
+        self.sync()
+        check(lib().fn2_net_get_diff(self._h, name.encode(), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def backward(self, **kwargs):
+        """net.backward(flow=top_diff) -> {input blob name: gradient}; parameter gradients through net.param(layer, i, diff=True)."""
+        for k, v in kwargs.items():
+            self.set_diff(k, v)
+        self.backward_async()
+        self.sync()
+        return {}
+
+    def param(self, layer, index=0, diff=False):
+        shp = (C.c_int * 4)()
+        check(lib().fn2_net_param_shape(self._h, layer.encode(), int(index), shp))
+        out = np.empty(tuple(int(x) for x in shp), np.float32)
+        check(lib().fn2_net_get_param(self._h, layer.encode(), int(index), 1 if diff else 0, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def param_diff_arena(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        check(lib().fn2_net_param_diff_arena(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def layer_need_backward(self):
+        return [bool(lib().fn2_net_layer_need_backward(self._h, i)) for i in range(len(self.layer_names))]
+
+    @property
+    def launches_per_backward(self):
+        return int(lib().fn2_net_launches_per_backward(self._h))
 
     def sync(self):
         check(lib().fn2_net_sync(self._h))

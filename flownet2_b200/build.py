@@ -33,6 +33,7 @@ SOURCES = [
     ("fn2_conv_nhwc.cu", []),
     ("fn2_conv_tc.cu", []),
     ("fn2_conv_tn.cu", []),
+    ("fn2_train.cu", []),
     ("caffe/proto.cpp", []),
     ("caffe/blob.cpp", []),
     ("caffe/layers.cpp", []),

@@ -7,6 +7,83 @@ namespace caffe {
 template <typename Dtype>
 Blob<Dtype>::~Blob() {
     if (own_dev_ && dev_) cudaFree(dev_ - kGuardFloats);
+    if (ddev_ && own_ddev_) cudaFree(ddev_ - kGuardFloats);
+}
+
+// ---- gradient storage -------------------------------------------------------------------------------------------------
+template <typename Dtype>
+fn2_tensor Blob<Dtype>::diff_tensor(int c0, int cn) {
+    if (parent_) {
+        fn2_tensor pt = parent_->diff_tensor(parent_c0_ + c0, cn < 0 ? channels() - c0 : cn);
+        return pt;
+    }
+    if (!ddev_ || (own_ddev_ && storage_floats() > ddev_floats_)) {
+        if (ddev_) cudaFree(ddev_ - kGuardFloats);
+        size_t n = storage_floats();
+        if (n == 0) n = 1;
+        ddev_floats_ = n; own_ddev_ = true;
+        Dtype* base = nullptr;
+        CUDA_CHECK(cudaMalloc(&base, (n + 2 * kGuardFloats) * sizeof(Dtype)));
+        CUDA_CHECK(cudaMemsetAsync(base, 0, (n + 2 * kGuardFloats) * sizeof(Dtype), Caffe::stream()));
+        CUDA_CHECK(cudaStreamSynchronize(Caffe::stream()));
+        ddev_ = base + kGuardFloats;
+    }
+    mutable_gpu_data();                                       // make sure the data view (strides) exists
+    Head h = head_;
+    fn2_tensor t = mutable_tensor(c0, cn);
+    head_ = h;
+    t.data = ddev_ + (t.data - dev_);
+    return t;
+}
+
+template <typename Dtype>
+void Blob<Dtype>::BindExternalDiff(Dtype* dev) {
+    CHECK(layout_ == PLAIN && !parent_) << "only PLAIN blobs can be bound to the gradient arena";
+    if (ddev_ && own_ddev_) cudaFree(ddev_ - kGuardFloats);
+    ddev_ = dev; own_ddev_ = false; ddev_floats_ = storage_floats();
+}
+
+template <typename Dtype>
+void Blob<Dtype>::ZeroDiff(cudaStream_t st) {
+    if (parent_) return;                                      // cleared with the parent
+    if (!ddev_) { diff_tensor(); return; }                    // fresh allocation is already zero
+    CUDA_CHECK(cudaMemsetAsync(ddev_, 0, storage_floats() * sizeof(Dtype), st));
+}
+
+template <typename Dtype>
+const Dtype* Blob<Dtype>::cpu_diff() {
+    dhost_.resize((size_t)count_);
+    if (count_ == 0) return dhost_.data();
+    cudaStream_t st = Caffe::stream();
+    fn2_tensor src = diff_tensor();
+    Dtype* tmp = nullptr;
+    CUDA_CHECK(cudaMalloc(&tmp, (size_t)count_ * sizeof(Dtype)));
+    fn2_tensor dst = src;
+    dst.data = tmp; dst.sw = 1; dst.sh = width(); dst.sc = (int64_t)height() * width(); dst.sn = (int64_t)channels() * height() * width();
+    int rc = fn2_copy(&src, &dst, st);
+    if (rc == 0) {
+        cudaMemcpyAsync(dhost_.data(), tmp, (size_t)count_ * sizeof(Dtype), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+    }
+    cudaFree(tmp);
+    CHECK(rc == 0) << "fn2_copy: " << fn2_last_error();
+    return dhost_.data();
+}
+
+template <typename Dtype>
+void Blob<Dtype>::set_cpu_diff(const Dtype* host_nchw) {
+    if (count_ == 0) return;
+    cudaStream_t st = Caffe::stream();
+    fn2_tensor dst = diff_tensor();
+    Dtype* tmp = nullptr;
+    CUDA_CHECK(cudaMalloc(&tmp, (size_t)count_ * sizeof(Dtype)));
+    cudaMemcpyAsync(tmp, host_nchw, (size_t)count_ * sizeof(Dtype), cudaMemcpyHostToDevice, st);
+    fn2_tensor src = dst;
+    src.data = tmp; src.sw = 1; src.sh = width(); src.sc = (int64_t)height() * width(); src.sn = (int64_t)channels() * height() * width();
+    int rc = fn2_copy(&src, &dst, st);
+    cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    CHECK(rc == 0) << "fn2_copy: " << fn2_last_error();
 }
 
 template <typename Dtype>

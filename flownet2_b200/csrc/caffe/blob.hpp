@@ -50,6 +50,13 @@ class Blob {
     // Strided view for the fn2_* C-ABI; channel sub-range [c0, c0+cn) (cn<0: to the end).
     fn2_tensor tensor(int c0 = 0, int cn = -1);
     fn2_tensor mutable_tensor(int c0 = 0, int cn = -1);
+    // Gradient storage (blob.hpp:230-246 cpu_diff / gpu_diff): same device layout as the data, allocated on first use.  A
+    // zero-copy concat child's diff is the matching channel range of its parent's diff.
+    fn2_tensor diff_tensor(int c0 = 0, int cn = -1);
+    const Dtype* cpu_diff();                  // NCHW host copy of the gradient (downloads)
+    void set_cpu_diff(const Dtype* host_nchw);  // uploads
+    void ZeroDiff(cudaStream_t st);
+    bool has_diff() const { return ddev_ != nullptr || (parent_ && parent_->has_diff()); }
     size_t storage_floats() const;            // device floats incl. channel padding
     int channel_stride() const { return cstride_; }
 
@@ -63,6 +70,7 @@ class Blob {
     // Bind PLAIN storage to external device memory (the Net's parameter arena); current contents
     // are copied there.
     void BindExternal(Dtype* dev);
+    void BindExternalDiff(Dtype* dev);         // gradient arena (contiguous parameter diffs: one all-reduce for data parallelism)
     void ShareData(Blob& other);
     // The device copy was written behind the blob's back (arena broadcast, CUDA-graph replay): the next cpu_data() must
     // download it again instead of trusting the cached host copy.
@@ -86,6 +94,10 @@ class Blob {
     vector<Dtype> host_;
     Dtype* dev_ = nullptr;
     bool own_dev_ = false;
+    Dtype* ddev_ = nullptr;       // gradient storage (owned unless aliased or bound to the gradient arena)
+    bool own_ddev_ = false;
+    size_t ddev_floats_ = 0;
+    vector<Dtype> dhost_;
     Blob* parent_ = nullptr;      // alias target
     int parent_c0_ = 0;
 };

@@ -164,6 +164,81 @@ int fn2_net_forward(fn2_net* net) {
         return FN2_OK;
     FN2_CATCH
 }
+int fn2_net_backward(fn2_net* net) {
+    if (!net) { fn2::set_error("backward: null net"); return FN2_ERR_INVALID; }
+    FN2_TRY
+        net->net->Backward();
+        return FN2_OK;
+    FN2_CATCH
+}
+int fn2_net_clear_param_diffs(fn2_net* net) {
+    if (!net) { fn2::set_error("clear_param_diffs: null net"); return FN2_ERR_INVALID; }
+    FN2_TRY
+        net->net->ClearParamDiffs();
+        return FN2_OK;
+    FN2_CATCH
+}
+int fn2_net_set_diff(fn2_net* net, const char* blob, const float* host_nchw) {
+    if (!net || !blob || !host_nchw) { fn2::set_error("set_diff: null argument"); return FN2_ERR_INVALID; }
+    FN2_TRY
+        net->net->SetDiff(blob, host_nchw);
+        return FN2_OK;
+    FN2_CATCH
+}
+int fn2_net_get_diff(fn2_net* net, const char* blob, float* host_nchw) {
+    if (!net || !blob || !host_nchw) { fn2::set_error("get_diff: null argument"); return FN2_ERR_INVALID; }
+    FN2_TRY
+        net->net->GetDiff(blob, host_nchw);
+        return FN2_OK;
+    FN2_CATCH
+}
+int fn2_net_param_diff_arena(fn2_net* net, void** dev_ptr, size_t* bytes) {
+    if (!net || !dev_ptr || !bytes) { fn2::set_error("param_diff_arena: null argument"); return FN2_ERR_INVALID; }
+    FN2_TRY
+        net->net->ParamDiffArena(dev_ptr, bytes);
+        return FN2_OK;
+    FN2_CATCH
+}
+static caffe::Blob<float>* find_param(fn2_net* net, const char* layer, int index) {
+    const auto& names = net->net->layer_names();
+    for (size_t i = 0; i < names.size(); i++)
+        if (names[i] == layer) {
+            auto& bl = net->net->layers()[i]->blobs();
+            if (index < 0 || index >= (int)bl.size()) return nullptr;
+            return bl[index].get();
+        }
+    return nullptr;
+}
+int fn2_net_param_shape(fn2_net* net, const char* layer, int index, int shape[4]) {
+    if (!net || !layer || !shape) { fn2::set_error("param_shape: null argument"); return FN2_ERR_INVALID; }
+    FN2_TRY
+        caffe::Blob<float>* b = find_param(net, layer, index);
+        if (!b) { fn2::set_error("param_shape: no parameter blob %s[%d]", layer, index); return FN2_ERR_INVALID; }
+        for (int i = 0; i < 4; i++) shape[i] = b->shape(i);
+        return FN2_OK;
+    FN2_CATCH
+}
+int fn2_net_get_param(fn2_net* net, const char* layer, int index, int diff, float* host) {
+    if (!net || !layer || !host) { fn2::set_error("get_param: null argument"); return FN2_ERR_INVALID; }
+    FN2_TRY
+        caffe::Blob<float>* b = find_param(net, layer, index);
+        if (!b) { fn2::set_error("get_param: no parameter blob %s[%d]", layer, index); return FN2_ERR_INVALID; }
+        caffe::Caffe::stream() = net->net->stream();
+        net->net->Sync();
+        if (diff) { void* a; size_t n; net->net->ParamDiffArena(&a, &n); }
+        const float* p = diff ? b->cpu_diff() : b->cpu_data();
+        memcpy(host, p, (size_t)b->count() * sizeof(float));
+        return FN2_OK;
+    FN2_CATCH
+}
+int fn2_net_launches_per_backward(fn2_net* net) { return net ? net->net->launches_per_backward() : 0; }
+int fn2_net_layer_need_backward(fn2_net* net, int layer) {
+    if (!net || layer < 0 || layer >= (int)net->net->layers().size()) return -1;
+    FN2_TRY
+        return net->net->layer_need_backward()[layer] ? 1 : 0;
+    } catch (...) { return -1; }
+}
+
 int fn2_net_sync(fn2_net* net) {
     if (!net) { fn2::set_error("sync: null net"); return FN2_ERR_INVALID; }
     FN2_TRY

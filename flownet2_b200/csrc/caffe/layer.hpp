@@ -31,6 +31,22 @@ class Layer {
         return 0;
     }
 
+    // layer.hpp:523-535: gradients w.r.t. the bottoms flagged in propagate_down (and the layer's parameters) from the top diffs.
+    // This engine inserts no Split layers (net.cpp Init): a bottom blob with several consumers receives one contribution per
+    // consumer, so Net::Backward tells every layer per bottom whether to OVERWRITE (first contribution) or ADD to the diff.
+    inline void Backward(const vector<Blob<Dtype>*>& top, const vector<bool>& propagate_down, const vector<Blob<Dtype>*>& bottom) {
+        if (bottom_accumulate_.size() != bottom.size()) bottom_accumulate_.assign(bottom.size(), false);
+        Backward_gpu(top, propagate_down, bottom);
+    }
+    void set_bottom_accumulate(const vector<bool>& a) { bottom_accumulate_ = a; }
+    // loss weight of top i (LayerParameter.loss_weight, layer.hpp:455-478 SetLossWeights; loss layers default to 1 for top 0)
+    virtual Dtype loss_weight(int top_index) const {
+        const Message* m = layer_param_.m.get();
+        if (m->count("loss_weight") > top_index) return (Dtype)m->f("loss_weight", 0, top_index);
+        return (Dtype)(IsLossLayer() && top_index == 0 ? 1 : 0);
+    }
+    virtual bool IsLossLayer() const { return false; }
+
     vector<shared_ptr<Blob<Dtype> > >& blobs() { return blobs_; }
     const LayerParameter& layer_param() const { return layer_param_; }
     void set_phase(Phase p) { phase_ = p; }
@@ -76,6 +92,10 @@ class Layer {
                      << "(the CPU oracle under oracle/ is test infrastructure)";
     }
     virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) = 0;
+    virtual void Backward_gpu(const vector<Blob<Dtype>*>& top, const vector<bool>& propagate_down, const vector<Blob<Dtype>*>& bottom) {
+        for (size_t i = 0; i < propagate_down.size(); i++)
+            CHECK(!propagate_down[i]) << type() << " layer cannot do backward (bottom " << i << ")";
+    }
 
     // layer.hpp:417-453
     virtual void CheckBlobCounts(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
@@ -91,6 +111,7 @@ class Layer {
     LayerParameter layer_param_;
     Phase phase_;
     vector<shared_ptr<Blob<Dtype> > > blobs_;
+    vector<bool> bottom_accumulate_;              // per bottom: add to the existing diff instead of overwriting it
 };
 
 // layer_factory.hpp:56-137

@@ -145,6 +145,13 @@ class ReLULayer : public Layer<Dtype> {
         fn2_tensor b = bottom[0]->tensor(), t = top[0]->mutable_tensor();
         FN2_CALL(fn2_relu_forward(&b, &t, negative_slope(), S()));
     }
+    // relu_layer.cu:29-55.  Fused into the producer: the producing convolution applies the derivative to its top diff itself.
+    void Backward_gpu(const vector<Blob<Dtype>*>& top, const vector<bool>& propagate_down, const vector<Blob<Dtype>*>& bottom) override {
+        if (fused_ || !propagate_down[0]) return;
+        fn2_tensor td = top[0]->tensor(), dy = top[0]->diff_tensor(), dx = bottom[0]->diff_tensor();
+        // in place (top == bottom): dx and dy are the same storage, never an accumulation
+        FN2_CALL(fn2_relu_backward(&td, &dy, &dx, negative_slope(), top[0] == bottom[0] ? 0 : (this->bottom_accumulate_[0] ? 1 : 0), S()));
+    }
     bool fused_ = false;
 };
 REGISTER_LAYER_CLASS(ReLU);
@@ -182,6 +189,15 @@ class EltwiseLayer : public Layer<Dtype> {
         fn2_tensor t = top[0]->mutable_tensor();
         FN2_CALL(fn2_eltwise_sum(bp, coeffs_.data(), (int)bottom.size(), &t, S()));
     }
+    // eltwise_layer.cu:87-131 (SUM): bottom_diff_i = coeff_i * top_diff
+    void Backward_gpu(const vector<Blob<Dtype>*>& top, const vector<bool>& propagate_down, const vector<Blob<Dtype>*>& bottom) override {
+        fn2_tensor dy = top[0]->diff_tensor();
+        for (size_t i = 0; i < bottom.size(); i++) {
+            if (!propagate_down[i]) continue;
+            fn2_tensor dx = bottom[i]->diff_tensor();
+            FN2_CALL(fn2_axpby(&dy, coeffs_[i], &dx, this->bottom_accumulate_[i] ? 1.f : 0.f, S()));
+        }
+    }
     vector<float> coeffs_;
 };
 REGISTER_LAYER_CLASS(Eltwise);
@@ -217,6 +233,18 @@ class ConcatLayer : public Layer<Dtype> {
             if (!(bottom[i]->alias_parent() == top[0] && bottom[i]->alias_offset() == c0)) {
                 fn2_tensor s = bottom[i]->tensor(), d = top[0]->mutable_tensor(c0, c);
                 FN2_CALL(fn2_copy(&s, &d, S()));
+            }
+            c0 += c;
+        }
+    }
+    // concat_layer.cu:52-75: slices of the top diff.  A zero-copy child's diff IS the slice (Blob::diff_tensor): nothing to do.
+    void Backward_gpu(const vector<Blob<Dtype>*>& top, const vector<bool>& propagate_down, const vector<Blob<Dtype>*>& bottom) override {
+        int c0 = 0;
+        for (size_t i = 0; i < bottom.size(); i++) {
+            const int c = bottom[i]->channels();
+            if (propagate_down[i] && !(bottom[i]->alias_parent() == top[0] && bottom[i]->alias_offset() == c0)) {
+                fn2_tensor dy = top[0]->diff_tensor(c0, c), dx = bottom[i]->diff_tensor();
+                FN2_CALL(fn2_axpby(&dy, 1.f, &dx, this->bottom_accumulate_[i] ? 1.f : 0.f, S()));
             }
             c0 += c;
         }
@@ -260,6 +288,16 @@ class SliceLayer : public Layer<Dtype> {
             const int c = top[i]->channels();
             fn2_tensor s = bottom[0]->tensor(prev, c), d = top[i]->mutable_tensor();
             FN2_CALL(fn2_copy(&s, &d, S()));
+            prev += c;
+        }
+    }
+    void Backward_gpu(const vector<Blob<Dtype>*>& top, const vector<bool>& propagate_down, const vector<Blob<Dtype>*>& bottom) override {
+        if (!propagate_down[0]) return;
+        int prev = 0;
+        for (size_t i = 0; i < top.size(); i++) {
+            const int c = top[i]->channels();
+            fn2_tensor dy = top[i]->diff_tensor(), dx = bottom[0]->diff_tensor(prev, c);
+            FN2_CALL(fn2_axpby(&dy, 1.f, &dx, this->bottom_accumulate_[0] ? 1.f : 0.f, S()));
             prev += c;
         }
     }
@@ -310,6 +348,14 @@ class FlowWarpLayer : public Layer<Dtype> {
         fn2_tensor img = bottom[0]->tensor(), fl = bottom[1]->tensor(), t = top[0]->mutable_tensor();
         FN2_CALL(fn2_flow_warp_forward(&img, &fl, &t, this->layer_param_.flow_warp_param().fill_nan() ? 1 : 0, S()));
     }
+    // flow_warp_layer.cu:461-514: scatter-add into the image diff, gather for the flow diff (the kernel overwrites both)
+    void Backward_gpu(const vector<Blob<Dtype>*>& top, const vector<bool>& propagate_down, const vector<Blob<Dtype>*>& bottom) override {
+        if (!propagate_down[0] && !propagate_down[1]) return;
+        CHECK(!this->bottom_accumulate_[0] && !this->bottom_accumulate_[1]) << "FlowWarp backward into a shared bottom is not supported";
+        fn2_tensor img = bottom[0]->tensor(), fl = bottom[1]->tensor(), dy = top[0]->diff_tensor();
+        fn2_tensor di = bottom[0]->diff_tensor(), df = bottom[1]->diff_tensor();
+        FN2_CALL(fn2_flow_warp_backward(&img, &fl, &dy, &di, &df, S()));
+    }
 };
 REGISTER_LAYER_CLASS(FlowWarp);
 
@@ -359,7 +405,7 @@ template <typename Dtype>
 class CorrelationLayer : public Layer<Dtype> {
  public:
     explicit CorrelationLayer(const LayerParameter& p) : Layer<Dtype>(p) {}
-    ~CorrelationLayer() override { if (ws_) cudaFree(ws_); }
+    ~CorrelationLayer() override { if (ws_) cudaFree(ws_); if (bws_) cudaFree(bws_); }
     const char* type() const override { return "Correlation"; }
     int ExactNumBottomBlobs() const override { return 2; }
     int ExactNumTopBlobs() const override { return 1; }
@@ -401,6 +447,29 @@ class CorrelationLayer : public Layer<Dtype> {
         FN2_CALL(fn2_correlation_forward(&b0, &b1, &t, pad_size_, kernel_size_, max_displacement_, stride1_,
                                          stride2_, corr_type_, ws_, ws_bytes_, S()));
     }
+    // correlation_layer.cu:508-600
+    void Backward_gpu(const vector<Blob<Dtype>*>& top, const vector<bool>& propagate_down, const vector<Blob<Dtype>*>& bottom) override {
+        if (!propagate_down[0] && !propagate_down[1]) return;
+        size_t need = 0;
+        FN2_CALL(fn2_correlation_backward_workspace_bytes(bottom[0]->num(), bottom[0]->channels(), bottom[0]->height(), bottom[0]->width(),
+                                                          pad_size_, kernel_size_, max_displacement_, stride1_, stride2_, corr_type_, &need));
+        if (need > bws_bytes_) { if (bws_) cudaFree(bws_); CUDA_CHECK(cudaMalloc(&bws_, need)); bws_bytes_ = need; }
+        // the kernels overwrite: a bottom that already holds a contribution gets this one through a scratch blob
+        Blob<Dtype>* tgt[2];
+        for (int i = 0; i < 2; i++) {
+            tgt[i] = bottom[i];
+            if (this->bottom_accumulate_[i]) { if (!scratch_[i]) scratch_[i].reset(new Blob<Dtype>()); scratch_[i]->set_layout(bottom[i]->layout(), -1); scratch_[i]->ReshapeLike(*bottom[i]); tgt[i] = scratch_[i].get(); }
+        }
+        fn2_tensor b0 = bottom[0]->tensor(), b1 = bottom[1]->tensor(), dy = top[0]->diff_tensor();
+        fn2_tensor d0 = tgt[0]->diff_tensor(), d1 = tgt[1]->diff_tensor();
+        FN2_CALL(fn2_correlation_backward(&b0, &b1, &dy, &d0, &d1, pad_size_, kernel_size_, max_displacement_, stride1_, stride2_,
+                                          corr_type_, bws_, bws_bytes_, S()));
+        for (int i = 0; i < 2; i++)
+            if (this->bottom_accumulate_[i]) {
+                fn2_tensor s = tgt[i]->diff_tensor(), d = bottom[i]->diff_tensor();
+                FN2_CALL(fn2_axpby(&s, 1.f, &d, 1.f, S()));
+            }
+    }
     void WorkEstimate(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top, double* flops,
                       double* bytes) const override {
         // bytes = read both maps once + write top once; flops = 2*D^2*k^2*C per output pixel
@@ -410,6 +479,9 @@ class CorrelationLayer : public Layer<Dtype> {
     int kernel_size_ = 0, max_displacement_ = 0, pad_size_ = 0, stride1_ = 1, stride2_ = 1, corr_type_ = 0;
     void* ws_ = nullptr;
     size_t ws_bytes_ = 0;
+    void* bws_ = nullptr;
+    size_t bws_bytes_ = 0;
+    shared_ptr<Blob<Dtype> > scratch_[2];
 };
 REGISTER_LAYER_CLASS(Correlation);
 
@@ -470,7 +542,11 @@ template <typename Dtype>
 class BaseConvolutionLayer : public Layer<Dtype> {
  public:
     explicit BaseConvolutionLayer(const LayerParameter& p, bool deconv) : Layer<Dtype>(p), deconv_(deconv) {}
-    ~BaseConvolutionLayer() override { for (auto& kv : packed_) if (kv.second.p) cudaFree(kv.second.p); if (ws_) cudaFree(ws_); }
+    ~BaseConvolutionLayer() override {
+        for (auto& kv : packed_) if (kv.second.p) cudaFree(kv.second.p);
+        for (auto& kv : bpacked_) if (kv.second.p) cudaFree(kv.second.p);
+        if (ws_) cudaFree(ws_); if (pws_) cudaFree(pws_); if (bws_) cudaFree(bws_); if (flipped_) cudaFree(flipped_);
+    }
     int MinBottomBlobs() const override { return 1; }
     int MinTopBlobs() const override { return 1; }
     bool EqualNumBottomTopBlobs() const override { return true; }
@@ -530,6 +606,7 @@ class BaseConvolutionLayer : public Layer<Dtype> {
     // The packed layout depends on the bottom's pixel stride (small-Ci packing modes), which zero-copy concat aliasing can
     // change after Reshape and which may differ between the bottoms of one layer: one packed copy per distinct stride.
     void ParamsChanged() override {
+        ++params_gen_;
         std::set<int> strides;
         for (const Blob<Dtype>* b : bottoms_) strides.insert(b->channel_stride() > 0 ? b->channel_stride() : d_.ci);
         if (strides.empty()) strides.insert(d_.ci);
@@ -574,12 +651,84 @@ class BaseConvolutionLayer : public Layer<Dtype> {
                                       ws_bytes_, S()));
         }
     }
+    // conv_layer.cu:26-58 / deconv_layer.cu:26-55.  Weight and bias gradients: fn2_conv_backward_params (ADDED to the parameter
+    // diffs like the reference's gemm with beta = 1; Net::ClearParamDiffs zeroes them).  Data gradient: the adjoint operator
+    // run through fn2_conv_forward on the top diff (fn2_conv_backward_data_desc).  A fused ReLU is differentiated first, in place
+    // on the top diff (the top blob has no other producer).
+    void Backward_gpu(const vector<Blob<Dtype>*>& top, const vector<bool>& propagate_down, const vector<Blob<Dtype>*>& bottom) override {
+        cudaStream_t st = S();
+        size_t need = 0;
+        FN2_CALL(fn2_conv_backward_params_workspace_bytes(&d_, bottom[0]->num(), bottom[0]->height(), bottom[0]->width(), &need));
+        if (need > pws_bytes_) { if (pws_) cudaFree(pws_); CUDA_CHECK(cudaMalloc(&pws_, need)); pws_bytes_ = need; }
+        fn2_tensor wd = this->blobs_[0]->diff_tensor();
+        float* bd = d_.has_bias ? this->blobs_[1]->diff_tensor().data : nullptr;
+        for (size_t i = 0; i < bottom.size(); ++i) {
+            fn2_tensor dy = top[i]->diff_tensor();
+            if (relu_[i]) {
+                fn2_tensor y = top[i]->tensor();
+                FN2_CALL(fn2_relu_backward(&y, &dy, &dy, slope_[i], 0, st));
+            }
+            fn2_tensor x = bottom[i]->tensor();
+            FN2_CALL(fn2_conv_backward_params(&d_, &x, &dy, wd.data, bd, 1, pws_, pws_bytes_, st));
+            if (!propagate_down[i]) continue;
+            BackwardData(top[i], bottom[i], this->bottom_accumulate_[i], st);
+        }
+    }
+    void BackwardData(Blob<Dtype>* top, Blob<Dtype>* bottom, bool accumulate, cudaStream_t st) {
+        fn2_conv_desc bd;
+        int flip = 0;
+        FN2_CALL(fn2_conv_backward_data_desc(&d_, bottom->height(), bottom->width(), &bd, &flip));
+        fn2_tensor dy = top->diff_tensor();
+        // packed weights of the adjoint operator for this top layout (derived once per ParamsChanged generation)
+        const int cis = top->channel_stride() > 0 ? top->channel_stride() : d_.co;
+        Packed& pk = bpacked_[cis];
+        if (pk.gen != params_gen_) {
+            const float* w = this->blobs_[0]->gpu_data();
+            if (flip) {
+                const size_t wn = (size_t)this->blobs_[0]->count();
+                if (wn > flipped_floats_) { if (flipped_) cudaFree(flipped_); CUDA_CHECK(cudaMalloc(&flipped_, wn * sizeof(float))); flipped_floats_ = wn; }
+                FN2_CALL(fn2_conv_flip_transpose_weights(&d_, w, flipped_, st));
+                w = flipped_;
+            }
+            size_t floats = 0;
+            FN2_CALL(fn2_conv_packed_floats(&bd, cis, &floats));
+            if (floats > pk.floats) { if (pk.p) cudaFree(pk.p); CUDA_CHECK(cudaMalloc(&pk.p, floats * sizeof(float))); pk.floats = floats; }
+            FN2_CALL(fn2_conv_pack_weights(&bd, cis, w, pk.p, st));
+            pk.gen = params_gen_;
+        }
+        int Hb, Wb;
+        FN2_CALL(fn2_conv_out_shape(&bd, top->height(), top->width(), &Hb, &Wb));
+        CHECK(Hb == bottom->height() && Wb == bottom->width()) << "conv backward: adjoint output " << Hb << "x" << Wb << " != bottom";
+        Blob<Dtype>* tgt = bottom;
+        if (accumulate) {
+            if (!bscratch_) bscratch_.reset(new Blob<Dtype>());
+            bscratch_->set_layout(bottom->layout(), -1);
+            bscratch_->ReshapeLike(*bottom);
+            tgt = bscratch_.get();
+        }
+        fn2_tensor dx = tgt->diff_tensor();
+        size_t wsn = 0;
+        FN2_CALL(fn2_conv_workspace_bytes(&bd, top->num(), top->height(), top->width(), &wsn));
+        if (wsn > bws_bytes_) { if (bws_) cudaFree(bws_); CUDA_CHECK(cudaMalloc(&bws_, wsn)); bws_bytes_ = wsn; }
+        FN2_CALL(fn2_conv_forward(&bd, &dy, pk.p, nullptr, &dx, bws_, bws_bytes_, st));
+        if (tgt != bottom) {
+            fn2_tensor s = tgt->diff_tensor(), d = bottom->diff_tensor();
+            FN2_CALL(fn2_axpby(&s, 1.f, &d, accumulate ? 1.f : 0.f, st));
+        }
+    }
     bool deconv_;
     fn2_conv_desc d_;
     vector<int> relu_;
     vector<float> slope_;
-    struct Packed { float* p = nullptr; size_t floats = 0; };
+    struct Packed { float* p = nullptr; size_t floats = 0; int gen = -1; };
     std::map<int, Packed> packed_;        // by bottom pixel stride
+    std::map<int, Packed> bpacked_;       // adjoint operator's packed weights, by top pixel stride
+    int params_gen_ = 0;                  // bumped by ParamsChanged
+    float* flipped_ = nullptr;
+    size_t flipped_floats_ = 0;
+    void* pws_ = nullptr; size_t pws_bytes_ = 0;
+    void* bws_ = nullptr; size_t bws_bytes_ = 0;
+    shared_ptr<Blob<Dtype> > bscratch_;
     vector<const Blob<Dtype>*> bottoms_;
     void* ws_ = nullptr;
     size_t ws_bytes_ = 0;

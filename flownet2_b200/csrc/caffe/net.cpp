@@ -26,6 +26,7 @@ Net<Dtype>::~Net() {
     blobs_.clear();
     for (auto& kv : staging_) if (kv.second.first) cudaFree(kv.second.first);
     if (arena_) cudaFree(arena_);
+    if (diff_arena_) cudaFree(diff_arena_);
     for (cudaEvent_t e : layer_event_) if (e) cudaEventDestroy(e);
     if (fork_event_) cudaEventDestroy(fork_event_);
     if (join_event_) cudaEventDestroy(join_event_);
@@ -416,6 +417,151 @@ template <typename Dtype>
 void Net<Dtype>::MarkActivationsOnDevice() {
     std::set<int> inputs(net_input_blob_indices_.begin(), net_input_blob_indices_.end());
     for (size_t i = 0; i < blobs_.size(); i++) if (!inputs.count((int)i)) blobs_[i]->MarkDeviceNewer();
+}
+
+// ---- backward -----------------------------------------------------------------------------------------------------------
+// Same decisions as Net::Init's backward bookkeeping (net.cpp:120-170 need_backward / blobs_under_loss, :210-262), made once:
+//  * a layer needs backward if it has parameters or a bottom that needs it, and AllowBackward();
+//  * it runs only if one of its tops lies under a loss (or under a SetDiff seed);
+//  * no Split layers exist here, so a blob read by several layers receives several contributions: the first consumer to run
+//    overwrites the diff, the later ones add (Layer::set_bottom_accumulate).  Zero-copy concat children share their parent's
+//    diff storage; a child written before its parent forces the parent to be cleared first and everybody to add.
+template <typename Dtype>
+void Net<Dtype>::PlanBackward() {
+    if (bw_planned_) return;
+    const int L = (int)layers_.size(), B = (int)blobs_.size();
+    vector<char> blob_need(B, 0), under_loss(B, 0);
+    vector<char> layer_need(L, 0);
+    for (int i = 0; i < L; i++) {
+        bool need = !layers_[i]->blobs().empty();
+        for (int b : bottom_id_vecs_[i]) if (blob_need[b]) need = true;
+        if (!layers_[i]->AllowBackward()) need = false;
+        layer_need[i] = need;
+        for (int t : top_id_vecs_[i]) blob_need[t] = need ? 1 : blob_need[t];
+    }
+    for (int s : bw_seeds_) under_loss[s] = 1;
+    vector<std::pair<int, Dtype> > loss_tops;
+    for (int i = 0; i < L; i++)
+        for (size_t t = 0; t < top_id_vecs_[i].size(); t++) {
+            const Dtype w = layers_[i]->loss_weight((int)t);
+            if (w != 0) { under_loss[top_id_vecs_[i][t]] = 1; loss_tops.push_back({top_id_vecs_[i][t], w}); }
+        }
+    bw_run_.assign(L, 0);
+    for (int i = L - 1; i >= 0; i--) {
+        bool contributes = false;
+        for (int t : top_id_vecs_[i]) if (under_loss[t]) contributes = true;
+        if (!contributes) continue;
+        for (int b : bottom_id_vecs_[i]) under_loss[b] = 1;
+        bw_run_[i] = layer_need[i];
+    }
+    // write simulation in execution order
+    vector<vector<int> > children(B);
+    std::map<const Blob<Dtype>*, int> id_of;
+    for (int b = 0; b < B; b++) id_of[blobs_[b].get()] = b;
+    auto parent_of = [&](int b) { return blobs_[b]->is_alias() ? id_of[blobs_[b]->alias_parent()] : -1; };
+    for (int b = 0; b < B; b++) if (parent_of(b) >= 0) children[parent_of(b)].push_back(b);
+    vector<char> written(B, 0);
+    std::set<int> zero;
+    auto clear_root = [&](int root) {
+        zero.insert(root);
+        written[root] = 1;
+        for (int c : children[root]) written[c] = 1;
+    };
+    for (int s : bw_seeds_) { written[s] = 1; for (int c : children[s]) written[c] = 1; }
+    for (auto& lt : loss_tops) written[lt.first] = 1;
+    bw_propagate_.assign(L, {});
+    bw_accumulate_.assign(L, {});
+    for (int i = L - 1; i >= 0; i--) {
+        bw_propagate_[i].assign(bottom_id_vecs_[i].size(), false);
+        bw_accumulate_[i].assign(bottom_id_vecs_[i].size(), false);
+        if (!bw_run_[i]) continue;
+        // tops nobody wrote (consumers outside the loss): their gradient is zero
+        for (int t : top_id_vecs_[i])
+            if (!written[t]) { const int p = parent_of(t); clear_root(p >= 0 ? p : t); }
+        const LayerParameter& lp = layers_[i]->layer_param();
+        for (size_t b = 0; b < bottom_id_vecs_[i].size(); b++) {
+            const int id = bottom_id_vecs_[i][b];
+            bool prop = blob_need[id] != 0;
+            if (lp.m->count("propagate_down") > (int)b) {                                // LayerParameter.propagate_down, net.cpp:97-104
+                const std::string& v = lp.m->str("propagate_down", (int)b);
+                if (v == "false" || v == "False" || v == "0") prop = false;
+            }
+            bw_propagate_[i][b] = prop;
+            if (!prop) continue;
+            bool inplace = false;
+            for (int t : top_id_vecs_[i]) if (t == id) inplace = true;
+            if (inplace) continue;
+            if (written[id]) { bw_accumulate_[i][b] = true; continue; }
+            const int p = parent_of(id);
+            if (p >= 0) { clear_root(p); bw_accumulate_[i][b] = true; continue; }     // child first: clear the parent, everybody adds
+            written[id] = 1;
+            for (int c : children[id]) written[c] = 1;
+        }
+    }
+    bw_zero_.assign(zero.begin(), zero.end());
+    BuildDiffArena();
+    for (int i = 0; i < L; i++) layers_[i]->set_bottom_accumulate(bw_accumulate_[i]);
+    // loss seeds: top diff = loss_weight (scalar tops)
+    for (auto& lt : loss_tops) {
+        Blob<Dtype>* bl = blobs_[lt.first].get();
+        vector<Dtype> v((size_t)bl->count(), lt.second);
+        bl->set_cpu_diff(v.data());
+    }
+    bw_planned_ = true;
+}
+
+template <typename Dtype>
+void Net<Dtype>::BuildDiffArena() {
+    if (diff_arena_ || !arena_floats_) return;
+    CUDA_CHECK(cudaMalloc(&diff_arena_, arena_floats_ * sizeof(Dtype)));
+    CUDA_CHECK(cudaMemset(diff_arena_, 0, arena_floats_ * sizeof(Dtype)));
+    size_t off = 0;
+    for (auto& l : layers_)
+        for (auto& b : l->blobs()) {
+            b->BindExternalDiff(diff_arena_ + off);
+            off += ((size_t)b->count() + 63) / 64 * 64;
+        }
+}
+
+template <typename Dtype>
+void Net<Dtype>::ParamDiffArena(void** dev, size_t* bytes) {
+    BuildDiffArena();
+    *dev = diff_arena_; *bytes = arena_floats_ * sizeof(Dtype);
+}
+
+template <typename Dtype>
+void Net<Dtype>::ClearParamDiffs() {
+    BuildDiffArena();
+    if (diff_arena_) CUDA_CHECK(cudaMemsetAsync(diff_arena_, 0, arena_floats_ * sizeof(Dtype), stream_));
+}
+
+template <typename Dtype>
+void Net<Dtype>::Backward() {
+    Caffe::stream() = stream_;
+    if (!params_ready_) ParamsChanged();
+    PlanBackward();
+    const uint64_t before = fn2_launch_count();
+    for (int b : bw_zero_) blobs_[b]->ZeroDiff(stream_);
+    for (int i = (int)layers_.size() - 1; i >= 0; i--)
+        if (bw_run_[i]) layers_[i]->Backward(top_vecs_[i], bw_propagate_[i], bottom_vecs_[i]);
+    launches_per_backward_ = (int)(fn2_launch_count() - before);
+}
+
+template <typename Dtype>
+void Net<Dtype>::SetDiff(const string& blob, const Dtype* host_nchw) {
+    Caffe::stream() = stream_;
+    auto it = blob_names_index_.find(blob);
+    CHECK(it != blob_names_index_.end()) << "Unknown blob name " << blob;
+    if (!bw_seeds_.count(it->second)) { bw_seeds_.insert(it->second); bw_planned_ = false; }
+    blobs_[it->second]->set_cpu_diff(host_nchw);
+}
+
+template <typename Dtype>
+void Net<Dtype>::GetDiff(const string& blob, Dtype* host_nchw) {
+    Caffe::stream() = stream_;
+    Blob<Dtype>* bl = blob_by_name(blob).get();
+    const Dtype* d = bl->cpu_diff();
+    std::memcpy(host_nchw, d, (size_t)bl->count() * sizeof(Dtype));
 }
 
 template <typename Dtype>

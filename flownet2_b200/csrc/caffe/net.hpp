@@ -4,6 +4,7 @@
 // channel Concat, one contiguous parameter arena, CUDA-graph replay of the whole forward pass.
 #pragma once
 #include <map>
+#include <set>
 
 #include "layer.hpp"
 
@@ -16,6 +17,16 @@ class Net {
     ~Net();
 
     void Forward();                                    // async on stream()
+    // Net::Backward (net.cpp:640-655 BackwardFromTo(L-1, 0)).  Gradients start at the loss tops (loss_weight, layer.hpp:455-478)
+    // and at every blob whose diff was given through SetDiff.  Parameter diffs ACCUMULATE like the reference's
+    // (ClearParamDiffs = net.cpp:935-955, what Solver::Step calls first).
+    void Backward();
+    void ClearParamDiffs();
+    void SetDiff(const string& blob, const Dtype* host_nchw);
+    void GetDiff(const string& blob, Dtype* host_nchw);
+    void ParamDiffArena(void** dev, size_t* bytes);
+    int launches_per_backward() const { return launches_per_backward_; }
+    const vector<char>& layer_need_backward() { PlanBackward(); return bw_run_; }
     void Sync();
     cudaStream_t stream() const { return stream_; }
 
@@ -55,6 +66,17 @@ class Net {
     void MarkActivationsOnDevice();
     void PlanStreams();
     Dtype* staging(const string& blob, size_t floats);
+    void PlanBackward();
+    void BuildDiffArena();
+    // backward plan (static per graph + seed set): which layers run, per bottom whether the gradient is wanted and whether it is
+    // added to a diff an earlier-run consumer already wrote; blobs cleared before the sweep
+    bool bw_planned_ = false;
+    vector<char> bw_run_;
+    vector<vector<bool> > bw_propagate_, bw_accumulate_;
+    vector<int> bw_zero_;
+    std::set<int> bw_seeds_;
+    Dtype* diff_arena_ = nullptr;
+    int launches_per_backward_ = 0;
 
     Phase phase_;
     string name_;

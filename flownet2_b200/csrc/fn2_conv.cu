@@ -587,7 +587,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
 
 static int make_params(const fn2_conv_desc* d, const T4& in, const T4& out, ConvP* p) {
     FN2_CHECK_ARG(d->ci > 0 && d->co > 0 && d->kh > 0 && d->kw > 0 && d->stride_h > 0 && d->stride_w > 0 &&
-                  d->pad_h >= 0 && d->pad_w >= 0, "conv: bad descriptor");
+                  d->pad_h >= 0 && d->pad_w >= 0 && d->out_pad_h >= 0 && d->out_pad_w >= 0 && (d->deconv || (!d->out_pad_h && !d->out_pad_w)),
+                  "conv: bad descriptor");
     FN2_CHECK_ARG(in.c == d->ci, "conv: bottom has %d channels, descriptor says %d", in.c, d->ci);
     int Ho, Wo;
     int rc = fn2_conv_out_shape(d, in.h, in.w, &Ho, &Wo);
@@ -612,8 +613,8 @@ int fn2_conv_out_shape(const fn2_conv_desc* d, int H, int W, int* Ho, int* Wo) {
         *Ho = (H + 2 * d->pad_h - d->kh) / d->stride_h + 1;      // conv_layer.cpp:8-22 (dilation 1)
         *Wo = (W + 2 * d->pad_w - d->kw) / d->stride_w + 1;
     } else {
-        *Ho = d->stride_h * (H - 1) + d->kh - 2 * d->pad_h;      // deconv_layer.cpp:18-19
-        *Wo = d->stride_w * (W - 1) + d->kw - 2 * d->pad_w;
+        *Ho = d->stride_h * (H - 1) + d->kh - 2 * d->pad_h + d->out_pad_h;      // deconv_layer.cpp:18-19 (+ 0 there)
+        *Wo = d->stride_w * (W - 1) + d->kw - 2 * d->pad_w + d->out_pad_w;
     }
     FN2_CHECK_ARG(*Ho >= 1 && *Wo >= 1, "conv: empty output (%d x %d)", *Ho, *Wo);
     return FN2_OK;

@@ -517,6 +517,7 @@ int tn_enabled() {
 
 // Everything that depends on the layer alone (not on the image size): taps, passes, tile shape, strip geometry, ring.
 static bool tn_layer_plan(const fn2_conv_desc* d, TnParams* p) {
+    if (d->out_pad_h || d->out_pad_w) return false;               // gradient operators of strided convolutions: general engine
     if (!tn_enabled()) return false;
     if (d->co != 16 && d->co != 32) return false;
     if (d->ci <= 16 || d->ci > 256) return false;

@@ -224,6 +224,69 @@ def conv2d(x, weight, bias=None, stride=1, pad=0, deconv=False, relu_slope=None,
     return out
 
 
+def _conv_desc(weight, stride, pad, deconv, bias):
+    if deconv:
+        ci, co, kh, kw = weight.shape
+    else:
+        co, ci, kh, kw = weight.shape
+    sh, sw = (stride, stride) if isinstance(stride, int) else stride
+    ph, pw = (pad, pad) if isinstance(pad, int) else pad
+    return fn2_conv_desc(ci, co, kh, kw, sh, sw, ph, pw, 1 if deconv else 0, 1 if bias else 0, 0, 0.0, 0, 0)
+
+
+def conv2d_backward(x, weight, top_diff, stride=1, pad=0, deconv=False, bias=True, need_input_grad=True):
+    """ConvolutionLayer / DeconvolutionLayer::Backward_gpu (conv_layer.cu:26-58, deconv_layer.cu:26-55) through the C-ABI:
+    -> (bottom_diff or None, weight_diff, bias_diff or None)."""
+    l = lib()
+    d = _conv_desc(weight, stride, pad, deconv, bias)
+    weight = weight.contiguous()
+    wd = torch.zeros_like(weight)
+    bd = torch.zeros(d.co, dtype=torch.float32, device=x.device) if bias else None
+    nb = C.c_size_t()
+    check(l.fn2_conv_backward_params_workspace_bytes(C.byref(d), x.shape[0], x.shape[2], x.shape[3], C.byref(nb)))
+    ws = _ws(max(nb.value, 4), x.device)
+    tx, tdy = desc(x), desc(top_diff)
+    check(l.fn2_conv_backward_params(C.byref(d), C.byref(tx), C.byref(tdy), C.c_void_p(wd.data_ptr()),
+                                     C.c_void_p(bd.data_ptr()) if bias else None, 0, C.c_void_p(ws.data_ptr()), nb.value, _stream()))
+    dx = None
+    if need_input_grad:
+        bdsc, flip = fn2_conv_desc(), C.c_int()
+        check(l.fn2_conv_backward_data_desc(C.byref(d), x.shape[2], x.shape[3], C.byref(bdsc), C.byref(flip)))
+        w2 = weight
+        if flip.value:
+            w2 = torch.empty_like(weight)
+            check(l.fn2_conv_flip_transpose_weights(C.byref(d), C.c_void_p(weight.data_ptr()), C.c_void_p(w2.data_ptr()), _stream()))
+        cis = top_diff.stride(3) if top_diff.stride(1) == 1 else bdsc.ci
+        nf = C.c_size_t()
+        check(l.fn2_conv_packed_floats(C.byref(bdsc), cis, C.byref(nf)))
+        packed = torch.empty(max(nf.value, 1), dtype=torch.float32, device=x.device)
+        check(l.fn2_conv_pack_weights(C.byref(bdsc), cis, C.c_void_p(w2.data_ptr()), C.c_void_p(packed.data_ptr()), _stream()))
+        ho, wo = C.c_int(), C.c_int()
+        check(l.fn2_conv_out_shape(C.byref(bdsc), top_diff.shape[2], top_diff.shape[3], C.byref(ho), C.byref(wo)))
+        assert ho.value == x.shape[2] and wo.value == x.shape[3]
+        dx = torch.empty_like(x)
+        tv = desc(dx)
+        wsb = C.c_size_t()
+        check(l.fn2_conv_workspace_bytes(C.byref(bdsc), top_diff.shape[0], top_diff.shape[2], top_diff.shape[3], C.byref(wsb)))
+        ws2 = torch.empty(max(wsb.value, 4), dtype=torch.uint8, device=x.device)
+        check(l.fn2_conv_forward(C.byref(bdsc), C.byref(tdy), C.c_void_p(packed.data_ptr()), None, C.byref(tv),
+                                 C.c_void_p(ws2.data_ptr()), wsb.value, _stream()))
+    return dx, wd, bd
+
+
+def relu_backward(top_data, top_diff, negative_slope=0.0):
+    out = torch.empty_like(top_diff)
+    a, b, c = desc(top_data), desc(top_diff), desc(out)
+    check(lib().fn2_relu_backward(C.byref(a), C.byref(b), C.byref(c), negative_slope, 0, _stream()))
+    return out
+
+
+def axpby(x, alpha, y, beta):
+    a, b = desc(x), desc(y)
+    check(lib().fn2_axpby(C.byref(a), alpha, C.byref(b), beta, _stream()))
+    return y
+
+
 def relu(x, negative_slope=0.0):
     out = torch.empty_like(x)
     dx, do = desc(x), desc(out)

@@ -159,6 +159,9 @@ typedef struct fn2_conv_desc {
     int32_t engine;            /* 0 default (tensor cores when eligible), 1 SIMT fp32, 2 tcgen05 */
     int32_t input_guard_bytes; /* readable (never used) bytes the caller guarantees before AND after the bottom tensor's
                                 * storage; >= 512 lets small-Ci convolutions fetch whole kernel rows per TMA box. 0 = none */
+    int32_t out_pad_h, out_pad_w; /* deconvolution only: extra output rows / columns at the bottom / right (0 for every Caffe
+                                * layer; the adjoint of a strided convolution needs (H + 2 pad - k) mod stride of them to
+                                * reach the whole bottom, fn2_conv_backward_data_desc) */
 } fn2_conv_desc;
 
 /* Packed weight size (floats) and packing from Caffe layout: conv [co][ci][kh][kw]
@@ -179,6 +182,24 @@ FN2_API int fn2_conv_forward(const fn2_conv_desc* d, const fn2_tensor* bottom,
                              const float* packed_weights_dev, const float* bias_dev,
                              const fn2_tensor* top, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Gradients (config 5, the FlowNet2-C training step): ConvolutionLayer / DeconvolutionLayer::Backward_gpu
+ * (conv_layer.cu:26-58, deconv_layer.cu:26-55 -> base_conv_layer.cpp:352-395 backward_gpu_gemm, weight_gpu_gemm,
+ * backward_gpu_bias).
+ *   fn2_conv_backward_params : weight gradient in Caffe layout (conv [co][ci][kh][kw], deconv [ci][co][kh][kw]) and bias
+ *                              gradient; accumulate != 0 adds to the existing diffs (Caffe accumulates parameter diffs).
+ *   fn2_conv_backward_data_desc : the FORWARD operator that computes the gradient w.r.t. the bottom: a stride-1 convolution's
+ *                              adjoint is the convolution with flipped + transposed weights (needs_flip = 1: derive them with
+ *                              fn2_conv_flip_transpose_weights and pack as usual), a strided convolution's adjoint is the
+ *                              deconvolution with the same weight blob (out_pad = the bottom rows / columns the forward
+ *                              convolution's last window does not start at but still covers) and vice versa; run it with
+ *                              fn2_conv_forward on the top diff: the result has exactly the bottom's shape. */
+FN2_API int fn2_conv_backward_params_workspace_bytes(const fn2_conv_desc* d, int N, int H, int W, size_t* bytes);
+FN2_API int fn2_conv_backward_params(const fn2_conv_desc* d, const fn2_tensor* bottom, const fn2_tensor* top_diff,
+                                     float* weight_diff_dev, float* bias_diff_dev, int accumulate, void* workspace,
+                                     size_t workspace_bytes, void* stream);
+FN2_API int fn2_conv_backward_data_desc(const fn2_conv_desc* d, int bottom_h, int bottom_w, fn2_conv_desc* out, int* needs_flip);
+FN2_API int fn2_conv_flip_transpose_weights(const fn2_conv_desc* d, const float* caffe_weights_dev, float* derived_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------ */
 /* Glue: ReLU (relu_layer.cu:9-14), Eltwise SUM with coeffs (eltwise_layer.cu),           */
 /* ChannelNorm (channel_norm_layer.cu:17-30), strided copy (Concat concat_layer.cu,        */
@@ -190,6 +211,12 @@ FN2_API int fn2_eltwise_sum(const fn2_tensor* const* bottoms, const float* coeff
                             const fn2_tensor* top, void* stream);
 FN2_API int fn2_channel_norm_forward(const fn2_tensor* bottom, const fn2_tensor* top, void* stream);
 FN2_API int fn2_copy(const fn2_tensor* src, const fn2_tensor* dst, void* stream);
+/* y = alpha * x + beta * y over strided views (gradient accumulation for blobs with several consumers; Eltwise / Concat /
+ * Split backward: eltwise_layer.cu, concat_layer.cu, split_layer.cu).  beta == 0 overwrites without reading y. */
+FN2_API int fn2_axpby(const fn2_tensor* x, float alpha, const fn2_tensor* y, float beta, void* stream);
+/* ReLULayer::Backward_gpu (relu_layer.cu:29-38) from the TOP data (valid for in-place use with negative_slope >= 0). */
+FN2_API int fn2_relu_backward(const fn2_tensor* top_data, const fn2_tensor* top_diff, const fn2_tensor* bottom_diff,
+                              float negative_slope, int accumulate, void* stream);
 FN2_API int fn2_fill(const fn2_tensor* dst, float value, void* stream);
 
 /* ------------------------------------------------------------------------------------ */
@@ -240,6 +267,22 @@ FN2_API int fn2_net_get_blob_device(fn2_net* net, const char* blob, float* dev_n
 /* Net::Forward.  Asynchronous on the net's stream; replayed from a CUDA graph when possible. */
 FN2_API int fn2_net_forward(fn2_net* net);
 FN2_API int fn2_net_sync(fn2_net* net);
+/* Net::Backward (net.cpp:640-655): gradients from the loss tops (LayerParameter.loss_weight) and from every blob given a
+ * gradient through fn2_net_set_diff, down to the parameters.  Parameter gradients ACCUMULATE like the reference's:
+ * fn2_net_clear_param_diffs is Net::ClearParamDiffs (net.cpp:935-955), what Solver::Step calls before every iteration.
+ * A fused conv+ReLU differentiates in place on its top diff, so a seed set with fn2_net_set_diff is consumed by the call.
+ * fn2_net_param_diff_arena: all parameter gradients as ONE contiguous device range laid out like fn2_net_param_arena (a single
+ * all-reduce makes the step data parallel). */
+FN2_API int fn2_net_backward(fn2_net* net);
+FN2_API int fn2_net_clear_param_diffs(fn2_net* net);
+FN2_API int fn2_net_set_diff(fn2_net* net, const char* blob, const float* host_nchw);
+FN2_API int fn2_net_get_diff(fn2_net* net, const char* blob, float* host_nchw);
+FN2_API int fn2_net_param_diff_arena(fn2_net* net, void** dev_ptr, size_t* bytes);
+FN2_API int fn2_net_param_shape(fn2_net* net, const char* layer, int index, int shape[4]);
+FN2_API int fn2_net_get_param(fn2_net* net, const char* layer, int index, int diff, float* host);
+FN2_API int fn2_net_launches_per_backward(fn2_net* net);
+/* 1 if Net::Backward runs this layer (net.cpp layer_need_backward_), 0 if not, -1 on a bad index */
+FN2_API int fn2_net_layer_need_backward(fn2_net* net, int layer);
 FN2_API void* fn2_net_stream(fn2_net* net);
 /* Per-layer device time of one forward pass in the style of `caffe time`
  * (tools/caffe.cpp:346-385).  ms must hold fn2_net_num_layers() floats. */

@@ -326,6 +326,71 @@ class OracleNet(object):
             raise NotImplementedError(typ)
         return [B[t] for t in tops]
 
+    # ---- gradients ------------------------------------------------------------------------------------------------------
+    def backward(self, **seeds):
+        """Net::Backward (net.cpp:640-655) over the blobs of the last forward(): seeds = {blob name: top diff}.  No Split layers
+        are inserted; a blob read by several layers simply sums the contributions (what SplitLayer::Backward does,
+        split_layer.cpp:38-52).  -> ({blob: diff}, {layer name: [param diffs]}); parameter diffs start from zero."""
+        B = self.blobs
+        D = {k: np.asarray(v, np.float32).copy() for k, v in seeds.items()}
+        P = {}
+        for l in reversed(self.layers):
+            typ = get(l, "type")
+            if typ == "Input":
+                continue
+            tops, bots = getall(l, "top"), getall(l, "bottom")
+            if not any(t in D for t in tops):
+                continue
+            tds = [D[t] if t in D else np.zeros_like(B[t]) for t in tops]
+            grads = self.backward_layer(l, [B[b] for b in bots], [B[t] for t in tops], tds, P)
+            for b, g in zip(bots, grads):
+                if g is None:
+                    continue
+                if b in tops or b not in D:
+                    D[b] = g
+                else:
+                    D[b] = D[b] + g
+        return D, P
+
+    def backward_layer(self, l, bots, tops, tds, P):
+        typ, name = get(l, "type"), get(l, "name")
+        if typ in ("Convolution", "Deconvolution"):
+            cp = get(l, "convolution_param")
+            sh, sw = _hw(cp, "stride", "stride_h", "stride_w", 1)
+            ph, pw = _hw(cp, "pad", "pad_h", "pad_w", 0)
+            has_bias = get(cp, "bias_term", "true") == "true"
+            w = self.weights[name][0]
+            out, dw, db = [], 0, 0
+            for x, td in zip(bots, tds):
+                gx, gw, gb = O.conv_bwd(x, w, td, (sh, sw), (ph, pw), typ == "Deconvolution")
+                out.append(gx)
+                dw, db = dw + gw.astype(np.float64), db + gb.astype(np.float64)
+            P[name] = [np.asarray(dw, np.float32)] + ([np.asarray(db, np.float32)] if has_bias else [])
+            return out
+        if typ == "ReLU":
+            return [O.relu_bwd(tops[0], tds[0], float(get(get(l, "relu_param", []), "negative_slope", 0)))]
+        if typ == "Eltwise":
+            coeffs = [float(c) for c in getall(get(l, "eltwise_param", []), "coeff")] or [1.0] * len(bots)
+            return [np.float32(c) * tds[0] for c in coeffs]
+        if typ == "Concat":
+            out, c0 = [], 0
+            for b in bots:
+                out.append(tds[0][:, c0:c0 + b.shape[1]].copy())
+                c0 += b.shape[1]
+            return out
+        if typ == "Correlation":
+            cp = get(l, "correlation_param")
+            ct = {"MULTIPLY": 0, "SUBTRACT": 1}[get(cp, "correlation_type", "MULTIPLY")]
+            g0, g1 = O.correlation_bwd_ex(bots[0], bots[1], tds[0], int(get(cp, "pad", 0)), int(get(cp, "kernel_size")),
+                                          int(get(cp, "max_displacement")), int(get(cp, "stride_1", 1)), int(get(cp, "stride_2", 1)), ct)
+            return [g0, g1]
+        if typ == "FlowWarp":
+            g0, g1 = O.flow_warp_bwd(bots[0], bots[1], tds[0])
+            return [g0, g1]
+        if typ in ("DataAugmentation", "Resample", "Silence"):
+            return [None] * len(bots)
+        raise NotImplementedError("backward of " + typ)
+
     def _aug(self, l, name, x):
         ap = get(l, "augmentation_param")
         N, C, H, W = x.shape

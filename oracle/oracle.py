@@ -263,6 +263,54 @@ def deconv_fwd(x, weight, bias=None, stride=1, pad=0, group=1, f64acc=False):
     return out
 
 
+def conv_bwd(x, weight, top_diff, stride=1, pad=0, deconv=False):
+    """Gradients of ConvolutionLayer / DeconvolutionLayer (conv_layer.cpp:40-73, deconv_layer.cpp:40-74 ->
+    base_conv_layer.cpp:329-350 backward_cpu_gemm / weight_cpu_gemm / backward_cpu_bias), restated tap by tap with float64
+    accumulation: -> (bottom_diff, weight_diff, bias_diff), group 1, no dilation.  The deconvolution is the convolution with
+    the roles of bottom and top exchanged (its forward is conv's backward_cpu_gemm, its data gradient conv's forward_cpu_gemm)."""
+    x = np.asarray(x, np.float64)
+    w = np.asarray(weight, np.float64)
+    dy = np.asarray(top_diff, np.float64)
+    sh, sw = _pair(stride)
+    ph, pw = _pair(pad)
+    kh, kw = w.shape[2:]
+    if deconv:
+        small, big = x, dy            # weight [C_small][C_big][kh][kw]
+    else:
+        small, big = dy, x            # weight [C_small][C_big][kh][kw] with small = top
+    N, Cb, H, W = big.shape
+    Hs, Ws = small.shape[2:]
+    bp = np.zeros((N, Cb, H + 2 * ph + sh, W + 2 * pw + sw))
+    bp[:, :, ph:ph + H, pw:pw + W] = big
+    dw = np.zeros_like(w)
+    gbig = np.zeros_like(bp)
+    for ky in range(kh):
+        for kx in range(kw):
+            win = (slice(None), slice(None), slice(ky, ky + sh * (Hs - 1) + 1, sh), slice(kx, kx + sw * (Ws - 1) + 1, sw))
+            # small[n,a,i,j] pairs with big_padded[n,b,i*s+ky,j*s+kx] through w[a,b,ky,kx]
+            dw[:, :, ky, kx] = np.einsum("naij,nbij->ab", small, bp[win])
+            gbig[win] += np.einsum("naij,ab->nbij", small, w[:, :, ky, kx])
+    gbig = gbig[:, :, ph:ph + H, pw:pw + W]
+    if deconv:
+        # bottom = small: its gradient is the convolution of the top diff with the same weights
+        dx = np.zeros_like(x)
+        for ky in range(kh):
+            for kx in range(kw):
+                win = (slice(None), slice(None), slice(ky, ky + sh * (Hs - 1) + 1, sh), slice(kx, kx + sw * (Ws - 1) + 1, sw))
+                dx += np.einsum("nbij,ab->naij", bp[win], w[:, :, ky, kx])
+        db = dy.sum(axis=(0, 2, 3))
+        return dx.astype(np.float32), dw.astype(np.float32), db.astype(np.float32)
+    db = dy.sum(axis=(0, 2, 3))
+    return gbig.astype(np.float32), dw.astype(np.float32), db.astype(np.float32)
+
+
+def relu_bwd(top_data, top_diff, negative_slope=0.0):
+    """relu_layer.cpp:26-41 evaluated from the top data (the layer runs in place in every FlowNet prototxt)."""
+    t = np.asarray(top_data, np.float32)
+    d = np.asarray(top_diff, np.float32)
+    return (d * ((t > 0) + np.float32(negative_slope) * (t <= 0))).astype(np.float32)
+
+
 def relu(x, negative_slope=0.0):
     x, px = _f(x)
     out = np.empty_like(x)
