@@ -143,6 +143,21 @@ def fill_template(text, width, height):
     return text
 
 
+def train_template(name="FlowNet2-C"):
+    """Text of models/<name>_train.prototxt.template (the authored FlowNet2-C training graph of BASELINE config 5)."""
+    p = os.path.join(os.path.dirname(_HERE), "models", "%s_train.prototxt.template" % name)
+    with open(p) as f:
+        return f.read()
+
+
+def fill_train_template(text, crop_width, crop_height, data_width, data_height, batch):
+    """Training template variables: $TARGET_*$ = the augmentation crop (network input), $DATA_*$ = the frames read, $BATCH$."""
+    for key, value in (("TARGET_WIDTH", crop_width), ("TARGET_HEIGHT", crop_height), ("DATA_WIDTH", data_width),
+                       ("DATA_HEIGHT", data_height), ("BATCH", batch)):
+        text = text.replace("$%s$" % key, str(value))
+    return text
+
+
 def model_template(name):
     """Text of models/<name>_deploy.prototxt.template (FlowNet2, FlowNet2-C, -S, -CSS, -SD)."""
     p = os.path.join(os.path.dirname(_HERE), "models", "%s_deploy.prototxt.template" % name)

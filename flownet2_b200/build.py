@@ -34,6 +34,7 @@ SOURCES = [
     ("fn2_conv_tc.cu", []),
     ("fn2_conv_tn.cu", []),
     ("fn2_train.cu", []),
+    ("fn2_loss.cu", []),
     ("caffe/proto.cpp", []),
     ("caffe/blob.cpp", []),
     ("caffe/layers.cpp", []),

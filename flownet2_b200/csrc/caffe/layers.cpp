@@ -1230,6 +1230,267 @@ class DataAugmentationLayer : public Layer<Dtype> {
 };
 REGISTER_LAYER_CLASS(DataAugmentation);
 
+// ---------------------------------------------------------------------------------------------
+// Training-side layers next to the FlowNet2-C training step (SURVEY.md 8 "next" row 2)
+// ---------------------------------------------------------------------------------------------
+static TransMat TransMatFromArray(const float* arr, int cw, int ch, int bw, int bh) {
+    // array_to_coeff sets every field (augmentation_layer_base.cpp:368-379), so fromCoeff applies every factor (:38-48)
+    AugCoeff c;
+    c.from_array(arr);
+    TransMat t; t.toIdentity();
+    if (c.get(AugCoeff::MIRROR)) t.leftMultiply(-1, 0, 0, 1, .5f * (float)cw, -.5f * (float)ch);
+    else                         t.leftMultiply(1, 0, 0, 1, -.5f * (float)cw, -.5f * (float)ch);
+    const float a = c.get(AugCoeff::ANGLE);
+    t.leftMultiply(std::cos(a), std::sin(a), -std::sin(a), std::cos(a), 0, 0);
+    t.leftMultiply(1, 0, 0, 1, c.get(AugCoeff::DX) * (float)cw, c.get(AugCoeff::DY) * (float)ch);
+    t.leftMultiply((float)(1.0 / c.get(AugCoeff::ZOOM_X)), 0, 0, (float)(1.0 / c.get(AugCoeff::ZOOM_Y)), 0, 0);
+    t.leftMultiply(1, 0, 0, 1, .5f * (float)bw, .5f * (float)bh);
+    return t;
+}
+static TransMat TransMatInverse(const TransMat& m) {              // augmentation_layer_base.cpp:51-68
+    const float a = m.t0, c = m.t2, e = m.t4, b = m.t1, d = m.t3, f = m.t5;
+    const float denom = a * d - b * c;
+    TransMat r;
+    r.t0 = d / denom; r.t1 = -b / denom; r.t2 = -c / denom; r.t3 = a / denom;
+    r.t4 = (c * f - d * e) / denom; r.t5 = (b * e - a * f) / denom;
+    return r;
+}
+
+// L1Loss (l1_loss_layer.hpp, l1loss_layer.cpp:11-90, l1loss_layer.cu:67-192): NaN-masked L1 / end-point-error loss
+template <typename Dtype>
+class L1LossLayer : public Layer<Dtype> {
+ public:
+    explicit L1LossLayer(const LayerParameter& p) : Layer<Dtype>(p) {}
+    ~L1LossLayer() override { if (state_) cudaFree(state_); if (ws_) cudaFree(ws_); }
+    const char* type() const override { return "L1Loss"; }
+    bool IsLossLayer() const override { return true; }
+    typename Blob<Dtype>::Layout TopLayout() const override { return Blob<Dtype>::PLAIN; }
+    void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        CHECK(bottom.size() == 1 || bottom.size() == 2) << "L1LossLayer needs one or two input blobs.";
+        const Message& lp = this->layer_param_.m->msg("l1_loss_param");
+        d_.l2_per_location = lp.b("l2_per_location", false) ? 1 : 0;
+        d_.l2_prescale_by_channels = lp.b("l2_prescale_by_channels", false) ? 1 : 0;
+        d_.normalize_by_num_entries = lp.b("normalize_by_num_entries", false) ? 1 : 0;
+        d_.epsilon = lp.f("epsilon", 1e-2f);
+        d_.plateau = lp.f("plateau", 0.f);
+        CUDA_CHECK(cudaMalloc(&state_, 4 * sizeof(float)));
+        CUDA_CHECK(cudaMemset(state_, 0, 4 * sizeof(float)));
+    }
+    void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        if (bottom.size() > 1) CHECK(bottom[0]->shape() == bottom[1]->shape()) << "L1Loss: bottoms must have the same shape";
+        top[0]->set_layout(Blob<Dtype>::PLAIN);
+        top[0]->Reshape(vector<int>());                               // loss layers output a scalar (l1loss_layer.cpp:69-70)
+        size_t need = 0;
+        FN2_CALL(fn2_l1loss_workspace_bytes(bottom[0]->num(), bottom[0]->height(), bottom[0]->width(), &need));
+        if (need > ws_bytes_) { if (ws_) cudaFree(ws_); CUDA_CHECK(cudaMalloc(&ws_, need)); ws_bytes_ = need; }
+    }
+    void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        fn2_tensor b0 = bottom[0]->tensor(), b1 = b0;
+        if (bottom.size() > 1) b1 = bottom[1]->tensor();
+        FN2_CALL(fn2_l1loss_forward(&b0, bottom.size() > 1 ? &b1 : nullptr, &d_, state_, top[0]->mutable_gpu_data(), ws_, ws_bytes_, S()));
+    }
+    void Backward_gpu(const vector<Blob<Dtype>*>& top, const vector<bool>& propagate_down, const vector<Blob<Dtype>*>& bottom) override {
+        const bool p0 = propagate_down[0], p1 = bottom.size() > 1 && propagate_down[1];
+        if (!p0 && !p1) return;
+        fn2_tensor b0 = bottom[0]->tensor(), b1 = b0, d0 = b0, d1 = b0;
+        if (bottom.size() > 1) b1 = bottom[1]->tensor();
+        if (p0) d0 = bottom[0]->diff_tensor();
+        if (p1) d1 = bottom[1]->diff_tensor();
+        fn2_tensor td = top[0]->diff_tensor();
+        FN2_CALL(fn2_l1loss_backward(&b0, bottom.size() > 1 ? &b1 : nullptr, &d_, state_, td.data, p0 ? &d0 : nullptr, p1 ? &d1 : nullptr,
+                                     this->bottom_accumulate_[0] ? 1 : 0, bottom.size() > 1 && this->bottom_accumulate_[1] ? 1 : 0, S()));
+    }
+ protected:
+    fn2_l1loss_desc d_;
+    float* state_ = nullptr;
+    void* ws_ = nullptr;
+    size_t ws_bytes_ = 0;
+};
+REGISTER_LAYER_CLASS(L1Loss);
+
+// Downsample (downsample_layer.cpp:20-58, downsample_layer.cu:15-80): ground-truth pyramid for the multi-scale losses
+template <typename Dtype>
+class DownsampleLayer : public Layer<Dtype> {
+ public:
+    explicit DownsampleLayer(const LayerParameter& p) : Layer<Dtype>(p) {}
+    const char* type() const override { return "Downsample"; }
+    bool AllowBackward() const override { return false; }             // "DownsamplingLayer cannot do backward." (.cu:131-137)
+    typename Blob<Dtype>::Layout TopLayout() const override { return Blob<Dtype>::PLAIN; }
+    void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        CHECK(bottom.size() >= 1 && bottom.size() <= 2 && top.size() == 1) << "Downsample takes one or two bottoms and one top";
+        this->layer_param_.m->set("reshape_every_iter", "false");
+        int th, tw;
+        if (bottom.size() == 1) {
+            const Message& dp = this->layer_param_.m->msg("downsample_param");
+            th = dp.i("top_height", 0); tw = dp.i("top_width", 0);
+        } else { th = bottom[1]->height(); tw = bottom[1]->width(); }
+        CHECK_GE(th, 1) << "DownsampleLayer must have top_height > 0";
+        CHECK_GE(tw, 1) << "DownsampleLayer must have top_width > 0";
+        top[0]->Reshape(bottom[0]->num(), bottom[0]->channels(), th, tw);
+    }
+    void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        fn2_tensor b = bottom[0]->tensor(), t = top[0]->mutable_tensor();
+        FN2_CALL(fn2_downsample_forward(&b, &t, S()));
+    }
+};
+REGISTER_LAYER_CLASS(Downsample);
+
+// FlowAugmentation (flow_augmentation_layer.cpp:30-75, .cu:24-166): the ground-truth flow under the two images' spatial
+// transforms.  bottoms: flow, coefficient blob of image 1, coefficient blob of image 2 (N x 42 each).
+template <typename Dtype>
+class FlowAugmentationLayer : public Layer<Dtype> {
+ public:
+    explicit FlowAugmentationLayer(const LayerParameter& p) : Layer<Dtype>(p) {}
+    ~FlowAugmentationLayer() override { if (mats_dev_) cudaFree(mats_dev_); if (mats_host_) cudaFreeHost(mats_host_); }
+    const char* type() const override { return "FlowAugmentation"; }
+    bool AllowBackward() const override { return false; }             // flow_augmentation_layer.hpp
+    bool GraphSafe() const override { return false; }                 // the matrices come from host blobs every pass
+    typename Blob<Dtype>::Layout TopLayout() const override { return Blob<Dtype>::PLAIN; }
+    void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        AugmentationParameter aug = this->layer_param_.augmentation_param();
+        CHECK_GT(aug.crop_width(), 0) << "Please enter crop width if you want to perform augmentation";
+        CHECK_GT(aug.crop_height(), 0) << "Please enter crop height if you want to perform augmentation";
+        this->layer_param_.m->set("reshape_every_iter", "false");
+    }
+    void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        CHECK_EQ(bottom.size(), 3) << "Flow augmentation layer takes three input blobs: FlowField, Img1TransfParams, Img2TransfParams";
+        CHECK_EQ(top.size(), 1) << "Flow augmentation layer outputs one output blob: Augmented Flow";
+        CHECK_EQ(bottom[0]->channels(), 2) << "Flow data must have two channels";
+        AugmentationParameter aug = this->layer_param_.augmentation_param();
+        cw_ = aug.crop_width(); ch_ = aug.crop_height();
+        const int num = bottom[0]->num();
+        top[0]->Reshape(num, 2, ch_, cw_);
+        if (num > cap_) {
+            if (mats_dev_) cudaFree(mats_dev_);
+            if (mats_host_) cudaFreeHost(mats_host_);
+            CUDA_CHECK(cudaMalloc(&mats_dev_, (size_t)num * 12 * sizeof(float)));
+            CUDA_CHECK(cudaMallocHost(&mats_host_, (size_t)num * 12 * sizeof(float)));
+            cap_ = num;
+        }
+    }
+    void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        const int num = bottom[0]->num();
+        CHECK_EQ(bottom[1]->count(), num * AugCoeff::N) << "FlowAugmentation: coefficient blob 1 must be N x 42";
+        CHECK_EQ(bottom[2]->count(), num * AugCoeff::N) << "FlowAugmentation: coefficient blob 2 must be N x 42";
+        const float* p1 = bottom[1]->cpu_data();
+        const float* p2 = bottom[2]->cpu_data();
+        CUDA_CHECK(cudaStreamSynchronize(S()));                         // the previous pass may still read mats_host_
+        for (int n = 0; n < num; n++) {
+            const TransMat m1 = TransMatFromArray(p1 + (size_t)n * AugCoeff::N, cw_, ch_, bottom[0]->width(), bottom[0]->height());
+            const TransMat m2 = TransMatInverse(TransMatFromArray(p2 + (size_t)n * AugCoeff::N, cw_, ch_, bottom[0]->width(), bottom[0]->height()));
+            float* a = mats_host_ + 6 * n;
+            float* b = mats_host_ + 6 * num + 6 * n;
+            a[0] = m1.t0; a[1] = m1.t1; a[2] = m1.t2; a[3] = m1.t3; a[4] = m1.t4; a[5] = m1.t5;
+            b[0] = m2.t0; b[1] = m2.t1; b[2] = m2.t2; b[3] = m2.t3; b[4] = m2.t4; b[5] = m2.t5;
+        }
+        CUDA_CHECK(cudaMemcpyAsync(mats_dev_, mats_host_, (size_t)num * 12 * sizeof(float), cudaMemcpyHostToDevice, S()));
+        fn2_tensor b = bottom[0]->tensor(), t = top[0]->mutable_tensor();
+        FN2_CALL(fn2_flow_augmentation(&b, &t, mats_dev_, mats_dev_ + 6 * num, S()));
+    }
+ protected:
+    int cw_ = 0, ch_ = 0, cap_ = 0;
+    float* mats_dev_ = nullptr;
+    float* mats_host_ = nullptr;
+};
+REGISTER_LAYER_CLASS(FlowAugmentation);
+
+// GenerateAugmentationParameters (generate_augmentation_parameters_layer.cpp:33-105, .cu:16-117): host-only coefficient
+// generator; modes "add" / "replace" / "regenerate" against an incoming coefficient blob.
+template <typename Dtype>
+class GenerateAugmentationParametersLayer : public Layer<Dtype> {
+ public:
+    explicit GenerateAugmentationParametersLayer(const LayerParameter& p) : Layer<Dtype>(p), sampler_(seed_of(p.name())) {}
+    const char* type() const override { return "GenerateAugmentationParameters"; }
+    bool AllowBackward() const override { return false; }
+    bool GraphSafe() const override { return false; }
+    typename Blob<Dtype>::Layout TopLayout() const override { return Blob<Dtype>::PLAIN; }
+    void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        this->layer_param_.m->set("reshape_every_iter", "false");
+    }
+    void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        AugmentationParameter aug = this->layer_param_.augmentation_param();
+        CHECK(bottom.size() == 1 || bottom.size() == 3) << "Generate augmentation parameters layer takes one (any blob from which it can "
+            "take num and potentially original image size) or three (aug params, orig data, augmented data) input blobs.";
+        CHECK_EQ(top.size(), 1) << "Generate augmentation parameters layer outputs one output blob.";
+        mode_ = aug.m->str_or("mode", "add");
+        if (bottom.size() == 1 && (bottom[0]->width() > 1 || bottom[0]->height() > 1)) mode_ = "regenerate";
+        num_ = bottom[0]->num();
+        if (bottom.size() == 3) {
+            cw_ = bottom[2]->width(); ch_ = bottom[2]->height(); bw_ = bottom[1]->width(); bh_ = bottom[1]->height();
+        } else {
+            CHECK(aug.has_crop_width() && aug.has_crop_height()) << "Need crop_width and crop_height if there is no blob specifying these";
+            cw_ = aug.crop_width(); ch_ = aug.crop_height();
+            if (bottom[0]->width() > 1 || bottom[0]->height() > 1) { bw_ = bottom[0]->width(); bh_ = bottom[0]->height(); }
+            else {
+                CHECK(aug.m->has("bottomwidth") && aug.m->has("bottomheight")) << "Need bottomwidth and bottomheight if there is no blob specifying these";
+                bw_ = aug.m->i("bottomwidth", 0); bh_ = aug.m->i("bottomheight", 0);
+            }
+        }
+        CHECK_GE(num_, 1) << "Must provide num with a bottom blob or in the prototxt";
+        top[0]->set_layout(Blob<Dtype>::PLAIN);
+        top[0]->Reshape(num_, AugCoeff::N, 1, 1);
+        num_iter_ = 0;
+    }
+    void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        AugmentationParameter aug = this->layer_param_.augmentation_param();
+        num_iter_++;
+        const float dc = AugSampler::discount(this->layer_param_, (float)num_iter_);
+        bool spatial = false, chromatic = false, effect = false, eigen = false;
+        if (this->phase_ == TRAIN || aug.augment_during_test()) {
+            spatial = aug.has("mirror") || aug.has("rotate") || aug.has("zoom") || aug.has("translate") || aug.has("squeeze") ||
+                      aug.has("translate_x") || aug.has("translate_y");
+            chromatic = aug.has("brightness") || aug.has("gamma") || aug.has("contrast") || aug.has("color");
+            effect = aug.has("fog_size") || aug.has("fog_amount") || aug.has("motion_blur_angle") || aug.has("motion_blur_size") ||
+                     aug.has("shadow_angle") || aug.has("shadow_distance") || aug.has("shadow_strength") || aug.has("noise");
+            eigen = aug.has("lmult_pow") || aug.has("lmult_mult") || aug.has("lmult_add") || aug.has("sat_pow") || aug.has("sat_mult") ||
+                    aug.has("sat_add") || aug.has("col_pow") || aug.has("col_mult") || aug.has("col_add") || aug.has("ladd_pow") ||
+                    aug.has("ladd_mult") || aug.has("ladd_add") || aug.has("col_rotate");
+        }
+        if (spatial) CHECK(cw_ >= 1 && ch_ >= 1 && bw_ >= 1 && bh_ >= 1) << "Must provide crop and bottom sizes to do spatial augmentations";
+        const bool use_in = mode_ == "add" || mode_ == "replace";
+        const float* in = use_in ? bottom[0]->cpu_data() : nullptr;
+        float* out = top[0]->mutable_cpu_data();
+        const bool fresh = mode_ == "regenerate" || mode_ == "replace";
+        for (int n = 0; n < num_; n++) {
+            AugCoeff c;
+            if (use_in) c.from_array(in + (size_t)n * AugCoeff::N);
+            if (spatial) {
+                if (mode_ == "replace") for (int f = AugCoeff::MIRROR; f <= AugCoeff::ZOOM_Y; f++) c.clear(f);     // clear_spatial_coeffs
+                sampler_.generate_valid_spatial(aug, c, dc, bw_, bh_, cw_, ch_, 50);
+            }
+            float* o = out + (size_t)n * AugCoeff::N;
+            c.to_array(o);
+            // the other groups either overwrite fields of the running record ("regenerate" / "replace") or are drawn into a fresh
+            // record whose array form is ADDED (add_coeff_to_array, augmentation_layer_base.cpp:172-180)
+            auto group = [&](bool on, void (AugSampler::*gen)(const AugmentationParameter&, AugCoeff&, float)) {
+                if (!on) return;
+                if (fresh) { (sampler_.*gen)(aug, c, dc); c.to_array(o); }
+                else {
+                    AugCoeff tmp;
+                    (sampler_.*gen)(aug, tmp, dc);
+                    float arr[AugCoeff::N];
+                    tmp.to_array(arr);
+                    for (int f = 0; f < AugCoeff::N; f++) o[f] += arr[f];
+                }
+            };
+            group(chromatic, &AugSampler::generate_chromatic);
+            group(eigen, &AugSampler::generate_chromatic_eigen);
+            group(effect, &AugSampler::generate_effect);
+        }
+    }
+ protected:
+    static uint32_t seed_of(const std::string& name) {
+        uint32_t h = 1701u;
+        if (const char* e = getenv("FN2_SEED")) h = (uint32_t)strtoul(e, nullptr, 10);
+        for (char c : name) h = h * 16777619u ^ (unsigned char)c;
+        return h;
+    }
+    std::string mode_;
+    int num_ = 0, cw_ = 0, ch_ = 0, bw_ = 0, bh_ = 0, num_iter_ = 0;
+    AugSampler sampler_;
+};
+REGISTER_LAYER_CLASS(GenerateAugmentationParameters);
+
 // referenced by net.cpp to force this translation unit (and its static registrars) to link
 void RegisterFlowNetLayers() {}
 

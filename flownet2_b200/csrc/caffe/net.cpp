@@ -41,6 +41,7 @@ template <typename Dtype>
 void Net<Dtype>::Init(const NetParameter& param) {
     Caffe::stream() = stream_;
     name_ = param.name;
+    force_backward_ = param.force_backward;
     std::set<string> available;
     for (const LayerParameter& lp : param.layers) {
         if (!lp.included_in_phase((int)phase_)) continue;
@@ -432,8 +433,14 @@ void Net<Dtype>::PlanBackward() {
     const int L = (int)layers_.size(), B = (int)blobs_.size();
     vector<char> blob_need(B, 0), under_loss(B, 0);
     vector<char> layer_need(L, 0);
+    if (force_backward_) for (int b : net_input_blob_indices_) blob_need[b] = 1;       // net.cpp:96-100, :262-267
     for (int i = 0; i < L; i++) {
-        bool need = !layers_[i]->blobs().empty();
+        bool need = false;                                           // a parameter with lr_mult != 0 (net.cpp:223-262; default 1)
+        for (size_t pi = 0; pi < layers_[i]->blobs().size(); pi++) {
+            const LayerParameter& lpp = layers_[i]->layer_param();
+            const float lr = (int)pi < lpp.m->count("param") ? lpp.m->msg("param", (int)pi).f("lr_mult", 1.f) : 1.f;
+            if (lr != 0.f) need = true;
+        }
         for (int b : bottom_id_vecs_[i]) if (blob_need[b]) need = true;
         if (!layers_[i]->AllowBackward()) need = false;
         layer_need[i] = need;
@@ -503,6 +510,7 @@ void Net<Dtype>::PlanBackward() {
     for (int i = 0; i < L; i++) layers_[i]->set_bottom_accumulate(bw_accumulate_[i]);
     // loss seeds: top diff = loss_weight (scalar tops)
     for (auto& lt : loss_tops) {
+        if (bw_seeds_.count(lt.first)) continue;                     // an explicit SetDiff on a loss top wins over its loss_weight
         Blob<Dtype>* bl = blobs_[lt.first].get();
         vector<Dtype> v((size_t)bl->count(), lt.second);
         bl->set_cpu_diff(v.data());

@@ -70,6 +70,7 @@ class Net {
     void BuildDiffArena();
     // backward plan (static per graph + seed set): which layers run, per bottom whether the gradient is wanted and whether it is
     // added to a diff an earlier-run consumer already wrote; blobs cleared before the sweep
+    bool force_backward_ = false;
     bool bw_planned_ = false;
     vector<char> bw_run_;
     vector<vector<bool> > bw_propagate_, bw_accumulate_;

@@ -353,6 +353,7 @@ NetParameter NetParameter::FromText(const std::string& prototxt) {
     Message root = ParseTextFormat(prototxt);
     NetParameter np;
     np.name = root.str("name");
+    np.force_backward = root.b("force_backward", false);
     if (root.count("layers"))
         throw ParseError("V1 'layers' prototxt is not supported; upgrade it with upgrade_net_proto_text");
     // legacy top-level inputs -> one Input layer named "input" placed first (upgrade_proto.cpp:953-992)

@@ -176,6 +176,7 @@ struct LayerParameter {                        // caffe.proto:312-425
 
 struct NetParameter {
     std::string name;
+    bool force_backward = false;               // caffe.proto:88-91: gradients also for blobs no parameter depends on (inputs)
     std::vector<LayerParameter> layers;
     // Builds the layer list from a parsed prototxt, rewriting legacy `input:` +
     // `input_shape{}` / `input_dim:` into one Input layer placed first

@@ -200,6 +200,31 @@ FN2_API int fn2_conv_backward_params(const fn2_conv_desc* d, const fn2_tensor* b
 FN2_API int fn2_conv_backward_data_desc(const fn2_conv_desc* d, int bottom_h, int bottom_w, fn2_conv_desc* out, int* needs_flip);
 FN2_API int fn2_conv_flip_transpose_weights(const fn2_conv_desc* d, const float* caffe_weights_dev, float* derived_dev, void* stream);
 
+/* Training-side neighbours of config 5 (SURVEY.md 8 "next" row 2).
+ * L1Loss -- replaces L1LossLayer::Forward_gpu / Backward_gpu (l1loss_layer.cu:67-192; the CPU paths are NOT_IMPLEMENTED in the
+ * reference, l1loss_layer.cpp:93-102).  bottom1 may be NULL (single-bottom form).  state_dev: 4 device floats the forward
+ * writes and the backward reads: {loss, normalize_coeff, masked sum, not-NaN count}; loss_dev (may be NULL) also receives the
+ * loss.  top_diff_dev: device scalar (the loss weight).  The backward recomputes the difference and the NaN / plateau masks from
+ * the bottoms; a NULL diff pointer means "do not propagate to this bottom"; accumulate != 0 adds to the diff. */
+typedef struct fn2_l1loss_desc {
+    int32_t l2_per_location, l2_prescale_by_channels, normalize_by_num_entries;   /* L1LossParameter, caffe.proto:619-625 */
+    float epsilon, plateau;
+} fn2_l1loss_desc;
+FN2_API int fn2_l1loss_workspace_bytes(int N, int H, int W, size_t* bytes);
+FN2_API int fn2_l1loss_forward(const fn2_tensor* bottom0, const fn2_tensor* bottom1, const fn2_l1loss_desc* d, float* state_dev,
+                               float* loss_dev, void* workspace, size_t workspace_bytes, void* stream);
+FN2_API int fn2_l1loss_backward(const fn2_tensor* bottom0, const fn2_tensor* bottom1, const fn2_l1loss_desc* d,
+                                const float* state_dev, const float* top_diff_dev, const fn2_tensor* bottom0_diff,
+                                const fn2_tensor* bottom1_diff, int accumulate0, int accumulate1, void* stream);
+/* Downsample -- replaces DownsampleFeatures (downsample_layer.cu:15-80): NaN-aware weighted average around the rounded source
+ * position; equal sizes copy (the reference shares the data, downsample_layer.cpp:55-58). */
+FN2_API int fn2_downsample_forward(const fn2_tensor* bottom, const fn2_tensor* top, void* stream);
+/* FlowAugmentation -- replaces WarpData (flow_augmentation_layer.cu:24-66).  mats: device arrays, 6 floats per sample in NAME
+ * order t0..t5 as for fn2_spatial_augmentation; the second one already inverted (tTransMat::inverse,
+ * augmentation_layer_base.cpp:51-68). */
+FN2_API int fn2_flow_augmentation(const fn2_tensor* flow, const fn2_tensor* top, const float* mats1_dev,
+                                  const float* mats2_inverse_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------ */
 /* Glue: ReLU (relu_layer.cu:9-14), Eltwise SUM with coeffs (eltwise_layer.cu),           */
 /* ChannelNorm (channel_norm_layer.cu:17-30), strided copy (Concat concat_layer.cu,        */

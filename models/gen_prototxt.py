@@ -268,6 +268,60 @@ def build_full():
     return p.text()
 
 
+# ---- FlowNet2-C training net (BASELINE.json config 5) ------------------------------------------------------------------------
+# NOT-IN-REF like the deploy templates: authored from the public description of the FlowNetC training setup (FlyingChairs 512x384
+# frames cropped to 448x320 by the augmentation, multi-scale end-point-error losses with weights 0.32 / 0.08 / 0.02 / 0.01 / 0.005,
+# ground truth scaled by 1/20 and downsampled per level) with the layer types of the reference's caffe.proto.  The CustomData /
+# LMDB reader is out of scope: img0, img1, flow_gt are Input blobs.
+def _gen(kind, exp, mean, spread):
+    return ('{ rand_type: "%s" exp: %s mean: %g spread: %g prob: 1.0 }' % (kind, "true" if exp else "false", mean, spread))
+
+
+EIGVEC = [0.51, 0.56, 0.65, 0.79, 0.01, -0.62, 0.35, -0.83, 0.44]
+
+
+def build_c_train():
+    p = P()
+    p.add('name: "FlowNet2-C-train"\n')
+    p.layer("data", "Input", [], ["img0", "img1", "flow_gt"],
+            "  input_param {\n" + "".join("    shape { dim: $BATCH$ dim: %d dim: $DATA_HEIGHT$ dim: $DATA_WIDTH$ }\n" % c for c in (3, 3, 2)) + "  }\n")
+    for i in (0, 1):
+        scale(p, "Eltwise%d" % (i + 1), "img%d" % i, "img%ds" % i, "0.00392156862745")
+    ub, gb = "uniform_bernoulli", "gaussian_bernoulli"
+    common = ("    max_multiplier: 1\n    augment_during_test: false\n    recompute_mean: 1000\n    mean_per_pixel: false\n"
+              "    crop_width: $TARGET_WIDTH$\n    crop_height: $TARGET_HEIGHT$\n")
+    spatial0 = ("    translate %s\n    rotate %s\n    zoom %s\n    squeeze %s\n"
+                % (_gen(ub, False, 0, 0.4), _gen(ub, False, 0, 0.4), _gen(ub, True, 0.2, 0.4), _gen(ub, True, 0, 0.3)))
+    chroma = "".join("    %s %s\n" % (n, g) for n, g in (
+        ("lmult_pow", _gen(ub, True, -0.2, 0.4)), ("lmult_mult", _gen(ub, True, 0.0, 0.4)), ("lmult_add", _gen(ub, False, 0, 0.03)),
+        ("sat_pow", _gen(ub, True, 0, 0.4)), ("sat_mult", _gen(ub, True, -0.3, 0.5)), ("sat_add", _gen(ub, False, 0, 0.03)),
+        ("col_pow", _gen(gb, True, 0, 0.4)), ("col_mult", _gen(gb, True, 0, 0.2)), ("col_add", _gen(gb, False, 0, 0.02)),
+        ("ladd_pow", _gen(gb, True, 0, 0.4)), ("ladd_mult", _gen(gb, True, 0.0, 0.4)), ("ladd_add", _gen(gb, False, 0, 0.04)),
+        ("col_rotate", _gen(ub, False, 0, 1)), ("noise", _gen(ub, False, 0.03, 0.03))))
+    eig = "".join("    chromatic_eigvec: %g\n" % e for e in EIGVEC)
+    sched = "  coeff_schedule_param {\n    half_life: 50000\n    initial_coeff: 0.5\n    final_coeff: 1\n  }\n"
+    p.layer("img0s_aug", "DataAugmentation", ["img0s"], ["img0_aug", "img0_aug_params"],
+            "  propagate_down: false\n  augmentation_param {\n" + common + spatial0 + chroma + eig + "  }\n" + sched)
+    # second frame: the first frame's coefficients plus a small relative transform and colour change
+    p.layer("aug_params1", "GenerateAugmentationParameters", ["img0_aug_params", "img0s", "img0_aug"], ["img1_aug_params"],
+            "  augmentation_param {\n    augment_during_test: false\n    mode: \"add\"\n"
+            "    translate %s\n    rotate %s\n    zoom %s\n    gamma %s\n    brightness %s\n    contrast %s\n    color %s\n  }\n"
+            % (_gen(ub, False, 0, 0.03), _gen(ub, False, 0, 0.03), _gen(ub, True, 0, 0.03), _gen(gb, True, 0, 0.02),
+               _gen(gb, False, 0, 0.02), _gen(gb, True, 0, 0.02), _gen(gb, True, 0, 0.02)) + sched)
+    p.layer("img1s_aug", "DataAugmentation", ["img1s", "img1_aug_params"], ["img1_aug"],
+            "  propagate_down: false\n  propagate_down: false\n  augmentation_param {\n" + common + eig + "  }\n")
+    p.layer("flow_aug", "FlowAugmentation", ["flow_gt", "img0_aug_params", "img1_aug_params"], ["flow_gt_aug"],
+            "  augmentation_param {\n    crop_width: $TARGET_WIDTH$\n    crop_height: $TARGET_HEIGHT$\n  }\n")
+    scale(p, "scale_gt", "flow_gt_aug", "scaled_flow_gt_aug", "0.05")
+    flownet_c(p, "", "img0_aug", "img1_aug")
+    for lvl, wgt in ((6, 0.32), (5, 0.08), (4, 0.02), (3, 0.01), (2, 0.005)):
+        p.layer("Downsample%d" % lvl, "Downsample", ["scaled_flow_gt_aug", "predict_flow%d" % lvl], ["blob_gt%d" % lvl],
+                "  propagate_down: false\n  propagate_down: false\n")
+        p.layer("flow_loss%d" % lvl, "L1Loss", ["predict_flow%d" % lvl, "blob_gt%d" % lvl], ["flow_loss%d" % lvl],
+                "  loss_weight: %g\n  l1_loss_param {\n    l2_per_location: true\n  }\n" % wgt)
+    return p.text()
+
+
 MODELS = {"FlowNet2-S": build_s, "FlowNet2-C": build_c, "FlowNet2-CSS": build_css, "FlowNet2-SD": build_sd,
           "FlowNet2": build_full}
 
@@ -277,3 +331,7 @@ if __name__ == "__main__":
         with open(path, "w") as f:
             f.write(fn())
         print("wrote", path)
+    path = os.path.join(HERE, "FlowNet2-C_train.prototxt.template")
+    with open(path, "w") as f:
+        f.write(build_c_train())
+    print("wrote", path)

@@ -153,3 +153,66 @@ def check_eigenspace(ref_space, true_space):
     mx = ref_space[6:9].astype(np.float64)                                             # derived values follow THEIR max_abs_eig
     assert abs(float(ref_space[15]) - float(np.sqrt((mx * mx).sum()))) <= 1e-6
     return bool(np.array_equal(ref_space[6:15], true_space[6:15]))
+
+
+# ---- training-side cases (tests/golden/train_cases.py) ----------------------------------------------------------------------
+def _gens_of(layer_text):
+    """{generator name: {field: value}} of the augmentation_param of a layer block."""
+    from oracle.net import parse_prototxt, get
+    ap = get(parse_prototxt(layer_text), "augmentation_param", [])
+    gens = {}
+    for k, v in ap:
+        if isinstance(v, list):
+            d = {}
+            for kk, vv in v:
+                d[kk] = vv if kk == "rand_type" else (vv == "true" if vv in ("true", "false") else float(vv))
+            gens[k] = d
+    return gens
+
+
+def train_oracle_eval(name):
+    """-> {key: ndarray} with the keys tests/golden/train_golden.npz holds for this case, computed by the oracle."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import train_cases as TC
+    c = TC.TRAIN_CASES[name]
+    bottoms, params, r = TC.train_inputs(name)
+    k, out = c["kind"], {}
+    if k == "conv_bwd":
+        st, pd, dec = c["args"]
+        out["top0"] = (O.deconv_fwd if dec else O.conv_fwd)(bottoms[0], params[0], params[1], st, pd, f64acc=True)
+        td = r.standard_normal(out["top0"].shape).astype(np.float32)
+        out["bdiff0"], out["pdiff0"], out["pdiff1"] = O.conv_bwd(bottoms[0], params[0], td, st, pd, dec)
+    elif k == "l1loss":
+        b1 = bottoms[1] if len(bottoms) > 1 else None
+        loss, _ = O.l1loss_fwd(bottoms[0], b1, **c["args"])
+        out["top0"] = np.array([loss], np.float32)
+        g0, g1 = O.l1loss_bwd(bottoms[0], b1, c["top_diff"], **c["args"])
+        out["bdiff0"] = g0
+        if b1 is not None:
+            out["bdiff1"] = g1
+    elif k == "downsample":
+        out["top0"] = O.downsample_fwd(bottoms[0], *c["args"])
+    elif k == "flow_aug":
+        cw, ch = c["args"]
+        out["top0"] = O.flow_augmentation(bottoms[0], bottoms[1], bottoms[2], cw, ch)
+    elif k == "gen_aug":
+        mode, image = c["args"]
+        gens = _gens_of(c["text"])
+        if image:
+            arr = O.generate_augmentation_parameters(None, "regenerate", gens, 48, 32, bottoms[0].shape[3], bottoms[0].shape[2], num=bottoms[0].shape[0])
+        else:
+            arr = O.generate_augmentation_parameters(bottoms[0], mode, gens, 48, 32, 64, 48)
+        out["top0"] = arr.reshape(-1, 42, 1, 1)
+    else:
+        raise KeyError(k)
+    return out
+
+
+TRAIN_TOL = {
+    # relative to the largest entry of the tensor
+    "conv_bwd": 2e-6,        # fp32 cuBLAS gemm orders against float64 accumulation
+    "l1loss": 2e-6,          # cublasSdot order; powf(x, 0.5) against sqrtf
+    "downsample": 2e-6,      # FMA contraction of the reference's accumulation
+    "flow_aug": 2e-6,        # cos/sin/exp of the host libm, FMA contraction in the kernel (|flow| ~ 10)
+    "gen_aug": 2e-6,         # log/exp round trips of the array form
+}

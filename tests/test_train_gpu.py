@@ -170,3 +170,123 @@ def test_backward_without_fusion_or_aliasing_is_the_same(fn2, monkeypatch):
     assert len(res[0]) >= 20
     for k in res[0]:
         assert rel(res[0][k], res[1][k]) <= 1e-5, (k, rel(res[0][k], res[1][k]))
+
+
+# ---- training-side layers against the reference's recorded outputs (tests/golden/train_golden.npz) and the oracle -----------
+import os      # noqa: E402
+import sys     # noqa: E402
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import train_cases as TC                                       # noqa: E402
+from tests.refcheck import TRAIN_TOL, train_oracle_eval        # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_golden.npz")
+
+
+def single_layer_net(fn2, case, bottoms):
+    names = [n for n in __import__("re").findall(r'bottom:\s*"([^"]+)"', case["text"])]
+    shapes = "".join(" shape { %s }" % " ".join("dim: %d" % d for d in b.shape) for b in bottoms)
+    proto = ('force_backward: true\nlayer { name: "in" type: "Input" %s input_param {%s } }\nlayer { %s }\n'
+             % (" ".join('top: "%s"' % n for n in names), shapes, case["text"]))
+    net = fn2.Net(proto, None, fn2.TEST)
+    return net, names
+
+
+@pytest.mark.parametrize("name", list(TC.TRAIN_CASES))
+def test_training_layers_match_reference_and_oracle(fn2, name):
+    c = TC.TRAIN_CASES[name]
+    bottoms, params, r = TC.train_inputs(name)
+    net, names = single_layer_net(fn2, c, bottoms)
+    lname = net.layer_names[-1]
+    if params is not None:
+        from oracle.net import write_caffemodel
+        net.copy_from(write_caffemodel([(lname, net.layer_types[-1], params)]))
+    top = net.outputs[0]
+    out = {"top0": net.forward(**dict(zip(names, bottoms)))[top]}
+    k = c["kind"]
+    if k == "conv_bwd":
+        net.clear_param_diffs()
+        net.backward(**{top: r.standard_normal(out["top0"].shape).astype(np.float32)})
+        out["bdiff0"] = net.get_diff(names[0])
+        out["pdiff0"] = net.param(lname, 0, diff=True)
+        out["pdiff1"] = net.param(lname, 1, diff=True)
+    elif k == "l1loss":
+        net.backward(**{top: np.full(net.blobs[top].shape, c["top_diff"], np.float32)})
+        for i, n in enumerate(names):
+            out["bdiff%d" % i] = net.get_diff(n)
+    want_o = train_oracle_eval(name)
+    gold = np.load(GOLD) if os.path.exists(GOLD) else None
+    assert gold is not None, "tests/golden/train_golden.npz is missing"
+    tol = 5 * TRAIN_TOL[k]
+    for key, got in out.items():
+        for label, want in (("oracle", want_o[key]), ("reference", gold["T/%s/%s" % (name, key)])):
+            want = np.asarray(want)
+            g = np.asarray(got).reshape(want.shape)
+            scale = max(float(np.nanmax(np.abs(want))), 1e-6)
+            assert maxabs(g, want) <= tol * scale, (name, key, label, maxabs(g, want), scale)
+
+
+def test_l1loss_accumulates_into_a_shared_bottom(fn2):
+    """predict_flow blobs feed both the loss and the next decoder stage: the loss gradient must ADD to what the other consumer wrote."""
+    proto = ('force_backward: true\n'
+             'layer { name: "in" type: "Input" top: "a" top: "gt" input_param { shape { dim: 2 dim: 2 dim: 6 dim: 8 } shape { dim: 2 dim: 2 dim: 6 dim: 8 } } }\n'
+             'layer { name: "scale" type: "Eltwise" bottom: "a" top: "a2" eltwise_param { operation: SUM coeff: 3 } }\n'
+             'layer { name: "l1" type: "L1Loss" bottom: "a" bottom: "gt" top: "loss1" loss_weight: 0.5 l1_loss_param { l2_per_location: true } }\n'
+             'layer { name: "l2" type: "L1Loss" bottom: "a2" bottom: "gt" top: "loss2" loss_weight: 2 }\n')
+    net = fn2.Net(proto, None, fn2.TEST)
+    r = rng(21)
+    a = r.standard_normal((2, 2, 6, 8)).astype(np.float32)
+    gt = r.standard_normal((2, 2, 6, 8)).astype(np.float32)
+    out = net.forward(a=a, gt=gt)
+    l1, _ = O.l1loss_fwd(a, gt, l2_per_location=True)
+    l2, _ = O.l1loss_fwd(3 * a, gt)
+    assert abs(float(out["loss1"].reshape(-1)[0]) - l1) <= 1e-5 * l1 and abs(float(out["loss2"].reshape(-1)[0]) - l2) <= 1e-5 * l2
+    net.backward()
+    g1, _ = O.l1loss_bwd(a, gt, 0.5, l2_per_location=True)
+    g2, h2 = O.l1loss_bwd(3 * a, gt, 2.0)
+    assert maxabs(net.get_diff("a"), g1 + 3 * g2) <= 1e-6
+    assert maxabs(net.get_diff("gt"), -g1 + h2) <= 1e-6
+
+
+def test_flownet_c_training_net_step(fn2):
+    """The authored FlowNet2-C training graph (models/FlowNet2-C_train.prototxt.template): random augmentation of both frames and
+    of the ground truth, multi-scale end-point-error losses, backward.  Every training-side layer is checked in place against the
+    oracle given the blobs the net itself produced; the conv stack's gradients are covered by the deploy-graph test above."""
+    cw, ch, dw, dh, batch = 192, 128, 224, 160, 2     # predict_flow6 is 2 x 3 (a 1-row level divides by zero in Downsample)
+    proto = fn2.fill_train_template(fn2.train_template("FlowNet2-C"), cw, ch, dw, dh, batch)
+    net = fn2.Net(proto, None, fn2.TRAIN)
+    net.fill_params(11)
+    img0, img1 = smooth_images(rng(12), batch, dh, dw)
+    r = rng(13)
+    gt = (3 * r.standard_normal((batch, 2, dh, dw))).astype(np.float32)
+    gt[0, :, 60:75, 80:110] = np.nan                              # invalid ground truth
+    net.clear_param_diffs()
+    out = net.forward(img0=img0, img1=img1, flow_gt=gt)
+    B = lambda n: net.blobs[n].data
+    p0, p1 = B("img0_aug_params"), B("img1_aug_params")
+    assert p0.shape == (batch, 42, 1, 1) and np.abs(p0).max() > 0 and maxabs(p0, p1) > 0
+    assert B("img0_aug").shape == (batch, 3, ch, cw)
+    want = O.flow_augmentation(gt, p0, p1, cw, ch)
+    got = B("flow_gt_aug")
+    both = ~np.isnan(want) & ~np.isnan(got)
+    # nearest-neighbour lookup into a white-noise field: a source position within rounding of x.5 may pick the neighbouring sample
+    off = np.abs(got[both] - want[both]) > 2e-5 * max(1.0, np.abs(want[both]).max())
+    assert both.mean() > 0.9 and off.mean() < 2e-3, (both.mean(), off.mean())
+    total = 0.0
+    for lvl, wgt in ((6, 0.32), (5, 0.08), (4, 0.02), (3, 0.01), (2, 0.005)):
+        pf, g = B("predict_flow%d" % lvl), B("blob_gt%d" % lvl)
+        assert maxabs(g, O.downsample_fwd(B("scaled_flow_gt_aug"), pf.shape[2], pf.shape[3])) <= 1e-5
+        loss, _ = O.l1loss_fwd(pf, g, l2_per_location=True)
+        mine = float(out["flow_loss%d" % lvl].reshape(-1)[0])
+        assert abs(mine - loss) <= 1e-5 * abs(loss), (lvl, mine, loss)
+        total += wgt * mine
+    assert np.isfinite(total)
+    net.backward()
+    pf, g = B("predict_flow2"), B("blob_gt2")
+    g0, _ = O.l1loss_bwd(pf, g, 0.005, l2_per_location=True)
+    assert rel(net.get_diff("predict_flow2"), g0) <= 1e-5
+    for lname in ("conv1", "conv3", "conv_redir", "conv6_1", "deconv2", "predict_flow2", "upsample_flow6to5"):
+        gw = net.param(lname, 0, diff=True)
+        assert np.isfinite(gw).all() and np.abs(gw).max() > 0, lname
+    need = dict(zip(net.layer_names, net.layer_need_backward()))
+    assert need["corr"] and need["flow_loss6"] and not need["Downsample6"] and not need["flow_aug"] and not need["img0s_aug"]
