@@ -48,7 +48,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=4, help="frame pairs per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the config 2 / config 3 / 448x320 side measurements")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config 2 / config 3 / 448x320 / config 5 side measurements")
+    ap.add_argument("--config5-only", action="store_true", help="print only the config 5 (FlowNet2-C training step) measurement")
     return ap.parse_args()
 
 
@@ -267,6 +268,70 @@ def side_config(torch, F, model, w, h, batch, steps=10, warmup=3):
     del net
     torch.cuda.empty_cache()
     return res
+
+
+def train_config(torch, F, batch=8, crop=(448, 320), data=(512, 384), steps=10, warmup=3):
+    """BASELINE.json config 5: one FlowNet2-C training step (random augmentation of both frames and of the ground truth, forward,
+    multi-scale EPE losses, backward down to every parameter gradient) on FlyingChairs-shaped synthetic data, batch 8, N=1.
+    `value`: inputs resident in HBM; `e2e`: the same step fed from pinned host buffers, the five loss values read back."""
+    cw, ch = crop
+    dw, dh = data
+    proto = F.fill_train_template(F.train_template("FlowNet2-C"), cw, ch, dw, dh, batch)
+    net = F.Net(proto, None, F.TRAIN)
+    net.fill_params(1701)
+    r = np.random.default_rng(7)
+    img0 = np.round(r.uniform(0, 255, (batch, 3, dh, dw))).astype(np.float32)
+    img1 = np.clip(img0 + np.round(r.normal(0, 4, img0.shape)), 0, 255).astype(np.float32)
+    gt = (4 * r.standard_normal((batch, 2, dh, dw))).astype(np.float32)
+    dev = [torch.from_numpy(a).cuda() for a in (img0, img1, gt)]
+    pin = [torch.from_numpy(a).pin_memory() for a in (img0, img1, gt)]
+    names = ("img0", "img1", "flow_gt")
+    losses = ["flow_loss%d" % l for l in (6, 5, 4, 3, 2)]
+    host_loss = torch.empty(8, dtype=torch.float32).pin_memory()
+    stream = torch.cuda.ExternalStream(net.stream)
+    res = {}
+    with torch.cuda.stream(stream):
+        def step():
+            for n, d in zip(names, dev):
+                net.set_input_device(n, d.data_ptr())
+            net.clear_param_diffs()
+            net.forward_async()
+            net.backward_async()
+
+        def step_host():
+            for n, h in zip(names, pin):
+                net.set_input_ptr(n, h.data_ptr())
+            net.clear_param_diffs()
+            net.forward_async()
+            net.backward_async()
+            for i, l in enumerate(losses):
+                net.get_blob_ptr(l, host_loss.data_ptr() + 4 * i)       # synchronous D2H of the scalar
+
+        for fn, key in ((step, "device"), (step_host, "host")):
+            for _ in range(warmup):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            res[key] = e0.elapsed_time(e1) / steps
+        lt = net.time_layers()
+    loss_vals = [float(net.blobs[l].data.reshape(-1)[0]) for l in losses]
+    gw = net.param("conv3_1", 0, diff=True)
+    out = {"workload": "FlowNet2-C training step (augmentation + forward + EPE losses + backward), crop %dx%d from %dx%d, batch %d" % (cw, ch, dw, dh, batch),
+           "value": batch / (res["device"] * 1e-3), "unit": UNIT, "ms_per_step": res["device"], "steps": steps, "warmup": warmup,
+           "e2e": {"value": batch / (res["host"] * 1e-3), "unit": UNIT, "ms_per_step": res["host"],
+                   "h2d_bytes_per_step": int(sum(a.nbytes for a in (img0, img1, gt))), "d2h_bytes_per_step": 4 * len(losses)},
+           "launches_per_step": int(net.launches_per_forward + net.launches_per_backward),
+           "forward_ms_layer_sum": float(sum(t for _, _, t in lt)),
+           "losses": loss_vals, "losses_finite": bool(np.isfinite(loss_vals).all()),
+           "grad_finite": bool(np.isfinite(gw).all() and np.abs(gw).max() > 0)}
+    del net
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(args):
@@ -516,7 +581,8 @@ def run_ours(args):
             torch.cuda.empty_cache()
             line["extra"] = {"config2": side_config(torch, F, "FlowNet2-C", 448, 320, 8),
                              "config3": side_config(torch, F, "FlowNet2-CSS", 768, 384, 4),
-                             "flownet2_448x320": side_config(torch, F, "FlowNet2", 448, 320, 4)}
+                             "flownet2_448x320": side_config(torch, F, "FlowNet2", 448, 320, 4),
+                             "config5": train_config(torch, F)}
         if world == 1 and not args.no_cpu_baseline:
             arm = CpuArm(args)
             v, mean = arm.run(2, 1)
@@ -531,7 +597,11 @@ def run_ours(args):
 
 if __name__ == "__main__":
     a = parse_args()
-    if a.impl == "reference":
+    if a.config5_only:
+        import torch
+        import flownet2_b200 as F
+        print(json.dumps(train_config(torch, F, steps=a.steps, warmup=max(a.warmup, 3))), flush=True)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)

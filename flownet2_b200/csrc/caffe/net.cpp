@@ -550,9 +550,26 @@ void Net<Dtype>::Backward() {
     PlanBackward();
     const uint64_t before = fn2_launch_count();
     for (int b : bw_zero_) blobs_[b]->ZeroDiff(stream_);
-    for (int i = (int)layers_.size() - 1; i >= 0; i--)
+    static const bool profile = getenv("FN2_BWD_PROFILE") != nullptr;      // per-layer device times of this pass on stderr
+    vector<cudaEvent_t> ev;
+    if (profile) { ev.resize(layers_.size() + 1); for (auto& e : ev) cudaEventCreate(&e); cudaEventRecord(ev[layers_.size()], stream_); }
+    for (int i = (int)layers_.size() - 1; i >= 0; i--) {
         if (bw_run_[i]) layers_[i]->Backward(top_vecs_[i], bw_propagate_[i], bottom_vecs_[i]);
+        if (profile) cudaEventRecord(ev[i], stream_);
+    }
     launches_per_backward_ = (int)(fn2_launch_count() - before);
+    if (profile) {
+        CUDA_CHECK(cudaStreamSynchronize(stream_));
+        float total = 0;
+        for (int i = (int)layers_.size() - 1; i >= 0; i--) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[i + 1], ev[i]);
+            total += ms;
+            if (bw_run_[i]) fprintf(stderr, "[fn2 bwd] %-24s %-16s %8.3f ms\n", layer_names_[i].c_str(), layers_[i]->type(), ms);
+        }
+        fprintf(stderr, "[fn2 bwd] total %.3f ms, %d launches\n", total, launches_per_backward_);
+        for (auto& e : ev) cudaEventDestroy(e);
+    }
 }
 
 template <typename Dtype>

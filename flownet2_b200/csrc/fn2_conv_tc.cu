@@ -61,6 +61,9 @@ struct TcParams {
     // kernel-row packing for Ci <= 16 on a dense input (pixel stride == rcs floats, guard band around the blob): the kw taps
     // of one kernel row are CONTIGUOUS in memory for every output pixel, so one K block = 32 consecutive floats of that run.
     int rowmode, rcs, rblocks, rsteps, rkw, rpad, rW;   // rblocks = ceil(kw*rcs/32) K blocks per kernel row, rsteps = kh*rblocks
+    // Weight gradient on the same pipeline (conv_tc_wgrad): a unit = (kernel tap, 128 channels of the shifted map, NT channels of
+    // the unshifted map, range of 32-pixel K segments); D[big channel][small channel] = sum over the segments' pixels.
+    int wg_S, wg_ST, wg_BT, wg_segs, wg_segs_x, wg_sx;
     int dbg;                                      // FN2_TC_DBG bits: 1 skip MMAs, 2 skip conversion math, 4 skip drain loads, 8 skip TMA A
     short dy[49], dx[49], widx[49];
 };
@@ -130,7 +133,7 @@ struct TcTile {
 };
 // MODE (compile time, so that each instantiation's role loops stay small -- the all-in-one kernel had ~1900 SASS instructions in
 // the converter loop and stalled on instruction fetch): 0 plain K blocks, 1 tap groups, 2 kernel rows, 3 correlation
-enum { TC_PLAIN = 0, TC_GROUP = 1, TC_ROW = 2, TC_CORR = 3 };
+enum { TC_PLAIN = 0, TC_GROUP = 1, TC_ROW = 2, TC_CORR = 3, TC_WGRAD = 4 };
 
 template <int NT, int MODE>
 __device__ __forceinline__ TcTile tc_decode_tile(const TcParams& p, int tile) {
@@ -152,6 +155,20 @@ __device__ __forceinline__ TcTile tc_decode_tile(const TcParams& p, int tile) {
         t.steps = p.cblocks;
         const int py = t.cls / p.cS, px = t.cls % p.cS;
         t.valid = t.u0 * p.cS + py < p.Ho && t.v0 * p.cS + px < p.Wo;
+        return t;
+    }
+    if constexpr (MODE == TC_WGRAD) {
+        // unit -> (K range, small-channel tile, big-channel tile, tap); u0 carries the first big channel, slot the unit itself
+        int q = tile / p.wg_S;
+        t.split = tile - q * p.wg_S;
+        const int q2 = q / p.wg_ST;
+        t.co0 = (q - q2 * p.wg_ST) * NT;
+        t.tap0 = q2 / p.wg_BT;
+        t.u0 = (q2 - t.tap0 * p.wg_BT) * 128;
+        t.n = 0; t.v0 = 0; t.cls = 0; t.ntaps = 1; t.slot = tile; t.valid = true;
+        const int per = (p.wg_segs + p.wg_S - 1) / p.wg_S;
+        t.k0 = min(p.wg_segs, t.split * per);
+        t.steps = min(p.wg_segs, t.k0 + per) - t.k0;
         return t;
     }
     int tseg = 0;
@@ -278,6 +295,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         tma_load_4d(st, &mapA, &full[s], i * 32, ax, ay, T.n);
                         tma_load_4d(st + A_TILE_BYTES, &mapW, &full[s], i * 32, bx, by, T.n);
                         tma_load_4d(st + A_TILE_BYTES + G::B_TILE_BYTES, &mapW, &full[s], i * 32, bx, by, p.N + T.n);
+                        if (++s == G::R) { s = 0; ph ^= 1u; }
+                    }
+                } else if constexpr (MODE == TC_WGRAD) {
+                    // K segment = 32 consecutive output columns of one output row of one sample.  A: the tap's shifted window of
+                    // the big map, 128 channel rows x 32 pixels (column-parity plane widx[tap], so that a strided convolution
+                    // still reads consecutive floats); B: the same 32 pixels of the small map's hi and lo planes.
+                    // (TMA needs the innermost coordinate on a 16-byte boundary: the big map is stored in 4 copies delayed by 0..3
+                    // columns, widx[tap] >> 4 picks the copy that makes the tap's column shift a multiple of 4.)
+                    const int tap = T.tap0, shift = p.dx[tap], par = p.widx[tap] & 15, qy = p.dy[tap], plane = (p.widx[tap] >> 4) * p.N;
+                    int xs = T.k0 % p.wg_segs_x, r = T.k0 / p.wg_segs_x;
+                    int oy = r % p.Ho, n = r / p.Ho;
+#pragma unroll 1
+                    for (int i = 0; i < T.steps; i++) {
+                        mbar_wait_t(&done[s], ph, &w0, timed);
+                        unsigned char* st = smem + (size_t)s * G::STAGE_BYTES;
+                        mbar_expect_tx(&full[s], (uint32_t)G::STAGE_BYTES);
+                        tma_load_4d(st, &mapA, &full[s], xs * 32 + shift, (oy * p.sv + qy) * p.wg_sx + par, T.u0, plane + n);
+                        tma_load_4d(st + A_TILE_BYTES, &mapW, &full[s], xs * 32, oy, T.co0, n);
+                        tma_load_4d(st + A_TILE_BYTES + G::B_TILE_BYTES, &mapW, &full[s], xs * 32, oy, T.co0, p.N + n);
+                        if (++xs == p.wg_segs_x) { xs = 0; if (++oy == p.Ho) { oy = 0; ++n; } }
                         if (++s == G::R) { s = 0; ph ^= 1u; }
                     }
                 } else if constexpr (MODE == TC_ROW) {
@@ -586,6 +623,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         asm volatile("bar.sync 1, 128;" ::: "memory");
                     }
                 }
+                continue;
+            }
+            if constexpr (MODE == TC_WGRAD) {
+                // raw partial sums of this unit, [unit][128 big channels][NT small channels]; conv_tc_wgrad's reduction sums the
+                // K ranges in a fixed order and scatters into the Caffe weight layout
+                float* o = ws + ((long long)T.slot * 128 + m) * NT;
+#pragma unroll
+                for (int j = 0; j < NT; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
                 continue;
             }
             const int u = T.u0 + yy, v = T.v0 + xx;
@@ -1157,6 +1202,196 @@ __global__ void corr_split_kernel(const float* __restrict__ b, long long sn, lon
         *reinterpret_cast<float4*>(hi + o) = make_float4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<float4*>(lo + o) = make_float4(l[0], l[1], l[2], l[3]);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Weight gradient of Convolution / Deconvolution on the tensor cores (base_conv_layer.cpp:352-372 weight_gpu_gemm).
+//   dW[a][b][ky][kx] = sum over (n, u, v) small[n, a, u, v] * big[n, b, u*s + ky - pad, v*s + kx - pad]
+// with (small, big) = (top diff, bottom) for a convolution and (bottom, top diff) for a deconvolution: in both cases the Caffe
+// blob is [small channels][big channels][kh][kw].  Per kernel tap this is a GEMM D[big ch x small ch] over K = pixels, and with
+// both maps transposed to channel-major planes (pixels contiguous) its operands are K-major tiles exactly like the forward
+// engine's: A = 128 channel rows x 32 consecutive pixels of the big map (raw FP32, split into TF32 hi/lo by the converter warps),
+// B = NT channel rows x the same 32 pixels of the small map, pre-split once by the transposition pass.  The tap's shift is a TMA
+// coordinate offset (zero fill = the convolution's padding); a strided layer reads the column-parity plane the tap falls into.
+// Same FP32-faithful accumulation as the forward pass (short RZ chains drained to FP32 registers).
+// ---------------------------------------------------------------------------------------------------------------------
+struct WgPlan {
+    int Cb, Cs, Hb, Wb, Hs, Ws, N, sx, sy;
+    int NT, BT, ST, S, segs_x, segs, taps;
+    int Wq, Wq_p, Ws_p;                           // columns per parity plane (and its padded pitch), padded pitch of the small map
+    size_t big_floats, small_floats, part_floats; // workspace pieces (each a multiple of 64 floats)
+};
+static size_t up64(size_t x) { return (x + 63) / 64 * 64; }
+
+static WgPlan wg_plan(const fn2_conv_desc* d, int N, int H, int W) {
+    WgPlan g;
+    int Ho = 0, Wo = 0;
+    fn2_conv_out_shape(d, H, W, &Ho, &Wo);
+    g.N = N; g.sx = d->stride_w; g.sy = d->stride_h; g.taps = d->kh * d->kw;
+    if (!d->deconv) { g.Cb = d->ci; g.Cs = d->co; g.Hb = H; g.Wb = W; g.Hs = Ho; g.Ws = Wo; }
+    else            { g.Cb = d->co; g.Cs = d->ci; g.Hb = Ho; g.Wb = Wo; g.Hs = H; g.Ws = W; }
+    g.NT = g.Cs >= 128 ? 128 : (g.Cs >= 64 ? 64 : (g.Cs >= 32 ? 32 : 16));
+    g.BT = (g.Cb + 127) / 128; g.ST = (g.Cs + g.NT - 1) / g.NT;
+    g.segs_x = (g.Ws + 31) / 32; g.segs = N * g.Hs * g.segs_x;
+    const int base = g.taps * g.BT * g.ST;
+    int S = (3 * tc_num_sms() + base - 1) / base;
+    S = max(1, min(S, g.segs / 8));
+    if (const char* e = getenv("FN2_WG_SPLITS")) { const int v = atoi(e); if (v >= 1) S = min(v, max(1, g.segs)); }
+    g.S = S;
+    g.Wq = (g.Wb + g.sx - 1) / g.sx + 3;          // + 3: room for the column delay of the 4 copies
+    g.Wq_p = (g.Wq + 3) / 4 * 4; g.Ws_p = (g.Ws + 3) / 4 * 4;
+    g.big_floats = up64((size_t)4 * N * g.Cb * g.Hb * g.sx * g.Wq_p);          // 4 copies, delayed by 0..3 columns
+    g.small_floats = up64((size_t)2 * N * g.Cs * g.Hs * g.Ws_p);
+    g.part_floats = up64((size_t)base * S * 128 * g.NT);
+    return g;
+}
+
+// channel-major planes: dst[dl][((n*C + c)*H + h)*sx + par][j] = src[n, c, h, (j - dl)*sx + par] (zero outside the row) for
+// dl < nadv column delays; SPLIT writes the TF32 hi plane there and the lo plane `lo_off` floats further
+template <bool SPLIT>
+__global__ void wg_transpose_kernel(T4 src, float* __restrict__ dst, int sx, int Wq, int Wq_p, long long lo_off, int nadv) {
+    __shared__ float tile[32][33];
+    const int wq0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    int z = blockIdx.z;
+    const int rp = z % (src.h * sx); z /= src.h * sx;
+    const int n = z % src.n, adv = z / src.n;
+    const int h = rp / sx, par = rp % sx;
+    dst += (long long)adv * src.n * src.c * src.h * sx * Wq_p;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int wq = wq0 + j - adv, w = wq * sx + par, c = c0 + threadIdx.x;
+        tile[j][threadIdx.x] = (c < src.c && wq >= 0 && w < src.w) ? src.p[src.off(n, c, h, w)] : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int c = c0 + j, wq = wq0 + threadIdx.x;
+        if (c < src.c && wq < Wq_p) {
+            const float v = tile[threadIdx.x][j];
+            float* o = dst + (((long long)n * src.c + c) * src.h * sx + rp) * Wq_p + wq;
+            if (SPLIT) {
+                const float hi = __uint_as_float(to_tf32(v));
+                *o = hi;
+                o[lo_off] = __uint_as_float(to_tf32(v - hi));
+            } else {
+                *o = v;
+            }
+        }
+    }
+}
+
+__global__ void wg_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, WgPlan g, int accumulate) {
+    const long long total = (long long)g.Cs * g.Cb * g.taps;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int tap = (int)(idx % g.taps);
+        const long long r = idx / g.taps;
+        const int b = (int)(r % g.Cb), a = (int)(r / g.Cb);
+        const long long unit0 = ((long long)(tap * g.BT + b / 128) * g.ST + a / g.NT) * g.S;
+        const float* src = part + (unit0 * 128 + (b % 128)) * g.NT + (a % g.NT);
+        float acc = 0.f;
+        for (int k = 0; k < g.S; k++) acc += src[(long long)k * 128 * g.NT];
+        dw[idx] = accumulate ? dw[idx] + acc : acc;
+    }
+}
+
+int conv_tc_wgrad_eligible(const fn2_conv_desc* d) {
+    if (!tc_enabled() || getenv("FN2_WGRAD_SIMT")) return 0;
+    if (d->kh * d->kw > 49 || d->stride_w > 8 || d->stride_h > 8) return 0;
+    if (!tc_encode_fn()) return 0;
+    return 1;
+}
+size_t conv_tc_wgrad_workspace_floats(const fn2_conv_desc* d, int N, int H, int W) {
+    const WgPlan g = wg_plan(d, N, H, W);
+    return g.big_floats + g.small_floats + g.part_floats + 64;
+}
+
+int conv_tc_wgrad(const fn2_conv_desc* d, const T4& bottom, const T4& top_diff, float* dw, int accumulate, float* ws, size_t ws_floats,
+                  cudaStream_t st) {
+    EncodeTiledFn enc = tc_encode_fn();
+    if (!enc) { set_error("conv_tc_wgrad: cuTensorMapEncodeTiled unavailable"); return FN2_ERR_CUDA; }
+    const WgPlan g = wg_plan(d, bottom.n, bottom.h, bottom.w);
+    if (!ws || ws_floats < conv_tc_wgrad_workspace_floats(d, bottom.n, bottom.h, bottom.w)) { set_error("conv_tc_wgrad: workspace too small"); return FN2_ERR_WORKSPACE; }
+    const T4& big = d->deconv ? top_diff : bottom;
+    const T4& small = d->deconv ? bottom : top_diff;
+    if (big.h != g.Hb || big.w != g.Wb || small.h != g.Hs || small.w != g.Ws || big.c != g.Cb || small.c != g.Cs) {
+        set_error("conv_tc_wgrad: tensor shapes do not match the descriptor"); return FN2_ERR_INVALID;
+    }
+    ws = reinterpret_cast<float*>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    float* bigT = ws; float* smallT = ws + g.big_floats; float* part = smallT + g.small_floats;
+    {
+        dim3 blk(32, 8);
+        dim3 gb((unsigned)((g.Wq_p + 31) / 32), (unsigned)((g.Cb + 31) / 32), (unsigned)(4 * g.N * g.Hb * g.sx));
+        wg_transpose_kernel<false><<<gb, blk, 0, st>>>(big, bigT, g.sx, g.Wq, g.Wq_p, 0, 4);
+        FN2_LAUNCH_CHECK();
+        dim3 gs((unsigned)((g.Ws_p + 31) / 32), (unsigned)((g.Cs + 31) / 32), (unsigned)(g.N * g.Hs));
+        wg_transpose_kernel<true><<<gs, blk, 0, st>>>(small, smallT, 1, g.Ws, g.Ws_p, (long long)g.N * g.Cs * g.Hs * g.Ws_p, 1);
+        FN2_LAUNCH_CHECK();
+    }
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = g.N; p.Co = g.Cs; p.cblocks = 1;
+    p.Ho = g.Hs; p.Wo = g.Ws;
+    p.splits = 1; p.cl = 1; p.tail_z = 1; p.su = g.sx; p.sv = g.sy; p.ou = p.ov = 1; p.ncls = 1;
+    p.tw = 128; p.th = 1; p.tiles_x = p.tiles_y = 1;
+    p.wg_S = g.S; p.wg_ST = g.ST; p.wg_BT = g.BT; p.wg_segs = g.segs; p.wg_segs_x = g.segs_x; p.wg_sx = g.sx;
+    p.kd = g.NT == 128 ? 6 : 4;
+    if (const char* e = getenv(g.NT == 128 ? "FN2_TC_KD" : "FN2_TC_KDW")) { const int v = atoi(e); if (v >= 1 && v <= 1024) p.kd = v; }
+    const char* nocomp = getenv("FN2_TC_COMP");
+    p.comp_a = (nocomp && nocomp[0] == '0') ? 0.f : 2.0e-8f;
+    p.comp_b = (nocomp && nocomp[0] == '0') ? 0.f : 1.67e-8f;
+    for (int ky = 0; ky < d->kh; ky++)
+        for (int kx = 0; kx < d->kw; kx++) {
+            const int t = ky * d->kw + kx, q = kx - d->pad_w;
+            const int par = ((q % g.sx) + g.sx) % g.sx;
+            const int shift = (q - par) / g.sx, dl = (((-shift) % 4) + 4) % 4;    // copy `dl` holds column j - dl at index j
+            p.dy[t] = (short)(ky - d->pad_h); p.dx[t] = (short)(shift + dl); p.widx[t] = (short)(par | (dl << 4));
+        }
+    p.total = g.taps * g.BT * g.ST * g.S;
+    p.ntotal = p.total; p.tail_first = p.total;
+    CUtensorMap mapA, mapB;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)g.Wq, (cuuint64_t)g.Hb * g.sx, (cuuint64_t)g.Cb, (cuuint64_t)4 * g.N};
+        cuuint64_t strides[3] = {(cuuint64_t)g.Wq_p * 4, (cuuint64_t)g.Hb * g.sx * g.Wq_p * 4, (cuuint64_t)g.Cb * g.Hb * g.sx * g.Wq_p * 4};
+        cuuint32_t box[4] = {32, 1, 128, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)bigT, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv_tc_wgrad: big-map tensor map failed (%d)", (int)r); return FN2_ERR_CUDA; }
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)g.Ws, (cuuint64_t)g.Hs, (cuuint64_t)g.Cs, (cuuint64_t)2 * g.N};
+        cuuint64_t strides[3] = {(cuuint64_t)g.Ws_p * 4, (cuuint64_t)g.Hs * g.Ws_p * 4, (cuuint64_t)g.Cs * g.Hs * g.Ws_p * 4};
+        cuuint32_t box[4] = {32, 1, (cuuint32_t)g.NT, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = enc(&mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)smallT, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv_tc_wgrad: small-map tensor map failed (%d)", (int)r); return FN2_ERR_CUDA; }
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)min(p.total, tc_num_sms()), 1, 1);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+#define FN2_WG_LAUNCH(NTV)                                                                                              \
+    {                                                                                                                   \
+        static bool attr_set = false;                                                                                   \
+        if (!attr_set) {                                                                                                \
+            FN2_CUDA(cudaFuncSetAttribute(conv_tc_kernel<NTV, TC_WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGeo<NTV>::SMEM)); \
+            attr_set = true;                                                                                            \
+        }                                                                                                               \
+        cfg.dynamicSmemBytes = TcGeo<NTV>::SMEM;                                                                        \
+        FN2_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<NTV, TC_WGRAD>, mapA, mapB, (const float*)nullptr, (float*)nullptr, part, p, tc_prof_buffer())); \
+    }
+    if (g.NT == 128) FN2_WG_LAUNCH(128)
+    else if (g.NT == 64) FN2_WG_LAUNCH(64)
+    else if (g.NT == 32) FN2_WG_LAUNCH(32)
+    else FN2_WG_LAUNCH(16)
+#undef FN2_WG_LAUNCH
+    FN2_LAUNCH_CHECK();
+    wg_reduce_kernel<<<ew_grid((long long)g.Cs * g.Cb * g.taps, 256), 256, 0, st>>>(part, dw, g, accumulate);
+    FN2_LAUNCH_CHECK();
+    return FN2_OK;
 }
 
 int corr_tc_eligible(const T4& b0, const T4& b1, const T4& top, int md, int s2) {

@@ -151,6 +151,41 @@ __global__ void downsample_kernel(T4 src, T4 dst, float wscale, float hscale, in
     }
 }
 
+// Wide windows (the 1/64 level averages 161 x 151 source pixels per output): one warp-group per output element, the window
+// spread over the threads, fixed-order tree reduction.
+__global__ void downsample_wide_kernel(T4 src, T4 dst, float wscale, float hscale, int wrad, int hrad) {
+    const long long idx = blockIdx.x;
+    const int dx = (int)(idx % dst.w);
+    long long r = idx / dst.w;
+    const int dy = (int)(r % dst.h); r /= dst.h;
+    const int c = (int)(r % dst.c), n = (int)(r / dst.c);
+    const float bx = ((float)dx / (float)(dst.w - 1)) * (float)(src.w - 1);
+    const float by = ((float)dy / (float)(dst.h - 1)) * (float)(src.h - 1);
+    const int ix = (int)roundf(bx), iy = (int)roundf(by);
+    const int ww = 2 * wrad + 1, wh = 2 * hrad + 1;
+    float val = 0.f, wsum = 0.f, wnan = 0.f;
+    for (int t = threadIdx.x; t < ww * wh; t += blockDim.x) {
+        const int sy = iy - hrad + t / ww, sx = ix - wrad + t % ww;
+        if (sx < 0 || sy < 0 || sx >= src.w || sy >= src.h) continue;
+        float sample = src.p[src.off(n, c, sy, sx)];
+        float wgt = fmaxf(0.f, 1.f - fabsf((float)sx - bx) / wscale) * fmaxf(0.f, 1.f - fabsf((float)sy - by) / hscale);
+        if (sample != sample) { wnan += wgt; sample = 0.f; wgt = 0.f; }
+        val += sample * wgt;
+        wsum += wgt;
+    }
+    __shared__ float s[3][8];
+    for (int o = 16; o; o >>= 1) {
+        val += __shfl_xor_sync(0xffffffffu, val, o); wsum += __shfl_xor_sync(0xffffffffu, wsum, o); wnan += __shfl_xor_sync(0xffffffffu, wnan, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s[0][threadIdx.x >> 5] = val; s[1][threadIdx.x >> 5] = wsum; s[2][threadIdx.x >> 5] = wnan; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        val = wsum = wnan = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) { val += s[0][i]; wsum += s[1][i]; wnan += s[2][i]; }
+        dst.p[dst.off(n, c, dy, dx)] = (wnan / wsum > 0.5f) ? __int_as_float(0x7fffffff) : val / wsum;
+    }
+}
+
 // ---- FlowAugmentation ------------------------------------------------------------------------------------------------------
 // m1 / m2: 6 floats per sample in NAME order t0..t5 (x' = x*t0 + y*t2 + t4, y' = x*t1 + y*t3 + t5); m2 is already inverted.
 __global__ void flow_aug_kernel(T4 src, T4 dst, const float* __restrict__ m1, const float* __restrict__ m2) {
@@ -251,7 +286,10 @@ int fn2_downsample_forward(const fn2_tensor* bottom, const fn2_tensor* top, void
     if (s.h == t.h && s.w == t.w) return fn2_copy(bottom, top, stream);            // downsample_layer.cpp:55-58 (shared data)
     const float wscale = (float)(s.w - 1) / (float)(t.w - 1), hscale = (float)(s.h - 1) / (float)(t.h - 1);
     const int wrad = (int)ceilf(wscale), hrad = (int)ceilf(hscale);
-    downsample_kernel<<<ew_grid(t.count(), 256), 256, 0, (cudaStream_t)stream>>>(s, t, wscale, hscale, wrad, hrad);
+    if ((2 * wrad + 1) * (2 * hrad + 1) >= 256 && t.count() <= (1 << 20))
+        downsample_wide_kernel<<<(unsigned)t.count(), 256, 0, (cudaStream_t)stream>>>(s, t, wscale, hscale, wrad, hrad);
+    else
+        downsample_kernel<<<ew_grid(t.count(), 256), 256, 0, (cudaStream_t)stream>>>(s, t, wscale, hscale, wrad, hrad);
     FN2_LAUNCH_CHECK();
     return FN2_OK;
 }

@@ -12,6 +12,12 @@
 
 namespace fn2 {
 
+// fn2_conv_tc.cu: weight gradient on the tcgen05 pipeline
+int conv_tc_wgrad_eligible(const fn2_conv_desc* d);
+size_t conv_tc_wgrad_workspace_floats(const fn2_conv_desc* d, int N, int H, int W);
+int conv_tc_wgrad(const fn2_conv_desc* d, const T4& bottom, const T4& top_diff, float* dw, int accumulate, float* ws, size_t ws_floats,
+                  cudaStream_t st);
+
 namespace {
 
 // ---- y = alpha * x + beta * y ----------------------------------------------------------------------------------------
@@ -46,19 +52,33 @@ __global__ void relu_bwd_kernel(T4 data, T4 dy, T4 dx, float slope, int accumula
 
 // ---- bias gradient: db[c] = sum over (n, y, x) of dy, two stages, fixed order ---------------------------------------------
 __global__ void bias_grad_partial_kernel(T4 dy, float* __restrict__ part, int chunks) {
-    // block b sums pixels [b*per, (b+1)*per) for every channel; thread = channel (strided), pixels serial
+    // block b sums pixels [b*per, (b+1)*per) for every channel.  Channel-fast maps: thread = channel (coalesced), the 256 / C
+    // thread groups take interleaved pixels and are combined through shared memory in a fixed order.
     const long long P = (long long)dy.n * dy.h * dy.w;
     const long long per = (P + chunks - 1) / chunks;
     const long long p0 = blockIdx.x * per, p1 = min(P, p0 + per);
-    for (int c = threadIdx.x; c < dy.c; c += blockDim.x) {
+    __shared__ float sm[256];
+    int lanes = 1;
+    while (lanes < dy.c && lanes < 256) lanes *= 2;                 // channels per pass (power of two <= 256)
+    const int groups = 256 / lanes, grp = threadIdx.x / lanes, cl = threadIdx.x % lanes;
+    for (int c0 = 0; c0 < dy.c; c0 += lanes) {
+        const int c = c0 + cl;
         float acc = 0.f;
-        for (long long p = p0; p < p1; p++) {
-            const int w = (int)(p % dy.w);
-            const long long r = p / dy.w;
-            const int h = (int)(r % dy.h), n = (int)(r / dy.h);
-            acc += dy.p[dy.off(n, c, h, w)];
+        if (c < dy.c)
+            for (long long p = p0 + grp; p < p1; p += groups) {
+                const int w = (int)(p % dy.w);
+                const long long r = p / dy.w;
+                const int h = (int)(r % dy.h), n = (int)(r / dy.h);
+                acc += dy.p[dy.off(n, c, h, w)];
+            }
+        sm[threadIdx.x] = acc;
+        __syncthreads();
+        if (grp == 0 && c < dy.c) {
+            float t = 0.f;
+            for (int g = 0; g < groups; g++) t += sm[g * lanes + cl];
+            part[(long long)blockIdx.x * dy.c + c] = t;
         }
-        part[(long long)blockIdx.x * dy.c + c] = acc;
+        __syncthreads();
     }
 }
 __global__ void bias_grad_final_kernel(const float* __restrict__ part, float* __restrict__ db, int C, int chunks, int accumulate) {
@@ -82,6 +102,7 @@ struct WgP {
     long long per;                                 // pixels of S per split
 };
 constexpr int WG_T = 64, WG_PX = 16;
+constexpr int BIAS_CHUNKS = 296;                   // two blocks per SM
 
 __global__ void __launch_bounds__(256) weight_grad_kernel(T4 S, T4 B, float* __restrict__ ws, WgP p) {
     __shared__ float sS[WG_PX][WG_T + 4], sB[WG_PX][WG_T + 4];
@@ -197,9 +218,10 @@ int fn2_conv_backward_params_workspace_bytes(const fn2_conv_desc* d, int N, int 
     int splits = (int)max(1LL, min((long long)64, (long long)(num_sms() * 4) / max(1, tiles)));
     splits = (int)min((long long)splits, (P + 255) / 256);
     if (splits < 1) splits = 1;
-    const size_t wfloats = (size_t)splits * d->ci * d->co * d->kh * d->kw;
-    const size_t bfloats = (size_t)64 * d->co;
-    *bytes = (wfloats + bfloats) * sizeof(float);
+    size_t wfloats = (size_t)splits * d->ci * d->co * d->kh * d->kw;
+    if (conv_tc_wgrad_eligible(d)) wfloats = max(wfloats, conv_tc_wgrad_workspace_floats(d, N, H, W));
+    const size_t bfloats = (size_t)BIAS_CHUNKS * d->co;
+    *bytes = (wfloats + bfloats + 64) * sizeof(float);
     return FN2_OK;
 }
 
@@ -230,14 +252,20 @@ int fn2_conv_backward_params(const fn2_conv_desc* d, const fn2_tensor* bottom, c
     p.per = ((P + splits - 1) / splits + WG_PX - 1) / WG_PX * WG_PX;
     float* ws = (float*)workspace;
     const long long count = (long long)d->ci * d->co * d->kh * d->kw;
-    dim3 grid((unsigned)tiles, (unsigned)(d->kh * d->kw), (unsigned)splits);
-    weight_grad_kernel<<<grid, 256, 0, st>>>(S, B, ws, p);
-    FN2_LAUNCH_CHECK();
-    weight_grad_reduce_kernel<<<ew_grid(count, 256), 256, 0, st>>>(ws, weight_diff_dev, count, splits, accumulate);
-    FN2_LAUNCH_CHECK();
+    const size_t bias_floats = (size_t)BIAS_CHUNKS * d->co + 64;
+    if (conv_tc_wgrad_eligible(d)) {
+        rc = conv_tc_wgrad(d, x, dy, weight_diff_dev, accumulate, ws, workspace_bytes / sizeof(float) - bias_floats, st);
+        if (rc) return rc;
+    } else {
+        dim3 grid((unsigned)tiles, (unsigned)(d->kh * d->kw), (unsigned)splits);
+        weight_grad_kernel<<<grid, 256, 0, st>>>(S, B, ws, p);
+        FN2_LAUNCH_CHECK();
+        weight_grad_reduce_kernel<<<ew_grid(count, 256), 256, 0, st>>>(ws, weight_diff_dev, count, splits, accumulate);
+        FN2_LAUNCH_CHECK();
+    }
     if (d->has_bias && bias_diff_dev) {
-        float* part = ws + (size_t)splits * count;
-        const int chunks = 64;
+        float* part = ws + (workspace_bytes / sizeof(float) - bias_floats);
+        const int chunks = BIAS_CHUNKS;
         bias_grad_partial_kernel<<<chunks, 256, 0, st>>>(dy, part, chunks);
         FN2_LAUNCH_CHECK();
         bias_grad_final_kernel<<<(d->co + 127) / 128, 128, 0, st>>>(part, bias_diff_dev, d->co, chunks, accumulate);

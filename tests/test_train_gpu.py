@@ -41,6 +41,10 @@ CONV_BWD_CASES = [
     ("d4x4_s2", 2, 32, 6, 8, 16, 4, 2, 1, True, True),
     ("d4x4_s2_flow", 2, 2, 6, 8, 2, 4, 2, 1, True, True),                 # upsample_flow: 2 -> 2
     ("d4x4_s2_wide", 1, 256, 8, 12, 128, 4, 2, 1, True, True),
+    ("c3x3_473", 2, 473, 10, 14, 256, 3, 1, 1, False, True),              # conv3_1: channel tail of the 128-row tiles
+    ("c3x3_s2_tiny", 2, 160, 5, 7, 192, 3, 2, 1, False, True),            # 3 x 4 output map: one K segment per row, mostly zero fill
+    ("c5x5_s2_w57", 1, 64, 41, 57, 128, 5, 2, 2, False, True),            # odd width: the parity planes differ in length
+    ("d4x4_s2_1026", 1, 130, 5, 7, 64, 4, 2, 1, True, True),              # deconv: the shifted map is the top diff
 ]
 
 
