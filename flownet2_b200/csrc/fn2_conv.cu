@@ -585,6 +585,43 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
     }
 }
 
+// Few input channels, many output channels (the gradient operator of the 2-channel predict_flow convolutions: 2 -> 194 .. 1026):
+// K = taps * Ci is tiny, the layer is a pure store stream.  Lanes = output channels (coalesced weight reads and stores), the
+// input patch of FEW_PX consecutive output pixels sits in shared memory and is broadcast.
+constexpr int FEW_PX = 16;
+__global__ void __launch_bounds__(256) conv_fewci_kernel(T4 in, const float* __restrict__ wp, const float* __restrict__ bias, T4 out, ConvP p) {
+    extern __shared__ float sIn[];                            // [FEW_PX][K]
+    const int K = p.kh * p.kw * p.Ci;
+    const int xt = (p.Wo + FEW_PX - 1) / FEW_PX;
+    const int ox0 = (blockIdx.x % xt) * FEW_PX;
+    const int oy = (blockIdx.x / xt) % p.Ho, n = blockIdx.x / (xt * p.Ho);
+    for (int e = threadIdx.x; e < FEW_PX * K; e += blockDim.x) {
+        const int px = e / K, k = e % K;
+        const int ci = k % p.Ci, tap = k / p.Ci;
+        const int iy = oy * p.sh + tap / p.kw - p.ph, ix = (ox0 + px) * p.sw + tap % p.kw - p.pw;
+        sIn[e] = (ox0 + px < p.Wo && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) ? in.p[in.off(n, ci, iy, ix)] : 0.f;
+    }
+    __syncthreads();
+    for (int co = threadIdx.x; co < p.Co; co += blockDim.x) {
+        float acc[FEW_PX];
+        const float b = p.has_bias ? bias[co] : 0.f;
+#pragma unroll
+        for (int px = 0; px < FEW_PX; px++) acc[px] = b;
+        for (int k = 0; k < K; k++) {
+            const float w = __ldg(wp + (long long)k * p.Co + co);
+#pragma unroll
+            for (int px = 0; px < FEW_PX; px++) acc[px] = fmaf(w, sIn[px * K + k], acc[px]);
+        }
+#pragma unroll
+        for (int px = 0; px < FEW_PX; px++)
+            if (ox0 + px < p.Wo) {
+                float v = acc[px];
+                if (p.relu) v = v > 0.f ? v : v * p.slope;
+                out.p[out.off(n, co, oy, ox0 + px)] = v;
+            }
+    }
+}
+
 static int make_params(const fn2_conv_desc* d, const T4& in, const T4& out, ConvP* p) {
     FN2_CHECK_ARG(d->ci > 0 && d->co > 0 && d->kh > 0 && d->kw > 0 && d->stride_h > 0 && d->stride_w > 0 &&
                   d->pad_h >= 0 && d->pad_w >= 0 && d->out_pad_h >= 0 && d->out_pad_w >= 0 && (d->deconv || (!d->out_pad_h && !d->out_pad_w)),
@@ -674,6 +711,14 @@ int fn2_conv_forward(const fn2_conv_desc* d, const fn2_tensor* bottom, const flo
     if (d->engine != 1 && conv_tc_eligible(d, in, out))
         return conv_tc_forward(d, in, packed_weights_dev + simt_floats, bias_dev, out, (float*)workspace, workspace_bytes / sizeof(float), st);
     FN2_CHECK_ARG(d->engine != 2, "conv: tcgen05 engine requested but the shape/layout is not eligible");
+    if (!d->deconv && d->ci <= 4 && d->co >= 32 && out.sc == 1 && d->kh * d->kw * d->ci <= 200) {
+        p.cis = d->ci;
+        const int xt = (p.Wo + FEW_PX - 1) / FEW_PX;
+        const size_t smem = (size_t)FEW_PX * d->kh * d->kw * d->ci * sizeof(float);
+        conv_fewci_kernel<<<(unsigned)(p.N * p.Ho * xt), 256, smem, st>>>(in, packed_weights_dev, bias_dev, out, p);
+        FN2_LAUNCH_CHECK();
+        return FN2_OK;
+    }
     if (conv_nhwc_eligible(d, in, out))
         return conv_nhwc_forward(d, in, packed_weights_dev, bias_dev, out, (float*)workspace, workspace_bytes / sizeof(float), st);
     p.cis = d->ci;

@@ -63,7 +63,8 @@ struct TcParams {
     int rowmode, rcs, rblocks, rsteps, rkw, rpad, rW;   // rblocks = ceil(kw*rcs/32) K blocks per kernel row, rsteps = kh*rblocks
     // Weight gradient on the same pipeline (conv_tc_wgrad): a unit = (kernel tap, 128 channels of the shifted map, NT channels of
     // the unshifted map, range of 32-pixel K segments); D[big channel][small channel] = sum over the segments' pixels.
-    int wg_S, wg_ST, wg_BT, wg_segs, wg_segs_x, wg_sx;
+    // Maps with few channels (wg_G = 8 .. 64 rows per tap) put 128 / wg_G taps side by side in one 128-row tile (wg_TPT).
+    int wg_S, wg_ST, wg_BT, wg_segs, wg_segs_x, wg_sx, wg_G, wg_TPT, wg_taps;
     int dbg;                                      // FN2_TC_DBG bits: 1 skip MMAs, 2 skip conversion math, 4 skip drain loads, 8 skip TMA A
     short dy[49], dx[49], widx[49];
 };
@@ -165,6 +166,7 @@ __device__ __forceinline__ TcTile tc_decode_tile(const TcParams& p, int tile) {
         t.co0 = (q - q2 * p.wg_ST) * NT;
         t.tap0 = q2 / p.wg_BT;
         t.u0 = (q2 - t.tap0 * p.wg_BT) * 128;
+        t.tap0 *= p.wg_TPT;                                        // first tap of the group
         t.n = 0; t.v0 = 0; t.cls = 0; t.ntaps = 1; t.slot = tile; t.valid = true;
         const int per = (p.wg_segs + p.wg_S - 1) / p.wg_S;
         t.k0 = min(p.wg_segs, t.split * per);
@@ -303,15 +305,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     // still reads consecutive floats); B: the same 32 pixels of the small map's hi and lo planes.
                     // (TMA needs the innermost coordinate on a 16-byte boundary: the big map is stored in 4 copies delayed by 0..3
                     // columns, widx[tap] >> 4 picks the copy that makes the tap's column shift a multiple of 4.)
-                    const int tap = T.tap0, shift = p.dx[tap], par = p.widx[tap] & 15, qy = p.dy[tap], plane = (p.widx[tap] >> 4) * p.N;
                     int xs = T.k0 % p.wg_segs_x, r = T.k0 / p.wg_segs_x;
                     int oy = r % p.Ho, n = r / p.Ho;
+                    const int tpt = p.wg_TPT, gbytes = p.wg_G * 128;
 #pragma unroll 1
                     for (int i = 0; i < T.steps; i++) {
                         mbar_wait_t(&done[s], ph, &w0, timed);
                         unsigned char* st = smem + (size_t)s * G::STAGE_BYTES;
                         mbar_expect_tx(&full[s], (uint32_t)G::STAGE_BYTES);
-                        tma_load_4d(st, &mapA, &full[s], xs * 32 + shift, (oy * p.sv + qy) * p.wg_sx + par, T.u0, plane + n);
+                        for (int j = 0; j < tpt; j++) {
+                            // a group past the last tap repeats tap 0 (its rows are never read back)
+                            const int tap = T.tap0 + j < p.wg_taps ? T.tap0 + j : 0;
+                            tma_load_4d(st + j * gbytes, &mapA, &full[s], xs * 32 + p.dx[tap], (oy * p.sv + p.dy[tap]) * p.wg_sx + (p.widx[tap] & 15),
+                                        T.u0, (p.widx[tap] >> 4) * p.N + n);
+                        }
                         tma_load_4d(st + A_TILE_BYTES, &mapW, &full[s], xs * 32, oy, T.co0, n);
                         tma_load_4d(st + A_TILE_BYTES + G::B_TILE_BYTES, &mapW, &full[s], xs * 32, oy, T.co0, p.N + n);
                         if (++xs == p.wg_segs_x) { xs = 0; if (++oy == p.Ho) { oy = 0; ++n; } }
@@ -1217,7 +1224,7 @@ __global__ void corr_split_kernel(const float* __restrict__ b, long long sn, lon
 // ---------------------------------------------------------------------------------------------------------------------
 struct WgPlan {
     int Cb, Cs, Hb, Wb, Hs, Ws, N, sx, sy;
-    int NT, BT, ST, S, segs_x, segs, taps;
+    int NT, BT, ST, S, segs_x, segs, taps, G, TPT, TG;   // G rows per tap, TPT taps per 128-row tile, TG tap groups
     int Wq, Wq_p, Ws_p;                           // columns per parity plane (and its padded pitch), padded pitch of the small map
     size_t big_floats, small_floats, part_floats; // workspace pieces (each a multiple of 64 floats)
 };
@@ -1232,8 +1239,11 @@ static WgPlan wg_plan(const fn2_conv_desc* d, int N, int H, int W) {
     else            { g.Cb = d->co; g.Cs = d->ci; g.Hb = Ho; g.Wb = Wo; g.Hs = H; g.Ws = W; }
     g.NT = g.Cs >= 128 ? 128 : (g.Cs >= 64 ? 64 : (g.Cs >= 32 ? 32 : 16));
     g.BT = (g.Cb + 127) / 128; g.ST = (g.Cs + g.NT - 1) / g.NT;
+    g.G = 128;
+    if (g.Cb <= 64 && !getenv("FN2_WG_NOGROUP")) { g.G = 8; while (g.G < g.Cb) g.G *= 2; }
+    g.TPT = 128 / g.G; g.TG = (g.taps + g.TPT - 1) / g.TPT;
     g.segs_x = (g.Ws + 31) / 32; g.segs = N * g.Hs * g.segs_x;
-    const int base = g.taps * g.BT * g.ST;
+    const int base = g.TG * g.BT * g.ST;
     int S = (3 * tc_num_sms() + base - 1) / base;
     S = max(1, min(S, g.segs / 8));
     if (const char* e = getenv("FN2_WG_SPLITS")) { const int v = atoi(e); if (v >= 1) S = min(v, max(1, g.segs)); }
@@ -1248,31 +1258,33 @@ static WgPlan wg_plan(const fn2_conv_desc* d, int N, int H, int W) {
 
 // channel-major planes: dst[dl][((n*C + c)*H + h)*sx + par][j] = src[n, c, h, (j - dl)*sx + par] (zero outside the row) for
 // dl < nadv column delays; SPLIT writes the TF32 hi plane there and the lo plane `lo_off` floats further
+// `dlmask`: which of the 4 delays are written (bit dl); the source is read once per block (32 channels x 35 columns).
 template <bool SPLIT>
-__global__ void wg_transpose_kernel(T4 src, float* __restrict__ dst, int sx, int Wq, int Wq_p, long long lo_off, int nadv) {
-    __shared__ float tile[32][33];
+__global__ void wg_transpose_kernel(T4 src, float* __restrict__ dst, int sx, int Wq, int Wq_p, long long lo_off, int dlmask) {
+    __shared__ float tile[35][33];
     const int wq0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-    int z = blockIdx.z;
-    const int rp = z % (src.h * sx); z /= src.h * sx;
-    const int n = z % src.n, adv = z / src.n;
+    const int rp = blockIdx.z % (src.h * sx), n = blockIdx.z / (src.h * sx);
     const int h = rp / sx, par = rp % sx;
-    dst += (long long)adv * src.n * src.c * src.h * sx * Wq_p;
-    for (int j = threadIdx.y; j < 32; j += 8) {
-        const int wq = wq0 + j - adv, w = wq * sx + par, c = c0 + threadIdx.x;
+    const int halo = SPLIT ? 0 : 3;
+    for (int j = threadIdx.y; j < 32 + halo; j += 8) {
+        const int wq = wq0 + j - halo, w = wq * sx + par, c = c0 + threadIdx.x;       // tile row j = column wq0 + j - halo
         tile[j][threadIdx.x] = (c < src.c && wq >= 0 && w < src.w) ? src.p[src.off(n, c, h, w)] : 0.f;
     }
     __syncthreads();
+    const long long copy = (long long)src.n * src.c * src.h * sx * Wq_p;
     for (int j = threadIdx.y; j < 32; j += 8) {
         const int c = c0 + j, wq = wq0 + threadIdx.x;
         if (c < src.c && wq < Wq_p) {
-            const float v = tile[threadIdx.x][j];
             float* o = dst + (((long long)n * src.c + c) * src.h * sx + rp) * Wq_p + wq;
             if (SPLIT) {
+                const float v = tile[threadIdx.x][j];
                 const float hi = __uint_as_float(to_tf32(v));
                 *o = hi;
                 o[lo_off] = __uint_as_float(to_tf32(v - hi));
             } else {
-                *o = v;
+#pragma unroll
+                for (int dl = 0; dl < 4; dl++)
+                    if (dlmask >> dl & 1) o[dl * copy] = tile[threadIdx.x + 3 - dl][j];     // index wq holds column wq - dl
             }
         }
     }
@@ -1284,8 +1296,8 @@ __global__ void wg_reduce_kernel(const float* __restrict__ part, float* __restri
         const int tap = (int)(idx % g.taps);
         const long long r = idx / g.taps;
         const int b = (int)(r % g.Cb), a = (int)(r / g.Cb);
-        const long long unit0 = ((long long)(tap * g.BT + b / 128) * g.ST + a / g.NT) * g.S;
-        const float* src = part + (unit0 * 128 + (b % 128)) * g.NT + (a % g.NT);
+        const long long unit0 = ((long long)((tap / g.TPT) * g.BT + b / 128) * g.ST + a / g.NT) * g.S;
+        const float* src = part + (unit0 * 128 + (tap % g.TPT) * g.G + (b % 128)) * g.NT + (a % g.NT);
         float acc = 0.f;
         for (int k = 0; k < g.S; k++) acc += src[(long long)k * 128 * g.NT];
         dw[idx] = accumulate ? dw[idx] + acc : acc;
@@ -1318,8 +1330,13 @@ int conv_tc_wgrad(const fn2_conv_desc* d, const T4& bottom, const T4& top_diff, 
     float* bigT = ws; float* smallT = ws + g.big_floats; float* part = smallT + g.small_floats;
     {
         dim3 blk(32, 8);
-        dim3 gb((unsigned)((g.Wq_p + 31) / 32), (unsigned)((g.Cb + 31) / 32), (unsigned)(4 * g.N * g.Hb * g.sx));
-        wg_transpose_kernel<false><<<gb, blk, 0, st>>>(big, bigT, g.sx, g.Wq, g.Wq_p, 0, 4);
+        int dlmask = 0;                                     // column delays the layer's taps actually use
+        for (int kx = 0; kx < d->kw; kx++) {
+            const int q = kx - d->pad_w, par = ((q % g.sx) + g.sx) % g.sx, shift = (q - par) / g.sx;
+            dlmask |= 1 << ((((-shift) % 4) + 4) % 4);
+        }
+        dim3 gb((unsigned)((g.Wq_p + 31) / 32), (unsigned)((g.Cb + 31) / 32), (unsigned)(g.N * g.Hb * g.sx));
+        wg_transpose_kernel<false><<<gb, blk, 0, st>>>(big, bigT, g.sx, g.Wq, g.Wq_p, 0, dlmask);
         FN2_LAUNCH_CHECK();
         dim3 gs((unsigned)((g.Ws_p + 31) / 32), (unsigned)((g.Cs + 31) / 32), (unsigned)(g.N * g.Hs));
         wg_transpose_kernel<true><<<gs, blk, 0, st>>>(small, smallT, 1, g.Ws, g.Ws_p, (long long)g.N * g.Cs * g.Hs * g.Ws_p, 1);
@@ -1332,6 +1349,7 @@ int conv_tc_wgrad(const fn2_conv_desc* d, const T4& bottom, const T4& top_diff, 
     p.splits = 1; p.cl = 1; p.tail_z = 1; p.su = g.sx; p.sv = g.sy; p.ou = p.ov = 1; p.ncls = 1;
     p.tw = 128; p.th = 1; p.tiles_x = p.tiles_y = 1;
     p.wg_S = g.S; p.wg_ST = g.ST; p.wg_BT = g.BT; p.wg_segs = g.segs; p.wg_segs_x = g.segs_x; p.wg_sx = g.sx;
+    p.wg_G = g.G; p.wg_TPT = g.TPT; p.wg_taps = g.taps;
     p.kd = g.NT == 128 ? 6 : 4;
     if (const char* e = getenv(g.NT == 128 ? "FN2_TC_KD" : "FN2_TC_KDW")) { const int v = atoi(e); if (v >= 1 && v <= 1024) p.kd = v; }
     const char* nocomp = getenv("FN2_TC_COMP");
@@ -1344,13 +1362,13 @@ int conv_tc_wgrad(const fn2_conv_desc* d, const T4& bottom, const T4& top_diff, 
             const int shift = (q - par) / g.sx, dl = (((-shift) % 4) + 4) % 4;    // copy `dl` holds column j - dl at index j
             p.dy[t] = (short)(ky - d->pad_h); p.dx[t] = (short)(shift + dl); p.widx[t] = (short)(par | (dl << 4));
         }
-    p.total = g.taps * g.BT * g.ST * g.S;
+    p.total = g.TG * g.BT * g.ST * g.S;
     p.ntotal = p.total; p.tail_first = p.total;
     CUtensorMap mapA, mapB;
     {
         cuuint64_t dims[4] = {(cuuint64_t)g.Wq, (cuuint64_t)g.Hb * g.sx, (cuuint64_t)g.Cb, (cuuint64_t)4 * g.N};
         cuuint64_t strides[3] = {(cuuint64_t)g.Wq_p * 4, (cuuint64_t)g.Hb * g.sx * g.Wq_p * 4, (cuuint64_t)g.Cb * g.Hb * g.sx * g.Wq_p * 4};
-        cuuint32_t box[4] = {32, 1, 128, 1};
+        cuuint32_t box[4] = {32, 1, (cuuint32_t)g.G, 1};
         cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult r = enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)bigT, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

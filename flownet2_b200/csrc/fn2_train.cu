@@ -50,6 +50,21 @@ __global__ void relu_bwd_kernel(T4 data, T4 dy, T4 dx, float slope, int accumula
     }
 }
 
+// dense channel-fast maps with identical strides (every blob pair Net::Backward passes): 128-bit accesses
+__global__ void relu_bwd_vec_kernel(const float* __restrict__ data, const float* __restrict__ dy, float* __restrict__ dx, long long pixels,
+                                    int c4, long long pstride, float slope, int accumulate) {
+    const long long total = pixels * c4;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long off = (idx / c4) * pstride + (idx % c4) * 4;
+        const float4 d = *reinterpret_cast<const float4*>(data + off), g = *reinterpret_cast<const float4*>(dy + off);
+        float4 o = make_float4(g.x * (d.x > 0.f ? 1.f : slope), g.y * (d.y > 0.f ? 1.f : slope), g.z * (d.z > 0.f ? 1.f : slope),
+                               g.w * (d.w > 0.f ? 1.f : slope));
+        float4* out = reinterpret_cast<float4*>(dx + off);
+        if (accumulate) { const float4 p = *out; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+        *out = o;
+    }
+}
+
 // ---- bias gradient: db[c] = sum over (n, y, x) of dy, two stages, fixed order ---------------------------------------------
 __global__ void bias_grad_partial_kernel(T4 dy, float* __restrict__ part, int chunks) {
     // block b sums pixels [b*per, (b+1)*per) for every channel.  Channel-fast maps: thread = channel (coalesced), the 256 / C
@@ -201,6 +216,14 @@ int fn2_relu_backward(const fn2_tensor* top_data, const fn2_tensor* top_diff, co
     FN2_CHECK_ARG(valid(top_data) && valid(top_diff) && valid(bottom_diff), "relu_backward: null/empty tensor");
     T4 d = view(top_data), dy = view(top_diff), dx = view(bottom_diff);
     FN2_CHECK_ARG(same_dims(d, dy) && same_dims(d, dx), "relu_backward: shape mismatch");
+    auto dense = [](const T4& t) { return t.sc == 1 && !(t.c & 3) && !(t.sw & 3) && t.sh == (long long)t.w * t.sw && t.sn == (long long)t.h * t.sh &&
+                                          !((uintptr_t)t.p & 15); };
+    if (dense(d) && dense(dy) && dense(dx) && d.sw == dy.sw && d.sw == dx.sw) {
+        const long long pixels = (long long)d.n * d.h * d.w;
+        relu_bwd_vec_kernel<<<ew_grid(pixels * (d.c / 4), 256), 256, 0, (cudaStream_t)stream>>>(d.p, dy.p, dx.p, pixels, d.c / 4, d.sw, negative_slope, accumulate);
+        FN2_LAUNCH_CHECK();
+        return FN2_OK;
+    }
     relu_bwd_kernel<<<ew_grid(dx.count(), 256), 256, 0, (cudaStream_t)stream>>>(d, dy, dx, negative_slope, accumulate);
     FN2_LAUNCH_CHECK();
     return FN2_OK;
