@@ -679,15 +679,23 @@ class BaseConvolutionLayer : public Layer<Dtype> {
         int flip = 0;
         FN2_CALL(fn2_conv_backward_data_desc(&d_, bottom->height(), bottom->width(), &bd, &flip));
         fn2_tensor dy = top->diff_tensor();
+        // The tensor-core engine wants output channels in multiples of 16; concat-sized bottoms (1026, 770, 386, 473 channels)
+        // are not.  Their adjoint convolution runs with zero weight rows appended, into a scratch blob whose first channels are
+        // then copied / added to the bottom diff.
+        const int co_real = bd.co;
+        const bool pad_co = !bd.deconv && bd.co > 16 && bd.co % 16 != 0;
+        if (pad_co) bd.co = (bd.co + 15) / 16 * 16;
         // packed weights of the adjoint operator for this top layout (derived once per ParamsChanged generation)
         const int cis = top->channel_stride() > 0 ? top->channel_stride() : d_.co;
         Packed& pk = bpacked_[cis];
         if (pk.gen != params_gen_) {
             const float* w = this->blobs_[0]->gpu_data();
-            if (flip) {
-                const size_t wn = (size_t)this->blobs_[0]->count();
+            if (flip || pad_co) {
+                const size_t wn = (size_t)bd.co * bd.ci * bd.kh * bd.kw, wreal = (size_t)this->blobs_[0]->count();
                 if (wn > flipped_floats_) { if (flipped_) cudaFree(flipped_); CUDA_CHECK(cudaMalloc(&flipped_, wn * sizeof(float))); flipped_floats_ = wn; }
-                FN2_CALL(fn2_conv_flip_transpose_weights(&d_, w, flipped_, st));
+                if (flip) FN2_CALL(fn2_conv_flip_transpose_weights(&d_, w, flipped_, st));
+                else CUDA_CHECK(cudaMemcpyAsync(flipped_, w, wreal * sizeof(float), cudaMemcpyDeviceToDevice, st));
+                if (wn > wreal) CUDA_CHECK(cudaMemsetAsync(flipped_ + wreal, 0, (wn - wreal) * sizeof(float), st));
                 w = flipped_;
             }
             size_t floats = 0;
@@ -700,10 +708,10 @@ class BaseConvolutionLayer : public Layer<Dtype> {
         FN2_CALL(fn2_conv_out_shape(&bd, top->height(), top->width(), &Hb, &Wb));
         CHECK(Hb == bottom->height() && Wb == bottom->width()) << "conv backward: adjoint output " << Hb << "x" << Wb << " != bottom";
         Blob<Dtype>* tgt = bottom;
-        if (accumulate) {
+        if (accumulate || pad_co) {
             if (!bscratch_) bscratch_.reset(new Blob<Dtype>());
             bscratch_->set_layout(bottom->layout(), -1);
-            bscratch_->ReshapeLike(*bottom);
+            bscratch_->Reshape(bottom->num(), bd.co, bottom->height(), bottom->width());
             tgt = bscratch_.get();
         }
         fn2_tensor dx = tgt->diff_tensor();
@@ -712,7 +720,7 @@ class BaseConvolutionLayer : public Layer<Dtype> {
         if (wsn > bws_bytes_) { if (bws_) cudaFree(bws_); CUDA_CHECK(cudaMalloc(&bws_, wsn)); bws_bytes_ = wsn; }
         FN2_CALL(fn2_conv_forward(&bd, &dy, pk.p, nullptr, &dx, bws_, bws_bytes_, st));
         if (tgt != bottom) {
-            fn2_tensor s = tgt->diff_tensor(), d = bottom->diff_tensor();
+            fn2_tensor s = tgt->diff_tensor(0, co_real), d = bottom->diff_tensor();
             FN2_CALL(fn2_axpby(&s, 1.f, &d, accumulate ? 1.f : 0.f, st));
         }
     }

@@ -1227,6 +1227,8 @@ struct WgPlan {
     int NT, BT, ST, S, segs_x, segs, taps, G, TPT, TG;   // G rows per tap, TPT taps per 128-row tile, TG tap groups
     int Wq, Wq_p, Ws_p;                           // columns per parity plane (and its padded pitch), padded pitch of the small map
     size_t big_floats, small_floats, part_floats; // workspace pieces (each a multiple of 64 floats)
+    size_t bias_floats;                           // per-block channel sums of the top diff (bias gradient, fused into its transposition)
+    int bias_blocks;
 };
 static size_t up64(size_t x) { return (x + 63) / 64 * 64; }
 
@@ -1253,15 +1255,21 @@ static WgPlan wg_plan(const fn2_conv_desc* d, int N, int H, int W) {
     g.big_floats = up64((size_t)4 * N * g.Cb * g.Hb * g.sx * g.Wq_p);          // 4 copies, delayed by 0..3 columns
     g.small_floats = up64((size_t)2 * N * g.Cs * g.Hs * g.Ws_p);
     g.part_floats = up64((size_t)base * S * 128 * g.NT);
+    // the top diff is the small map of a convolution and the big map of a deconvolution
+    g.bias_blocks = d->deconv ? ((g.Wq_p + 31) / 32) * (N * g.Hb * g.sx) : ((g.Ws_p + 31) / 32) * (N * g.Hs);
+    g.bias_floats = d->has_bias ? up64((size_t)g.bias_blocks * d->co) : 0;
     return g;
 }
 
 // channel-major planes: dst[dl][((n*C + c)*H + h)*sx + par][j] = src[n, c, h, (j - dl)*sx + par] (zero outside the row) for
 // dl < nadv column delays; SPLIT writes the TF32 hi plane there and the lo plane `lo_off` floats further
 // `dlmask`: which of the 4 delays are written (bit dl); the source is read once per block (32 channels x 35 columns).
+// bias_part != nullptr: also the per-block channel sums of src, [block (x, z)][C] (the bias gradient when src is the top diff).
 template <bool SPLIT>
-__global__ void wg_transpose_kernel(T4 src, float* __restrict__ dst, int sx, int Wq, int Wq_p, long long lo_off, int dlmask) {
+__global__ void wg_transpose_kernel(T4 src, float* __restrict__ dst, int sx, int Wq, int Wq_p, long long lo_off, int dlmask,
+                                    float* __restrict__ bias_part) {
     __shared__ float tile[35][33];
+    __shared__ float red[8][33];
     const int wq0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int rp = blockIdx.z % (src.h * sx), n = blockIdx.z / (src.h * sx);
     const int h = rp / sx, par = rp % sx;
@@ -1271,6 +1279,18 @@ __global__ void wg_transpose_kernel(T4 src, float* __restrict__ dst, int sx, int
         tile[j][threadIdx.x] = (c < src.c && wq >= 0 && w < src.w) ? src.p[src.off(n, c, h, w)] : 0.f;
     }
     __syncthreads();
+    if (bias_part) {
+        float a = 0.f;
+        for (int j = threadIdx.y; j < 32; j += 8) a += tile[j + halo][threadIdx.x];          // the 32 core columns, fixed order
+        red[threadIdx.y][threadIdx.x] = a;
+        __syncthreads();
+        if (threadIdx.y == 0 && c0 + threadIdx.x < src.c) {
+            float t = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; k++) t += red[k][threadIdx.x];
+            bias_part[((long long)blockIdx.z * gridDim.x + blockIdx.x) * src.c + c0 + threadIdx.x] = t;
+        }
+    }
     const long long copy = (long long)src.n * src.c * src.h * sx * Wq_p;
     for (int j = threadIdx.y; j < 32; j += 8) {
         const int c = c0 + j, wq = wq0 + threadIdx.x;
@@ -1287,6 +1307,23 @@ __global__ void wg_transpose_kernel(T4 src, float* __restrict__ dst, int sx, int
                     if (dlmask >> dl & 1) o[dl * copy] = tile[threadIdx.x + 3 - dl][j];     // index wq holds column wq - dl
             }
         }
+    }
+}
+
+// db[c] (+)= sum over the blocks' partial sums, fixed order: 8 strided groups per channel, then the 8 group sums
+__global__ void wg_bias_final_kernel(const float* __restrict__ part, float* __restrict__ db, int C, int blocks, int accumulate) {
+    __shared__ float red[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    float a = 0.f;
+    if (c < C)
+        for (int k = threadIdx.y; k < blocks; k += 8) a += part[(long long)k * C + c];
+    red[threadIdx.y][threadIdx.x] = a;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) t += red[k][threadIdx.x];
+        db[c] = accumulate ? db[c] + t : t;
     }
 }
 
@@ -1312,11 +1349,11 @@ int conv_tc_wgrad_eligible(const fn2_conv_desc* d) {
 }
 size_t conv_tc_wgrad_workspace_floats(const fn2_conv_desc* d, int N, int H, int W) {
     const WgPlan g = wg_plan(d, N, H, W);
-    return g.big_floats + g.small_floats + g.part_floats + 64;
+    return g.big_floats + g.small_floats + g.part_floats + g.bias_floats + 64;
 }
 
-int conv_tc_wgrad(const fn2_conv_desc* d, const T4& bottom, const T4& top_diff, float* dw, int accumulate, float* ws, size_t ws_floats,
-                  cudaStream_t st) {
+int conv_tc_wgrad(const fn2_conv_desc* d, const T4& bottom, const T4& top_diff, float* dw, float* db, int accumulate, float* ws,
+                  size_t ws_floats, cudaStream_t st) {
     EncodeTiledFn enc = tc_encode_fn();
     if (!enc) { set_error("conv_tc_wgrad: cuTensorMapEncodeTiled unavailable"); return FN2_ERR_CUDA; }
     const WgPlan g = wg_plan(d, bottom.n, bottom.h, bottom.w);
@@ -1328,6 +1365,7 @@ int conv_tc_wgrad(const fn2_conv_desc* d, const T4& bottom, const T4& top_diff, 
     }
     ws = reinterpret_cast<float*>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
     float* bigT = ws; float* smallT = ws + g.big_floats; float* part = smallT + g.small_floats;
+    float* bias_part = (d->has_bias && db) ? part + g.part_floats : nullptr;
     {
         dim3 blk(32, 8);
         int dlmask = 0;                                     // column delays the layer's taps actually use
@@ -1336,11 +1374,16 @@ int conv_tc_wgrad(const fn2_conv_desc* d, const T4& bottom, const T4& top_diff, 
             dlmask |= 1 << ((((-shift) % 4) + 4) % 4);
         }
         dim3 gb((unsigned)((g.Wq_p + 31) / 32), (unsigned)((g.Cb + 31) / 32), (unsigned)(g.N * g.Hb * g.sx));
-        wg_transpose_kernel<false><<<gb, blk, 0, st>>>(big, bigT, g.sx, g.Wq, g.Wq_p, 0, dlmask);
+        wg_transpose_kernel<false><<<gb, blk, 0, st>>>(big, bigT, g.sx, g.Wq, g.Wq_p, 0, dlmask, d->deconv ? bias_part : nullptr);
         FN2_LAUNCH_CHECK();
         dim3 gs((unsigned)((g.Ws_p + 31) / 32), (unsigned)((g.Cs + 31) / 32), (unsigned)(g.N * g.Hs));
-        wg_transpose_kernel<true><<<gs, blk, 0, st>>>(small, smallT, 1, g.Ws, g.Ws_p, (long long)g.N * g.Cs * g.Hs * g.Ws_p, 1);
+        wg_transpose_kernel<true><<<gs, blk, 0, st>>>(small, smallT, 1, g.Ws, g.Ws_p, (long long)g.N * g.Cs * g.Hs * g.Ws_p, 1,
+                                                      d->deconv ? nullptr : bias_part);
         FN2_LAUNCH_CHECK();
+        if (bias_part) {
+            wg_bias_final_kernel<<<(unsigned)((d->co + 31) / 32), blk, 0, st>>>(bias_part, db, d->co, g.bias_blocks, accumulate);
+            FN2_LAUNCH_CHECK();
+        }
     }
     TcParams p;
     memset(&p, 0, sizeof(p));

@@ -15,8 +15,8 @@ namespace fn2 {
 // fn2_conv_tc.cu: weight gradient on the tcgen05 pipeline
 int conv_tc_wgrad_eligible(const fn2_conv_desc* d);
 size_t conv_tc_wgrad_workspace_floats(const fn2_conv_desc* d, int N, int H, int W);
-int conv_tc_wgrad(const fn2_conv_desc* d, const T4& bottom, const T4& top_diff, float* dw, int accumulate, float* ws, size_t ws_floats,
-                  cudaStream_t st);
+int conv_tc_wgrad(const fn2_conv_desc* d, const T4& bottom, const T4& top_diff, float* dw, float* db, int accumulate, float* ws,
+                  size_t ws_floats, cudaStream_t st);
 
 namespace {
 
@@ -277,8 +277,9 @@ int fn2_conv_backward_params(const fn2_conv_desc* d, const fn2_tensor* bottom, c
     const long long count = (long long)d->ci * d->co * d->kh * d->kw;
     const size_t bias_floats = (size_t)BIAS_CHUNKS * d->co + 64;
     if (conv_tc_wgrad_eligible(d)) {
-        rc = conv_tc_wgrad(d, x, dy, weight_diff_dev, accumulate, ws, workspace_bytes / sizeof(float) - bias_floats, st);
-        if (rc) return rc;
+        // (the bias gradient comes out of the top diff's transposition pass)
+        return conv_tc_wgrad(d, x, dy, weight_diff_dev, d->has_bias ? bias_diff_dev : nullptr, accumulate, ws,
+                             workspace_bytes / sizeof(float) - bias_floats, st);
     } else {
         dim3 grid((unsigned)tiles, (unsigned)(d->kh * d->kw), (unsigned)splits);
         weight_grad_kernel<<<grid, 256, 0, st>>>(S, B, ws, p);

@@ -7,6 +7,9 @@ NVLink/NVSwitch on the GPU box, gloo in the CPU tests):
   * gather_flows    : all ranks' (b_r, 2, H, W) flow fields -> (B, 2, H, W) in global pair order on EVERY rank
   * gather_flows_to_root : the same, delivered to one rank only (what a serving front end needs: 1/world of the
                       all-gather traffic, and issued on a side stream it overlaps the next step's forward)
+  * allreduce_gradients : data-parallel TRAINING (BASELINE config 5): every rank runs the step on its own pairs, then ONE
+                      all-reduce over the contiguous parameter-gradient arena (fn2_net_param_diff_arena) averages the
+                      gradients -- the reference's P2PSync tree (src/caffe/parallel.cpp:271-380) as a single NVSwitch collective
 No collective exists inside a pair.  The reference has no inference data parallelism at all (its P2PSync
 is training-only, src/caffe/parallel.cpp:271-380).
 """
@@ -74,3 +77,18 @@ def gather_flows_to_root(local, out=None, dst=0):
         return out
     dist.gather(local, None, dst=dst)
     return None
+
+
+def grad_arena_tensor(net):
+    ptr, nbytes = net.param_diff_arena()
+    return torch.as_tensor(DevicePtr(ptr, nbytes // 4), device="cuda")
+
+
+def allreduce_gradients(grads, average=True):
+    """grads: the contiguous gradient arena (grad_arena_tensor(net), or any tensor in the CPU tests).  Sum over the ranks, divided
+    by the world size when `average` (each rank normalised its loss by its own batch, l1loss_layer.cu:83-88)."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(grads, op=dist.ReduceOp.SUM)
+        if average:
+            grads.mul_(1.0 / dist.get_world_size())
+    return grads

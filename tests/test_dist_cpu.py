@@ -38,6 +38,10 @@ def _worker(rank, world, port, total, q):
         if total % world == 0:                      # equal shards: root-only gather (what bench.py uses at N > 1)
             root = P.gather_flows_to_root(local)
             ok_g = ok_g and ((root is None) if rank != 0 else bool(torch.equal(root, allf)))
+        # data-parallel training: one all-reduce of the gradient arena, averaged
+        g = torch.full((257,), float(rank + 1))
+        P.allreduce_gradients(g)
+        ok_g = ok_g and bool(torch.allclose(g, torch.full((257,), sum(range(1, world + 1)) / world)))
         q.put((rank, ok_w, bool(ok_g)))
     finally:
         dist.destroy_process_group()
