@@ -173,8 +173,150 @@ __global__ void __launch_bounds__(128) corr1d_fwd_kernel(T4 b0, T4 b1, T4 top, i
     }
 }
 
+// ---- fast path: FlowNet2-C's layer (MULTIPLY, k = 1, stride_1 = 1, pad = md, R = md / stride_2 = 10, C % 32 == 0) ----------------
+// out[q][c] = scale * sum over (dj, di) of Gx[q][dj][di] * M[q + SGN * (dj - R, di - R) * stride_2][c]
+//   bottom0 gradient: Gx = top diff, M = bottom1, SGN = +1
+//   bottom1 gradient: Gx = the top diff SHIFTED per displacement (corr_shift_kernel: Gx[q][d] = topdiff[q - disp(d)][d]), M = bottom0, SGN = -1
+// A displacement only connects pixels of the same stride_2 parity class, so a work unit is (sample, parity class, 8 x 16 tile of
+// that class's plane, 32 channels): the (8 + 2R) x (16 + 2R) plane-pixel halo of M sits in shared memory (129 KB), the tile's Gx
+// values of one displacement row (128 x 21) are re-staged per dj.  Thread = 4 consecutive pixels x 4 channels: a halo float4 is
+// loaded once and feeds up to 4 pixels (pixel i meets it with di = t - i), the pixel's 21 Gx values of the row live in registers:
+// 336 FMAs per 24 + 24 128-bit shared loads.  Fixed summation order (dj, then the halo column), no atomics.
+constexpr int CF_R = 10, CF_DW = 2 * CF_R + 1, CF_TH = 8, CF_TW = 16, CF_HH = CF_TH + 2 * CF_R, CF_HW = CF_TW + 2 * CF_R, CF_GROW = 24;
+constexpr int CF_SMEM = (CF_HH * CF_HW * 32 + CF_TH * CF_TW * CF_GROW) * (int)sizeof(float);
+
+struct CfP { int N, C, H, W, S, tiles_x, tiles_y, cchunks; float scale; };
+
+template <int SGN>
+__global__ void __launch_bounds__(256, 1) corr_bwd_fast_kernel(T4 g, T4 m, T4 out, CfP p) {
+    extern __shared__ __align__(16) float cfsm[];
+    float* halo = cfsm;                                   // [HH * HW][32]
+    float* gs = cfsm + CF_HH * CF_HW * 32;                // [128][GROW]
+    const int tid = threadIdx.x;
+    const int cg = tid & 7, pg = tid >> 3;                // channel float4 0..7, pixel group 0..31
+    const int row = pg >> 2, xg = pg & 3;                 // tile row 0..7, group of 4 pixels 0..3
+    const int units = p.N * p.S * p.S * p.tiles_y * p.tiles_x * p.cchunks;
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        int r = unit;
+        const int cc = r % p.cchunks; r /= p.cchunks;
+        const int tx = r % p.tiles_x; r /= p.tiles_x;
+        const int ty = r % p.tiles_y; r /= p.tiles_y;
+        const int cls = r % (p.S * p.S), n = r / (p.S * p.S);
+        const int py = cls / p.S, px = cls % p.S;
+        const int u0 = ty * CF_TH, v0 = tx * CF_TW, c0 = cc * 32;
+        __syncthreads();
+        for (int idx = tid; idx < CF_HH * CF_HW * 8; idx += 256) {
+            const int hp = idx >> 3, c4 = idx & 7;
+            const int hy = hp / CF_HW, hx = hp - hy * CF_HW;
+            const int y = (u0 - CF_R + hy) * p.S + py, x = (v0 - CF_R + hx) * p.S + px;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (y >= 0 && y < p.H && x >= 0 && x < p.W) v = *reinterpret_cast<const float4*>(m.p + m.off(n, c0 + 4 * c4, y, x));
+            *reinterpret_cast<float4*>(halo + hp * 32 + 4 * c4) = v;
+        }
+        float4 acc[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+        for (int dj = 0; dj < CF_DW; dj++) {
+            __syncthreads();
+            for (int idx = tid; idx < CF_TH * CF_TW * CF_GROW; idx += 256) {
+                const int q = idx / CF_GROW, di = idx - q * CF_GROW;
+                const int y = (u0 + (q >> 4)) * p.S + py, x = (v0 + (q & 15)) * p.S + px;
+                gs[idx] = (di < CF_DW && y < p.H && x < p.W) ? g.p[g.off(n, dj * CF_DW + di, y, x)] : 0.f;
+            }
+            __syncthreads();
+            float gr[4][CF_GROW];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int k4 = 0; k4 < CF_GROW / 4; k4++) {
+                    const float4 t = *reinterpret_cast<const float4*>(gs + (row * CF_TW + xg * 4 + i) * CF_GROW + 4 * k4);
+                    gr[i][4 * k4] = t.x; gr[i][4 * k4 + 1] = t.y; gr[i][4 * k4 + 2] = t.z; gr[i][4 * k4 + 3] = t.w;
+                }
+            // halo row / first halo column of this thread for displacement row dj
+            const int hrow = SGN > 0 ? row + dj : row + 2 * CF_R - dj;
+            const float* hb = halo + (hrow * CF_HW + xg * 4) * 32 + 4 * cg;
+#pragma unroll
+            for (int t = 0; t < CF_DW + 3; t++) {
+                const float4 mv = *reinterpret_cast<const float4*>(hb + t * 32);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    // halo column xg*4 + t is pixel i's column + di (SGN > 0) resp. + 2R - di (SGN < 0)
+                    const int e = t - i;
+                    if (e >= 0 && e < CF_DW) {
+                        const float gv = gr[i][SGN > 0 ? e : 2 * CF_R - e];
+                        acc[i].x = fmaf(gv, mv.x, acc[i].x); acc[i].y = fmaf(gv, mv.y, acc[i].y);
+                        acc[i].z = fmaf(gv, mv.z, acc[i].z); acc[i].w = fmaf(gv, mv.w, acc[i].w);
+                    }
+                }
+            }
+        }
+        const int y = (u0 + row) * p.S + py;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int x = (v0 + xg * 4 + i) * p.S + px;
+            if (y < p.H && x < p.W)
+                *reinterpret_cast<float4*>(out.p + out.off(n, c0 + 4 * cg, y, x)) =
+                    make_float4(acc[i].x * p.scale, acc[i].y * p.scale, acc[i].z * p.scale, acc[i].w * p.scale);
+        }
+    }
+}
+
+// Gx[n][y][x][d] = topdiff[n][d][y - dy(d)][x - dx(d)] (0 outside): the bottom1 gradient then has the bottom0 gradient's form
+__global__ void corr_shift_kernel(T4 td, float* __restrict__ gx, int R, int S) {
+    const int Dw = 2 * R + 1, D = Dw * Dw;
+    const long long total = (long long)td.n * td.h * td.w * D;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int d = (int)(idx % D);
+        long long r = idx / D;
+        const int x = (int)(r % td.w); r /= td.w;
+        const int y = (int)(r % td.h);
+        const int n = (int)(r / td.h);
+        const int yy = y - (d / Dw - R) * S, xx = x - (d % Dw - R) * S;
+        gx[idx] = (yy >= 0 && yy < td.h && xx >= 0 && xx < td.w) ? td.p[td.off(n, d, yy, xx)] : 0.f;
+    }
+}
+
+static bool corr_fast_ok(const T4& b0, const T4& b1, const T4& td, const T4& d0, const T4& d1, const CbP& p, int corr_type, int s2) {
+    if (getenv("FN2_CORR_BWD_SLOW")) return false;
+    if (corr_type != 0 || !p.identity_g || p.D != CF_DW * CF_DW || s2 < 1 || s2 > 2 || p.reach_x != CF_R * s2 || p.C % 32) return false;
+    const T4* ts[4] = {&b0, &b1, &d0, &d1};
+    for (const T4* t : ts)
+        if (t->sc != 1 || ((uintptr_t)t->p & 15) || (t->sw & 3) || (t->sh & 3) || (t->sn & 3)) return false;
+    return true;
+}
+
+static int corr_fast_run(const T4& b0, const T4& b1, const T4& td, const T4& d0, const T4& d1, const CbP& p, int s2, float* ws, cudaStream_t st) {
+    CfP f;
+    f.N = p.N; f.C = p.C; f.H = p.H; f.W = p.W; f.S = s2; f.scale = p.scale; f.cchunks = p.C / 32;
+    const int Hp = (p.H + s2 - 1) / s2, Wp = (p.W + s2 - 1) / s2;
+    f.tiles_y = (Hp + CF_TH - 1) / CF_TH; f.tiles_x = (Wp + CF_TW - 1) / CF_TW;
+    const int units = f.N * s2 * s2 * f.tiles_y * f.tiles_x * f.cchunks;
+    static bool attr = false;
+    if (!attr) {
+        FN2_CUDA(cudaFuncSetAttribute(corr_bwd_fast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM));
+        FN2_CUDA(cudaFuncSetAttribute(corr_bwd_fast_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM));
+        attr = true;
+    }
+    const int grid = min(units, num_sms());
+    corr_bwd_fast_kernel<1><<<grid, 256, CF_SMEM, st>>>(td, b1, d0, f);
+    FN2_LAUNCH_CHECK();
+    corr_shift_kernel<<<ew_grid((long long)p.N * p.H * p.W * p.D, 256), 256, 0, st>>>(td, ws, CF_R, s2);
+    FN2_LAUNCH_CHECK();
+    T4 gx;
+    gx.p = ws; gx.n = p.N; gx.c = p.D; gx.h = p.H; gx.w = p.W;
+    gx.sc = 1; gx.sw = p.D; gx.sh = (long long)p.W * p.D; gx.sn = (long long)p.H * p.W * p.D;
+    corr_bwd_fast_kernel<-1><<<grid, 256, CF_SMEM, st>>>(gx, b0, d1, f);
+    FN2_LAUNCH_CHECK();
+    return FN2_OK;
+}
+
 int corr_bwd_run(const T4& b0, const T4& b1, const T4& td, const T4& d0, const T4& d1, CbP& p, int corr_type, float* ws, size_t ws_floats,
-                 cudaStream_t st) {
+                 cudaStream_t st, int s2_2d = 0) {
+    if (s2_2d > 0 && corr_fast_ok(b0, b1, td, d0, d1, p, corr_type, s2_2d)) {
+        if (!ws || ws_floats < (size_t)p.N * p.H * p.W * p.D) { set_error("correlation_backward: workspace too small"); return FN2_ERR_WORKSPACE; }
+        return corr_fast_run(b0, b1, td, d0, d1, p, s2_2d, ws, st);
+    }
     const size_t gfloats = p.identity_g ? 0 : (size_t)p.N * p.H * p.W * p.D;
     const size_t sfloats = corr_type == 1 ? (size_t)p.N * p.H * p.W * p.C : 0;
     if (gfloats + sfloats > ws_floats || (!ws && gfloats + sfloats)) { set_error("correlation_backward: workspace too small (%zu floats needed)", gfloats + sfloats); return FN2_ERR_WORKSPACE; }
@@ -213,8 +355,8 @@ int corr_bwd_run(const T4& b0, const T4& b1, const T4& td, const T4& d0, const T
 
 size_t corr_bwd_workspace_floats(int N, int C, int H, int W, int D, int k, int s1, int pad, int md, int topH, int topW, int corr_type, int one_d) {
     const bool ident = k == 1 && s1 == 1 && pad == md && topH == H && topW == W;
-    (void)one_d;
-    return (ident ? 0 : (size_t)N * H * W * D) + (corr_type == 1 ? (size_t)N * H * W * C : 0);
+    // (the identity case of the 2-D MULTIPLY layer may take the fast path, which stages the shifted top diff there)
+    return ((ident && (one_d || corr_type == 1)) ? 0 : (size_t)N * H * W * D) + (corr_type == 1 ? (size_t)N * H * W * C : 0);
 }
 
 // 2-D layer: top channel tc <-> displacement ((tc / Dw - R) * s2, (tc % Dw - R) * s2)   (correlation_layer.cu:81-82)
@@ -231,7 +373,7 @@ int corr_bwd_2d(const T4& b0, const T4& b1, const T4& td, const T4& d0, const T4
     p.reach_y = p.reach_x = R * s2;
     p.identity_g = (k == 1 && s1 == 1 && pad == md && td.h == b0.h && td.w == b0.w) ? 1 : 0;
     p.scale = 1.f / (float)(k * k * p.C);
-    return corr_bwd_run(b0, b1, td, d0, d1, p, corr_type, ws, ws_floats, st);
+    return corr_bwd_run(b0, b1, td, d0, d1, p, corr_type, ws, ws_floats, st, s2);
 }
 
 // 1-D layer: tc <-> (0, (tc + x_shift) * s2), x_shift = -R (both directions or left only) or 0 (right only)
