@@ -183,7 +183,10 @@ __global__ void __launch_bounds__(128) corr1d_fwd_kernel(T4 b0, T4 b1, T4 top, i
 // loaded once and feeds up to 4 pixels (pixel i meets it with di = t - i), the pixel's 21 Gx values of the row live in registers:
 // 336 FMAs per 24 + 24 128-bit shared loads.  Fixed summation order (dj, then the halo column), no atomics.
 constexpr int CF_R = 10, CF_DW = 2 * CF_R + 1, CF_TH = 8, CF_TW = 16, CF_HH = CF_TH + 2 * CF_R, CF_HW = CF_TW + 2 * CF_R, CF_GROW = 24;
-constexpr int CF_SMEM = (CF_HH * CF_HW * 32 + CF_TH * CF_TW * CF_GROW) * (int)sizeof(float);
+constexpr int CF_GB = 3;                                  // displacement rows staged per step (Gx values prefetched one step ahead)
+constexpr int CF_GSTAGE = CF_GB * CF_TH * CF_TW * CF_GROW; // floats per stage
+constexpr int CF_SMEM = (CF_HH * CF_HW * 32 + CF_GSTAGE) * (int)sizeof(float);
+static_assert(CF_DW % CF_GB == 0 && CF_GSTAGE % 256 == 0, "stage shape");
 
 struct CfP { int N, C, H, W, S, tiles_x, tiles_y, cchunks; float scale; };
 
@@ -216,21 +219,35 @@ __global__ void __launch_bounds__(256, 1) corr_bwd_fast_kernel(T4 g, T4 m, T4 ou
         float4 acc[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // Gx values of CF_GB displacement rows per step; the next step's values are fetched into registers while this one computes
+        float pre[CF_GSTAGE / 256];
+        auto gfetch = [&](int dj0) {
+#pragma unroll
+            for (int j = 0; j < CF_GSTAGE / 256; j++) {
+                const int idx = tid + 256 * j;
+                const int b = idx / (CF_TH * CF_TW * CF_GROW), rem = idx - b * (CF_TH * CF_TW * CF_GROW);
+                const int q = rem / CF_GROW, di = rem - q * CF_GROW;
+                const int y = (u0 + (q >> 4)) * p.S + py, x = (v0 + (q & 15)) * p.S + px;
+                pre[j] = (di < CF_DW && y < p.H && x < p.W) ? g.p[g.off(n, (dj0 + b) * CF_DW + di, y, x)] : 0.f;
+            }
+        };
+        gfetch(0);
 #pragma unroll 1
         for (int dj = 0; dj < CF_DW; dj++) {
-            __syncthreads();
-            for (int idx = tid; idx < CF_TH * CF_TW * CF_GROW; idx += 256) {
-                const int q = idx / CF_GROW, di = idx - q * CF_GROW;
-                const int y = (u0 + (q >> 4)) * p.S + py, x = (v0 + (q & 15)) * p.S + px;
-                gs[idx] = (di < CF_DW && y < p.H && x < p.W) ? g.p[g.off(n, dj * CF_DW + di, y, x)] : 0.f;
+            if (dj % CF_GB == 0) {
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < CF_GSTAGE / 256; j++) gs[tid + 256 * j] = pre[j];
+                __syncthreads();
+                if (dj + CF_GB < CF_DW) gfetch(dj + CF_GB);
             }
-            __syncthreads();
+            const float* gsr = gs + (dj % CF_GB) * (CF_TH * CF_TW * CF_GROW);
             float gr[4][CF_GROW];
 #pragma unroll
             for (int i = 0; i < 4; i++)
 #pragma unroll
                 for (int k4 = 0; k4 < CF_GROW / 4; k4++) {
-                    const float4 t = *reinterpret_cast<const float4*>(gs + (row * CF_TW + xg * 4 + i) * CF_GROW + 4 * k4);
+                    const float4 t = *reinterpret_cast<const float4*>(gsr + (row * CF_TW + xg * 4 + i) * CF_GROW + 4 * k4);
                     gr[i][4 * k4] = t.x; gr[i][4 * k4 + 1] = t.y; gr[i][4 * k4 + 2] = t.z; gr[i][4 * k4 + 3] = t.w;
                 }
             // halo row / first halo column of this thread for displacement row dj
