@@ -101,6 +101,87 @@ void Net<Dtype>::Init(const NetParameter& param) {
     AliasConcats();
     BuildArena();
     PlanStreams();
+    FuseWarpBlocks();
+}
+
+// Resample(LINEAR, 2 bottoms, up-sampling a 2-channel flow) -> FlowWarp(img1, flow) -> Eltwise(img0, warped; 1, -1) -> ChannelNorm,
+// and Eltwise(flow; coeff): FlowNet2's hand-over between stacked networks.  Deploy nets only (no backward through the fused pass).
+template <typename Dtype>
+void Net<Dtype>::FuseWarpBlocks() {
+    absorbed_.assign(layers_.size(), 0);
+    if (phase_ != TEST || getenv("FN2_NO_WARPFUSE")) return;
+    const int L = (int)layers_.size();
+    auto consumers = [&](int blob, int after) {
+        vector<int> c;
+        for (int j = after + 1; j < L; j++) for (int b : bottom_id_vecs_[j]) if (b == blob) { c.push_back(j); break; }
+        return c;
+    };
+    auto inplace = [&](int j) { for (int t : top_id_vecs_[j]) for (int b : bottom_id_vecs_[j]) if (t == b) return true; return false; };
+    for (int r = 0; r < L; r++) {
+        if (string(layers_[r]->type()) != "Resample" || bottom_id_vecs_[r].size() != 2 || top_id_vecs_[r].size() != 1) continue;
+        const LayerParameter& rl = layers_[r]->layer_param();
+        if (rl.resample_param().type() != 2) continue;
+        Blob<Dtype>* fin = bottom_vecs_[r][0];
+        Blob<Dtype>* ff = top_vecs_[r][0];
+        if (fin->channels() != 2 || fin->height() > ff->height() || fin->width() > ff->width()) continue;
+        const int ffid = top_id_vecs_[r][0];
+        WarpBlock wb; wb.resample = r; wb.warp = wb.sub = wb.norm = wb.scale = -1; wb.coeff = 0; wb.fill_nan = 0;
+        for (int j : consumers(ffid, r)) {
+            const string ty = layers_[j]->type();
+            if (ty == "FlowWarp" && bottom_id_vecs_[j].size() == 2 && bottom_id_vecs_[j][1] == ffid && wb.warp < 0) wb.warp = j;
+            else if (ty == "Eltwise" && bottom_id_vecs_[j].size() == 1 && !inplace(j) && wb.scale < 0) {
+                EltwiseParameter ep = layers_[j]->layer_param().eltwise_param();
+                if (ep.operation() == "SUM" && ep.coeff_size() == 1) { wb.scale = j; wb.coeff = ep.coeff(0); }
+            }
+        }
+        if (wb.warp < 0 || wb.scale < 0 || inplace(wb.warp)) continue;
+        wb.fill_nan = layers_[wb.warp]->layer_param().flow_warp_param().fill_nan() ? 1 : 0;
+        const int wid = top_id_vecs_[wb.warp][0];
+        if (bottom_vecs_[wb.warp][0]->channels() > 4) continue;
+        for (int j : consumers(wid, wb.warp)) {
+            if (string(layers_[j]->type()) != "Eltwise" || bottom_id_vecs_[j].size() != 2 || bottom_id_vecs_[j][1] != wid || inplace(j)) continue;
+            EltwiseParameter ep = layers_[j]->layer_param().eltwise_param();
+            if (ep.operation() == "SUM" && ep.coeff_size() == 2 && ep.coeff(0) == 1.f && ep.coeff(1) == -1.f) { wb.sub = j; break; }
+        }
+        if (wb.sub < 0) continue;
+        const int eid = top_id_vecs_[wb.sub][0];
+        for (int j : consumers(eid, wb.sub))
+            if (string(layers_[j]->type()) == "ChannelNorm" && !inplace(j)) { wb.norm = j; break; }
+        if (wb.norm < 0) continue;
+        // the second image must exist before the Resample layer runs, and everything has to sit on one stream
+        const int members[4] = {wb.warp, wb.sub, wb.norm, wb.scale};
+        bool ok = true;
+        for (int m : members) if (!layer_stream_.empty() && layer_stream_[m] != layer_stream_[r]) ok = false;
+        auto produced_before = [&](int blob) {
+            for (int j = r; j < L; j++) for (int t : top_id_vecs_[j]) if (t == blob) return false;
+            return true;
+        };
+        if (!produced_before(bottom_id_vecs_[wb.warp][0]) || !produced_before(bottom_id_vecs_[wb.sub][0])) ok = false;
+        // nobody between the Resample layer and a member may touch the member's top early
+        for (int m : members)
+            for (int j = r + 1; j < m && ok; j++) {
+                if (j == wb.warp || j == wb.sub || j == wb.norm || j == wb.scale) continue;
+                for (int b : bottom_id_vecs_[j]) if (b == top_id_vecs_[m][0]) ok = false;
+            }
+        if (!ok) continue;
+        if (!layer_wait_.empty()) for (int m : members) layer_wait_[r] = std::max(layer_wait_[r], layer_wait_[m]);
+        warp_head_[r] = wb;
+        for (int m : members) absorbed_[m] = 1;
+    }
+}
+
+template <typename Dtype>
+void Net<Dtype>::RunLayer(int i) {
+    if (absorbed_[i]) return;
+    auto it = warp_head_.find(i);
+    if (it == warp_head_.end()) { layers_[i]->Forward(bottom_vecs_[i], top_vecs_[i]); return; }
+    const WarpBlock& w = it->second;
+    fn2_tensor fin = bottom_vecs_[i][0]->tensor(), ff = top_vecs_[i][0]->mutable_tensor();
+    fn2_tensor i1 = bottom_vecs_[w.warp][0]->tensor(), wp = top_vecs_[w.warp][0]->mutable_tensor();
+    fn2_tensor i0 = bottom_vecs_[w.sub][0]->tensor(), er = top_vecs_[w.sub][0]->mutable_tensor();
+    fn2_tensor en = top_vecs_[w.norm][0]->mutable_tensor(), fs = top_vecs_[w.scale][0]->mutable_tensor();
+    int rc = fn2_warp_block_forward(&fin, &i0, &i1, &ff, &wp, &er, &en, &fs, w.coeff, w.fill_nan, Caffe::stream());
+    CHECK(rc == 0) << "fn2_warp_block_forward: " << fn2_last_error();
 }
 
 template <typename Dtype>
@@ -348,7 +429,7 @@ void Net<Dtype>::PlanStreams() {
 template <typename Dtype>
 void Net<Dtype>::ForwardEager() {
     if (!uses_stream2_) {
-        for (size_t i = 0; i < layers_.size(); ++i) layers_[i]->Forward(bottom_vecs_[i], top_vecs_[i]);
+        for (size_t i = 0; i < layers_.size(); ++i) RunLayer((int)i);
         return;
     }
     // fork: everything already queued on the main stream (input copies) precedes the second stream's work; under graph
@@ -359,7 +440,7 @@ void Net<Dtype>::ForwardEager() {
         cudaStream_t st = layer_stream_[i] ? stream2_ : stream_;
         if (layer_wait_[i] >= 0) CUDA_CHECK(cudaStreamWaitEvent(st, layer_event_[layer_wait_[i]], 0));
         Caffe::stream() = st;
-        layers_[i]->Forward(bottom_vecs_[i], top_vecs_[i]);
+        RunLayer((int)i);
         if (layer_record_[i]) CUDA_CHECK(cudaEventRecord(layer_event_[i], st));
     }
     Caffe::stream() = stream_;
@@ -659,7 +740,7 @@ void Net<Dtype>::TimeLayers(float* ms) {
     for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
     CUDA_CHECK(cudaEventRecord(ev[0], stream_));
     for (size_t i = 0; i < layers_.size(); ++i) {
-        layers_[i]->Forward(bottom_vecs_[i], top_vecs_[i]);
+        RunLayer((int)i);
         CUDA_CHECK(cudaEventRecord(ev[i + 1], stream_));
     }
     CUDA_CHECK(cudaStreamSynchronize(stream_));

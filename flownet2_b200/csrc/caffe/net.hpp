@@ -66,6 +66,13 @@ class Net {
     void MarkActivationsOnDevice();
     void PlanStreams();
     Dtype* staging(const string& blob, size_t floats);
+    void FuseWarpBlocks();
+    void RunLayer(int i);
+    // warp block between stacked networks run as one kernel at the Resample layer's position (fn2_warp_block_forward); the
+    // other four layers of the chain become no-ops
+    struct WarpBlock { int resample, warp, sub, norm, scale; float coeff; int fill_nan; };
+    std::map<int, WarpBlock> warp_head_;        // by the Resample layer's index
+    vector<char> absorbed_;
     void PlanBackward();
     void BuildDiffArena();
     // backward plan (static per graph + seed set): which layers run, per bottom whether the gradient is wanted and whether it is

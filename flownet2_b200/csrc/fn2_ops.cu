@@ -108,6 +108,115 @@ __global__ void flow_warp_bwd_kernel(T4 img, T4 flow, T4 wdiff, T4 idiff, T4 fdi
 }
 
 // ---------------------------------------------------------------------------------------------
+// Warp block between two stacked networks (FlowNet2-CSS / FlowNet2): the chain
+//   Resample(LINEAR, up-sampling) -> FlowWarp -> Eltwise(img0 - warped) -> ChannelNorm, and Eltwise(coeff * flow)
+// as ONE pass: one thread per full-resolution pixel computes the interpolated flow, samples the second image, and writes all
+// five tops (most of them channel ranges of the next network's input concat).  Every value goes through exactly the
+// expressions of the stand-alone kernels below (resample_kernel<2>, flow_warp_fwd_kernel, eltwise_sum_kernel with coefficients
+// (1, -1) resp. (coeff), channel_norm_kernel; this file is compiled -fmad=false), so the tops are bit-identical to the layer
+// chain's.  References: resample_layer.cu:40-95, flow_warp_layer.cu:59-122, eltwise_layer.cu:36-60, channel_norm_layer.cu:17-30.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float triangleCoeffW(float x) {
+    if (-1 <= x && x < 0) return x + 1;
+    if (0 <= x && x <= 1) return 1 - x;
+    return 0;
+}
+__global__ void warp_block_kernel(T4 fin, T4 img0, T4 img1, T4 ffull, T4 warped, T4 err, T4 errn, T4 fscaled, float fx, float fy,
+                                  float coeff, float fill, int vec4) {
+    const long long total = (long long)ffull.n * ffull.h * ffull.w;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int x_out = (int)(idx % ffull.w);
+        const int y_out = (int)((idx / ffull.w) % ffull.h);
+        const int n = (int)(idx / ((long long)ffull.w * ffull.h));
+        // ---- Resample (LINEAR, no antialias: up-sampling), 2 channels: resample_kernel<2> with the window of <= 8 columns
+        const float x_in = (x_out * fx + fy / 2.0f) - 0.5f;
+        const float y_in = (y_out * fy + fx / 2.0f) - 0.5f;
+        const int x_in_round = (int)roundf(x_in);
+        const int y_in_round = (int)roundf(y_in);
+        const float ax = 1.0f / 1.0f, ay = 1.0f / 1.0f;
+        const int rx = (fx < 1.0f) ? 2 : (int)ceilf(2.0f / ax);
+        const int ry = (fy < 1.0f) ? 2 : (int)ceilf(2.0f / ay);
+        const int xl = max(x_in_round - rx, (int)floorf(x_in - 1.0f / ax)), xh = min(x_in_round + rx, (int)ceilf(x_in + 1.0f / ax));
+        const int yl = max(y_in_round - ry, (int)floorf(y_in - 1.0f / ay)), yh = min(y_in_round + ry, (int)ceilf(y_in + 1.0f / ay));
+        float tx_[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float dx = x_in - (xl + k);
+            tx_[k] = (ax * triangleCoeffW(ax * dx)) * ay;
+        }
+        float sum0 = 0.f, sum1 = 0.f, wsum = 0.f;
+        for (int y = yl; y <= yh; y++) {
+            if (y < 0 || y >= fin.h) continue;
+            const float dy = y_in - y;
+            const float cy = triangleCoeffW(ay * dy);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int x = xl + k;
+                if (x > xh) break;
+                if (x < 0 || x >= fin.w) continue;
+                const float w = tx_[k] * cy;
+                if (w == 0.f) continue;
+                const float* ip = fin.p + fin.off(n, 0, y, x);
+                sum0 = sum0 + w * __ldg(ip);
+                sum1 = sum1 + w * __ldg(ip + fin.sc);
+                wsum += w;
+            }
+        }
+        const float f0 = (!wsum) ? 0 : (sum0 / wsum), f1 = (!wsum) ? 0 : (sum1 / wsum);
+        ffull.p[ffull.off(n, 0, y_out, x_out)] = f0;
+        ffull.p[ffull.off(n, 1, y_out, x_out)] = f1;
+        // ---- Eltwise(coeff): acc = 0 + coeff * v
+        fscaled.p[fscaled.off(n, 0, y_out, x_out)] = 0.f + coeff * f0;
+        fscaled.p[fscaled.off(n, 1, y_out, x_out)] = 0.f + coeff * f1;
+        // ---- FlowWarp of img1 (flow_warp_fwd_kernel)
+        const float x2 = (float)x_out + f0;
+        const float y2 = (float)y_out + f1;
+        const int width = img1.w, height = img1.h;
+        float wv[4] = {fill, fill, fill, fill};
+        if (x2 >= 0 && y2 >= 0 && x2 < width && y2 < height) {
+            const int ix2_L = (int)x2;
+            const int iy2_T = (int)y2;
+            const int ix2_R = min(ix2_L + 1, width - 1);
+            const int iy2_B = min(iy2_T + 1, height - 1);
+            const float alpha = x2 - ix2_L;
+            const float beta = y2 - iy2_T;
+            const float cTL = (1 - alpha) * (1 - beta);
+            const float cTR = alpha * (1 - beta);
+            const float cBL = (1 - alpha) * beta;
+            const float cBR = alpha * beta;
+            const long long oTL = img1.off(n, 0, iy2_T, ix2_L), oTR = img1.off(n, 0, iy2_T, ix2_R);
+            const long long oBL = img1.off(n, 0, iy2_B, ix2_L), oBR = img1.off(n, 0, iy2_B, ix2_R);
+            if (vec4) {
+                const float4 TL = __ldg(reinterpret_cast<const float4*>(img1.p + oTL)), TR = __ldg(reinterpret_cast<const float4*>(img1.p + oTR));
+                const float4 BL = __ldg(reinterpret_cast<const float4*>(img1.p + oBL)), BR = __ldg(reinterpret_cast<const float4*>(img1.p + oBR));
+                const float tl[4] = {TL.x, TL.y, TL.z, TL.w}, tr[4] = {TR.x, TR.y, TR.z, TR.w};
+                const float bl[4] = {BL.x, BL.y, BL.z, BL.w}, br[4] = {BR.x, BR.y, BR.z, BR.w};
+#pragma unroll
+                for (int c = 0; c < 4; c++) wv[c] = ((cTL * tl[c] + cTR * tr[c]) + cBL * bl[c]) + cBR * br[c];
+            } else {
+                for (int c = 0; c < img1.c; c++) {
+                    const float TL = __ldg(img1.p + oTL + c * img1.sc);
+                    const float TR = __ldg(img1.p + oTR + c * img1.sc);
+                    const float BL = __ldg(img1.p + oBL + c * img1.sc);
+                    const float BR = __ldg(img1.p + oBR + c * img1.sc);
+                    wv[c] = ((cTL * TL + cTR * TR) + cBL * BL) + cBR * BR;
+                }
+            }
+        }
+        // ---- Eltwise(1, -1): acc = (0 + 1 * a) + (-1) * b, then ChannelNorm
+        float norm = 0;
+        for (int c = 0; c < img1.c; c++) {
+            warped.p[warped.off(n, c, y_out, x_out)] = wv[c];
+            float acc = 0.f + 1.0f * img0.p[img0.off(n, c, y_out, x_out)];
+            acc = acc + (-1.0f) * wv[c];
+            err.p[err.off(n, c, y_out, x_out)] = acc;
+            norm = norm + acc * acc;
+        }
+        errn.p[errn.off(n, 0, y_out, x_out)] = sqrtf(norm);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Resample.  Reference: resample_layer.cu:14-33 (filters), :40-95 InterpolationKernel,
 // :98-125 NearestNeighborKernel.  Including the swapped half-pixel offsets (:62-63).
 // ---------------------------------------------------------------------------------------------
@@ -767,6 +876,27 @@ int fn2_resample_forward(const fn2_tensor* bottom, const fn2_tensor* top, int ty
     else if (type == 2) resample_kernel<2><<<grid, 256, 0, s>>>(in, out, fx, fy, aa);
     else if (type == 3) resample_kernel<3><<<grid, 256, 0, s>>>(in, out, fx, fy, aa);
     else { set_error("resample: unsupported type %d (resample_layer.cu:204)", type); return FN2_ERR_INVALID; }
+    FN2_LAUNCH_CHECK();
+    return FN2_OK;
+}
+
+int fn2_warp_block_forward(const fn2_tensor* flow_in, const fn2_tensor* image0, const fn2_tensor* image1, const fn2_tensor* flow_full,
+                           const fn2_tensor* warped, const fn2_tensor* err, const fn2_tensor* err_norm, const fn2_tensor* flow_scaled,
+                           float scale_coeff, int fill_nan, void* stream) {
+    FN2_CHECK_ARG(valid(flow_in) && valid(image0) && valid(image1) && valid(flow_full) && valid(warped) && valid(err) && valid(err_norm) &&
+                  valid(flow_scaled), "warp_block: null/empty tensor");
+    T4 fin = view(flow_in), i0 = view(image0), i1 = view(image1), ff = view(flow_full), wp = view(warped), er = view(err), en = view(err_norm),
+       fs = view(flow_scaled);
+    FN2_CHECK_ARG(fin.c == 2 && ff.c == 2 && fs.c == 2 && en.c == 1 && i1.c <= 4, "warp_block: channel counts");
+    FN2_CHECK_ARG(same_dims(i0, i1) && same_dims(i0, wp) && same_dims(i0, er) && same_dims(ff, fs) && ff.n == i0.n && ff.h == i0.h && ff.w == i0.w &&
+                  en.n == i0.n && en.h == i0.h && en.w == i0.w && fin.n == ff.n, "warp_block: shape mismatch");
+    const float fx = (float)fin.w / (float)ff.w, fy = (float)fin.h / (float)ff.h;
+    FN2_CHECK_ARG(fx <= 1.f && fy <= 1.f, "warp_block: the flow must be up-sampled (use the layer chain otherwise)");
+    float fill = 0.f;
+    if (fill_nan) { unsigned u = 0xFFE00000u; memcpy(&fill, &u, 4); }
+    const int vec4 = i1.sc == 1 && i1.c <= 4 && i1.sw >= 4 && !((uintptr_t)i1.p & 15) && !(i1.sw & 3) && !(i1.sh & 3) && !(i1.sn & 3);
+    const long long total = (long long)ff.n * ff.h * ff.w;
+    warp_block_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(fin, i0, i1, ff, wp, er, en, fs, fx, fy, scale_coeff, fill, vec4);
     FN2_LAUNCH_CHECK();
     return FN2_OK;
 }

@@ -110,6 +110,15 @@ FN2_API int fn2_flow_warp_backward(const fn2_tensor* image, const fn2_tensor* fl
 FN2_API int fn2_resample_forward(const fn2_tensor* bottom, const fn2_tensor* top, int type,
                                  int antialias, void* stream);
 
+/* The warp block between two stacked networks as one pass (what Net::Init substitutes for the layer chain
+ * Resample(LINEAR, 2 bottoms) -> FlowWarp -> Eltwise(1, -1) -> ChannelNorm plus Eltwise(coeff) on the up-sampled flow):
+ * flow_in (N,2,h,w) is up-sampled to flow_full (N,2,H,W); image1 is warped by it; err = image0 - warped; err_norm = |err|_2
+ * over the channels; flow_scaled = scale_coeff * flow_full.  Bit-identical to the layer chain. */
+FN2_API int fn2_warp_block_forward(const fn2_tensor* flow_in, const fn2_tensor* image0, const fn2_tensor* image1,
+                                   const fn2_tensor* flow_full, const fn2_tensor* warped, const fn2_tensor* err,
+                                   const fn2_tensor* err_norm, const fn2_tensor* flow_scaled, float scale_coeff, int fill_nan,
+                                   void* stream);
+
 /* ------------------------------------------------------------------------------------ */
 /* DataAugmentation kernels -- replace the device side of                                 */
 /* DataAugmentationLayer::Forward_gpu (data_augmentation_layer.cu:321-637).               */

@@ -282,3 +282,24 @@ def test_full_size_properties(fn2, monkeypatch):
     if corr_tc is not None:
         corr_fp32 = simt.blobs["net1_corr"].data
         assert maxabs(corr_fp32, corr_tc) <= 1e-5 * max(1.0, float(np.abs(corr_fp32).max()))
+
+
+def test_fused_warp_block_is_bit_identical_to_the_layer_chain(fn2, monkeypatch):
+    """Net::FuseWarpBlocks runs Resample -> FlowWarp -> Eltwise(1,-1) -> ChannelNorm (+ the Eltwise that rescales the flow) of every
+    hand-over between stacked networks as one kernel; its five tops must equal the separate layers' bit for bit."""
+    proto = fn2.fill_template(fn2.model_template("FlowNet2-CSS"), 192, 128)
+    img0, img1 = smooth_images(rng(5), 2, 128, 192)
+    blobs = ["net2_in_flow_full", "net2_in_img1_warped", "net2_in_err", "net2_in_err_norm", "net2_in_flow_scaled",
+             "net3_in_flow_full", "net3_in_img1_warped", "net3_in_err_norm", "net3_in_flow_scaled", "predict_flow_final"]
+    got = []
+    for fused in (True, False):
+        if not fused:
+            monkeypatch.setenv("FN2_NO_WARPFUSE", "1")
+        net = fn2.Net(proto, None, fn2.TEST, batch=2)
+        net.fill_params(9)
+        net.forward(img0=img0, img1=img1)
+        got.append(({b: net.blobs[b].data for b in blobs}, net.launches_per_forward))
+    assert got[0][1] < got[1][1], (got[0][1], got[1][1])                    # the fusion actually happened (8 launches fewer)
+    for b in blobs:
+        assert np.array_equal(got[0][0][b], got[1][0][b], equal_nan=True), b
+    assert np.abs(got[0][0]["net2_in_err_norm"]).max() > 0
