@@ -163,6 +163,23 @@ def profile_traffic(pattern):
         return None, os.path.relpath(path, ROOT)
 
 
+def profile_metric(pattern, metric):
+    """Value of `metric` for the (first) launch in the newest committed profiles/rNN_<pattern>.csv written by
+    `ncu --metrics ... --csv` (one row per launch and metric), or (None, None)."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r[0-9][0-9]_%s.csv" % pattern)))
+    if not files:
+        return None, None
+    try:
+        for r in csv.reader(open(files[-1])):
+            if len(r) > 3 and r[-3] == metric:
+                return float(r[-1].replace(",", "")), os.path.relpath(files[-1], ROOT)
+    except Exception:
+        pass
+    return None, os.path.relpath(files[-1], ROOT)
+
+
 # ----------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------
@@ -543,10 +560,14 @@ def run_ours(args):
         # 473->256 3x3 at 56x128x4), read from the committed ncu capture; its algorithmic bytes are 4*(in + out + weights) = 62.8 MB
         tc_traffic, tc_traffic_file = profile_traffic("prof_tc128")
         corr_traffic, corr_traffic_file = profile_traffic("prof_corr")
+        # tensor-pipe counter of the same conv3_1 launch (ncu --metrics pass, tools/gpu_profile_r02.sh)
+        tp_pct, tp_file = profile_metric("tensor_pipe_tc128", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")
         roofline = {"kernel": "conv/deconv stack: conv_tc_kernel<NT> (tcgen05 3xTF32 implicit GEMM, fused bias+ReLU), summed over the layers",
                     "bound": "tensor", "achieved": conv_tf, "peak": peak_bf16, "unit": "TFLOP/s", "frac": conv_tf / peak_bf16,
                     "traffic": tc_traffic, "traffic_of": "conv3_1 launch (algorithmic 62.8e6 B), %s" % tc_traffic_file,
                     "tf32_dense_peak_measured": tf32_peak,
+                    "tensor_pipe_active_pct_of_elapsed": tp_pct,
+                    "tensor_pipe_counter": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed of the conv3_1 launch, %s" % tp_file,
                     "peak_source": pk["source"] + ", sustained bf16 dense (kernel timed inside a long step)",
                     "share_of_step": conv_ms / total_ms if total_ms else None,
                     "algorithmic_gflop_per_step": conv_fl / 1e9,

@@ -684,7 +684,11 @@ class BaseConvolutionLayer : public Layer<Dtype> {
         // then copied / added to the bottom diff.
         const int co_real = bd.co;
         const bool pad_co = !bd.deconv && bd.co > 16 && bd.co % 16 != 0;
-        if (pad_co) bd.co = (bd.co + 15) / 16 * 16;
+        if (pad_co) {
+            // wide tiles: a multiple of 128 when that costs <= 1/8 more channels, else of 64 (of 16 for narrow outputs)
+            const int c128 = (bd.co + 127) / 128 * 128, c64 = (bd.co + 63) / 64 * 64;
+            bd.co = bd.co <= 64 ? (bd.co + 15) / 16 * 16 : ((c128 - bd.co) * 8 <= bd.co ? c128 : c64);
+        }
         // packed weights of the adjoint operator for this top layout (derived once per ParamsChanged generation)
         const int cis = top->channel_stride() > 0 ? top->channel_stride() : d_.co;
         Packed& pk = bpacked_[cis];

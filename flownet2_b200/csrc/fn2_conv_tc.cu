@@ -1312,17 +1312,17 @@ __global__ void wg_transpose_kernel(T4 src, float* __restrict__ dst, int sx, int
 
 // db[c] (+)= sum over the blocks' partial sums, fixed order: 8 strided groups per channel, then the 8 group sums
 __global__ void wg_bias_final_kernel(const float* __restrict__ part, float* __restrict__ db, int C, int blocks, int accumulate) {
-    __shared__ float red[8][33];
+    __shared__ float red[32][33];
     const int c = blockIdx.x * 32 + threadIdx.x;
     float a = 0.f;
     if (c < C)
-        for (int k = threadIdx.y; k < blocks; k += 8) a += part[(long long)k * C + c];
+        for (int k = threadIdx.y; k < blocks; k += 32) a += part[(long long)k * C + c];
     red[threadIdx.y][threadIdx.x] = a;
     __syncthreads();
     if (threadIdx.y == 0 && c < C) {
         float t = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; k++) t += red[k][threadIdx.x];
+        for (int k = 0; k < 32; k++) t += red[k][threadIdx.x];
         db[c] = accumulate ? db[c] + t : t;
     }
 }
@@ -1381,7 +1381,7 @@ int conv_tc_wgrad(const fn2_conv_desc* d, const T4& bottom, const T4& top_diff, 
                                                       d->deconv ? nullptr : bias_part);
         FN2_LAUNCH_CHECK();
         if (bias_part) {
-            wg_bias_final_kernel<<<(unsigned)((d->co + 31) / 32), blk, 0, st>>>(bias_part, db, d->co, g.bias_blocks, accumulate);
+            wg_bias_final_kernel<<<(unsigned)((d->co + 31) / 32), dim3(32, 32), 0, st>>>(bias_part, db, d->co, g.bias_blocks, accumulate);
             FN2_LAUNCH_CHECK();
         }
     }
