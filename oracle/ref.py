@@ -263,13 +263,52 @@ def _names(text, key):
     return re.findall(r"\b%s\s*:\s*[\"']([^\"']*)[\"']" % key, text)
 
 
+def insert_splits(specs):
+    """InsertSplits (util/insert_splits.cpp:12-72) on a list of (name, type, block text): every top that is read by more than one
+    later layer gets a Split layer, the readers are renamed to its tops.  Names follow SplitBlobName (:120-128)."""
+    prod = {}                                   # blob name -> (layer index, top index) of its latest producer
+    readers = {}                                # (layer, top) -> [(reader layer, bottom index)]
+    for li, (name, typ, blk) in enumerate(specs):
+        for bi, b in enumerate(_names(blk, "bottom")):
+            if b in prod:
+                readers.setdefault(prod[b], []).append((li, bi))
+        for ti, t in enumerate(_names(blk, "top")):
+            prod[t] = (li, ti)
+    rename = {}                                 # (reader layer, bottom index) -> new bottom name
+    after = {}                                  # layer index -> [split layer specs to insert after it]
+    for (li, ti), rs in readers.items():
+        if len(rs) < 2:
+            continue
+        blob = _names(specs[li][2], "top")[ti]
+        lname = specs[li][0]
+        tops = ["%s_%s_%d_split_%d" % (blob, lname, ti, k) for k in range(len(rs))]
+        for k, r in enumerate(rs):
+            rename[r] = tops[k]
+        text = 'name: "%s_%s_%d_split" type: "Split" bottom: "%s" %s' % (blob, lname, ti, blob, " ".join('top: "%s"' % t for t in tops))
+        after.setdefault(li, []).append(("%s_%s_%d_split" % (blob, lname, ti), "Split", text))
+    out = []
+    for li, (name, typ, blk) in enumerate(specs):
+        cnt = [0]
+
+        def repl(m):
+            i = cnt[0]
+            cnt[0] += 1
+            return 'bottom: "%s"' % rename.get((li, i), m.group(1))
+        out.append((name, typ, re.sub(r'\bbottom\s*:\s*["\']([^"\']*)["\']', repl, blk)))
+        out.extend(after.get(li, []))
+    return out
+
+
+NO_BACKWARD_TYPES = ("DataAugmentation", "GenerateAugmentationParameters", "FlowAugmentation", "Downsample", "Resample", "Input", "Silence")
+
+
 class RefNet(object):
     """Runs a deploy prototxt through the reference's layer classes (see module docstring).
 
     weights: {layer name: [ndarray, ...]} as oracle.net.parse_caffemodel returns; source blobs are copied into the
     layer's params like Net::CopyTrainedLayersFrom (net.cpp:752-802), DataAugmentation through its CustomCopyBlobs."""
 
-    def __init__(self, prototxt_text, weights=None, batch=0, phase=1):
+    def __init__(self, prototxt_text, weights=None, batch=0, phase=1, splits=False):
         from .net import parse_prototxt, getall, get
         header, blocks = split_layers(prototxt_text)
         root = parse_prototxt(header)
@@ -290,6 +329,12 @@ class RefNet(object):
                 s[0] = batch
         for n, s in zip(self.input_names, self.input_shapes):
             self.blobs[n] = Blob(shape=s)
+        if splits:                              # a net that will run Backward: fan-out through Split layers like Net::Init
+            specs = [("__in__", "Input", " ".join('top: "%s"' % n for n in self.input_names))] + specs
+            specs = insert_splits(specs)[1:]
+            if specs and specs[0][0].startswith("__in__"):
+                pass
+        self.specs = specs
         for name, typ, blk in specs:
             bots = [self.blobs[b] for b in _names(blk, "bottom")]
             tops = []
@@ -317,6 +362,31 @@ class RefNet(object):
 
     def blob(self, name):
         return self.blobs[name].get()
+
+    def backward(self):
+        """Net::Backward (net.cpp:640-655): loss tops seeded with their loss_weight (layer.hpp:455-478), layers in reverse order;
+        a layer runs if it has parameters or a bottom that needs a gradient (net.cpp:120-170), never the augmentation / data side."""
+        from .net import parse_prototxt, getall, get
+        need_blob, plan = set(), []
+        for name, typ, layer in self.layers:
+            blk = next(b for n, t, b in self.specs if n == name)
+            bots, tops = _names(blk, "bottom"), _names(blk, "top")
+            need = typ not in NO_BACKWARD_TYPES and (len(layer.params) > 0 or any(b in need_blob for b in bots))
+            if need:
+                need_blob.update(tops)
+            pd = [b in need_blob and typ not in NO_BACKWARD_TYPES for b in bots]
+            if typ == "L1Loss":
+                pd = [b in need_blob for b in bots]
+            plan.append((need, pd, blk, tops))
+        for (name, typ, layer), (need, pd, blk, tops) in zip(self.layers, plan):
+            if typ.endswith("Loss"):
+                lw = [float(x) for x in getall(parse_prototxt(blk), "loss_weight")] or [1.0]
+                t = self.blobs[tops[0]]
+                t.set(np.full(t.shape if t.shape else (1,), lw[0], np.float32).reshape(t.shape), diff=True)
+        for (name, typ, layer), (need, pd, blk, tops) in reversed(list(zip(self.layers, plan))):
+            if need:
+                layer.backward(pd)
+        return self
 
     def time_layers(self, iters=1):
         return [(n, t, l.time_forward(iters)) for n, t, l in self.layers]
