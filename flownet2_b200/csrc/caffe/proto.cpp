@@ -1,5 +1,7 @@
 #include "proto.hpp"
 
+#include <map>
+
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -349,13 +351,59 @@ bool LayerParameter::included_in_phase(int phase) const {
     return true;
 }
 
+// UpgradeV1LayerParameter (util/upgrade_proto.cpp:680-862) + UpgradeV1LayerType (:864-949): a V1 `layers { type: CONVOLUTION
+// blobs_lr: 1 weight_decay: 1 ... }` entry as a `layer { type: "Convolution" param { lr_mult: 1 decay_mult: 1 } ... }` message.
+static std::shared_ptr<Message> UpgradeV1Layer(const Message& v1) {
+    static const std::map<std::string, std::string> types = {
+        {"NONE", ""}, {"ABSVAL", "AbsVal"}, {"ACCURACY", "Accuracy"}, {"ARGMAX", "ArgMax"}, {"BNLL", "BNLL"}, {"CONCAT", "Concat"},
+        {"CONTRASTIVE_LOSS", "ContrastiveLoss"}, {"CONVOLUTION", "Convolution"}, {"DECONVOLUTION", "Deconvolution"}, {"DATA", "Data"},
+        {"DROPOUT", "Dropout"}, {"DUMMY_DATA", "DummyData"}, {"EUCLIDEAN_LOSS", "EuclideanLoss"}, {"ELTWISE", "Eltwise"}, {"EXP", "Exp"},
+        {"FLATTEN", "Flatten"}, {"HDF5_DATA", "HDF5Data"}, {"HDF5_OUTPUT", "HDF5Output"}, {"HINGE_LOSS", "HingeLoss"}, {"IM2COL", "Im2col"},
+        {"IMAGE_DATA", "ImageData"}, {"INFOGAIN_LOSS", "InfogainLoss"}, {"INNER_PRODUCT", "InnerProduct"}, {"LRN", "LRN"},
+        {"MEMORY_DATA", "MemoryData"}, {"MULTINOMIAL_LOGISTIC_LOSS", "MultinomialLogisticLoss"}, {"MVN", "MVN"}, {"POOLING", "Pooling"},
+        {"POWER", "Power"}, {"RELU", "ReLU"}, {"SIGMOID", "Sigmoid"}, {"SIGMOID_CROSS_ENTROPY_LOSS", "SigmoidCrossEntropyLoss"},
+        {"SILENCE", "Silence"}, {"SOFTMAX", "Softmax"}, {"SOFTMAX_LOSS", "SoftmaxWithLoss"}, {"SPLIT", "Split"}, {"SLICE", "Slice"},
+        {"TANH", "TanH"}, {"WINDOW_DATA", "WindowData"}, {"THRESHOLD", "Threshold"}};
+    auto out = std::make_shared<Message>();
+    auto copy_all = [&](const char* name) { for (const auto& f : v1.fields) if (f.name == name) out->fields.push_back(f); };
+    copy_all("bottom"); copy_all("top"); copy_all("name"); copy_all("include"); copy_all("exclude");
+    if (v1.has("type")) {
+        const std::string& t = v1.str("type");
+        auto it = types.find(t);
+        if (it == types.end()) throw ParseError("Unknown V1LayerParameter layer type: " + t);       // :946-947
+        out->add("type", it->second);
+    }
+    copy_all("blobs");
+    // param (shared-weight names), blob_share_mode, blobs_lr, weight_decay -> one ParamSpec per blob (:705-736)
+    const int nparam = std::max(std::max(v1.count("param"), v1.count("blob_share_mode")), std::max(v1.count("blobs_lr"), v1.count("weight_decay")));
+    for (int i = 0; i < nparam; i++) {
+        Field f;
+        f.name = "param"; f.is_msg = true; f.msg = std::make_shared<Message>();
+        if (i < v1.count("param")) f.msg->add("name", v1.str("param", i));
+        if (i < v1.count("blob_share_mode")) f.msg->add("share_mode", v1.str("blob_share_mode", i));
+        if (i < v1.count("blobs_lr")) f.msg->add("lr_mult", v1.str("blobs_lr", i));
+        if (i < v1.count("weight_decay")) f.msg->add("decay_mult", v1.str("weight_decay", i));
+        out->fields.push_back(f);
+    }
+    copy_all("loss_weight");
+    static const char* const subs[] = {"accuracy_param", "argmax_param", "concat_param", "contrastive_loss_param", "convolution_param",
+        "data_param", "dropout_param", "dummy_data_param", "eltwise_param", "exp_param", "hdf5_data_param", "hdf5_output_param",
+        "hinge_loss_param", "image_data_param", "infogain_loss_param", "inner_product_param", "lrn_param", "memory_data_param",
+        "mvn_param", "pooling_param", "power_param", "relu_param", "sigmoid_param", "softmax_param", "slice_param", "tanh_param",
+        "threshold_param", "window_data_param", "transform_param", "loss_param"};
+    for (const char* n : subs) copy_all(n);
+    if (v1.has("layer")) throw ParseError("Input NetParameter has V0 layer -- not supported (upgrade_proto.cpp:858-861 ignores it)");
+    return out;
+}
+
 NetParameter NetParameter::FromText(const std::string& prototxt) {
     Message root = ParseTextFormat(prototxt);
     NetParameter np;
     np.name = root.str("name");
     np.force_backward = root.b("force_backward", false);
-    if (root.count("layers"))
-        throw ParseError("V1 'layers' prototxt is not supported; upgrade it with upgrade_net_proto_text");
+    const bool v1 = root.count("layers") > 0;                 // NetNeedsV1ToV2Upgrade, upgrade_proto.cpp:27-36
+    if (v1 && root.count("layer"))
+        throw ParseError("prototxt mixes V1 'layers' and 'layer' fields (upgrade_proto.cpp:655-660 refuses it too)");
     // legacy top-level inputs -> one Input layer named "input" placed first (upgrade_proto.cpp:953-992)
     int nin = root.count("input");
     if (nin) {
@@ -383,8 +431,10 @@ NetParameter NetParameter::FromText(const std::string& prototxt) {
         }
         np.layers.emplace_back(lm);
     }
-    for (const auto& f : root.fields)
+    for (const auto& f : root.fields) {
         if (f.name == "layer" && f.is_msg) np.layers.emplace_back(f.msg);
+        if (f.name == "layers" && f.is_msg) np.layers.emplace_back(UpgradeV1Layer(*f.msg));
+    }
     return np;
 }
 

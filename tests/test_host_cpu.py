@@ -285,3 +285,36 @@ def test_augmentation_coefficient_sampling(fn2):
     again = np.zeros((N, 42), np.float32)
     assert lib.fn2_aug_sample(AUG_LAYER.encode(), 7, N, W, H, C.c_float(1e9), again.ctypes.data_as(C.POINTER(C.c_float))) == 0
     assert np.array_equal(again, out)
+
+
+def _norm_tree(msg):
+    """Order-insensitive form of a parsed prototxt (protobuf's DebugString orders by field number; here: by name, scalars as
+    numbers where they parse as such, enum / string tokens as text)."""
+    out = []
+    for k, v in msg:
+        if isinstance(v, list):
+            out.append((k, _norm_tree(v)))
+        else:
+            try:
+                out.append((k, float(v)))
+            except ValueError:
+                out.append((k, v))
+    return sorted(out, key=lambda kv: (kv[0], repr(kv[1])))
+
+
+def test_v1_prototxt_upgrade_matches_the_reference_tests(fn2):
+    """NetParameter::FromText upgrades V1 `layers { type: CONVOLUTION blobs_lr: ... }` nets like UpgradeV1Net
+    (util/upgrade_proto.cpp:640-949).  Golden pairs: the reference's own NetUpgradeTest.TestSimple / TestImageNet
+    (tests/golden/make_upgrade_golden.py)."""
+    import json
+    from oracle.net import parse_prototxt
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "upgrade_v1_fixtures.json")) as f:
+        cases = json.load(f)["cases"]
+    assert len(cases) == 2
+    for c in cases:
+        got = parse_prototxt(canonical(fn2, c["v1"]))
+        want = parse_prototxt(canonical(fn2, c["v2"]))
+        assert [k for k, _ in got if k == "layers"] == [] and len([1 for k, _ in got if k == "layer"]) >= 4
+        assert _norm_tree(got) == _norm_tree(want)
+    with pytest.raises(fn2.Fn2Error):
+        canonical(fn2, "layers { name: 'x' type: NO_SUCH_TYPE }")
