@@ -325,7 +325,7 @@ def side_config(torch, F, model, w, h, batch, steps=10, warmup=3):
     return res
 
 
-def train_config(torch, F, batch=8, crop=(448, 320), data=(512, 384), steps=10, warmup=3):
+def train_config(torch, F, batch=8, crop=(448, 320), data=(512, 384), steps=10, warmup=3, dist=None):
     """BASELINE.json config 5: one FlowNet2-C training step (random augmentation of both frames and of the ground truth, forward,
     multi-scale EPE losses, backward down to every parameter gradient) on FlyingChairs-shaped synthetic data, batch 8, N=1.
     `value`: inputs resident in HBM; `e2e`: the same step fed from pinned host buffers, the five loss values read back."""
@@ -345,6 +345,16 @@ def train_config(torch, F, batch=8, crop=(448, 320), data=(512, 384), steps=10, 
     host_loss = torch.empty(8, dtype=torch.float32).pin_memory()
     stream = torch.cuda.ExternalStream(net.stream)
     res = {}
+    world = dist.get_world_size() if dist is not None else 1
+    grads = None
+    if world > 1:
+        # data parallel: the same weights everywhere (one broadcast of the arena), every rank its own `batch` pairs, one all-reduce
+        # of the contiguous gradient arena per step
+        from flownet2_b200 import parallel as P
+        with torch.cuda.stream(stream):
+            P.broadcast_arena(P.arena_tensor(net), src=0)
+            net.params_changed()
+            grads = P.grad_arena_tensor(net)
     with torch.cuda.stream(stream):
         def step():
             for n, d in zip(names, dev):
@@ -352,6 +362,8 @@ def train_config(torch, F, batch=8, crop=(448, 320), data=(512, 384), steps=10, 
             net.clear_param_diffs()
             net.forward_async()
             net.backward_async()
+            if grads is not None:
+                P.allreduce_gradients(grads)
 
         def step_host():
             for n, h in zip(names, pin):
@@ -359,6 +371,8 @@ def train_config(torch, F, batch=8, crop=(448, 320), data=(512, 384), steps=10, 
             net.clear_param_diffs()
             net.forward_async()
             net.backward_async()
+            if grads is not None:
+                P.allreduce_gradients(grads)
             for i, l in enumerate(losses):
                 net.get_blob_ptr(l, host_loss.data_ptr() + 4 * i)       # synchronous D2H of the scalar
 
@@ -366,6 +380,8 @@ def train_config(torch, F, batch=8, crop=(448, 320), data=(512, 384), steps=10, 
             for _ in range(warmup):
                 fn()
             torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(steps):
@@ -373,12 +389,17 @@ def train_config(torch, F, batch=8, crop=(448, 320), data=(512, 384), steps=10, 
             e1.record()
             torch.cuda.synchronize()
             res[key] = e0.elapsed_time(e1) / steps
+            if world > 1:                                   # max over the ranks
+                t = torch.tensor([res[key]], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                res[key] = float(t.item())
         lt = net.time_layers()
     loss_vals = [float(net.blobs[l].data.reshape(-1)[0]) for l in losses]
     gw = net.param("conv3_1", 0, diff=True)
     out = {"workload": "FlowNet2-C training step (augmentation + forward + EPE losses + backward), crop %dx%d from %dx%d, batch %d" % (cw, ch, dw, dh, batch),
-           "value": batch / (res["device"] * 1e-3), "unit": UNIT, "ms_per_step": res["device"], "steps": steps, "warmup": warmup,
-           "e2e": {"value": batch / (res["host"] * 1e-3), "unit": UNIT, "ms_per_step": res["host"],
+           "value": world * batch / (res["device"] * 1e-3), "unit": UNIT, "ms_per_step": res["device"], "steps": steps, "warmup": warmup,
+           "n_gpus": world, "parallelism": "data parallel, one all-reduce of the %.0f MB gradient arena per step" % (net.param_diff_arena()[1] / 1e6) if world > 1 else "single GPU",
+           "e2e": {"value": world * batch / (res["host"] * 1e-3), "unit": UNIT, "ms_per_step": res["host"],
                    "h2d_bytes_per_step": int(sum(a.nbytes for a in (img0, img1, gt))), "d2h_bytes_per_step": 4 * len(losses)},
            "launches_per_step": int(net.launches_per_forward + net.launches_per_backward),
            "forward_ms_layer_sum": float(sum(t for _, _, t in lt)),
@@ -386,6 +407,8 @@ def train_config(torch, F, batch=8, crop=(448, 320), data=(512, 384), steps=10, 
            "grad_finite": bool(np.isfinite(gw).all() and np.abs(gw).max() > 0)}
     del net
     torch.cuda.empty_cache()
+    if world > 1:
+        return out
     # the reference's own GPU training step on the same graph (subprocess: a CHECK failure inside the reference aborts)
     try:
         import subprocess
@@ -671,7 +694,18 @@ if __name__ == "__main__":
     if a.config5_only:
         import torch
         import flownet2_b200 as F
-        print(json.dumps(train_config(torch, F, steps=a.steps, warmup=max(a.warmup, 3))), flush=True)
+        world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist = None
+        if world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        line = train_config(torch, F, steps=a.steps, warmup=max(a.warmup, 3), dist=dist)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        if rank == 0:
+            print(json.dumps(line), flush=True)
     elif a.impl == "reference":
         run_reference(a)
     else:
