@@ -83,6 +83,22 @@ def test_correlation_backward(ops, case):
     assert maxabs(host(g1), w1) <= 2e-5 * max(1.0, np.abs(w1).max())
 
 
+@pytest.mark.parametrize("case", [(2, 64, 24, 40, 2), (1, 32, 37, 21, 2), (1, 32, 19, 45, 1)])
+def test_correlation_backward_fast_path(ops, case):
+    """FlowNet2-C's layer (MULTIPLY, k = 1, pad = md, 21 x 21 displacements, C % 32 == 0, channel-fast maps): the parity-plane
+    kernel of fn2_corr_bwd.cu, including plane / tile tails (odd sizes) and stride_2 = 1."""
+    N, C, H, W, s2 = case
+    md = 10 * s2
+    r = rng(N * 100 + H)
+    a = r.standard_normal((N, C, H, W)).astype(np.float32)
+    b = r.standard_normal((N, C, H, W)).astype(np.float32)
+    td = r.standard_normal((N, 441, H, W)).astype(np.float32)
+    w0, w1 = O.correlation_bwd(a, b, td, md, 1, md, 1, s2)
+    g0, g1 = ops.correlation_backward(dev(a, True), dev(b, True), dev(td, True), md, 1, md, 1, s2)
+    assert maxabs(host(g0), w0) <= 1e-5 * max(1.0, np.abs(w0).max())
+    assert maxabs(host(g1), w1) <= 1e-5 * max(1.0, np.abs(w1).max())
+
+
 @pytest.mark.parametrize("channels_last", [False, True])
 @pytest.mark.parametrize("fill_nan", [False, True])
 def test_flow_warp_forward_bit_exact(ops, channels_last, fill_nan):

@@ -294,3 +294,36 @@ def test_flownet_c_training_net_step(fn2):
         assert np.isfinite(gw).all() and np.abs(gw).max() > 0, lname
     need = dict(zip(net.layer_names, net.layer_need_backward()))
     assert need["corr"] and need["flow_loss6"] and not need["Downsample6"] and not need["flow_aug"] and not need["img0s_aug"]
+
+
+def _random_conv_cases(count, seed):
+    r = np.random.default_rng(seed)
+    cases = []
+    while len(cases) < count:
+        deconv = bool(r.integers(0, 4) == 0)
+        k = int(r.choice([1, 2, 3, 4, 5, 7]))
+        s = int(r.choice([1, 1, 2, 2, 3]))
+        p = int(r.integers(0, (k + 1) // 2 + 1))
+        N = int(r.integers(1, 4))
+        Ci = int(r.choice([1, 2, 3, 5, 8, 17, 32, 48, 70, 130]))
+        Co = int(r.choice([1, 2, 4, 16, 24, 33, 64, 96, 144]))
+        H, W = int(r.integers(k + 1, 30)), int(r.integers(k + 1, 45))
+        if deconv:
+            if s * (H - 1) + k - 2 * p < 1 or s * (W - 1) + k - 2 * p < 1 or p > k - 1:
+                continue
+            H, W = min(H, 12), min(W, 14)
+        elif H + 2 * p < k or W + 2 * p < k or p > k - 1:
+            continue
+        cases.append(("rand%d_%s_c%d_o%d_k%d_s%d_p%d_%dx%dx%d" % (len(cases), "d" if deconv else "c", Ci, Co, k, s, p, N, H, W),
+                      N, Ci, H, W, Co, k, s, p, deconv, True))
+    return cases
+
+
+RANDOM_CONV_CASES = _random_conv_cases(16, 2024)
+
+
+@pytest.mark.parametrize("case", RANDOM_CONV_CASES, ids=[c[0] for c in RANDOM_CONV_CASES])
+def test_conv_backward_random_shapes(fn2, case):
+    """Seeded random layer shapes (odd channel counts, even kernels, stride 3, one-pixel-wide tails): every gradient path the engine
+    may pick (tensor-core weight gradient with / without tap grouping, padded adjoints, SIMT fall-backs) against the float64 oracle."""
+    test_conv_backward_matches_oracle(fn2, case)

@@ -16,4 +16,8 @@ run tc_ops racecheck python -m pytest tests/test_ops_gpu.py -q -x -k "tcgen05 or
 run wgrad memcheck python -m pytest tests/test_train_gpu.py -q -x -k "conv_backward"
 run wgrad racecheck python -m pytest tests/test_train_gpu.py -q -x -k "c3x3_s1_wide or c5x5_s2_w57 or d4x4_s2_wide"
 run net_c memcheck python -m pytest tests/test_train_gpu.py -q -x -k "without_fusion"
+run corr_bwd memcheck python -m pytest tests/test_ops_gpu.py -q -x -k "correlation_backward"
+run corr_bwd racecheck python -m pytest tests/test_ops_gpu.py -q -x -k "correlation_backward_fast"
+run warp_block memcheck python -m pytest tests/test_net_gpu.py -q -x -k "fused_warp_block"
+run train_layers memcheck python -m pytest tests/test_train_gpu.py -q -x -k "training_layers or random_shapes"
 cat gpurun_out/r02_sanitizer_summary.txt
