@@ -49,6 +49,8 @@ struct TcParams {
     // tail split: the tiles of the last, partial wave [tail_first, ntotal) are cut into tail_z K ranges each so that they
     // spread over all SMs (448 tiles on 148 SMs: 3 + 1/8 rounds instead of 4); their partials are summed by a fix-up kernel
     int tail_first, tail_z, ntotal;
+    int tail_fix;                                 // 1: the K range that finishes LAST sums the tail_z partial tiles itself (no fix-up launch)
+    int* tail_cnt;                                // arrival counters of the tail tiles (zeroed before the launch)
     FastDiv d_ntiles_p, d_cotiles, d_tiles_x, d_tiles_y, d_splits, d_tail_z;
     // Correlation on the same pipeline (corr_tc_forward): a unit = (sample, parity plane, 128-pixel tile of map 0, block of
     // cbw x cbh halo pixels of map 1); D[pixel][halo pixel] = <a, b> over C channels; the epilogue keeps the band that
@@ -130,6 +132,7 @@ struct TcTile {
     int n, u0, v0, co0, cls, tap0, ntaps, steps;
     int k0, split;                                // first K step of this unit, split index
     int slot;                                     // >= 0: raw partial sums go to workspace slot `slot` (tail split)
+    int tq;                                       // tail split: index of the tile among the tail tiles (slot / tail_z)
     bool valid;
 };
 // MODE (compile time, so that each instantiation's role loops stay small -- the all-in-one kernel had ~1900 SASS instructions in
@@ -178,6 +181,7 @@ __device__ __forceinline__ TcTile tc_decode_tile(const TcParams& p, int tile) {
         t.slot = tile - p.tail_first;
         int q;
         p.d_tail_z.divmod(t.slot, q, tseg);
+        t.tq = q;
         tile = p.tail_first + q;
     }
     if (p.splits > 1) { int q; p.d_splits.divmod(tile, q, t.split); tile = q; }   // splits of a tile run side by side (shared A tiles in L2)
@@ -641,6 +645,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 continue;
             }
             const int u = T.u0 + yy, v = T.v0 + xx;
+            if (MODE == TC_PLAIN && T.slot >= 0 && p.tail_fix) {
+                // tail split, fixed up in the kernel: every K range stores its raw partial tile; the range that arrives LAST (an
+                // atomic counter per tile) sums the tail_z partials in slot order -- the order does not depend on who is last -- and
+                // writes the finished tile.  bar.sync 1 = the 128 drain threads.
+                const bool live = T.valid && u < p.cls_Hu[T.cls] && v < p.cls_Wu[T.cls];
+                float* o = ws + ((long long)T.slot * 128 + m) * NT;
+#pragma unroll
+                for (int j = 0; j < NT; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                uint32_t* flag = tmem_slot + 1;
+                if (m == 0) {
+                    const int prev = atomicAdd(p.tail_cnt + T.tq, 1);
+                    const bool l = prev == p.tail_z - 1;
+                    if (l) p.tail_cnt[T.tq] = 0;                         // everybody has arrived: leave the counter ready for the next launch
+                    *flag = l ? 1u : 0u;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const bool last = *flag != 0;
+                asm volatile("bar.sync 1, 128;" ::: "memory");            // flag is rewritten by the next tail unit
+                if (last && live) {
+                    __threadfence();
+                    const int oy = u * p.ou + p.cls_oy0[T.cls], ox = v * p.ov + p.cls_ox0[T.cls];
+                    float* dst = out + T.n * p.out_sn + (long long)oy * p.out_sh + (long long)ox * p.out_sw + T.co0;
+                    const float* src = ws + ((long long)T.tq * p.tail_z * 128 + m) * NT;
+#pragma unroll 4
+                    for (int j = 0; j < NT; j += 4) {
+                        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int z = 0; z < p.tail_z; z++) {
+                            const float4 x = __ldcg(reinterpret_cast<const float4*>(src + (long long)z * 128 * NT + j));
+                            a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+                        }
+                        float r[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            if (p.has_bias) r[e] += __ldg(bias + T.co0 + j + e);
+                            if (p.relu) r[e] = r[e] > 0 ? r[e] : r[e] * p.slope;
+                        }
+                        *reinterpret_cast<float4*>(dst + j) = make_float4(r[0], r[1], r[2], r[3]);
+                    }
+                }
+                continue;
+            }
             if (T.valid && u < p.cls_Hu[T.cls] && v < p.cls_Wu[T.cls]) {
                 const int oy = u * p.ou + p.cls_oy0[T.cls], ox = v * p.ov + p.cls_ox0[T.cls];
                 if (T.slot >= 0) {
@@ -799,6 +846,22 @@ __global__ void tc_tail_reduce_kernel(const float* __restrict__ ws, const float*
         const int oy = u * p.ou + p.cls_oy0[T.cls], ox = v * p.ov + p.cls_ox0[T.cls];
         *reinterpret_cast<float4*>(out + T.n * p.out_sn + (long long)oy * p.out_sh + (long long)ox * p.out_sw + co) = a;
     }
+}
+
+// Arrival counters of the in-kernel tail fix-up: a pool of zeroed regions handed out round-robin per launch (captured launches keep
+// theirs).  Every launch leaves its counters at zero again (the last arriver resets them), so a region may be reused as soon as the
+// launch that had it has finished; with 256 regions that is 256 tail-split launches later.
+constexpr int TAIL_CNT_REGION = 1024, TAIL_CNT_REGIONS = 256;
+static int* tc_tail_counters() {
+    static int* pool = nullptr;
+    static std::mutex mu;
+    static unsigned next = 0;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!pool) {
+        if (cudaMalloc(&pool, (size_t)TAIL_CNT_REGION * TAIL_CNT_REGIONS * sizeof(int)) != cudaSuccess) { pool = nullptr; return nullptr; }
+        cudaMemset(pool, 0, (size_t)TAIL_CNT_REGION * TAIL_CNT_REGIONS * sizeof(int));
+    }
+    return pool + (size_t)(next++ % TAIL_CNT_REGIONS) * TAIL_CNT_REGION;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1083,7 +1146,7 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
         p.ntiles_p = (p.ntiles + p.cl - 1) / p.cl * p.cl;
         p.cotiles = d->co / NT;
         p.total = p.ntiles_p * p.cotiles * p.ncls * p.splits;
-        p.ntotal = p.total; p.tail_first = p.total; p.tail_z = 1;
+        p.ntotal = p.total; p.tail_first = p.total; p.tail_z = 1; p.tail_fix = 0; p.tail_cnt = nullptr;
         p.d_ntiles_p.init(p.ntiles_p); p.d_cotiles.init(p.cotiles); p.d_tiles_x.init(p.tiles_x); p.d_tiles_y.init(p.tiles_y);
         p.d_splits.init(max(1, p.splits)); p.d_tail_z.init(1);
         if (p.splits == 1 && p.cl == 1 && !sm.mode && ws) {
@@ -1093,6 +1156,13 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
             if (tz > 1 && ws_floats >= (size_t)(p.total - first) * tz * 128 * NT) {
                 p.tail_first = first; p.tail_z = tz; p.d_tail_z.init(tz);
                 p.total = first + (p.ntotal - first) * tz;
+                // FN2_TC_TAILFIX=1: the last K range to arrive sums the partial tiles inside the kernel instead of a fix-up launch.
+                // Built and parity-tested, but measured SLOWER (FlowNet2 1024x436 b4: 16.55 vs 15.84 ms per step, 36 launches fewer):
+                // the last arriver's drain warps hold their SM's pipeline while they re-read tail_z tiles, whereas the separate kernel
+                // spreads that over all SMs and overlaps the next layer's prologue (PDL).  Off by default.
+                static const bool fix = getenv("FN2_TC_TAILFIX") != nullptr;
+                p.tail_cnt = (fix && p.ntotal - first <= TAIL_CNT_REGION) ? tc_tail_counters() : nullptr;
+                p.tail_fix = p.tail_cnt ? 1 : 0;
             }
         }
         cudaLaunchConfig_t cfg = {};
@@ -1126,7 +1196,7 @@ int conv_tc_forward(const fn2_conv_desc* d, const T4& in, const float* wp, const
 #undef FN2_TC_LAUNCH_NT
 #undef FN2_TC_LAUNCH
         FN2_LAUNCH_CHECK();
-        if (p.tail_z > 1) {
+        if (p.tail_z > 1 && !p.tail_fix) {
             const long long work = (long long)(p.ntotal - p.tail_first) * 128 * (NT / 4);
             if (NT == 128) tc_tail_reduce_kernel<128><<<ew_grid(work, 256), 256, 0, st>>>(ws, bias, out.p, p);
             else if (NT == 64) tc_tail_reduce_kernel<64><<<ew_grid(work, 256), 256, 0, st>>>(ws, bias, out.p, p);
