@@ -412,7 +412,7 @@ def train_config(torch, F, batch=8, crop=(448, 320), data=(512, 384), steps=10, 
     # the reference's own GPU training step on the same graph (subprocess: a CHECK failure inside the reference aborts)
     try:
         import subprocess
-        pr = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_train_time.py"), str(batch), "3"], capture_output=True,
+        pr = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_train_time.py"), str(batch), "5"], capture_output=True,
                             text=True, timeout=600)
         last = [l for l in pr.stdout.strip().splitlines() if l.startswith("{")]
         out["reference_gpu"] = json.loads(last[-1]) if last else {"unavailable": "exit %d: %s" % (pr.returncode, pr.stderr.strip()[-300:])}

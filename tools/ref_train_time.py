@@ -30,17 +30,18 @@ def main():
     img1 = np.clip(img0 + np.round(r.normal(0, 4, img0.shape)), 0, 255).astype(np.float32)
     gt = (4 * r.standard_normal((batch, 2, dh, dw))).astype(np.float32)
     times, losses = [], None
-    for i in range(steps + 1):
+    warmup = 2
+    for i in range(steps + warmup):
         t0 = time.perf_counter()
         net.forward(img0=img0, img1=img1, flow_gt=gt)
         net.backward()
         g = net.layers[[n for n, _, _ in net.layers].index("conv1")][2].params[0].get(diff=True)      # D2H read = synchronisation
         dt = time.perf_counter() - t0
-        if i > 0:
+        if i >= warmup:
             times.append(dt)
         losses = [float(net.blob("flow_loss%d" % l).reshape(-1)[0]) for l in (6, 5, 4, 3, 2)]
     mean = float(np.mean(times))
-    print(json.dumps({"value": batch / mean, "unit": "frame-pairs/s", "ms_per_step": mean * 1e3, "steps": steps, "warmup": 1,
+    print(json.dumps({"value": batch / mean, "unit": "frame-pairs/s", "ms_per_step": mean * 1e3, "steps": steps, "warmup": warmup, "ms_min": min(times) * 1e3, "ms_max": max(times) * 1e3,
                       "what": "reference layer classes (oracle/_ref) in GPU mode: FlowNet2-C training step, crop %dx%d from %dx%d, batch %d, "
                               "host-timed including its input uploads" % (cw, ch, dw, dh, batch),
                       "losses": losses, "grad_finite": bool(np.isfinite(g).all() and np.abs(g).max() > 0)}))
