@@ -35,6 +35,26 @@ __global__ void axpby_kernel(T4 x, float alpha, T4 y, float beta) {
     }
 }
 
+// both views channel-fast and pixel-linear (pixel p at p * sw), channels a multiple of 4: 128-bit accesses
+__global__ void axpby_vec_kernel(const float* __restrict__ x, long long xs, float alpha, float* __restrict__ y, long long ys, float beta,
+                                 long long pixels, int c4) {
+    const long long total = pixels * c4;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long p = idx / c4;
+        const int c = (int)(idx - p * c4) * 4;
+        const float4 xv = *reinterpret_cast<const float4*>(x + p * xs + c);
+        float4* yp = reinterpret_cast<float4*>(y + p * ys + c);
+        float4 o;
+        if (beta == 0.f) { o.x = alpha * xv.x; o.y = alpha * xv.y; o.z = alpha * xv.z; o.w = alpha * xv.w; }
+        else {
+            const float4 yv = *yp;
+            o.x = fmaf(alpha, xv.x, beta * yv.x); o.y = fmaf(alpha, xv.y, beta * yv.y);
+            o.z = fmaf(alpha, xv.z, beta * yv.z); o.w = fmaf(alpha, xv.w, beta * yv.w);
+        }
+        *yp = o;
+    }
+}
+
 // dx (+)= dy * (y > 0 ? 1 : slope); `data` is the layer's TOP data (in-place ReLU keeps no bottom data; for slope > 0 the
 // sign is the same, which is what the reference's in-place ReLU relies on, relu_layer.cu:29-38)
 __global__ void relu_bwd_kernel(T4 data, T4 dy, T4 dx, float slope, int accumulate) {
@@ -206,6 +226,17 @@ int fn2_axpby(const fn2_tensor* x, float alpha, const fn2_tensor* y, float beta,
     FN2_CHECK_ARG(valid(x) && valid(y), "axpby: null/empty tensor");
     T4 xv = view(x), yv = view(y);
     FN2_CHECK_ARG(same_dims(xv, yv), "axpby: shape mismatch");
+    auto linear = [](const T4& t) { return t.sc == 1 && t.c >= 4 && !(t.sw & 3) && t.sh == (long long)t.w * t.sw && t.sn == (long long)t.h * t.sh &&
+                                           !((uintptr_t)t.p & 15); };
+    if (linear(xv) && linear(yv)) {
+        // whole float4 groups through the vector kernel, the (c mod 4) tail channels (concat-sized blobs: 1026, 770, ...) through the scalar one
+        const long long pixels = (long long)yv.n * yv.h * yv.w;
+        const int cv = yv.c & ~3;
+        axpby_vec_kernel<<<ew_grid(pixels * (cv / 4), 256), 256, 0, (cudaStream_t)stream>>>(xv.p, xv.sw, alpha, yv.p, yv.sw, beta, pixels, cv / 4);
+        FN2_LAUNCH_CHECK();
+        if (cv == yv.c) return FN2_OK;
+        xv.p += cv; yv.p += cv; xv.c -= cv; yv.c -= cv;
+    }
     axpby_kernel<<<ew_grid(yv.count(), 256), 256, 0, (cudaStream_t)stream>>>(xv, alpha, yv, beta);
     FN2_LAUNCH_CHECK();
     return FN2_OK;
