@@ -125,7 +125,7 @@ class CpuArm(object):
         return self.scale / mean, mean
 
 
-def reference_gpu_arm(args, batch, steps=3, warmup=1):
+def reference_gpu_arm(args, batch, steps=5, warmup=2):
     """The reference's OWN GPU path (its unmodified layer classes from oracle/_ref: im2col + cuBLAS convolutions, its correlation /
     warp / resample kernels) on the same workload and the same B200, inputs resident on the host side of its Blobs.  A reported
     baseline like cpu_baseline, N = 1 only; None when oracle/_ref is not built."""
@@ -155,7 +155,8 @@ def reference_gpu_arm(args, batch, steps=3, warmup=1):
                 times.append(dt)
         mean = float(np.mean(times))
         R.set_mode(False)
-        return {"value": batch / mean, "unit": UNIT, "ms_per_step": mean * 1e3, "steps": steps, "warmup": warmup,
+        return {"value": batch / mean, "unit": UNIT, "ms_per_step": mean * 1e3, "ms_min": min(times) * 1e3, "ms_max": max(times) * 1e3,
+                "steps": steps, "warmup": warmup,
                 "what": "reference layer classes (oracle/_ref) in GPU mode on the same B200: %s %dx%d, %d pairs per step, host-timed "
                         "including its H2D/D2H blob copies" % (args.model, args.width, args.height, batch),
                 "output_finite": bool(np.isfinite(flow).all())}
