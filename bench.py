@@ -655,7 +655,12 @@ def run_ours(args):
             rc = {"kernel": "Correlation d=21 k=1 s2=2 C=256: conv_tc_kernel<128> in correlation mode (3xTF32 tile x halo-block GEMMs) + hi/lo split", "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                   "frac": gbs / pk["hbm_gbs"], "traffic": corr_traffic, "traffic_of": "%s (4x256x56x128 launch; algorithmic 109.3e6 B)" % corr_traffic_file, "peak_source": pk["source"],
                   "algorithmic_bytes_per_launch": by / len(corr), "ms_per_launch": t_ms / len(corr),
-                  "fp32_tflops": fl / (t_ms * 1e-3) / 1e12, "share_of_step": t_ms / total_ms if total_ms else None}
+                  "fp32_tflops": fl / (t_ms * 1e-3) / 1e12, "share_of_step": t_ms / total_ms if total_ms else None,
+                  # both fractions, and which one binds
+                  "tensor_pipe_active_pct_of_elapsed": profile_metric("tensor_pipe_corr", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")[0],
+                  "executed_tf32_tflops": 3.0 * (1008.0 / 441.0) * fl / (t_ms * 1e-3) / 1e12,
+                  "binding": "tensor pipe / tensor-memory port (3xTF32 products of all 1008 halo pixels per tile, 441 kept); DRAM traffic equals the "
+                             "algorithmic bytes, so HBM does not bind: frac is low because exact FP32 products cost 3 TF32 MMAs each"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": config(args, world), "clocks": clocks,
