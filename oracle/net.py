@@ -322,9 +322,26 @@ class OracleNet(object):
             B[tops[0]] = O.flow_warp_fwd(bots[0], bots[1], get(fp, "fill_value", "ZERO") == "NOT_A_NUMBER")
         elif typ == "ChannelNorm":
             B[tops[0]] = O.channel_norm(bots[0])
+        elif typ == "L1Loss":
+            loss, _ = O.l1loss_fwd(bots[0], bots[1] if len(bots) > 1 else None, **self._l1_args(l))
+            B[tops[0]] = np.array([loss], np.float32)
+        elif typ == "Downsample":
+            dp = get(l, "downsample_param", [])
+            th, tw = (bots[1].shape[2], bots[1].shape[3]) if len(bots) > 1 else (int(get(dp, "top_height")), int(get(dp, "top_width")))
+            B[tops[0]] = O.downsample_fwd(bots[0], th, tw)
+        elif typ == "Silence":
+            pass
         else:
             raise NotImplementedError(typ)
         return [B[t] for t in tops]
+
+    @staticmethod
+    def _l1_args(l):
+        lp = get(l, "l1_loss_param", [])
+        tf = lambda k: get(lp, k, "false") == "true"
+        return dict(l2_per_location=tf("l2_per_location"), l2_prescale_by_channels=tf("l2_prescale_by_channels"),
+                    normalize_by_num_entries=tf("normalize_by_num_entries"), epsilon=float(get(lp, "epsilon", 1e-2)),
+                    plateau=float(get(lp, "plateau", 0)))
 
     # ---- gradients ------------------------------------------------------------------------------------------------------
     def backward(self, **seeds):
@@ -333,6 +350,12 @@ class OracleNet(object):
         split_layer.cpp:38-52).  -> ({blob: diff}, {layer name: [param diffs]}); parameter diffs start from zero."""
         B = self.blobs
         D = {k: np.asarray(v, np.float32).copy() for k, v in seeds.items()}
+        for l in self.layers:                   # loss tops are seeded with their loss_weight (layer.hpp:455-478; default 1 for top 0)
+            if get(l, "type", "").endswith("Loss"):
+                t = getall(l, "top")[0]
+                if t not in D:
+                    lw = getall(l, "loss_weight")
+                    D[t] = np.full(B[t].shape, float(lw[0]) if lw else 1.0, np.float32)
         P = {}
         for l in reversed(self.layers):
             typ = get(l, "type")
@@ -387,7 +410,10 @@ class OracleNet(object):
         if typ == "FlowWarp":
             g0, g1 = O.flow_warp_bwd(bots[0], bots[1], tds[0])
             return [g0, g1]
-        if typ in ("DataAugmentation", "Resample", "Silence"):
+        if typ == "L1Loss":
+            g0, g1 = O.l1loss_bwd(bots[0], bots[1] if len(bots) > 1 else None, float(np.asarray(tds[0]).reshape(-1)[0]), **self._l1_args(l))
+            return [g0, g1][:len(bots)]
+        if typ in ("DataAugmentation", "Resample", "Silence", "Downsample"):
             return [None] * len(bots)
         raise NotImplementedError("backward of " + typ)
 

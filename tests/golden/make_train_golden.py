@@ -64,6 +64,26 @@ def main():
             g["T/%s/%s" % (name, k)] = v
         meta["cases"][name] = {k: list(v.shape) for k, v in out.items()}
         print(name, meta["cases"][name], flush=True)
+    # whole-net gradients: the reference's Net semantics (Split layers, loss weights) on the FlowNet2-C graph + five EPE losses
+    import flownet2_b200 as F
+    from oracle.net import synth_weights
+    proto = TC.loss_net_proto()
+    ins = TC.loss_net_inputs()
+    small = F.fill_template(F.model_template("FlowNet2-C"), 64, 64)
+    weights, _ = synth_weights(small, TC.LOSS_NET["seed"], F.fill_template(F.model_template("FlowNet2-C"), TC.LOSS_NET["w"], TC.LOSS_NET["h"]))
+    net = R.RefNet(proto, weights, batch=TC.LOSS_NET["batch"], splits=True)
+    net.forward(**ins)
+    net.backward()
+    for lvl in TC.LOSS_NET["weights"]:
+        g["N/lossnet/loss%d" % lvl] = net.blob("flow_loss%d" % lvl).reshape(-1)
+    ngrads = 0
+    for name, typ, layer in net.layers:
+        if typ in ("Convolution", "Deconvolution"):
+            for i, pb in enumerate(layer.params):
+                g["N/lossnet/grad/%s/%d" % (name, i)] = TC.grad_signature(name, i, pb.get(diff=True))
+                ngrads += 1
+    meta["lossnet"] = {"losses": {str(l): float(g["N/lossnet/loss%d" % l][0]) for l in TC.LOSS_NET["weights"]}, "param_blobs": ngrads}
+    print("lossnet", meta["lossnet"], flush=True)
     np.savez_compressed(outbase + ".npz", **g)
     with open(outbase + ".json", "w") as f:
         json.dump(meta, f, indent=1, sort_keys=True)

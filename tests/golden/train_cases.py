@@ -136,3 +136,60 @@ def train_inputs(name):
     bottoms = c["inputs"](r)
     params = c["params"](r) if c.get("params") else None
     return bottoms, params, r
+
+
+# ---- whole-net gradients against the reference's own Net semantics ------------------------------------------------------------
+# FlowNet2-C deploy graph up to predict_flow2 + one L1Loss (end-point error) per pyramid level against ground-truth inputs: what
+# Net::Backward (Split layers inserted, net.cpp:640-655) makes of it in the reference, for OracleNet.backward and the engine.
+LOSS_NET = dict(w=192, h=100, batch=1, seed=1701, weights={6: 0.32, 5: 0.08, 4: 0.02, 3: 0.01, 2: 0.005})
+# small parameter blobs are stored whole, the others as 4 seeded random projections + their L2 norm
+LOSS_NET_FULL = ("predict_flow6", "predict_flow2", "upsample_flow6to5", "conv_redir", "conv1")
+
+
+def loss_net_proto():
+    import re
+    import flownet2_b200 as F
+    w, h, batch = LOSS_NET["w"], LOSS_NET["h"], LOSS_NET["batch"]
+    proto = F.fill_template(F.model_template("FlowNet2-C"), w, h)
+    cut = proto.index('layer {\n  name: "Eltwise_final_x20"')
+    body = proto[:cut]
+    aw, ah = (w + 63) // 64 * 64, (h + 63) // 64 * 64
+    first_layer = body.index("layer {")
+    gts, losses = "", ""
+    for lvl, wgt in LOSS_NET["weights"].items():
+        sw, sh = aw >> lvl, ah >> lvl
+        gts += 'input: "gt%d"\ninput_shape {\n  dim: %d\n  dim: 2\n  dim: %d\n  dim: %d\n}\n' % (lvl, batch, sh, sw)
+        losses += ('layer {\n  name: "flow_loss%d"\n  type: "L1Loss"\n  bottom: "predict_flow%d"\n  bottom: "gt%d"\n  top: "flow_loss%d"\n'
+                   '  loss_weight: %g\n  l1_loss_param {\n    l2_per_location: true\n  }\n}\n' % (lvl, lvl, lvl, lvl, wgt))
+    text = body[:first_layer] + gts + body[first_layer:] + losses
+    if batch != 1:
+        text = re.sub(r"dim: 1\n  dim: 3", "dim: %d\n  dim: 3" % batch, text)
+    return text
+
+
+def loss_net_inputs():
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from util import rng, smooth_images
+    w, h, batch = LOSS_NET["w"], LOSS_NET["h"], LOSS_NET["batch"]
+    img0, img1 = smooth_images(rng(21), batch, h, w)
+    r = rng(22)
+    aw, ah = (w + 63) // 64 * 64, (h + 63) // 64 * 64
+    ins = {"img0": img0, "img1": img1}
+    for lvl in LOSS_NET["weights"]:
+        g = (0.5 * r.standard_normal((batch, 2, ah >> lvl, aw >> lvl))).astype(np.float32)
+        if lvl == 2:
+            g[0, :, 3:6, 10:20] = np.nan                     # invalid ground truth
+        ins["gt%d" % lvl] = g
+    return ins
+
+
+def grad_signature(name, blob_index, g):
+    """What the golden file keeps of one parameter gradient."""
+    g = np.asarray(g, np.float64).reshape(-1)
+    if name in LOSS_NET_FULL:
+        return g.astype(np.float32)
+    r = np.random.default_rng([77, blob_index] + [ord(c) for c in name])
+    proj = r.standard_normal((4, g.size)) / np.sqrt(g.size)
+    return np.concatenate([proj @ g, [np.sqrt((g * g).sum())]]).astype(np.float32)
