@@ -64,3 +64,23 @@ def test_oracle_net_matches_reference_net(gold, cname):
     want = gold["N/%s/flow" % cname]
     assert np.abs(want).max() > 1.0, "degenerate: flow ~ 0"
     assert maxabs(flow, want) <= 1e-4, maxabs(flow, want)
+
+
+def test_insert_splits_matches_the_reference_tests():
+    """oracle.ref.insert_splits (used to run the reference's layers as a net that can do Backward) against the reference's own
+    InsertSplits expectations (test_split_layer.cpp SplitLayerInsertionTest: TestInsertion, TestInsertionTwoTop, TestWithInPlace;
+    extracted by tests/golden/make_split_golden.py).  Pure text processing: needs neither oracle/_ref nor a GPU."""
+    import json
+    from oracle import ref as R
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "insert_splits_fixtures.json")) as f:
+        cases = json.load(f)["cases"]
+
+    def specs_of(text):
+        _, blocks = R.split_layers(text)
+        return [(R._names(b, "name")[0], R._names(b, "type")[0], b) for b in blocks]
+
+    def sig(specs):
+        return [(n, t, R._names(b, "bottom"), R._names(b, "top")) for n, t, b in specs]
+    assert len(cases) == 3
+    for c in cases:
+        assert sig(R.insert_splits(specs_of(c["input"]))) == sig(specs_of(c["expected"])), c["test"]
