@@ -644,6 +644,10 @@ class BaseConvolutionLayer : public Layer<Dtype> {
             fn2_conv_desc d = d_;
             d.relu = relu_[i]; d.negative_slope = slope_[i];
             fn2_tensor b = bottom[i]->tensor(), t = top[i]->mutable_tensor();
+            // input_guard_bytes promises readable slack around the bottom's OWN allocation (Blob::kGuardFloats), which the kernel-row
+            // packing of small-Ci layers relies on; a zero-copy concat child has none.  Net::AliasConcats keeps such bottoms dense.
+            CHECK(!(!deconv_ && bottom[i]->is_alias() && d_.ci <= 16 && d_.input_guard_bytes > 0))
+                << "a zero-copy concat child must not feed a convolution with <= 16 input channels (layer " << this->layer_param_.name() << ")";
             auto it = packed_.find(bottom[i]->channel_stride() > 0 ? bottom[i]->channel_stride() : d_.ci);
             CHECK(it != packed_.end() && it->second.p) << "convolution weights were never packed for this bottom layout";
             const float* packed = it->second.p;
