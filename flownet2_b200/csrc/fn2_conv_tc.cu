@@ -1418,7 +1418,7 @@ __global__ void wg_reduce_kernel(const float* __restrict__ part, float* __restri
 }
 
 int conv_tc_wgrad_eligible(const fn2_conv_desc* d) {
-    if (!tc_enabled() || getenv("FN2_WGRAD_SIMT")) return 0;
+    if (!tc_enabled() || getenv("FN2_WGRAD_SIMT") || d->engine == 1) return 0;      // engine 1 = `engine: CAFFE`: exact-FP32 SIMT everywhere
     if (d->kh * d->kw > 49 || d->stride_w > 8 || d->stride_h > 8) return 0;
     if (!tc_encode_fn()) return 0;
     return 1;

@@ -224,21 +224,21 @@ def conv2d(x, weight, bias=None, stride=1, pad=0, deconv=False, relu_slope=None,
     return out
 
 
-def _conv_desc(weight, stride, pad, deconv, bias):
+def _conv_desc(weight, stride, pad, deconv, bias, engine=0):
     if deconv:
         ci, co, kh, kw = weight.shape
     else:
         co, ci, kh, kw = weight.shape
     sh, sw = (stride, stride) if isinstance(stride, int) else stride
     ph, pw = (pad, pad) if isinstance(pad, int) else pad
-    return fn2_conv_desc(ci, co, kh, kw, sh, sw, ph, pw, 1 if deconv else 0, 1 if bias else 0, 0, 0.0, 0, 0)
+    return fn2_conv_desc(ci, co, kh, kw, sh, sw, ph, pw, 1 if deconv else 0, 1 if bias else 0, 0, 0.0, engine, 0)
 
 
-def conv2d_backward(x, weight, top_diff, stride=1, pad=0, deconv=False, bias=True, need_input_grad=True):
+def conv2d_backward(x, weight, top_diff, stride=1, pad=0, deconv=False, bias=True, need_input_grad=True, engine=0):
     """ConvolutionLayer / DeconvolutionLayer::Backward_gpu (conv_layer.cu:26-58, deconv_layer.cu:26-55) through the C-ABI:
     -> (bottom_diff or None, weight_diff, bias_diff or None)."""
     l = lib()
-    d = _conv_desc(weight, stride, pad, deconv, bias)
+    d = _conv_desc(weight, stride, pad, deconv, bias, engine)
     weight = weight.contiguous()
     wd = torch.zeros_like(weight)
     bd = torch.zeros(d.co, dtype=torch.float32, device=x.device) if bias else None

@@ -67,6 +67,20 @@ def test_conv_backward_matches_oracle(fn2, case):
     assert rel(gb.cpu().numpy(), wb) <= 1e-5, ("bias diff", rel(gb.cpu().numpy(), wb))
 
 
+@pytest.mark.parametrize("case", [CONV_BWD_CASES[0], CONV_BWD_CASES[2], CONV_BWD_CASES[7], CONV_BWD_CASES[9]], ids=lambda c: c[0] + "_simt")
+def test_conv_backward_simt_engine(fn2, case):
+    """`engine: CAFFE` (fn2_conv_desc.engine = 1): gradients on the exact-FP32 SIMT kernels instead of the tensor cores."""
+    name, N, Ci, H, W, Co, k, s, p, deconv, cl = case
+    r = rng(sum(ord(c) for c in name) + 1)
+    x = r.standard_normal((N, Ci, H, W)).astype(np.float32)
+    w = (r.standard_normal((Ci, Co, k, k) if deconv else (Co, Ci, k, k)) / np.sqrt(Ci * k * k)).astype(np.float32)
+    Ho, Wo = (s * (H - 1) + k - 2 * p, s * (W - 1) + k - 2 * p) if deconv else ((H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1)
+    dy = r.standard_normal((N, Co, Ho, Wo)).astype(np.float32)
+    gx, gw, gb = OPS.conv2d_backward(dev(x, cl), dev(w), dev(dy, cl), s, p, deconv, engine=1)
+    wx, ww, wb = O.conv_bwd(x, w, dy, s, p, deconv)
+    assert rel(gx.cpu().numpy(), wx) <= 1e-5 and rel(gw.cpu().numpy(), ww) <= 1e-5 and rel(gb.cpu().numpy(), wb) <= 1e-5
+
+
 def test_conv_backward_params_accumulates(fn2):
     import ctypes as C
     r = rng(5)
