@@ -1341,8 +1341,9 @@ __global__ void __launch_bounds__(256) wg_transpose_kernel(T4 src, float* __rest
                                                            float* __restrict__ bias_part) {
     __shared__ float tile[WG_TW + 3][33];
     __shared__ float red[8][33];
-    const int wq0 = blockIdx.x * WG_TW, c0 = blockIdx.y * 32;
-    const int rp = blockIdx.z % (src.h * sx), n = blockIdx.z / (src.h * sx);
+    // grid: x = (sample, row, parity) -- the long dimension --, y = channel tile, z = column tile
+    const int wq0 = blockIdx.z * WG_TW, c0 = blockIdx.y * 32;
+    const int rp = blockIdx.x % (src.h * sx), n = blockIdx.x / (src.h * sx);
     const int h = rp / sx, par = rp % sx;
     const int halo = SPLIT ? 0 : 3;
     const int cols = min(WG_TW, Wq_p - wq0);                         // columns of this block that exist in the destination row
@@ -1449,10 +1450,10 @@ int conv_tc_wgrad(const fn2_conv_desc* d, const T4& bottom, const T4& top_diff, 
             const int q = kx - d->pad_w, par = ((q % g.sx) + g.sx) % g.sx, shift = (q - par) / g.sx;
             dlmask |= 1 << ((((-shift) % 4) + 4) % 4);
         }
-        dim3 gb((unsigned)((g.Wq_p + WG_TW - 1) / WG_TW), (unsigned)((g.Cb + 31) / 32), (unsigned)(g.N * g.Hb * g.sx));
+        dim3 gb((unsigned)(g.N * g.Hb * g.sx), (unsigned)((g.Cb + 31) / 32), (unsigned)((g.Wq_p + WG_TW - 1) / WG_TW));
         wg_transpose_kernel<false><<<gb, blk, 0, st>>>(big, bigT, g.sx, g.Wq, g.Wq_p, 0, dlmask, d->deconv ? bias_part : nullptr);
         FN2_LAUNCH_CHECK();
-        dim3 gs((unsigned)((g.Ws_p + WG_TW - 1) / WG_TW), (unsigned)((g.Cs + 31) / 32), (unsigned)(g.N * g.Hs));
+        dim3 gs((unsigned)(g.N * g.Hs), (unsigned)((g.Cs + 31) / 32), (unsigned)((g.Ws_p + WG_TW - 1) / WG_TW));
         wg_transpose_kernel<true><<<gs, blk, 0, st>>>(small, smallT, 1, g.Ws, g.Ws_p, (long long)g.N * g.Cs * g.Hs * g.Ws_p, 1,
                                                       d->deconv ? nullptr : bias_part);
         FN2_LAUNCH_CHECK();
