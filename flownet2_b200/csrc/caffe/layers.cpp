@@ -1507,6 +1507,41 @@ class GenerateAugmentationParametersLayer : public Layer<Dtype> {
 };
 REGISTER_LAYER_CLASS(GenerateAugmentationParameters);
 
+// Split (split_layer.cpp:9-52): the layer Net::Init's InsertSplits puts behind every blob with several readers.  This executor
+// needs none (fan-out costs nothing in the forward pass, Net::PlanBackward accumulates the gradients), but a prototxt that already
+// contains Split layers -- e.g. one written back by the reference's upgrade tools -- must load: tops are copies of the bottom,
+// the backward sums the top diffs (split_layer.cpp:38-52).
+template <typename Dtype>
+class SplitLayer : public Layer<Dtype> {
+ public:
+    explicit SplitLayer(const LayerParameter& p) : Layer<Dtype>(p) {}
+    const char* type() const override { return "Split"; }
+    void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        CHECK_EQ(bottom.size(), 1u) << "Split takes one bottom";
+        for (Blob<Dtype>* t : top) {
+            CHECK(t != bottom[0]) << this->type() << " Layer does not allow in-place computation.";       // split_layer.cpp:17-19
+            t->ReshapeLike(*bottom[0]);
+        }
+    }
+ protected:
+    void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) override {
+        fn2_tensor s = bottom[0]->tensor();
+        for (Blob<Dtype>* t : top) {
+            fn2_tensor d = t->mutable_tensor();
+            FN2_CALL(fn2_copy(&s, &d, S()));
+        }
+    }
+    void Backward_gpu(const vector<Blob<Dtype>*>& top, const vector<bool>& propagate_down, const vector<Blob<Dtype>*>& bottom) override {
+        if (!propagate_down[0]) return;
+        fn2_tensor dx = bottom[0]->diff_tensor();
+        for (size_t i = 0; i < top.size(); i++) {
+            fn2_tensor dy = top[i]->diff_tensor();
+            FN2_CALL(fn2_axpby(&dy, 1.f, &dx, (i > 0 || this->bottom_accumulate_[0]) ? 1.f : 0.f, S()));
+        }
+    }
+};
+REGISTER_LAYER_CLASS(Split);
+
 // referenced by net.cpp to force this translation unit (and its static registrars) to link
 void RegisterFlowNetLayers() {}
 

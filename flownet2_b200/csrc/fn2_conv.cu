@@ -731,11 +731,11 @@ int fn2_conv_forward(const fn2_conv_desc* d, const fn2_tensor* bottom, const flo
         const size_t smem = (size_t)d->kh * d->kw * C4 * 4 * sizeof(float2);
         const bool k3 = d->kh == 3 && d->kw == 3 && d->stride_h == 1 && d->stride_w == 1;
         if (C4 <= 8) {
-            const int grid = (int)min((long long)148 * 8, (M + 255) / 256);
+            const int grid = (int)min((long long)num_sms() * 8, (M + 255) / 256);
 #define FN2_PF_THREAD(C)                                                                                                   \
             case C: if (k3 && d->pad_h == 1 && d->pad_w == 1 && !getenv("FN2_PF_NOTILE")) {                                \
                         const size_t tsm = smem + (size_t)10 * 34 * (C + 1) * sizeof(float4);                               \
-                        const int tgrid = (int)min((long long)148 * 4, (long long)p.N * ((p.Wo + 31) / 32) * ((p.Ho + 7) / 8)); \
+                        const int tgrid = (int)min((long long)num_sms() * 4, (long long)p.N * ((p.Wo + 31) / 32) * ((p.Ho + 7) / 8)); \
                         if (tsm > 48 * 1024) FN2_CUDA(cudaFuncSetAttribute(conv_pf3_tile_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm)); \
                         conv_pf3_tile_kernel<C><<<tgrid, 256, tsm, st>>>(in, packed_weights_dev, bias_dev, out, p);            \
                     } else if (k3) conv_pf3_thread_kernel<C><<<grid, 256, smem, st>>>(in, packed_weights_dev, bias_dev, out, p);  \
@@ -754,10 +754,10 @@ int fn2_conv_forward(const fn2_conv_desc* d, const fn2_tensor* bottom, const flo
             const int per_sm = (int)max((size_t)1, min((size_t)8, (size_t)(220 * 1024) / (smem + 1024)));
             if (k3) {
                 const long long groups = (long long)p.N * p.Ho * ((p.Wo + 3) / 4);
-                const int grid = (int)min((long long)148 * per_sm, (groups + 7) / 8);
+                const int grid = (int)min((long long)num_sms() * per_sm, (groups + 7) / 8);
                 conv_pf3_warp_kernel<<<grid, 256, smem, st>>>(in, packed_weights_dev, bias_dev, out, p, C4);
             } else {
-                const int grid = (int)min((long long)148 * per_sm, (M + 7) / 8);
+                const int grid = (int)min((long long)num_sms() * per_sm, (M + 7) / 8);
                 conv_pf_warp_kernel<<<grid, 256, smem, st>>>(in, packed_weights_dev, bias_dev, out, p, C4);
             }
         }

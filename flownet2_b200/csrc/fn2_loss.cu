@@ -222,7 +222,7 @@ __global__ void flow_aug_kernel(T4 src, T4 dst, const float* __restrict__ m1, co
     }
 }
 
-int loss_grid(long long P) { return (int)max(1LL, min((long long)148 * 4, (P + 255) / 256)); }
+int loss_grid(long long P) { return (int)max(1LL, min((long long)num_sms() * 4, (P + 255) / 256)); }
 
 }  // namespace
 }  // namespace fn2

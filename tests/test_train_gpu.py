@@ -365,3 +365,25 @@ def test_loss_net_gradients_match_reference_net(fn2):
         got = TC.grad_signature(name, int(i), net.param(name, int(i), diff=True))
         scale = float(np.abs(want).max())
         assert np.abs(got - want).max() <= 5e-5 * scale, (k, float(np.abs(got - want).max()), scale)      # measured: 2.2e-6
+
+
+def test_explicit_split_layers_load_and_sum_gradients(fn2):
+    """A prototxt that already went through the reference's InsertSplits (explicit Split layers, split_layer.cpp): forward copies,
+    backward sums the top diffs -- the same gradients as the implicit fan-out."""
+    shape = "dim: 2 dim: 4 dim: 6 dim: 8"
+    head = 'force_backward: true\nlayer { name: "in" type: "Input" top: "a" input_param { shape { %s } } }\n' % shape
+    tail = ('layer { name: "s1" type: "Eltwise" bottom: "%s" top: "b1" eltwise_param { operation: SUM coeff: 2 } }\n'
+            'layer { name: "s2" type: "Eltwise" bottom: "%s" top: "b2" eltwise_param { operation: SUM coeff: -3 } }\n'
+            'layer { name: "l1" type: "L1Loss" bottom: "b1" top: "loss1" loss_weight: 1 }\n'
+            'layer { name: "l2" type: "L1Loss" bottom: "b2" top: "loss2" loss_weight: 0.5 l1_loss_param { l2_per_location: true } }\n')
+    split = 'layer { name: "a_in_0_split" type: "Split" bottom: "a" top: "a_in_0_split_0" top: "a_in_0_split_1" }\n'
+    a = rng(31).standard_normal((2, 4, 6, 8)).astype(np.float32)
+    grads = []
+    for proto in (head + tail % ("a", "a"), head + split + tail % ("a_in_0_split_0", "a_in_0_split_1")):
+        net = fn2.Net(proto, None, fn2.TEST)
+        out = net.forward(a=a)
+        net.backward()
+        grads.append((net.get_diff("a"), float(out["loss1"].reshape(-1)[0]), float(out["loss2"].reshape(-1)[0])))
+    assert "Split" in fn2.Net(head + split + tail % ("a_in_0_split_0", "a_in_0_split_1"), None, fn2.TEST).layer_types
+    assert grads[0][1:] == grads[1][1:]
+    assert np.abs(grads[0][0]).max() > 0 and maxabs(grads[0][0], grads[1][0]) <= 1e-6
