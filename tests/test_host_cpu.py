@@ -318,3 +318,38 @@ def test_v1_prototxt_upgrade_matches_the_reference_tests(fn2):
         assert _norm_tree(got) == _norm_tree(want)
     with pytest.raises(fn2.Fn2Error):
         canonical(fn2, "layers { name: 'x' type: NO_SUCH_TYPE }")
+
+
+def test_train_prototxt_parser_matches_reference_protobuf(fn2):
+    """The authored FlowNet2-C training prototxt, as the reference's own caffe_pb2 reads it (tests/golden/make_train_proto_golden.py:
+    every field exists in the reference's caffe.proto) against the engine's parser: layers, bottoms / tops, loss weights,
+    propagate_down, L1Loss parameters, augmentation generators, coefficient schedule."""
+    ref = json.load(open(os.path.join(GOLD, "ref_pb2_train_prototxt.json")))
+    text = fn2.fill_train_template(fn2.train_template("FlowNet2-C"), 448, 320, 512, 384, 8)
+    msg = onet.parse_prototxt(canonical(fn2, text))
+    layers = onet.getall(msg, "layer")
+    assert len(layers) == len(ref["layers"]) == 67
+    for got, want in zip(layers, ref["layers"]):
+        assert onet.get(got, "name") == want["name"] and onet.get(got, "type") == want["type"]
+        assert onet.getall(got, "bottom") == want["bottom"] and onet.getall(got, "top") == want["top"]
+        assert np.allclose([float(x) for x in onet.getall(got, "loss_weight")], want["loss_weight"], rtol=1e-6)
+        assert [x == "true" for x in onet.getall(got, "propagate_down")] == want["propagate_down"]
+        if "l1" in want:
+            lp = onet.get(got, "l1_loss_param", [])
+            assert [onet.get(lp, "l2_per_location", "false") == "true", onet.get(lp, "l2_prescale_by_channels", "false") == "true",
+                    onet.get(lp, "normalize_by_num_entries", "false") == "true"] == want["l1"][:3]
+        if "aug" in want:
+            ap = onet.get(got, "augmentation_param")
+            assert [int(onet.get(ap, "crop_width", 0)), int(onet.get(ap, "crop_height", 0))] == want["aug"]["crop"]
+            assert onet.get(ap, "mode", "add") == want["aug"]["mode"]
+            gens = {k: v for k, v in ap if isinstance(v, list)}
+            assert sorted(gens) == sorted(want["aug"]["generators"])
+            for k, g in gens.items():
+                w = want["aug"]["generators"][k]
+                assert onet.get(g, "rand_type") == w[0] and (onet.get(g, "exp", "false") == "true") == w[1]
+                assert np.allclose([float(onet.get(g, "mean", 0)), float(onet.get(g, "spread", 0)), float(onet.get(g, "prob", 1))], w[2:], rtol=1e-6)
+        if "schedule" in want:
+            cs = onet.get(got, "coeff_schedule_param")
+            assert np.allclose([float(onet.get(cs, k)) for k in ("half_life", "initial_coeff", "final_coeff")], want["schedule"])
+        if "shapes" in want:
+            assert [[int(d) for d in onet.getall(s, "dim")] for s in onet.getall(onet.get(got, "input_param"), "shape")] == want["shapes"]
