@@ -127,40 +127,18 @@ class CpuArm(object):
 
 def reference_gpu_arm(args, batch, steps=5, warmup=2):
     """The reference's OWN GPU path (its unmodified layer classes from oracle/_ref: im2col + cuBLAS convolutions, its correlation /
-    warp / resample kernels) on the same workload and the same B200, inputs resident on the host side of its Blobs.  A reported
-    baseline like cpu_baseline, N = 1 only; None when oracle/_ref is not built."""
+    warp / resample kernels) on the same workload and the same B200 (tools/ref_forward_time.py).  A reported baseline like
+    cpu_baseline, N = 1 only; None when oracle/_ref is not built.  Runs as a subprocess: a CHECK failure inside the reference aborts
+    its process and must never take the bench line down."""
     try:
-        import torch
-        import flownet2_b200 as F
         from oracle import ref as R
-        from oracle.net import synth_weights
         if not R.available():
             return None
-        R.set_mode(True, 0)
-        small = F.fill_template(F.model_template(args.model), 64, 64)
-        proto = F.fill_template(F.model_template(args.model), args.width, args.height)
-        weights, _ = synth_weights(small, 1701, proto)
-        net = R.RefNet(proto, weights, batch=batch)
-        r = np.random.default_rng(3)
-        a = np.round(r.uniform(0, 255, (batch, 3, args.height, args.width))).astype(np.float32)
-        b = np.clip(a + np.round(r.normal(0, 3, a.shape)), 0, 255).astype(np.float32)
-        times = []
-        for i in range(warmup + steps):
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            net.forward(img0=a, img1=b)
-            flow = net.blob("predict_flow_final")            # device -> host read = synchronisation
-            dt = time.perf_counter() - t0
-            if i >= warmup:
-                times.append(dt)
-        mean = float(np.mean(times))
-        R.set_mode(False)
-        return {"value": batch / mean, "unit": UNIT, "ms_per_step": mean * 1e3, "ms_min": min(times) * 1e3, "ms_max": max(times) * 1e3,
-                "steps": steps, "warmup": warmup,
-                "what": "reference layer classes (oracle/_ref) in GPU mode on the same B200: %s %dx%d, %d pairs per step, host-timed "
-                        "including its H2D/D2H blob copies" % (args.model, args.width, args.height, batch),
-                "output_finite": bool(np.isfinite(flow).all())}
-    except Exception as e:                                   # a baseline must never take the bench line down
+        pr = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_forward_time.py"), args.model, str(args.width), str(args.height),
+                             str(batch), str(steps), str(warmup)], capture_output=True, text=True, timeout=600)
+        last = [l for l in pr.stdout.strip().splitlines() if l.startswith("{")]
+        return json.loads(last[-1]) if last else {"unavailable": "exit %d: %s" % (pr.returncode, pr.stderr.strip()[-300:])}
+    except Exception as e:
         return {"unavailable": "%s: %s" % (type(e).__name__, e)}
 
 
