@@ -39,6 +39,7 @@ SOURCES = [
     ("caffe/blob.cpp", []),
     ("caffe/layers.cpp", []),
     ("caffe/net.cpp", []),
+    ("caffe/hdf5_min.cpp", []),
     ("caffe/capi.cpp", []),
 ]
 

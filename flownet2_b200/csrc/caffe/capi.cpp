@@ -2,6 +2,7 @@
 #include <cstring>
 
 #include "net.hpp"
+#include "hdf5_min.hpp"
 
 namespace fn2 { void set_error(const char* fmt, ...); }
 
@@ -297,6 +298,29 @@ int fn2_aug_sample(const char* layer_prototxt, unsigned int seed, int num, int w
         caffe::SampleAugmentationCoeffs(*lp, seed, num, width, height, num_iter, coeffs_out);
         return FN2_OK;
     FN2_CATCH
+}
+
+int fn2_hdf5_summary(const void* h5, size_t n, char* out, size_t* bytes) {
+    if (!h5) { fn2::set_error("hdf5_summary: null data"); return FN2_ERR_INVALID; }
+    try {
+        caffe::H5File f(h5, n);
+        std::string s;
+        char buf[128];
+        for (const auto& kv : f.datasets()) {
+            s += kv.first + " f" + std::to_string(kv.second.elem_size * 8) + " [";
+            for (size_t i = 0; i < kv.second.dims.size(); i++) { snprintf(buf, sizeof(buf), i ? ",%d" : "%d", kv.second.dims[i]); s += buf; }
+            std::vector<float> v = f.read(kv.first);
+            double sum = 0;
+            for (float x : v) sum += (double)x;
+            snprintf(buf, sizeof(buf), "] n=%zu sum=%.9g first=%.9g last=%.9g", v.size(), sum, v.empty() ? 0.0 : (double)v.front(), v.empty() ? 0.0 : (double)v.back());
+            s += buf;
+            s += "\n";
+        }
+        return emit_string(s, out, bytes);
+    } catch (const std::exception& e) {
+        fn2::set_error("%s", e.what());
+        return FN2_ERR_PARSE;
+    }
 }
 
 int fn2_caffemodel_summary(const void* caffemodel, size_t n, char* out, size_t* bytes) {

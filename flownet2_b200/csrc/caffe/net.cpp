@@ -1,4 +1,5 @@
 #include "net.hpp"
+#include "hdf5_min.hpp"
 
 #include <cstdlib>
 #include <cstring>
@@ -304,8 +305,52 @@ static vector<int> strip_leading_ones(const vector<int>& s) {
 }
 
 // Net::CopyTrainedLayersFrom(const NetParameter&), net.cpp:752-802
+// Net::CopyTrainedLayersFromHDF5 (net.cpp:823-870): /data/<layer name>/<blob index>, unknown source layers ignored, a source
+// layer may not have more blobs than the target, every target blob must be present; the blob takes the dataset's shape
+// (hdf5_load_nd_dataset, util/hdf5.cpp:20-76).  Parsed by the minimal reader of hdf5_min.cpp (no HDF5 library in this image).
+template <typename Dtype>
+void Net<Dtype>::CopyTrainedLayersFromHDF5(const void* h5, size_t bytes) {
+    Caffe::stream() = stream_;
+    H5File f(h5, bytes);
+    CHECK(f.has("/data")) << "Error reading weights: the file has no /data group";
+    std::map<string, int> index;
+    for (size_t i = 0; i < layer_names_.size(); i++) index[layer_names_[i]] = (int)i;
+    for (const string& src : f.links("/data")) {
+        auto it = index.find(src);
+        if (it == index.end()) continue;                               // "Ignoring source layer"
+        auto& target = layers_[it->second]->blobs();
+        const string base = "/data/" + src;
+        const vector<string> links = f.links(base);
+        CHECK_LE(links.size(), target.size()) << "Incompatible number of blobs for layer " << src;
+        vector<Blob<Dtype>*> staged;
+        vector<shared_ptr<Blob<Dtype> > > tmp;
+        for (size_t j = 0; j < target.size(); j++) {
+            const string ds = base + "/" + std::to_string(j);
+            CHECK(f.has(ds)) << "Incompatible number of blobs for layer " << src;
+            vector<int> dims;
+            vector<float> v = f.read(ds, &dims);
+            CHECK_LE(dims.size(), 4u) << "dataset " << ds << " has more than 4 axes";
+            if (layers_[it->second]->DoesUseCustomCopyBlobs()) {           // DataAugmentation adjusts sizes itself (net.cpp:769-778)
+                shared_ptr<Blob<Dtype> > b(new Blob<Dtype>());
+                b->Reshape(dims);
+                if (!v.empty()) memcpy(b->mutable_cpu_data(), v.data(), v.size() * sizeof(float));
+                tmp.push_back(b); staged.push_back(b.get());
+                continue;
+            }
+            CHECK_EQ((size_t)target[j]->count(), v.size()) << "Cannot copy param " << j << " weights from layer '" << src
+                << "'; shape mismatch (" << v.size() << " values in the file)";
+            target[j]->Reshape(dims);
+            if (!v.empty()) memcpy(target[j]->mutable_cpu_data(), v.data(), v.size() * sizeof(float));
+        }
+        if (!staged.empty()) layers_[it->second]->CustomCopyBlobs(staged);
+    }
+    ParamsChanged();
+}
+
 template <typename Dtype>
 void Net<Dtype>::CopyTrainedLayersFrom(const void* caffemodel, size_t bytes) {
+    static const unsigned char h5sig[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
+    if (bytes >= 8 && !memcmp(caffemodel, h5sig, 8)) { CopyTrainedLayersFromHDF5(caffemodel, bytes); return; }   // .caffemodel.h5
     Caffe::stream() = stream_;
     vector<LayerBlobs> src = ParseCaffemodel(caffemodel, bytes);
     for (const LayerBlobs& sl : src) {

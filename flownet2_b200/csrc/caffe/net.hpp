@@ -30,7 +30,8 @@ class Net {
     void Sync();
     cudaStream_t stream() const { return stream_; }
 
-    void CopyTrainedLayersFrom(const void* caffemodel, size_t bytes);     // net.cpp:752-802
+    void CopyTrainedLayersFrom(const void* caffemodel, size_t bytes);     // net.cpp:752-802 (binary proto) / :823-870 (HDF5, by signature)
+    void CopyTrainedLayersFromHDF5(const void* h5, size_t bytes);
     std::string ToCaffemodel();
     void FillParams(uint64_t seed);
     void ParamsChanged();

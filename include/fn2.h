@@ -343,6 +343,11 @@ FN2_API int fn2_proto_canonical(const char* prototxt_text, char* out, size_t* by
 FN2_API int fn2_aug_sample(const char* layer_prototxt, unsigned int seed, int num, int width, int height, float num_iter,
                            float* coeffs_out);
 FN2_API int fn2_caffemodel_summary(const void* caffemodel, size_t n, char* out, size_t* bytes);
+/* HDF5 weight files (.caffemodel.h5, net.cpp:823-870; hdf5_load_nd_dataset util/hdf5.cpp:20-76).  fn2_net_copy_trained_layers
+ * recognises them by their signature.  fn2_hdf5_summary (host only): one line per dataset of the file: path, f32/f64, shape, count,
+ * sum, first and last value.  The reader covers what libhdf5 writes for such files by default (superblock 0, symbol-table groups,
+ * contiguous little-endian float datasets); chunked / gzip datasets and new-style groups return FN2_ERR_PARSE with the reason. */
+FN2_API int fn2_hdf5_summary(const void* h5, size_t n, char* out, size_t* bytes);
 
 /* .flo files (util/output.cpp:16-64): "PIEH", int32 w, int32 h, interleaved (u,v) fp32. */
 FN2_API int fn2_write_flo(const char* path, const float* flow_nchw_2hw, int h, int w);

@@ -353,3 +353,51 @@ def test_train_prototxt_parser_matches_reference_protobuf(fn2):
             assert np.allclose([float(onet.get(cs, k)) for k in ("half_life", "initial_coeff", "final_coeff")], want["schedule"])
         if "shapes" in want:
             assert [[int(d) for d in onet.getall(s, "dim")] for s in onet.getall(onet.get(got, "input_param"), "shape")] == want["shapes"]
+
+
+def _h5_summary(fn2, data):
+    lib = fn2.lib()
+    lib.fn2_hdf5_summary.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p, C.POINTER(C.c_size_t)]
+    buf = (C.c_char * len(data)).from_buffer_copy(data)
+    n = C.c_size_t()
+    if lib.fn2_hdf5_summary(buf, len(data), None, C.byref(n)):
+        raise fn2.Fn2Error(lib.fn2_last_error().decode())
+    out = C.create_string_buffer(n.value)
+    assert lib.fn2_hdf5_summary(buf, len(data), out, C.byref(n)) == 0
+    return out.value.decode().strip().splitlines()
+
+
+def test_hdf5_reader_on_files_written_by_the_real_library(fn2):
+    """The minimal HDF5 reader (csrc/caffe/hdf5_min.cpp) on the reference's own test data, written with h5py / libhdf5
+    (tests/golden/ref_hdf5/): shapes, every value (data = arange), and a loud refusal of the gzip-compressed variant."""
+    d = os.path.join(GOLD, "ref_hdf5")
+    lines = _h5_summary(fn2, open(os.path.join(d, "sample_data.h5"), "rb").read())
+    assert lines == ["/data f32 [10,8,6,5] n=2400 sum=2878800 first=0 last=2399", "/label f32 [10,1] n=10 sum=55 first=1 last=10",
+                     "/label2 f32 [10,1] n=10 sum=65 first=2 last=11"]
+    lines = _h5_summary(fn2, open(os.path.join(d, "solver_data.h5"), "rb").read())
+    assert [l.split(" n=")[0] for l in lines] == ["/data f32 [8,3,10,10]", "/targets f32 [8,1]"]
+    with pytest.raises(fn2.Fn2Error, match="gzip"):
+        _h5_summary(fn2, open(os.path.join(d, "sample_data_2_gzip.h5"), "rb").read())
+    with pytest.raises(fn2.Fn2Error, match="signature"):
+        _h5_summary(fn2, b"\x00" * 200)
+    trunc = open(os.path.join(d, "sample_data.h5"), "rb").read()[:5000]
+    with pytest.raises(fn2.Fn2Error, match="outside the file"):
+        _h5_summary(fn2, trunc)
+
+
+def test_hdf5_reader_nested_caffemodel_layout(fn2):
+    """/data/<layer>/<blob index> (Net::ToHDF5's layout, net.cpp:905-960) through a test-side writer of the same on-disk structures."""
+    from tests.util_h5 import write_caffemodel_h5
+    r = np.random.default_rng(3)
+    layers = {"conv1": [r.standard_normal((4, 3, 3, 3)).astype(np.float32), r.standard_normal(4).astype(np.float32)],
+              "deconv2": [r.standard_normal((2, 5, 4, 4)).astype(np.float32)],
+              "img0s_aug": [np.full((1, 1, 1, 1), 1001, np.float32), np.full((1, 3, 1, 1), 0.4, np.float32), np.full((1, 3, 1, 1), 0.4, np.float32)]}
+    for k in range(20):                                   # more than one symbol node per group
+        layers["extra%02d" % k] = [np.full((2, 2), float(k), np.float32)]
+    lines = _h5_summary(fn2, write_caffemodel_h5(layers))
+    want = []
+    for name in sorted(layers):
+        for i, b in enumerate(layers[name]):
+            want.append("/data/%s/%d f32 [%s] n=%d sum=%.9g first=%.9g last=%.9g" % (name, i, ",".join(str(d) for d in b.shape), b.size,
+                                                                               float(b.astype(np.float64).sum()), float(b.ravel()[0]), float(b.ravel()[-1])))
+    assert lines == want

@@ -303,3 +303,22 @@ def test_fused_warp_block_is_bit_identical_to_the_layer_chain(fn2, monkeypatch):
     for b in blobs:
         assert np.array_equal(got[0][0][b], got[1][0][b], equal_nan=True), b
     assert np.abs(got[0][0]["net2_in_err_norm"]).max() > 0
+
+
+def test_weights_from_hdf5_equal_weights_from_caffemodel(fn2):
+    """Net::CopyTrainedLayersFromHDF5 (net.cpp:823-870): the same weights as /data/<layer>/<index> datasets of an HDF5 file
+    (recognised by its signature) must give the same flow, bit for bit, as the binary .caffemodel."""
+    from oracle.net import parse_caffemodel
+    from tests.util_h5 import write_caffemodel_h5
+    proto = fn2.fill_template(fn2.model_template("FlowNet2-S"), 128, 64)
+    a = fn2.Net(proto, None, fn2.TEST, batch=1)
+    a.fill_params(13)
+    binary = a.to_caffemodel()
+    h5 = write_caffemodel_h5(parse_caffemodel(binary))
+    img0, img1 = smooth_images(rng(13), 1, 64, 128)
+    want = a.forward(img0=img0, img1=img1)["predict_flow_final"]
+    b = fn2.Net(proto, h5, fn2.TEST, batch=1)
+    got = b.forward(img0=img0, img1=img1)["predict_flow_final"]
+    assert np.abs(want).max() > 1e-3 and np.array_equal(got, want)
+    with pytest.raises(fn2.Fn2Error):
+        fn2.Net(proto, h5[:4000], fn2.TEST, batch=1)                      # truncated file: loud failure, no partial load
