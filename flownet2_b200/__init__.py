@@ -73,6 +73,9 @@ def lib():
         l.fn2_net_layer_need_backward.argtypes = [C.c_void_p, C.c_int]
         l.fn2_net_copy_trained_layers.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         l.fn2_net_to_caffemodel.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]
+        l.fn2_net_to_hdf5.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]
+        l.fn2_caffemodel_to_hdf5.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]
+        l.fn2_hdf5_summary.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p, C.POINTER(C.c_size_t)]
         l.fn2_net_fill_params.argtypes = [C.c_void_p, C.c_uint64]
         l.fn2_net_param_arena.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         l.fn2_net_blob_shape.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]
@@ -249,6 +252,14 @@ class Net(object):
         check(lib().fn2_net_to_caffemodel(self._h, None, C.byref(n)))
         buf = (C.c_char * n.value)()
         check(lib().fn2_net_to_caffemodel(self._h, buf, C.byref(n)))
+        return bytes(buf[:n.value])
+
+    def to_hdf5(self):
+        """Net::ToHDF5 (net.cpp:905-960): the weights as the bytes of a .caffemodel.h5 file."""
+        n = C.c_size_t(0)
+        check(lib().fn2_net_to_hdf5(self._h, None, C.byref(n)))
+        buf = (C.c_char * n.value)()
+        check(lib().fn2_net_to_hdf5(self._h, buf, C.byref(n)))
         return bytes(buf[:n.value])
 
     def param_arena(self):

@@ -300,6 +300,46 @@ int fn2_aug_sample(const char* layer_prototxt, unsigned int seed, int num, int w
     FN2_CATCH
 }
 
+static std::string caffemodel_to_h5(const void* caffemodel, size_t n) {
+    std::vector<caffe::LayerBlobs> ls = caffe::ParseCaffemodel(caffemodel, n);
+    std::vector<std::pair<std::string, std::vector<caffe::H5Blob> > > layers;
+    for (const auto& l : ls) {
+        if (l.blobs.empty()) continue;
+        std::vector<caffe::H5Blob> bl;
+        for (const auto& b : l.blobs) { caffe::H5Blob hb; hb.dims = b.shape; hb.data = b.data; bl.push_back(std::move(hb)); }
+        layers.push_back({l.name, std::move(bl)});
+    }
+    return caffe::WriteCaffemodelH5(layers);
+}
+
+int fn2_caffemodel_to_hdf5(const void* caffemodel, size_t n, void* out, size_t* bytes) {
+    if (!caffemodel || !bytes) { fn2::set_error("caffemodel_to_hdf5: null argument"); return FN2_ERR_INVALID; }
+    try {
+        const std::string h5 = caffemodel_to_h5(caffemodel, n);
+        if (!out) { *bytes = h5.size(); return FN2_OK; }
+        if (*bytes < h5.size()) { fn2::set_error("caffemodel_to_hdf5: buffer too small"); return FN2_ERR_INVALID; }
+        memcpy(out, h5.data(), h5.size());
+        *bytes = h5.size();
+        return FN2_OK;
+    } catch (const std::exception& e) {
+        fn2::set_error("%s", e.what());
+        return FN2_ERR_PARSE;
+    }
+}
+
+int fn2_net_to_hdf5(fn2_net* net, void* buf, size_t* bytes) {
+    if (!net || !bytes) { fn2::set_error("to_hdf5: null argument"); return FN2_ERR_INVALID; }
+    FN2_TRY
+        const std::string cm = net->net->ToCaffemodel();
+        const std::string h5 = caffemodel_to_h5(cm.data(), cm.size());
+        if (!buf) { *bytes = h5.size(); return FN2_OK; }
+        if (*bytes < h5.size()) { fn2::set_error("to_hdf5: buffer too small"); return FN2_ERR_INVALID; }
+        memcpy(buf, h5.data(), h5.size());
+        *bytes = h5.size();
+        return FN2_OK;
+    FN2_CATCH
+}
+
 int fn2_hdf5_summary(const void* h5, size_t n, char* out, size_t* bytes) {
     if (!h5) { fn2::set_error("hdf5_summary: null data"); return FN2_ERR_INVALID; }
     try {

@@ -1,5 +1,6 @@
 #include "hdf5_min.hpp"
 
+#include <algorithm>
 #include <cstring>
 
 namespace caffe {
@@ -174,6 +175,105 @@ std::vector<float> H5File::read(const std::string& path, std::vector<int>* dims)
     }
     if (dims) *dims = d.dims;
     return out;
+}
+
+// ---- writer ------------------------------------------------------------------------------------------------------------------
+namespace {
+struct H5Out {
+    std::string buf;
+    H5Out() : buf(96, '\0') {}                              // superblock (56) + root symbol table entry (40), filled in last
+    void put(uint64_t v, int n) { for (int i = 0; i < n; i++) buf.push_back((char)((v >> (8 * i)) & 0xff)); }
+    uint64_t begin() { while (buf.size() % 8) buf.push_back('\0'); return buf.size(); }
+    void set(size_t off, uint64_t v, int n) { for (int i = 0; i < n; i++) buf[off + i] = (char)((v >> (8 * i)) & 0xff); }
+    void message(int type, const std::string& body) {
+        const size_t padded = (body.size() + 7) & ~(size_t)7;
+        put((uint64_t)type, 2); put(padded, 2); put(0, 1); put(0, 3);
+        buf += body;
+        buf.append(padded - body.size(), '\0');
+    }
+    uint64_t dataset(const H5Blob& b) {
+        const uint64_t raw = begin();
+        buf.append(reinterpret_cast<const char*>(b.data.data()), b.data.size() * sizeof(float));
+        std::string space, dtype, layout;
+        auto app = [](std::string& s, uint64_t v, int n) { for (int i = 0; i < n; i++) s.push_back((char)((v >> (8 * i)) & 0xff)); };
+        app(space, 1, 1); app(space, b.dims.size(), 1); app(space, 0, 2); app(space, 0, 4);
+        for (int d : b.dims) app(space, (uint64_t)d, 8);
+        // IEEE float32 little endian: class 1 / version 1; bit field 0x20 0x1f 0x00; size 4; offset 0, precision 32, exponent 23/8,
+        // mantissa 0/23, bias 127
+        app(dtype, 0x11, 1); app(dtype, 0x20, 1); app(dtype, 0x1f, 1); app(dtype, 0, 1); app(dtype, 4, 4);
+        app(dtype, 0, 2); app(dtype, 32, 2); app(dtype, 23, 1); app(dtype, 8, 1); app(dtype, 0, 1); app(dtype, 23, 1); app(dtype, 127, 4);
+        app(layout, 3, 1); app(layout, 1, 1); app(layout, raw, 8); app(layout, b.data.size() * sizeof(float), 8);
+        const uint64_t hdr = begin();
+        put(1, 1); put(0, 1); put(3, 2); put(1, 4);
+        const size_t size_at = buf.size();
+        put(0, 4); put(0, 4);
+        const size_t start = buf.size();
+        message(1, space); message(3, dtype); message(8, layout);
+        set(size_at, buf.size() - start, 4);
+        return hdr;
+    }
+    // one group: local heap, symbol nodes of <= 8 links under ONE level-0 B-tree node (<= 32 children)
+    void group(const std::vector<std::pair<std::string, uint64_t> >& sorted_links, uint64_t* hdr, uint64_t* btree, uint64_t* heap) {
+        if (sorted_links.size() > 256) throw H5Error("more than 256 links in one group are not supported by the writer");
+        std::string heap_data(8, '\0');
+        std::vector<uint64_t> offs;
+        for (const auto& l : sorted_links) {
+            offs.push_back(heap_data.size());
+            heap_data += l.first;
+            heap_data.push_back('\0');
+            while (heap_data.size() % 8) heap_data.push_back('\0');
+        }
+        const uint64_t data_addr = begin();
+        buf += heap_data;
+        *heap = begin();
+        buf += "HEAP"; put(0, 1); put(0, 3); put(heap_data.size(), 8); put(kUndef, 8); put(data_addr, 8);
+        std::vector<std::pair<uint64_t, uint64_t> > children;       // (symbol node address, heap offset of its largest name)
+        for (size_t i = 0; i < sorted_links.size() || i == 0; i += 8) {
+            const size_t n = sorted_links.size() > i ? std::min<size_t>(8, sorted_links.size() - i) : 0;
+            const uint64_t snod = begin();
+            buf += "SNOD"; put(1, 1); put(0, 1); put(n, 2);
+            for (size_t k = 0; k < n; k++) { put(offs[i + k], 8); put(sorted_links[i + k].second, 8); put(0, 4); put(0, 4); buf.append(16, '\0'); }
+            buf.append(40 * (8 - n), '\0');
+            children.push_back({snod, n ? offs[i + n - 1] : 0});
+            if (!n) break;
+        }
+        *btree = begin();
+        buf += "TREE"; put(0, 1); put(0, 1); put(children.size(), 2); put(kUndef, 8); put(kUndef, 8);
+        put(0, 8);
+        for (const auto& c : children) { put(c.first, 8); put(c.second, 8); }
+        buf.append(16 * (32 - children.size()), '\0');
+        *hdr = begin();
+        put(1, 1); put(0, 1); put(1, 2); put(1, 4); put(24, 4); put(0, 4);
+        std::string body;
+        for (int i = 0; i < 8; i++) body.push_back((char)((*btree >> (8 * i)) & 0xff));
+        for (int i = 0; i < 8; i++) body.push_back((char)((*heap >> (8 * i)) & 0xff));
+        message(0x11, body);
+    }
+};
+}  // namespace
+
+std::string WriteCaffemodelH5(const std::vector<std::pair<std::string, std::vector<H5Blob> > >& layers) {
+    H5Out w;
+    std::map<std::string, uint64_t> layer_groups;            // std::map: links sorted by name, as the B-tree requires
+    for (const auto& l : layers) {
+        std::map<std::string, uint64_t> links;
+        for (size_t i = 0; i < l.second.size(); i++) links[std::to_string(i)] = w.dataset(l.second[i]);
+        uint64_t hdr, bt, hp;
+        w.group(std::vector<std::pair<std::string, uint64_t> >(links.begin(), links.end()), &hdr, &bt, &hp);
+        if (layer_groups.count(l.first)) throw H5Error("duplicate layer name '" + l.first + "'");
+        layer_groups[l.first] = hdr;
+    }
+    uint64_t data_hdr, bt, hp;
+    w.group(std::vector<std::pair<std::string, uint64_t> >(layer_groups.begin(), layer_groups.end()), &data_hdr, &bt, &hp);
+    uint64_t root_hdr, root_bt, root_hp;
+    w.group({{"data", data_hdr}}, &root_hdr, &root_bt, &root_hp);
+    static const unsigned char sig[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
+    for (int i = 0; i < 8; i++) w.buf[i] = (char)sig[i];
+    w.buf[13] = 8; w.buf[14] = 8;                            // sizes of offsets / lengths; all version bytes 0
+    w.set(16, 4, 2); w.set(18, 16, 2);                       // group leaf / internal node K
+    w.set(24, 0, 8); w.set(32, kUndef, 8); w.set(40, w.buf.size(), 8); w.set(48, kUndef, 8);
+    w.set(56, 0, 8); w.set(64, root_hdr, 8); w.set(72, 1, 4); w.set(80, root_bt, 8); w.set(88, root_hp, 8);
+    return w.buf;
 }
 
 }  // namespace caffe

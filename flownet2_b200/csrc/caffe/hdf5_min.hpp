@@ -50,4 +50,9 @@ class H5File {
     std::vector<std::pair<std::string, H5Dataset> > datasets_;
 };
 
+// Writer for the same subset (Net::ToHDF5, net.cpp:905-960 / hdf5_save_nd_dataset, util/hdf5.cpp:130-160): /data/<layer>/<index>
+// float32 datasets with the blobs' shapes.  layers: (name, blobs as (dims, values)).
+struct H5Blob { std::vector<int> dims; std::vector<float> data; };
+std::string WriteCaffemodelH5(const std::vector<std::pair<std::string, std::vector<H5Blob> > >& layers);
+
 }  // namespace caffe

@@ -348,6 +348,11 @@ FN2_API int fn2_caffemodel_summary(const void* caffemodel, size_t n, char* out, 
  * sum, first and last value.  The reader covers what libhdf5 writes for such files by default (superblock 0, symbol-table groups,
  * contiguous little-endian float datasets); chunked / gzip datasets and new-style groups return FN2_ERR_PARSE with the reason. */
 FN2_API int fn2_hdf5_summary(const void* h5, size_t n, char* out, size_t* bytes);
+/* Net::ToHDF5 (net.cpp:905-960): the weights as /data/<layer>/<index> float32 datasets (superblock 0, symbol-table groups, contiguous
+ * data: the subset fn2_hdf5_summary / fn2_net_copy_trained_layers read).  Size-query convention (out / buf == NULL).
+ * fn2_caffemodel_to_hdf5 converts a binary .caffemodel on the host (no GPU needed). */
+FN2_API int fn2_caffemodel_to_hdf5(const void* caffemodel, size_t n, void* out, size_t* bytes);
+FN2_API int fn2_net_to_hdf5(fn2_net* net, void* buf, size_t* bytes);
 
 /* .flo files (util/output.cpp:16-64): "PIEH", int32 w, int32 h, interleaved (u,v) fp32. */
 FN2_API int fn2_write_flo(const char* path, const float* flow_nchw_2hw, int h, int w);

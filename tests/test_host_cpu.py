@@ -401,3 +401,29 @@ def test_hdf5_reader_nested_caffemodel_layout(fn2):
             want.append("/data/%s/%d f32 [%s] n=%d sum=%.9g first=%.9g last=%.9g" % (name, i, ",".join(str(d) for d in b.shape), b.size,
                                                                                float(b.astype(np.float64).sum()), float(b.ravel()[0]), float(b.ravel()[-1])))
     assert lines == want
+
+
+def test_caffemodel_to_hdf5_round_trip(fn2):
+    """fn2_caffemodel_to_hdf5 (the host half of Net::ToHDF5): a binary caffemodel -- here the fixture the reference's caffe_pb2 wrote --
+    converted to HDF5 and read back by the reader that is pinned on real libhdf5 files: same layers, shapes and values."""
+    lib = fn2.lib()
+    lib.fn2_caffemodel_to_hdf5.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]
+    data = open(os.path.join(GOLD, "ref_pb2_caffemodel.bin"), "rb").read()
+    desc = json.load(open(os.path.join(GOLD, "ref_pb2_caffemodel.json")))
+    buf = (C.c_char * len(data)).from_buffer_copy(data)
+    n = C.c_size_t()
+    assert lib.fn2_caffemodel_to_hdf5(buf, len(data), None, C.byref(n)) == 0
+    out = (C.c_char * n.value)()
+    assert lib.fn2_caffemodel_to_hdf5(buf, len(data), out, C.byref(n)) == 0
+    lines = _h5_summary(fn2, bytes(out[:n.value]))
+    want = {}
+    for l in desc:
+        for i, b in enumerate(l["blobs"]):
+            want["/data/%s/%d" % (l["name"], i)] = b
+    assert len(lines) == len(want) == 8
+    for line in lines:
+        path, rest = line.split(" ", 1)
+        b = want[path]
+        assert rest.startswith("f32 [%s] " % ",".join(str(d) for d in b["shape"]))
+        got_sum = float(rest.split("sum=")[1].split()[0]); got_first = float(rest.split("first=")[1].split()[0])
+        assert abs(got_sum - b["sum"]) <= 1e-5 * max(1.0, abs(b["sum"])) and abs(got_first - b["first"]) <= 1e-6 * max(1.0, abs(b["first"]))
